@@ -1,0 +1,212 @@
+/*
+ * rdpn6d_b200.h -- C ABI of librdpn6d_b200.so (hand-written sm_100a CUDA kernels).
+ *
+ * Drop-in boundary for RDPN6D's test-time dense-correspondence -> pose path and its FPS extension.
+ * Plain pointers and sizes only; no torch / C++ types.  Each entry cites the reference interface it
+ * replaces (paths relative to the RDPN6D repository root).
+ *
+ * Conventions
+ *   - "d_" arguments are DEVICE pointers; entry points that take them are stream-ordered, allocate
+ *     nothing, never synchronise, and return 0 on success, a positive cudaError_t, or a negative
+ *     RDPN_E_* code.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - "h_" arguments are HOST pointers; those entry points copy in, launch, copy out and
+ *     synchronise before returning (they are what a CPU caller of the reference binds to).
+ *   - All float tensors are FP32, C-contiguous.  ROI maps are 64 x 64 (P = 4096 pixels), the
+ *     reference's BACKBONE.OUTPUT_RES (configs/_base_/gdrn_base.py:26).
+ *   - There is NO CPU fallback anywhere in this library.
+ */
+#ifndef RDPN6D_B200_H
+#define RDPN6D_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RDPN_VERSION 100 /* 0.1.0 */
+
+/* negative error codes (positive values are cudaError_t) */
+#define RDPN_E_BADARG (-1)    /* NULL / non-positive size / unsupported option */
+#define RDPN_E_ALIGN (-2)     /* a ROI-map pointer is not 16-byte aligned (bulk-TMA requirement) */
+#define RDPN_E_WORKSPACE (-3) /* workspace too small */
+#define RDPN_E_TOOLARGE (-4)  /* problem exceeds what the kernel supports */
+#define RDPN_E_NOCOOP (-5)    /* device lacks cooperative launch */
+
+/* status codes written per ROI by rdpn_pose_solve (cf. gdrn_evaluator.py:293-301, 393-395) */
+#define RDPN_STATUS_OK 0
+#define RDPN_STATUS_FEW_POINTS 1   /* fewer than min_pts gated correspondences: pose = -100 fill  */
+#define RDPN_STATUS_T_SANITY 2     /* te(t_est, t_net) > 1 m: translation replaced by t_net       */
+#define RDPN_STATUS_NO_CONSENSUS 3 /* no valid hypothesis reached min_inliers: pose = -100 fill   */
+
+/* mask post-processing modes (engine_utils.py:118-136 get_out_mask) */
+#define RDPN_MASK_RAW 0 /* mask already is a probability                     */
+#define RDPN_MASK_L1 1  /* per-ROI (m - min) / (max - min), no epsilon       */
+#define RDPN_MASK_BCE 2 /* sigmoid                                           */
+
+int rdpn_version(void);
+const char* rdpn_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------------
+ * B1  Farthest point sampling -- replaces core/csrc/fps/src/ext.h:1-14 and
+ *     core/csrc/fps/src/farthest_point_sampling.cpp:166-204.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Exact drop-in symbols (same names, same signatures, HOST pointers, synchronous):
+ *   pts [pn,3] float, idxs [sn] int (written).  ext.h:1-6 and ext.h:9-14.
+ * farthest_point_sampling() keeps the reference's "random start" contract (cpp:93-94) by drawing the
+ * start index with srand(time(0)); rand() % pn on the host; everything after that is the GPU kernel. */
+void farthest_point_sampling(float* pts, int* idxs, int pn, int sn);
+void farthest_point_sampling_init_center(float* pts, int* idxs, int pn, int sn);
+
+/* Device-pointer entries.  d_ws: scratch of at least rdpn_fps_workspace_bytes(sn) bytes.
+ * Indices are bit-exact with the reference C++ (squared FP32 distances without FMA, lowest index
+ * wins ties, index 0 when nothing is left: cpp:40-73). */
+size_t rdpn_fps_workspace_bytes(int sn);
+int rdpn_fps_init_center(const float* d_pts, int32_t* d_idxs, int pn, int sn, void* d_ws, size_t ws_bytes,
+                         void* stream);
+int rdpn_fps_from_index(const float* d_pts, int32_t* d_idxs, int pn, int sn, int start, void* d_ws,
+                        size_t ws_bytes, void* stream);
+/* Gather pts[idxs] (fps_utils.py:21) and, when d_center != NULL, the per-axis mean row appended by
+ * get_fps_and_center (core/utils/data_utils.py:217-226) computed in FP64. out: [sn,3] (+[1,3]). */
+int rdpn_fps_gather(const float* d_pts, const int32_t* d_idxs, int pn, int sn, float* d_out, double* d_center,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a1  ROI crop intrinsics -- core/utils/data_utils.py:111-152 (rot = 0) + data_loader.py:553-568.
+ *     K [B,9] row-major, center [B,2], scale [B] -> Kp [B,4] = (fx', fy', cx', cy') of the
+ *     crop_res x crop_res crop (256 in the reference).  Computed in FP64, rounded once to FP32.
+ * ---------------------------------------------------------------------------------------------- */
+int rdpn_roi_intrinsics(const float* d_K, const float* d_center, const float* d_scale, int crop_res, float* d_Kp,
+                        int B, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * B4  Generic back-projection -- lib/pysixd/misc.py:319-349 (backproject / backproject_th).
+ *     depth [B,H,W], K [B,9] (or one K when k_stride == 0) -> out [B,H,W,3]; (X*depth)/fx order.
+ * ---------------------------------------------------------------------------------------------- */
+int rdpn_backproject(const float* d_depth, const float* d_K, int k_stride, float* d_out, int B, int H, int W,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * ROI inputs shared by S1 and the fused solver.  Per ROI b (P = 4096, planar, row-major 64x64):
+ *   depth  [B,P]   ROI depth at crop pixels (4i,4j), metres, 0 = no measurement
+ *                  (data_loader.py:532-535, 563, 625)
+ *   Kp     [B,4]   (fx',fy',cx',cy') of the 256 crop (rdpn_roi_intrinsics)
+ *   depth_div [B] or NULL: divide depth by this first (resize_ratio, data_loader.py:563)
+ *   coor_x/y/z [B,P]  head outputs in [0,1] (cdpn_rot_head_region.py:190-198); delta=(c-0.5)*extent
+ *   mask   [B,P]   raw head mask; mask_mode selects get_out_mask's post-processing
+ *   extent [B,3]   object extents (roi_extent)
+ *   region_idx [B,P] uint8 and anchors [B,R,3]: anchor mode (GDRN.py:206-218); both NULL: dense mode
+ *                  (obj = delta, cam = back-projected point)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rdpn_roi_inputs {
+    const float* depth;
+    const float* Kp;
+    const float* depth_div;
+    const float* coor_x;
+    const float* coor_y;
+    const float* coor_z;
+    const float* mask;
+    const float* extent;
+    const uint8_t* region_idx;
+    const float* anchors;
+    int32_t num_regions; /* R (<= 255); ignored in dense mode */
+    int32_t mask_mode;   /* RDPN_MASK_*                      */
+    float mask_thr;      /* MASK_THR_TEST, 0.5 (gdrn_base.py) */
+    int32_t B;
+} rdpn_roi_inputs;
+
+/* S1 (materialising): fused back-projection + residual + mask gate for every pixel.
+ *   d_cam  [B,3,P]  camera-side point of the correspondence (q - delta | q)
+ *   d_obj  [B,3,P]  object-side point (anchor | delta); may be NULL in anchor mode (region_idx says it)
+ *   d_w    [B,P]    mask probability
+ *   d_sel  [B,P]    uint8 gate: mask_prob > mask_thr && |delta_c| > 1e-4*extent_c (all c) && depth > 0
+ *                   (gdrn_evaluator.py:110-117 + depth validity)
+ *   d_nsel [B]      int32 number of gated pixels
+ * Replaces data_loader.py:563-576 + gdrn_evaluator.py:89-126 + engine_utils.py:118-136. */
+int rdpn_correspond(const rdpn_roi_inputs* in, float* d_cam, float* d_obj, float* d_w, uint8_t* d_sel,
+                    int32_t* d_nsel, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * B2  Fused pose solve: S1 + hypothesis generation + inlier scoring + best selection + weighted
+ *     Kabsch/Umeyama refit, one launch for the whole batch.  Replaces the per-ROI CPU loop of
+ *     gdrn_evaluator.py:316-435 (process_pnp_ransac) with the 3D-3D composite of
+ *     lib/pysixd/misc.py:58-142 (RANSAC semantics) and lib/pysixd/transform.py:913-980 (Kabsch).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rdpn_solve_params {
+    float inlier_thr;    /* metres; inlier <=> ||R a + t - c|| < thr (strict, misc.py:111)          */
+    int32_t num_hyp;     /* H                                                                       */
+    int32_t min_pts;     /* 4  (gdrn_evaluator.py:380)                                              */
+    int32_t min_inliers; /* 4  (misc.py:121)                                                        */
+    int32_t weighted;    /* 0: unweighted refit (transform.py), 1: mask-probability weights         */
+    int32_t refit_iters; /* >= 1: refit on inliers, re-score, refit ...                             */
+    int32_t with_scale;  /* Umeyama scale (transform.py:971-975)                                    */
+    int32_t adaptive;    /* misc.py:134-138 early stop emulated on the hypothesis order             */
+    float confidence;    /* 0.995 (misc.py:73)                                                      */
+    int32_t min_iter;    /* 10 (misc.py:63)                                                         */
+} rdpn_solve_params;
+
+typedef struct rdpn_solve_outputs {
+    float* pose;           /* [B,12] row-major 3x4 (R|t), FP32                                       */
+    int32_t* n_inliers;    /* [B] inliers of the winning hypothesis                                  */
+    int32_t* status;       /* [B] RDPN_STATUS_*                                                      */
+    int32_t* best_h;       /* [B] winning hypothesis index or -1            (may be NULL)            */
+    int32_t* n_sel;        /* [B] gated correspondences                     (may be NULL)            */
+    uint8_t* inlier_mask;  /* [B,P] pixels used by the last refit           (may be NULL)            */
+    int32_t* hyp_counts;   /* [B,H] inlier count per hypothesis (0 = invalid) (may be NULL)          */
+    float* hyp_poses;      /* [B,H,12] FP32 hypothesis poses                (may be NULL)            */
+    float* scale;          /* [B] Umeyama scale                             (may be NULL)            */
+} rdpn_solve_outputs;
+
+/* hyp_idx [B,H,3] int32 absolute pixel indices (0..4095); t_net [B,3] or NULL (translation sanity). */
+int rdpn_pose_solve(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, const float* d_t_net,
+                    const rdpn_solve_params* prm, const rdpn_solve_outputs* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * B4  Batched weighted Kabsch / Umeyama -- lib/pysixd/transform.py:913-1029
+ *     (affine_matrix_from_points(shear=False, usesvd=True) / superimposition_matrix).
+ *     src, dst [B,N,3]; w [B,N] or NULL; out_M [B,12] (3x4, maps src -> dst); out_scale [B] or NULL.
+ *     Warp-shuffle segmented reduction (FP64 accumulate) + closed-form rotation per ROI.
+ * ---------------------------------------------------------------------------------------------- */
+int rdpn_kabsch(const float* d_src, const float* d_dst, const float* d_w, int N, int with_scale, float* d_out_M,
+                float* d_out_scale, int B, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * B3  Pose assembly -- core/gdrn_modeling/models/pose_from_pred_centroid_z.py:52-141 (test branch)
+ *     with allocentric_to_egocentric (core/utils/utils.py:39-94) done on the GPU for all ROIs
+ *     (the reference loops on the CPU with one device->host sync per ROI).
+ *     rot_in: [B,9] rotation matrices, or [B,6] rot6d when rot_is_6d (core/utils/rot_reps.py:34-49).
+ *     z_type_rel: 1 = "REL" (z * resize_ratio), 0 = "ABS".
+ * ---------------------------------------------------------------------------------------------- */
+int rdpn_centroid_z_to_pose(const float* d_rot_in, int rot_is_6d, const float* d_centroid, const float* d_z,
+                            const float* d_K, const float* d_center, const float* d_resize_ratio,
+                            const float* d_wh, int is_allo, int z_type_rel, float* d_rot_out, float* d_trans_out,
+                            int B, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * f2  Region arg-max -- GDRN.py:206-209: argmax over channels 1..R of region [B,R+1,P] -> uint8.
+ * ---------------------------------------------------------------------------------------------- */
+int rdpn_region_argmax(const float* d_region, int R, uint8_t* d_region_idx, int B, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host-buffer plugin call (what a CPU caller of the reference's evaluator binds): every pointer in
+ * `in`, hyp_idx, t_net and `out` is a HOST pointer.  The context owns device scratch and streams;
+ * ROIs are pipelined in chunks so host->device copies overlap the kernels.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rdpn_ctx rdpn_ctx;
+int rdpn_ctx_create(int device, rdpn_ctx** out_ctx);
+void rdpn_ctx_destroy(rdpn_ctx* ctx);
+int rdpn_pose_solve_host(rdpn_ctx* ctx, const rdpn_roi_inputs* h_in, const int32_t* h_hyp_idx, const float* h_t_net,
+                         const rdpn_solve_params* prm, const rdpn_solve_outputs* h_out);
+/* Number of kernel launches issued by this library in this process (bench.py's gpu_launches). */
+unsigned long long rdpn_launch_count(void);
+
+/* FP32 FMA throughput probe (roofline denominator for the scoring stage): runs `iters` dependent FMA
+ * chains on every SM and returns achieved FLOP/s in *out_flops (synchronous). */
+int rdpn_fp32_peak_probe(int iters, double* out_flops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RDPN6D_B200_H */

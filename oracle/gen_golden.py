@@ -1,0 +1,188 @@
+"""oracle/gen_golden.py -- generates tests/golden/*.npz by EXECUTING THE REFERENCE in this container.
+
+Run from the repository root:  python -m oracle.gen_golden
+Needs /root/reference (read-only mount).  The reference modules that import cleanly here are loaded by
+file path (lib/pysixd/transform.py, core/utils/data_utils.py); the reference FPS C++ is compiled by
+oracle/Makefile into oracle/_ref/.  Nothing is copied from the reference: only inputs we generate and
+the outputs the reference computes for them are stored.
+
+Files written (small, committed):
+  fps_golden.npz      clouds (or their seeds) + indices from the reference C++ build
+  kabsch_golden.npz   point sets + 4x4 matrices from transform.affine_matrix_from_points /
+                      superimposition_matrix, incl. the doctest literal (transform.py:893-898),
+                      a reflection case (:945-948) and Umeyama scale (:971-975)
+  affine_golden.npz   (center, scale) + 2x3 matrices from data_utils.get_affine_transform (:111-152)
+  region_golden.npz   xyz crops + anchors + (region ids, delta) from data_utils.xyz_to_region (:229-244)
+  pose_golden.npz     a 4-ROI synthetic batch + the composite's outputs where EVERY Kabsch call
+                      (hypotheses and refit) went through the reference's affine_matrix_from_points
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+
+REF = os.environ.get("RDPN_REFERENCE", "/root/reference")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _load(name, rel):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def gen_fps():
+    from oracle.fps import fps_indices_reference
+    from rdpn6d_b200.synth import fps_cloud
+
+    out = {}
+    rng = np.random.default_rng(7)
+    small = {
+        "gauss_2000": (fps_cloud(2000, seed=1), 64),
+        "lattice_1000": (np.stack(np.meshgrid(*[np.arange(10)] * 3, indexing="ij"), -1).reshape(-1, 3).astype(np.float32), 200),
+        "dups_40": (np.repeat(rng.standard_normal((10, 3)).astype(np.float32), 4, 0), 24),
+        "n_eq_k_50": (rng.standard_normal((50, 3)).astype(np.float32), 50),
+        "n_lt_k_10": (rng.standard_normal((10, 3)).astype(np.float32), 20),
+        "cube_8": (np.array([[x, y, z] for x in (0, 1) for y in (0, 1) for z in (0, 1)], np.float32), 8),
+        "single_1": (np.array([[0.5, -1.0, 2.0]], np.float32), 3),
+    }
+    for name, (pts, k) in small.items():
+        out[name + "_pts"] = pts
+        out[name + "_idx"] = fps_indices_reference(pts, k)
+    # large clouds: store the generator seed only (rdpn6d_b200.synth.fps_cloud) + indices
+    for n, k, seed in [(200_000, 64, 3), (1_000_000, 8, 0), (1_000_000, 64, 0), (1_000_000, 512, 0)]:
+        out[f"seeded_{n}_{k}_{seed}_idx"] = fps_indices_reference(fps_cloud(n, seed=seed), k)
+    np.savez_compressed(os.path.join(GOLD, "fps_golden.npz"), **out)
+    print("fps_golden.npz", len(out))
+
+
+def gen_kabsch(tf):
+    rng = np.random.default_rng(11)
+    out = {}
+    # doctest literal transform.py:893-898 (2-D affine; pins the module itself)
+    v0 = [[0, 1031, 1031, 0], [0, 0, 1600, 1600]]
+    v1 = [[675, 826, 826, 677], [55, 52, 281, 277]]
+    out["doctest_v0"], out["doctest_v1"] = np.array(v0, float), np.array(v1, float)
+    out["doctest_M"] = tf.affine_matrix_from_points(v0, v1)
+    cases = []
+    for i, n in enumerate([3, 4, 10, 100, 2000]):
+        R = tf.random_rotation_matrix(rng.random(3))[:3, :3]
+        t = rng.uniform(-1, 1, 3)
+        a = rng.uniform(-0.2, 0.2, (3, n))
+        c = R @ a + t[:, None] + rng.normal(0, 1e-3, (3, n))
+        cases.append(("rigid%d" % i, a, c, False))
+    a = rng.uniform(-0.2, 0.2, (3, 50))
+    c = np.diag([1, 1, -1.0]) @ a + rng.normal(0, 1e-3, (3, 50))  # mirrored set -> det<0 branch
+    cases.append(("reflect", a, c, False))
+    a = rng.uniform(-0.2, 0.2, (3, 3))
+    c = np.diag([1, -1.0, 1]) @ a + 0.3  # flipped triangle
+    cases.append(("reflect_tri", a, c, False))
+    a = rng.uniform(-0.2, 0.2, (3, 200))
+    R = tf.random_rotation_matrix(rng.random(3))[:3, :3]
+    c = 1.7 * (R @ a) + np.array([[0.1], [0.2], [0.9]]) + rng.normal(0, 1e-3, (3, 200))
+    cases.append(("umeyama", a, c, True))
+    a = rng.uniform(-0.2, 0.2, (3, 60))
+    a[2] = 0.0  # planar
+    c = R @ a + 0.5
+    cases.append(("planar", a, c, False))
+    for name, a, c, sc in cases:
+        out[name + "_v0"], out[name + "_v1"] = a, c
+        out[name + "_M"] = tf.affine_matrix_from_points(a, c, shear=False, scale=sc, usesvd=True)
+        out[name + "_Msup"] = tf.superimposition_matrix(np.asarray(a, np.float64), np.asarray(c, np.float64), scale=sc)
+        out[name + "_scale"] = np.array(sc)
+    out["case_names"] = np.array([c[0] for c in cases])
+    np.savez_compressed(os.path.join(GOLD, "kabsch_golden.npz"), **out)
+    print("kabsch_golden.npz", len(cases))
+
+
+def gen_affine(du):
+    rng = np.random.default_rng(13)
+    centers = rng.uniform(50, 600, (32, 2))
+    scales = rng.uniform(20, 640, 32)
+    mats = np.stack([du.get_affine_transform(centers[i], float(scales[i]), 0, 256) for i in range(32)])
+    mats64 = np.stack([du.get_affine_transform(centers[i], float(scales[i]), 0, 64) for i in range(32)])
+    # float32-representable inputs (what the evaluator-side tensors hold: bbox_center.astype("float32"))
+    c32 = centers.astype(np.float32).astype(np.float64)
+    s32 = scales.astype(np.float32).astype(np.float64)
+    mats32 = np.stack([du.get_affine_transform(c32[i], float(s32[i]), 0, 256) for i in range(32)])
+    np.savez_compressed(os.path.join(GOLD, "affine_golden.npz"), centers=centers, scales=scales, A256=mats, A64=mats64,
+                        centers32=c32, scales32=s32, A256_32=mats32)
+    print("affine_golden.npz")
+
+
+def gen_region(du):
+    rng = np.random.default_rng(17)
+    xyz = rng.uniform(-0.1, 0.1, (4, 64, 64, 3))
+    xyz[:, :10] = 0.0  # background rows
+    fps = rng.uniform(-0.1, 0.1, (4, 32, 3))
+    ids, deltas = [], []
+    for i in range(4):
+        r, d = du.xyz_to_region(xyz[i], fps[i])
+        ids.append(r)
+        deltas.append(d)
+    np.savez_compressed(os.path.join(GOLD, "region_golden.npz"), xyz=xyz, fps=fps, region=np.stack(ids), delta=np.stack(deltas))
+    print("region_golden.npz")
+
+
+def gen_pose(tf):
+    """Composite outputs with the reference's Kabsch on every solve."""
+    from oracle import pose_oracle as po
+    from rdpn6d_b200 import synth
+
+    def ref_kabsch(v0, v1, w=None, scale=False):
+        assert w is None
+        return tf.affine_matrix_from_points(v0, v1, shear=False, scale=scale, usesvd=True)
+
+    def ref_hypothesis_poses(obj, cam, sel, hyp_idx):
+        Rt, valid = _orig_hyp(obj, cam, sel, hyp_idx)  # validity rule is ours
+        for h in np.nonzero(valid)[0]:
+            a = obj[:, hyp_idx[h]].astype(np.float64)
+            c = cam[:, hyp_idx[h]].astype(np.float64)
+            M = tf.affine_matrix_from_points(a, c, shear=False, scale=False, usesvd=True)
+            Rt[h] = M[:3, :4].astype(np.float32).reshape(12)
+        return Rt, valid
+
+    _orig_hyp, _orig_k = po.hypothesis_poses, po.kabsch
+    po.hypothesis_poses, po.kabsch = ref_hypothesis_poses, ref_kabsch
+    try:
+        models = synth.make_models(4, 32, seed=5, n_symmetric=1)
+        b = synth.make_batch(4, models=models, H=64, seed=20260101)
+        thr = 0.005
+        res = po.pose_solve_batch(b, b["hyp_idx"], thr)
+    finally:
+        po.hypothesis_poses, po.kabsch = _orig_hyp, _orig_k
+    out = {k: v for k, v in b.items() if v is not None}
+    out["thr"] = np.float32(thr)
+    out["out_pose"] = np.stack([r["pose"] for r in res])
+    out["out_ninl"] = np.array([r["n_inl"] for r in res], np.int32)
+    out["out_status"] = np.array([r["status"] for r in res], np.int32)
+    out["out_best_h"] = np.array([r["best_h"] for r in res], np.int32)
+    out["out_nsel"] = np.array([r["n_sel"] for r in res], np.int32)
+    out["out_counts"] = np.stack([r["counts"] for r in res])
+    out["out_valid"] = np.stack([r["valid"] for r in res])
+    out["out_Rt_hyp"] = np.stack([r["Rt_hyp"] for r in res])
+    out["out_inlier_mask"] = np.stack([r["inlier_mask"] for r in res])
+    out["out_sel"] = np.stack([r["s1"]["sel"] for r in res])
+    out["out_cam"] = np.stack([r["s1"]["cam"] for r in res])
+    np.savez_compressed(os.path.join(GOLD, "pose_golden.npz"), **out)
+    print("pose_golden.npz", out["out_status"], out["out_ninl"])
+
+
+def main():
+    if not os.path.isdir(REF):
+        sys.exit("reference not mounted at %s" % REF)
+    os.makedirs(GOLD, exist_ok=True)
+    tf = _load("ref_transform", "lib/pysixd/transform.py")
+    du = _load("ref_data_utils", "core/utils/data_utils.py")
+    gen_fps()
+    gen_kabsch(tf)
+    gen_affine(du)
+    gen_region(du)
+    gen_pose(tf)
+
+
+if __name__ == "__main__":
+    main()

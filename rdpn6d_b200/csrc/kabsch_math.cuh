@@ -1,0 +1,157 @@
+// FP64 closed-form rigid alignment helpers shared by the fused solver and the batched Kabsch entry.
+//
+//  * kabsch3(): minimal 3-pair Kabsch.  For three pairs the centred sets are planar, so the SVD
+//    solution of lib/pysixd/transform.py:940-951 (R = U diag(1,1,det) V^T) reduces to: map plane
+//    normal to plane normal and rotate in-plane by atan2(sum cross, sum dot).  No iteration.
+//  * rotation_from_cov(): rotation maximising tr(R^T S) for a 3x3 cross-covariance via Horn's
+//    quaternion matrix (the reference's own non-SVD branch, transform.py:953-969) solved with a
+//    cyclic Jacobi sweep on the symmetric 4x4.  Equals the SVD branch incl. the det<0 fix (:945-948).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace rdpn {
+
+#define RDPN_DEGENERATE_SIN2 1e-6
+
+// non-degeneracy of the triangle (p0,p1,p2); explicit _rn intrinsics so that no FMA is formed and the
+// result is bit-identical to oracle/pose_oracle.py:_triangle_ok (float64, one rounding per op).
+__device__ __forceinline__ bool triangle_ok(const double* p0, const double* p1, const double* p2) {
+    const double e1x = __dsub_rn(p1[0], p0[0]), e1y = __dsub_rn(p1[1], p0[1]), e1z = __dsub_rn(p1[2], p0[2]);
+    const double e2x = __dsub_rn(p2[0], p0[0]), e2y = __dsub_rn(p2[1], p0[1]), e2z = __dsub_rn(p2[2], p0[2]);
+    const double nx = __dsub_rn(__dmul_rn(e1y, e2z), __dmul_rn(e1z, e2y));
+    const double ny = __dsub_rn(__dmul_rn(e1z, e2x), __dmul_rn(e1x, e2z));
+    const double nz = __dsub_rn(__dmul_rn(e1x, e2y), __dmul_rn(e1y, e2x));
+    const double a2 = __dadd_rn(__dadd_rn(__dmul_rn(nx, nx), __dmul_rn(ny, ny)), __dmul_rn(nz, nz));
+    const double l1 = __dadd_rn(__dadd_rn(__dmul_rn(e1x, e1x), __dmul_rn(e1y, e1y)), __dmul_rn(e1z, e1z));
+    const double l2 = __dadd_rn(__dadd_rn(__dmul_rn(e2x, e2x), __dmul_rn(e2y, e2y)), __dmul_rn(e2z, e2z));
+    return a2 > __dmul_rn(RDPN_DEGENERATE_SIN2, __dmul_rn(l1, l2));
+}
+
+__device__ __forceinline__ void plane_basis(const double* p0, const double* p1, const double* p2, double* e1,
+                                            double* e2, double* n) {
+    double ax = p1[0] - p0[0], ay = p1[1] - p0[1], az = p1[2] - p0[2];
+    const double bx = p2[0] - p0[0], by = p2[1] - p0[1], bz = p2[2] - p0[2];
+    double nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+    const double il = 1.0 / sqrt(ax * ax + ay * ay + az * az);
+    const double in = 1.0 / sqrt(nx * nx + ny * ny + nz * nz);
+    ax *= il; ay *= il; az *= il;
+    nx *= in; ny *= in; nz *= in;
+    e1[0] = ax; e1[1] = ay; e1[2] = az;
+    n[0] = nx; n[1] = ny; n[2] = nz;
+    e2[0] = ny * az - nz * ay;
+    e2[1] = nz * ax - nx * az;
+    e2[2] = nx * ay - ny * ax;
+}
+
+// a[3][3], c[3][3]: three object / camera points (row = point).  Rt: 3x4 row-major (R | t), c ~ R a + t.
+__device__ __forceinline__ void kabsch3(const double (*a)[3], const double (*c)[3], double* Rt) {
+    double e1a[3], e2a[3], na[3], e1c[3], e2c[3], nc[3];
+    plane_basis(a[0], a[1], a[2], e1a, e2a, na);
+    plane_basis(c[0], c[1], c[2], e1c, e2c, nc);
+    double ma[3], mc[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        ma[k] = (a[0][k] + a[1][k] + a[2][k]) * (1.0 / 3.0);
+        mc[k] = (c[0][k] + c[1][k] + c[2][k]) * (1.0 / 3.0);
+    }
+    double sdot = 0.0, scross = 0.0;  // m11+m22 and m21-m12 of the in-plane 2x2 covariance
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double A0 = a[i][0] - ma[0], A1 = a[i][1] - ma[1], A2 = a[i][2] - ma[2];
+        const double C0 = c[i][0] - mc[0], C1 = c[i][1] - mc[1], C2 = c[i][2] - mc[2];
+        const double xa = A0 * e1a[0] + A1 * e1a[1] + A2 * e1a[2];
+        const double ya = A0 * e2a[0] + A1 * e2a[1] + A2 * e2a[2];
+        const double xc = C0 * e1c[0] + C1 * e1c[1] + C2 * e1c[2];
+        const double yc = C0 * e2c[0] + C1 * e2c[1] + C2 * e2c[2];
+        sdot += xc * xa + yc * ya;
+        scross += yc * xa - xc * ya;
+    }
+    const double ih = 1.0 / sqrt(sdot * sdot + scross * scross);
+    const double cs = sdot * ih, sn = scross * ih;
+    double f1[3], f2[3];  // images of e1a, e2a
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        f1[k] = cs * e1c[k] + sn * e2c[k];
+        f2[k] = cs * e2c[k] - sn * e1c[k];
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) Rt[4 * r + k] = f1[r] * e1a[k] + f2[r] * e2a[k] + nc[r] * na[k];
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) Rt[4 * r + 3] = mc[r] - (Rt[4 * r] * ma[0] + Rt[4 * r + 1] * ma[1] + Rt[4 * r + 2] * ma[2]);
+}
+
+// S[i*3+j] = sum_w c_i a_j (camera row, object column), i.e. v1 . v0^T of transform.py:942.
+// R (row-major) maximises sum c^T R a over SO(3).
+__device__ __noinline__ void rotation_from_cov(const double* S, double* R) {
+    // Horn's N with Sh_ij = sum a_i c_j = S[j*3+i]
+    const double Sxx = S[0], Sxy = S[3], Sxz = S[6];
+    const double Syx = S[1], Syy = S[4], Syz = S[7];
+    const double Szx = S[2], Szy = S[5], Szz = S[8];
+    double A[4][4], V[4][4];
+    A[0][0] = Sxx + Syy + Szz; A[0][1] = Syz - Szy;        A[0][2] = Szx - Sxz;         A[0][3] = Sxy - Syx;
+    A[1][1] = Sxx - Syy - Szz; A[1][2] = Sxy + Syx;        A[1][3] = Szx + Sxz;
+    A[2][2] = -Sxx + Syy - Szz; A[2][3] = Syz + Szy;
+    A[3][3] = -Sxx - Syy + Szz;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < i) A[i][j] = A[j][i];
+            V[i][j] = (i == j) ? 1.0 : 0.0;
+        }
+    for (int sweep = 0; sweep < 24; ++sweep) {
+        double off = 0.0, diag = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            diag += A[i][i] * A[i][i];
+#pragma unroll
+            for (int j = i + 1; j < 4; ++j) off += A[i][j] * A[i][j];
+        }
+        if (off <= 1e-32 * diag || off == 0.0) break;
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int q = p + 1; q < 4; ++q) {
+                const double apq = A[p][q];
+                if (apq != 0.0) {
+                    const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+                    const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                    const double cc = 1.0 / sqrt(tt * tt + 1.0), ss = tt * cc;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {  // A <- A J
+                        const double akp = A[k][p], akq = A[k][q];
+                        A[k][p] = cc * akp - ss * akq;
+                        A[k][q] = ss * akp + cc * akq;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {  // A <- J^T A ; V <- V J
+                        const double apk = A[p][k], aqk = A[q][k];
+                        A[p][k] = cc * apk - ss * aqk;
+                        A[q][k] = ss * apk + cc * aqk;
+                        const double vkp = V[k][p], vkq = V[k][q];
+                        V[k][p] = cc * vkp - ss * vkq;
+                        V[k][q] = ss * vkp + cc * vkq;
+                    }
+                }
+            }
+    }
+    int best = 0;
+    double bv = A[0][0];
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+        if (A[i][i] > bv) { bv = A[i][i]; best = i; }
+    double q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (i == best) { q0 = V[0][i]; q1 = V[1][i]; q2 = V[2][i]; q3 = V[3][i]; }
+    const double inv = 1.0 / sqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+    q0 *= inv; q1 *= inv; q2 *= inv; q3 *= inv;
+    R[0] = 1.0 - 2.0 * (q2 * q2 + q3 * q3); R[1] = 2.0 * (q1 * q2 - q3 * q0);       R[2] = 2.0 * (q1 * q3 + q2 * q0);
+    R[3] = 2.0 * (q1 * q2 + q3 * q0);       R[4] = 1.0 - 2.0 * (q1 * q1 + q3 * q3); R[5] = 2.0 * (q2 * q3 - q1 * q0);
+    R[6] = 2.0 * (q1 * q3 - q2 * q0);       R[7] = 2.0 * (q2 * q3 + q1 * q0);       R[8] = 1.0 - 2.0 * (q1 * q1 + q2 * q2);
+}
+
+}  // namespace rdpn

@@ -1,0 +1,100 @@
+"""Batched GPU versions of the pysixd geometry helpers the path uses (surface B4 of SURVEY.md 8b).
+
+reference function (under /root/reference)                     here
+-------------------------------------------------------------  ------------------------------
+lib/pysixd/misc.py:334-349   backproject_th(depth, K)           backproject_th (also batched)
+lib/pysixd/transform.py:983  superimposition_matrix(v0, v1)     superimposition_matrix, kabsch
+core/utils/data_utils.py:111-152 + data_loader.py:553-568      roi_intrinsics
+core/gdrn_modeling/models/GDRN.py:206-209                      region_argmax
+All compute happens in csrc/*.cu through the C ABI; CUDA tensors only.
+"""
+import torch
+
+from . import _lib
+
+
+def _cuda_f32(x, name):
+    if not x.is_cuda:
+        raise RuntimeError("rdpn6d_b200.geometry: %s must be a CUDA tensor (no CPU fallback)" % name)
+    return x.detach().to(torch.float32).contiguous()
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def backproject_th(depth, K):
+    """misc.py:334-349: depth [H,W] (or [B,H,W]), K [3,3] (or [B,3,3]) -> [H,W,3] (or [B,H,W,3])."""
+    single = depth.dim() == 2
+    assert depth.dim() in (2, 3), depth.dim()  # misc.py:343
+    d = _cuda_f32(depth, "depth")
+    d3 = d[None] if single else d
+    B, H, W = d3.shape
+    Kc = _cuda_f32(K, "K")
+    k_stride = 0 if Kc.dim() == 2 else 9
+    if Kc.dim() == 3:
+        assert Kc.shape[0] == B
+    out = torch.empty(B, H, W, 3, dtype=torch.float32, device=d.device)
+    with torch.cuda.device(d.device):
+        rc = _lib.lib().rdpn_backproject(d3.data_ptr(), Kc.data_ptr(), k_stride, out.data_ptr(), B, H, W, _stream(d.device))
+    _lib.check(rc, "backproject")
+    return out[0] if single else out
+
+
+def kabsch(src, dst, w=None, scale=False):
+    """Batched weighted Kabsch / Umeyama.  src, dst: [B,N,3]; w: [B,N] or None.
+
+    Returns (M [B,3,4] with dst ~ M[:, :, :3] src + M[:, :, 3], scale [B]).  Same solution as
+    transform.affine_matrix_from_points(src.T, dst.T, shear=False, scale=scale, usesvd=True).
+    """
+    s = _cuda_f32(src, "src")
+    d = _cuda_f32(dst, "dst")
+    if s.dim() != 3 or s.shape[2] != 3 or s.shape != d.shape or s.shape[1] < 3:
+        raise ValueError("input arrays are of wrong shape or type")  # transform.py:917-918
+    B, N, _ = s.shape
+    ww = _cuda_f32(w, "w") if w is not None else None
+    if ww is not None:
+        assert ww.shape == (B, N)
+    M = torch.empty(B, 3, 4, dtype=torch.float32, device=s.device)
+    sc = torch.empty(B, dtype=torch.float32, device=s.device)
+    with torch.cuda.device(s.device):
+        rc = _lib.lib().rdpn_kabsch(s.data_ptr(), d.data_ptr(), ww.data_ptr() if ww is not None else None, N,
+                                    int(bool(scale)), M.data_ptr(), sc.data_ptr(), B, _stream(s.device))
+    _lib.check(rc, "kabsch")
+    return M, sc
+
+
+def superimposition_matrix(v0, v1, scale=False):
+    """transform.py:983-1029 for one pair of [3,n] (or [4,n]) CUDA tensors -> 4x4 float32."""
+    a = v0[:3].t()[None]
+    c = v1[:3].t()[None]
+    M, _ = kabsch(a, c, None, scale)
+    out = torch.eye(4, dtype=torch.float32, device=M.device)
+    out[:3, :4] = M[0]
+    return out
+
+
+def roi_intrinsics(K, center, scale, crop_res=256):
+    """K [B,3,3], bbox center [B,2], scale [B] -> Kp [B,4] = (fx', fy', cx', cy') of the crop."""
+    Kc = _cuda_f32(K, "K")
+    B = Kc.shape[0]
+    c = _cuda_f32(center, "center")
+    s = _cuda_f32(scale.reshape(B), "scale")
+    out = torch.empty(B, 4, dtype=torch.float32, device=Kc.device)
+    with torch.cuda.device(Kc.device):
+        rc = _lib.lib().rdpn_roi_intrinsics(Kc.data_ptr(), c.data_ptr(), s.data_ptr(), int(crop_res), out.data_ptr(), B,
+                                            _stream(Kc.device))
+    _lib.check(rc, "roi_intrinsics")
+    return out
+
+
+def region_argmax(region):
+    """GDRN.py:206-209: region [B,R+1,64,64] logits -> uint8 [B,64,64] index in [0,R) (bg channel 0 skipped)."""
+    r = _cuda_f32(region, "region")
+    B, R1, h, w = r.shape
+    assert (h, w) == (64, 64)
+    out = torch.empty(B, 64, 64, dtype=torch.uint8, device=r.device)
+    with torch.cuda.device(r.device):
+        rc = _lib.lib().rdpn_region_argmax(r.data_ptr(), R1 - 1, out.data_ptr(), B, _stream(r.device))
+    _lib.check(rc, "region_argmax")
+    return out

@@ -1,0 +1,211 @@
+"""Python host side of the dense-correspondence -> pose path (PyTorch tensors in and out).
+
+`correspond` = stage S1 materialised (back-projection + residual + mask gate);
+`pose_solve` = the fused solver: one launch for S1 + hypothesis generation + H x n inlier scoring +
+best selection + weighted Kabsch/Umeyama refit (csrc/pose_solve.cu through the C ABI).
+
+Inputs follow the reference's tensors at the evaluator boundary
+(/root/reference/core/gdrn_modeling/gdrn_evaluator.py:187-207, models/GDRN.py:291-297):
+  depth        [B,64,64]   ROI depth (channel 2 of roi_coord_2d before the resize_ratio division, or
+                           pass roi_coord_2d[:,2] with depth_div=None -- it is already divided)
+  Kp           [B,4]       crop intrinsics (fx',fy',cx',cy'); see geometry.roi_intrinsics
+  coor_x/y/z   [B,1,64,64] or [B,64,64] head outputs
+  mask         [B,1,64,64] or [B,64,64] raw head mask
+  extent       [B,3]       roi_extent
+  region_idx   [B,64,64] uint8 (geometry.region_argmax of out_dict["region"]) + anchors [B,R,3] (fps)
+  hyp_idx      [B,H,3] int32 absolute pixel indices of each hypothesis' three correspondences
+There is no CPU path: tensors must live on a CUDA device.
+"""
+import ctypes
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+MASK_RAW, MASK_L1, MASK_BCE = 0, 1, 2
+_MASK_MODES = {"raw": MASK_RAW, "none": MASK_RAW, "l1": MASK_L1, "bce": MASK_BCE}
+STATUS_OK, STATUS_FEW_POINTS, STATUS_T_SANITY, STATUS_NO_CONSENSUS = 0, 1, 2, 3
+P = 64 * 64
+
+
+def _map(x, name, B):
+    """[B,1,64,64] | [B,64,64] float32 contiguous CUDA, 16-byte aligned."""
+    if x.dim() == 4:
+        assert x.shape[1] == 1, (name, x.shape)
+        x = x[:, 0]
+    assert x.shape == (B, 64, 64), (name, tuple(x.shape))
+    if not x.is_cuda:
+        raise RuntimeError("rdpn6d_b200: %s must be a CUDA tensor (no CPU fallback)" % name)
+    x = x.detach().to(torch.float32).contiguous()
+    if x.data_ptr() % 16:  # bulk-TMA staging needs 16-byte aligned planes; a fresh allocation is aligned
+        x = x.clone()
+    return x
+
+
+def _vec(x, shape, name, dtype=torch.float32):
+    assert tuple(x.shape) == tuple(shape), (name, tuple(x.shape), shape)
+    if not x.is_cuda:
+        raise RuntimeError("rdpn6d_b200: %s must be a CUDA tensor (no CPU fallback)" % name)
+    return x.detach().to(dtype).contiguous()
+
+
+def _mask_mode(m):
+    if isinstance(m, str):
+        return _MASK_MODES[m.lower()]
+    return int(m)
+
+
+class _Inputs:
+    """Keeps the prepared tensors alive next to the C struct that points at them."""
+
+    def __init__(self, depth, Kp, coor_x, coor_y, coor_z, mask, extent, region_idx=None, anchors=None,
+                 depth_div=None, mask_mode=MASK_L1, mask_thr=0.5):
+        B = depth.shape[0]
+        self.B = B
+        self.dev = depth.device
+        self.t = dict(
+            depth=_map(depth, "depth", B), coor_x=_map(coor_x, "coor_x", B), coor_y=_map(coor_y, "coor_y", B),
+            coor_z=_map(coor_z, "coor_z", B), mask=_map(mask, "mask", B),
+            Kp=_vec(Kp, (B, 4), "Kp"), extent=_vec(extent, (B, 3), "extent"))
+        if depth_div is not None:
+            self.t["depth_div"] = _vec(depth_div.reshape(B), (B,), "depth_div")
+        R = 0
+        if (region_idx is None) != (anchors is None):
+            raise ValueError("region_idx and anchors must be given together (anchor mode) or both None (dense mode)")
+        if region_idx is not None:
+            R = anchors.shape[1]
+            if R > 255:
+                raise ValueError("num_regions must be <= 255")
+            rid = region_idx.detach()
+            assert rid.shape == (B, 64, 64), tuple(rid.shape)
+            self.t["region_idx"] = rid.to(torch.uint8).contiguous()
+            self.t["anchors"] = _vec(anchors, (B, R, 3), "anchors")
+        s = _lib.RoiInputs()
+        for k in ("depth", "Kp", "depth_div", "coor_x", "coor_y", "coor_z", "mask", "extent", "region_idx", "anchors"):
+            setattr(s, k, self.t[k].data_ptr() if k in self.t else None)
+        s.num_regions = R
+        s.mask_mode = _mask_mode(mask_mode)
+        s.mask_thr = float(mask_thr)
+        s.B = B
+        self.struct = s
+
+
+def correspond(depth, Kp, coor_x, coor_y, coor_z, mask, extent, region_idx=None, anchors=None, depth_div=None,
+               mask_mode=MASK_L1, mask_thr=0.5, want_obj=True, stream=None):
+    """Stage S1.  Returns dict(cam[B,3,P], obj[B,3,P] | None, w[B,P], sel[B,P] uint8, n_sel[B] int32)."""
+    L = _lib.lib()
+    inp = _Inputs(depth, Kp, coor_x, coor_y, coor_z, mask, extent, region_idx, anchors, depth_div, mask_mode, mask_thr)
+    B, dev = inp.B, inp.dev
+    cam = torch.empty(B, 3, P, dtype=torch.float32, device=dev)
+    obj = torch.empty(B, 3, P, dtype=torch.float32, device=dev) if want_obj else None
+    w = torch.empty(B, P, dtype=torch.float32, device=dev)
+    sel = torch.empty(B, P, dtype=torch.uint8, device=dev)
+    nsel = torch.empty(B, dtype=torch.int32, device=dev)
+    st = (stream or torch.cuda.current_stream(dev)).cuda_stream
+    with torch.cuda.device(dev):
+        rc = L.rdpn_correspond(ctypes.byref(inp.struct), cam.data_ptr(), obj.data_ptr() if want_obj else None,
+                               w.data_ptr(), sel.data_ptr(), nsel.data_ptr(), st)
+    _lib.check(rc, "correspond")
+    return dict(cam=cam, obj=obj, w=w, sel=sel, n_sel=nsel)
+
+
+@dataclass
+class PoseSolveResult:
+    pose: torch.Tensor  # [B,3,4] float32 (R|t), -100 where status is FEW_POINTS / NO_CONSENSUS
+    n_inliers: torch.Tensor  # [B] int32
+    status: torch.Tensor  # [B] int32
+    best_h: torch.Tensor  # [B] int32
+    n_sel: torch.Tensor  # [B] int32
+    inlier_mask: Optional[torch.Tensor] = None  # [B,64,64] uint8
+    hyp_counts: Optional[torch.Tensor] = None  # [B,H] int32
+    hyp_poses: Optional[torch.Tensor] = None  # [B,H,3,4] float32
+    scale: Optional[torch.Tensor] = None  # [B] float32
+
+    def rows16(self):
+        """[B,16] float32 rows for the multi-GPU gather: pose(12) | n_inliers | status | n_sel | best_h."""
+        B = self.pose.shape[0]
+        return torch.cat([self.pose.reshape(B, 12), self.n_inliers.float()[:, None], self.status.float()[:, None],
+                          self.n_sel.float()[:, None], self.best_h.float()[:, None]], dim=1)
+
+
+class PoseSolver:
+    """Reusable launcher: output buffers are allocated once per (B, H) and reused (graph friendly)."""
+
+    def __init__(self, inlier_thr=0.005, min_pts=4, min_inliers=4, weighted=False, refit_iters=1, with_scale=False,
+                 adaptive=False, confidence=0.995, min_iter=10, mask_mode=MASK_L1, mask_thr=0.5,
+                 want_inlier_mask=False, want_hyp=False):
+        self.prm = dict(inlier_thr=float(inlier_thr), min_pts=int(min_pts), min_inliers=int(min_inliers),
+                        weighted=int(bool(weighted)), refit_iters=int(refit_iters), with_scale=int(bool(with_scale)),
+                        adaptive=int(bool(adaptive)), confidence=float(confidence), min_iter=int(min_iter))
+        self.mask_mode = mask_mode
+        self.mask_thr = mask_thr
+        self.want_inlier_mask = want_inlier_mask
+        self.want_hyp = want_hyp
+        self._out = {}
+
+    def _buffers(self, B, H, dev):
+        key = (B, H, str(dev))
+        if key not in self._out:
+            o = dict(pose=torch.empty(B, 12, dtype=torch.float32, device=dev),
+                     n_inliers=torch.empty(B, dtype=torch.int32, device=dev),
+                     status=torch.empty(B, dtype=torch.int32, device=dev),
+                     best_h=torch.empty(B, dtype=torch.int32, device=dev),
+                     n_sel=torch.empty(B, dtype=torch.int32, device=dev),
+                     scale=torch.empty(B, dtype=torch.float32, device=dev))
+            if self.want_inlier_mask:
+                o["inlier_mask"] = torch.empty(B, 64, 64, dtype=torch.uint8, device=dev)
+            if self.want_hyp:
+                o["hyp_counts"] = torch.empty(B, H, dtype=torch.int32, device=dev)
+                o["hyp_poses"] = torch.empty(B, H, 3, 4, dtype=torch.float32, device=dev)
+            self._out[key] = o
+        return self._out[key]
+
+    def __call__(self, depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx, region_idx=None, anchors=None,
+                 depth_div=None, t_net=None, stream=None):
+        L = _lib.lib()
+        inp = _Inputs(depth, Kp, coor_x, coor_y, coor_z, mask, extent, region_idx, anchors, depth_div,
+                      self.mask_mode, self.mask_thr)
+        B, dev = inp.B, inp.dev
+        assert hyp_idx.dim() == 3 and hyp_idx.shape[0] == B and hyp_idx.shape[2] == 3, tuple(hyp_idx.shape)
+        H = hyp_idx.shape[1]
+        hyp = _vec(hyp_idx, (B, H, 3), "hyp_idx", torch.int32)
+        tn = _vec(t_net, (B, 3), "t_net") if t_net is not None else None
+        prm = _lib.SolveParams(num_hyp=H, **self.prm)
+        o = self._buffers(B, H, dev)
+        outs = _lib.SolveOutputs()
+        for k in ("pose", "n_inliers", "status", "best_h", "n_sel", "inlier_mask", "hyp_counts", "hyp_poses", "scale"):
+            setattr(outs, k, o[k].data_ptr() if k in o else None)
+        st = (stream or torch.cuda.current_stream(dev)).cuda_stream
+        with torch.cuda.device(dev):
+            rc = L.rdpn_pose_solve(ctypes.byref(inp.struct), hyp.data_ptr(), tn.data_ptr() if tn is not None else None,
+                                   ctypes.byref(prm), ctypes.byref(outs), st)
+        _lib.check(rc, "pose_solve")
+        self._keep = (inp, hyp, tn)  # keep inputs alive until the next call (stream-ordered use)
+        return PoseSolveResult(pose=o["pose"].view(B, 3, 4), n_inliers=o["n_inliers"], status=o["status"],
+                               best_h=o["best_h"], n_sel=o["n_sel"], inlier_mask=o.get("inlier_mask"),
+                               hyp_counts=o.get("hyp_counts"), hyp_poses=o.get("hyp_poses"), scale=o["scale"])
+
+
+def pose_solve(depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx, region_idx=None, anchors=None,
+               depth_div=None, t_net=None, stream=None, **kw):
+    """One-shot functional form of PoseSolver (see its constructor for the keyword arguments)."""
+    return PoseSolver(**kw)(depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx, region_idx, anchors,
+                            depth_div, t_net, stream)
+
+
+def sample_hypotheses(sel, H, generator=None):
+    """Draw hyp_idx [B,H,3] int32 uniformly (with replacement) from each ROI's gated pixels.
+
+    The reference draws its RANSAC samples with np.random.choice inside the loop
+    (lib/pysixd/misc.py:91); here randomness is lifted out into an explicit tensor so that runs are
+    reproducible.  sel: [B,P] uint8/bool CUDA tensor (correspond()["sel"]).  ROIs with no gated pixel get
+    index 0 (their hypotheses are invalid and the solver reports FEW_POINTS).
+    """
+    B = sel.shape[0]
+    w = sel.reshape(B, -1).float()
+    empty = w.sum(dim=1) == 0
+    w[empty, 0] = 1.0
+    idx = torch.multinomial(w, H * 3, replacement=True, generator=generator)
+    return idx.view(B, H, 3).to(torch.int32)

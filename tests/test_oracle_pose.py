@@ -1,0 +1,156 @@
+"""CPU: the composite pose-path oracle (oracle/pose_oracle.py) against golden vectors produced by the
+reference's own functions (oracle/gen_golden.py) and against analytic properties."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pose_oracle as po
+from rdpn6d_b200 import synth
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return {k: np.load(os.path.join(golden_dir, k + "_golden.npz")) for k in ("affine", "region", "pose")}
+
+
+def test_roi_affine_closed_form_matches_reference(gold):
+    """a1: the restated closed form (with the reference's float32 point roundings) vs golden matrices from
+    core/utils/data_utils.get_affine_transform (cv2.getAffineTransform inside), float64 and float32 inputs."""
+    g = gold["affine"]
+    for ck, sk, ak in (("centers", "scales", "A256"), ("centers32", "scales32", "A256_32")):
+        for i in range(len(g[sk])):
+            A = po.roi_affine(g[ck][i], g[sk][i], 256)
+            ref = g[ak][i]
+            assert np.abs(A - ref).max() <= 1e-12 * np.abs(ref).max()
+            K = synth.K_LM
+            Kp = po.roi_intrinsics(K, g[ck][i], g[sk][i], 256)
+            Kref = np.vstack([ref, [0, 0, 1]]) @ K  # data_loader.py:555-564
+            np.testing.assert_allclose(Kp, [Kref[0, 0], Kref[1, 1], Kref[0, 2], Kref[1, 2]], rtol=1e-12)
+            # and the naive s = crop/scale form is only ~1e-6 away (why the roundings are restated)
+            s = 256.0 / g[sk][i]
+            assert abs(A[0, 0] - s) / s < 1e-5
+
+
+def test_xyz_to_region_matches_reference(gold):
+    g = gold["region"]
+    for i in range(g["xyz"].shape[0]):
+        r, d = po.xyz_to_region(g["xyz"][i], g["fps"][i])
+        assert np.array_equal(r, g["region"][i])
+        np.testing.assert_allclose(d, g["delta"][i], atol=0)
+
+
+def test_composite_matches_reference_kabsch_golden(gold):
+    """Whole path on 4 ROIs: the oracle (numpy SVD) vs the run where every Kabsch call went through the
+    reference's transform.affine_matrix_from_points."""
+    g = gold["pose"]
+    b = {k: g[k] for k in ("depth", "Kp", "coor", "mask", "extent", "region_idx", "anchors")}
+    res = po.pose_solve_batch(b, g["hyp_idx"], float(g["thr"]))
+    for i, r in enumerate(res):
+        assert r["status"] == g["out_status"][i]
+        assert r["n_sel"] == g["out_nsel"][i]
+        assert np.array_equal(r["s1"]["sel"], g["out_sel"][i])
+        assert np.array_equal(r["s1"]["cam"], g["out_cam"][i])
+        assert np.array_equal(r["valid"], g["out_valid"][i])
+        np.testing.assert_allclose(r["Rt_hyp"], g["out_Rt_hyp"][i], atol=2e-6)
+        # counts may differ only where a hypothesis pose differs in its last float32 bit
+        same = (r["Rt_hyp"] == g["out_Rt_hyp"][i]).all(axis=1)
+        assert np.array_equal(r["counts"][same], g["out_counts"][i][same])
+        assert same.mean() > 0.95
+        assert r["best_h"] == g["out_best_h"][i]
+        assert r["n_inl"] == g["out_ninl"][i]
+        assert np.array_equal(r["inlier_mask"], g["out_inlier_mask"][i])
+        assert po.re_rad_small(r["pose"][:, :3], g["out_pose"][i][:, :3]) < 1e-6
+        assert po.te(r["pose"][:, 3], g["out_pose"][i][:, 3]) < 1e-7
+
+
+def test_composite_recovers_ground_truth():
+    b = synth.make_batch(6, H=128, seed=77)
+    res = po.pose_solve_batch(b, b["hyp_idx"], 0.005)
+    for i, r in enumerate(res):
+        assert r["status"] == po.STATUS_OK
+        assert po.re_rad_small(r["pose"][:, :3], b["gt_pose"][i][:, :3]) < 0.01
+        assert po.te(r["pose"][:, 3], b["gt_pose"][i][:, 3]) < 0.001
+
+
+def test_dense_mode_recovers_ground_truth():
+    b = synth.make_batch(3, H=64, seed=5, dense=True)
+    res = po.pose_solve_batch(b, b["hyp_idx"], 0.005)
+    for i, r in enumerate(res):
+        assert r["status"] == po.STATUS_OK
+        assert po.re_rad_small(r["pose"][:, :3], b["gt_pose"][i][:, :3]) < 0.01
+
+
+def test_backprojection_is_float32_and_matches_formula():
+    rng = np.random.default_rng(0)
+    d = rng.uniform(0.5, 1.5, (64, 64)).astype(np.float32)
+    Kp = np.array([700.123, 701.5, 130.25, 126.75])
+    q = po.backproject_roi(d, Kp)
+    assert q.dtype == np.float32
+    x64 = (4.0 * np.arange(64)[None, :] - np.float32(Kp[2])) * d.astype(np.float64) / np.float32(Kp[0])
+    np.testing.assert_allclose(q[0], x64, rtol=3e-7)
+    q2 = po.backproject_roi(d, Kp, depth_div=0.25)
+    np.testing.assert_allclose(q2[2], d / np.float32(0.25), rtol=0)
+    full = po.backproject(d, np.array([[500.0, 0, 32], [0, 500, 32], [0, 0, 1]]))
+    assert full.shape == (64, 64, 3) and full.dtype == np.float32
+
+
+def test_gate_rules():
+    ext = np.array([0.1, 0.2, 0.3], np.float32)
+    delta = np.zeros((3, 2, 2), np.float32)
+    delta[:, 0, 0] = [0.01, 0.01, 0.01]
+    delta[:, 0, 1] = [0.01, 0.01, 0.00002]  # below 1e-4 * 0.3
+    delta[:, 1, 0] = [0.01, 0.01, 0.01]
+    delta[:, 1, 1] = [0.01, 0.01, 0.01]
+    mp = np.array([[0.9, 0.9], [0.5, 0.9]], np.float32)  # 0.5 is not > 0.5 (strict)
+    z = np.array([[1.0, 1.0], [1.0, 0.0]], np.float32)  # last pixel has no depth
+    sel = po.gate(mp, delta, ext, z)
+    assert sel.tolist() == [[True, False], [False, False]]
+
+
+def test_flat_mask_selects_nothing_and_reports_few_points():
+    b = synth.make_batch(1, H=16, seed=3)
+    b["mask"][:] = 0.7
+    r = po.pose_solve_batch(b, b["hyp_idx"], 0.005)[0]
+    assert r["n_sel"] == 0 and r["status"] == po.STATUS_FEW_POINTS
+    assert (r["pose"] == -100).all()
+
+
+def test_select_best_rules():
+    counts = np.array([3, 10, 10, 12, 12, 2], np.int32)
+    valid = np.ones(6, np.uint8)
+    assert po.select_best(counts, valid, 100)[0] == 3  # strictly greater -> earliest maximum
+    assert po.select_best(np.array([3, 3, 2]), np.ones(3), 100)[0] == -1  # below the >= 4 rule
+    valid[3] = 0
+    assert po.select_best(counts, valid, 100)[0] == 4
+    # adaptive stop: 11 hypotheses with zero inliers -> k = -inf -> stop once i_ransac > min_iter (10)
+    c = np.zeros(20, np.int32)
+    c[15] = 50
+    best, examined = po.select_best(c, np.ones(20), 100, adaptive=True)
+    assert best == -1 and examined == 11
+
+
+def test_sq_cut_equivalence():
+    rng = np.random.default_rng(1)
+    for thr in [0.005, 0.01, 1e-3, 0.123456]:
+        cut = po.sq_cut(thr)
+        x = np.concatenate([np.float32(thr) ** 2 * (1 + rng.uniform(-1e-6, 1e-6, 2000)), [cut, np.nextafter(cut, np.float32(0))]]).astype(np.float32)
+        assert np.array_equal(np.sqrt(x) < np.float32(thr), x < cut)
+
+
+def test_pose_assembly_allo_ego_roundtrip():
+    """a9: allo->ego leaves R unchanged on the optical axis and rotates by the ray angle elsewhere."""
+    R = po.axangle2mat([0.3, -0.5, 0.8], 0.7)
+    np.testing.assert_allclose(po.allocentric_to_egocentric_mat(R, [0, 0, 1.0]), R, atol=1e-15)
+    t = np.array([0.2, -0.1, 0.9])
+    Re = po.allocentric_to_egocentric_mat(R, t)
+    ang = np.arccos(t[2] / np.linalg.norm(t))
+    assert abs(po.re_rad_small(Re, R) - ang) < 1e-12
+    m = po.ortho6d_to_mat(np.array([[1, 0, 0, 0, 1, 0], [0.5, 0.1, -0.3, 0.2, 0.9, 0.4]], np.float32))
+    np.testing.assert_allclose(m[0], np.eye(3), atol=1e-7)
+    np.testing.assert_allclose(m[1] @ m[1].T, np.eye(3), atol=1e-6)
+    rot, tr = po.pose_from_pred_centroid_z_test(m, np.array([[0.1, -0.2], [0, 0]], np.float32), np.array([[1.5], [2.0]], np.float32),
+                                                synth.K_LM[None].repeat(2, 0), np.array([[300, 200], [320, 240]], np.float32),
+                                                np.array([0.5, 0.4], np.float32), np.array([[50, 60], [70, 80]], np.float32))
+    assert rot.shape == (2, 3, 3) and tr.shape == (2, 3)
+    np.testing.assert_allclose(tr[:, 2], [0.75, 0.8], rtol=1e-6)
