@@ -1,0 +1,494 @@
+#!/usr/bin/env python
+"""bench.py -- ROI poses/sec of the dense-correspondence -> pose path (backproject + residual + mask
+gate + RANSAC scoring + Kabsch refit) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the fused solver (one kernel launch) over one batch of synthetic ROIs.  The
+workload at N=1 is BASELINE.json configs[1]: LM-O, 8 objects, 1024 ROIs, 256 hypotheses/ROI; at N>1
+every rank processes its own 1024-ROI shard (weak scaling) and the [shard,16] result rows are
+all-gathered over NCCL each step (pipelined behind the next step's kernel).
+
+One JSON line is printed by rank 0 (see the keys at the bottom).  `value` is device-resident
+throughput (inputs already in HBM), `e2e` is the same metric through the host-buffer C-ABI plugin call
+rdpn_pose_solve_host with pinned host buffers (H2D + kernel + D2H inside the timed region).
+
+--impl reference times the CPU implementation of the same path (the oracle port of the reference's
+functions, oracle/pose_oracle.py + oracle/pose_oracle.c) on all host cores.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ROI poses/sec (backproject+residual+RANSAC-Kabsch)"
+UNIT = "ROI poses/s"
+ROIS_PER_GPU = 1024
+NUM_HYP = 256
+NUM_OBJECTS = 8
+NUM_REGIONS = 64  # LM-O config: NUM_REGIONS=64 (configs/gdrn/lmo/...40e.py:63)
+INLIER_THR = 0.005
+N_INPUT_SETS = 4  # rotating input sets so every step reads its ROI maps from HBM, not L2
+# algorithmic bytes per ROI (DESIGN.md "Kernels"): maps 5 x 16384 + 4096 region ids, hypothesis triplets
+# H x 12, anchors R x 12, Kp 16, extent 12, outputs 12 x 4 + 5 x 4
+BYTES_MAPS = 5 * 16384 + 4096
+
+
+def bytes_per_roi(H, R):
+    return BYTES_MAPS + H * 12 + R * 12 + 16 + 12 + 48 + 20
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": "LM-O 8-object batch of %d ROIs/GPU (64x64 maps: depth + residual xyz + mask + region id), "
+                    "%d RANSAC hypotheses/ROI, %d anchors/object" % (ROIS_PER_GPU, NUM_HYP, NUM_REGIONS),
+        "rois_per_gpu": ROIS_PER_GPU, "global_rois_per_step": ROIS_PER_GPU * n_gpus, "hypotheses": NUM_HYP,
+        "num_regions": NUM_REGIONS, "inlier_thr_m": INLIER_THR, "refit": "unweighted Kabsch on inliers, 1 iteration",
+        "l2": "%d rotating input sets (%.0f MB) > 126 MB L2" % (N_INPUT_SETS, N_INPUT_SETS * ROIS_PER_GPU * BYTES_MAPS / 1e6),
+        "parallelism": "roi-shard x%d + NCCL all-gather of [shard,16] rows" % n_gpus if n_gpus > 1 else "single GPU",
+    }
+
+
+def make_workload(seed=20260101, n_unique=128):
+    """configs[1]: 8 object models cycled, occlusion cut-outs U(0,60)%.  128 unique ROIs are
+    generated and tiled to 1024 (generation is numpy ray casting; uniqueness does not change the work)."""
+    from rdpn6d_b200 import synth
+
+    models = synth.make_models(NUM_OBJECTS, NUM_REGIONS, seed=1)
+    base = synth.make_batch(n_unique, models=models, H=NUM_HYP, seed=seed, occlusion_max=0.6)
+    return synth.tile_batch(base, ROIS_PER_GPU)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (oracle port of the reference path)
+# ------------------------------------------------------------------------------------------------
+_CPU_BATCH = None
+
+
+def _cpu_init(batch):
+    global _CPU_BATCH
+    _CPU_BATCH = batch
+    os.environ["OMP_NUM_THREADS"] = "1"  # the reference sets OMP/MKL threads to 1 (test_gdrn.sh:19-20)
+
+
+def _cpu_solve_range(rng):
+    from oracle import pose_oracle as po
+
+    b0, b1 = rng
+    sub = {k: (None if v is None else v[b0:b1]) for k, v in _CPU_BATCH.items()}
+    res = po.pose_solve_batch(sub, sub["hyp_idx"], INLIER_THR)
+    return [r["status"] for r in res]
+
+
+def _cpu_as_run_range(rng):
+    """What the reference executes today per ROI: loader back-projection formula + gate + cv2 EPnP RANSAC
+    (gdrn_evaluator.py:316-435 -> misc.pnp_v2)."""
+    import cv2
+
+    from oracle import pose_oracle as po
+
+    cv2.setNumThreads(0)  # main_gdrn.py:14
+    b0, b1 = rng
+    n_ok = 0
+    jj, ii = np.meshgrid(np.arange(64), np.arange(64), indexing="ij")
+    for b in range(b0, b1):
+        c = _CPU_BATCH
+        q = po.backproject_roi(c["depth"][b], c["Kp"][b])
+        delta = po.denormalise_residual(c["coor"][b], c["extent"][b])
+        mp_ = po.out_mask(c["mask"][b])
+        sel = po.gate(mp_, delta, c["extent"][b], q[2])
+        if sel.sum() < 4:
+            continue
+        # 2D-3D pairs as the evaluator builds them: model point = anchor + R^T-free residual is not
+        # available to EPnP, so use the dense object coordinate (anchor + object-frame delta surrogate)
+        p3 = (c["anchors"][b][c["region_idx"][b].astype(np.int64)][sel]).astype(np.float64)
+        fx, fy, cx, cy = [float(v) for v in c["Kp"][b]]
+        p2 = np.stack([4.0 * ii[sel], 4.0 * jj[sel]], 1).astype(np.float64)
+        K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]])
+        try:
+            po.pnp_v2_as_run(p3, p2, K, 3.0, 100)
+            n_ok += 1
+        except cv2.error:
+            pass
+    return n_ok
+
+
+def run_cpu(batch, n_rois, fn, cores, min_seconds=0.0, max_rounds=64):
+    """Throughput (ROIs/s) of `fn` over the first n_rois ROIs on `cores` processes; repeats the sample until
+    min_seconds of wall time has been measured."""
+    import multiprocessing as mp
+
+    cores = max(1, min(cores, n_rois))
+    chunk = max(1, n_rois // (cores * 4))
+    ranges = [(i, min(i + chunk, n_rois)) for i in range(0, n_rois, chunk)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(batch,)) as pool:
+        pool.map(_cpu_solve_range if fn == "port" else _cpu_as_run_range, ranges[:cores])  # warm-up (imports, page-in)
+        t0 = time.perf_counter()
+        rounds = 0
+        while True:
+            pool.map(_cpu_solve_range if fn == "port" else _cpu_as_run_range, ranges)
+            rounds += 1
+            dt = time.perf_counter() - t0
+            if dt >= min_seconds or rounds >= max_rounds:
+                break
+    return n_rois * rounds / dt, dt, rounds
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline_leg(batch):
+    """Oracle port on all host cores, bounded sample (about 10-20 s of CPU work)."""
+    cores = host_cores()
+    n = 256
+    v, dt, rounds = run_cpu(batch, n, "port", cores, min_seconds=4.0)
+    v1, dt1, r1 = run_cpu(batch, 32, "port", 1, min_seconds=1.0)
+    out = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": "first %d ROIs of the workload x %d passes, multiprocessing Pool(%d) over ROIs, "
+                     "oracle/pose_oracle.py (numpy float32 S1 + C float32 scoring + numpy SVD Kabsch)" % (n, rounds, cores),
+           "single_core_value": v1}
+    try:
+        va, _, _ = run_cpu(batch, 64, "as_run", cores, min_seconds=2.0)
+        out["as_run_cv2_value"] = va
+        out["as_run_cv2_note"] = ("reference-as-run per ROI: back-projection + gate + cv2.solvePnPRansac(EPnP, 3 px, 100 it) "
+                                  "(lib/pysixd/misc.py:145-194); third-party arithmetic, timing only")
+    except Exception as e:  # cv2 missing on the box: the port number stands alone
+        out["as_run_cv2_value"] = None
+        out["as_run_cv2_note"] = "unavailable: %r" % (e,)
+    return out
+
+
+def reference_arm(args):
+    """--impl reference: the CPU implementation of the path (oracle port) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import oracle
+
+    oracle.liboracle()
+    batch = make_workload()
+    cores = host_cores()
+    n = 256  # bounded sample per step
+    import multiprocessing as mp
+
+    chunk = max(1, n // (cores * 4))
+    ranges = [(i, min(i + chunk, n)) for i in range(0, n, chunk)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(min(cores, n), initializer=_cpu_init, initargs=(batch,)) as pool:
+        for _ in range(max(args.warmup, 1)):
+            pool.map(_cpu_solve_range, ranges)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_cpu_solve_range, ranges)
+        dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": min(cores, n), "kind": "port",
+                         "sample": "each step = first %d ROIs of the workload through oracle/pose_oracle.py on a "
+                                   "multiprocessing Pool(%d)" % (n, min(cores, n))},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (NVML in a thread; nvidia-smi fallback is not needed on the pool's image)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def start(self):
+        if self.ok:
+            self.t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self.ok:
+            self.t.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def gpu_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    batch = make_workload()
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+
+        oracle.liboracle()
+        cpu_base = cpu_baseline_leg(batch)  # before CUDA is initialised in this process (fork safety)
+
+    import torch
+    import torch.distributed as dist
+
+    from rdpn6d_b200 import _lib, pose_solver
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+
+    def to_dev(b, shift):
+        # distinct device copies; rolling the ROI order makes each set a different address stream
+        out = {}
+        for k, v in b.items():
+            if v is None:
+                out[k] = None
+            else:
+                out[k] = torch.from_numpy(np.roll(v, shift, axis=0).copy()).to(dev)
+        return out
+
+    sets = [to_dev(batch, 37 * i) for i in range(N_INPUT_SETS)]
+    solver = pose_solver.PoseSolver(inlier_thr=INLIER_THR)
+    plans = [pose_solver.make_plan(solver, s["depth"], s["Kp"], s["coor"][:, 0].contiguous(), s["coor"][:, 1].contiguous(),
+                                   s["coor"][:, 2].contiguous(), s["mask"], s["extent"], s["hyp_idx"], s["region_idx"],
+                                   s["anchors"]) for s in sets]
+    B, H, R = ROIS_PER_GPU, NUM_HYP, NUM_REGIONS
+    total = B * world
+    gather_out = [torch.empty(total, 16, dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
+
+    def step(i, pending):
+        p = plans[i % N_INPUT_SETS]
+        res = p.launch()
+        if world > 1:
+            rows = res.rows16()
+            if pending[i % 2] is not None:
+                pending[i % 2].wait()
+            pending[i % 2] = dist.all_gather_into_tensor(gather_out[i % 2], rows, async_op=True)
+        return res
+
+    def drain(pending):
+        for j in range(2):
+            if pending[j] is not None:
+                pending[j].wait()
+                pending[j] = None
+
+    pending = [None, None]
+    for i in range(max(args.warmup, 3)):
+        step(i, pending)
+    drain(pending)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank if os.environ.get("CUDA_VISIBLE_DEVICES") is None else
+                           int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
+    sampler.start()
+    # pre-heat ~0.7 s under the same load so that the sampled clocks are the steady-state ones
+    t_heat = time.perf_counter()
+    i = 0
+    while time.perf_counter() - t_heat < args.preheat:
+        for _ in range(50):
+            step(i, pending)
+            i += 1
+        drain(pending)
+        torch.cuda.synchronize()
+
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i, pending)
+    drain(pending)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+
+    # ---- kernel-only duration of the dominant kernel (no gather), for the roofline ----
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nk = max(args.steps, 20)
+    k0.record()
+    for i in range(nk):
+        plans[i % N_INPUT_SETS].launch()
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1) / nk
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host buffers) ----
+    pin = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in batch.items()
+           if v is not None and k in ("depth", "Kp", "mask", "extent", "region_idx", "anchors", "hyp_idx")}
+    for c, name in enumerate(("coor_x", "coor_y", "coor_z")):
+        pin[name] = torch.from_numpy(np.ascontiguousarray(batch["coor"][:, c])).pin_memory()
+    h_pose = torch.empty(B, 12, dtype=torch.float32).pin_memory()
+    h_ninl = torch.empty(B, dtype=torch.int32).pin_memory()
+    h_stat = torch.empty(B, dtype=torch.int32).pin_memory()
+    inp = _lib.RoiInputs(depth=pin["depth"].data_ptr(), Kp=pin["Kp"].data_ptr(), depth_div=None,
+                         coor_x=pin["coor_x"].data_ptr(), coor_y=pin["coor_y"].data_ptr(), coor_z=pin["coor_z"].data_ptr(),
+                         mask=pin["mask"].data_ptr(), extent=pin["extent"].data_ptr(),
+                         region_idx=pin["region_idx"].data_ptr(), anchors=pin["anchors"].data_ptr(), num_regions=R,
+                         mask_mode=1, mask_thr=0.5, B=B)
+    prm = _lib.SolveParams(inlier_thr=INLIER_THR, num_hyp=H, min_pts=4, min_inliers=4, weighted=0, refit_iters=1,
+                           with_scale=0, adaptive=0, confidence=0.995, min_iter=10)
+    outs = _lib.SolveOutputs(pose=h_pose.data_ptr(), n_inliers=h_ninl.data_ptr(), status=h_stat.data_ptr())
+    ctx = ctypes.c_void_p()
+    _lib.check(L.rdpn_ctx_create(local_rank, ctypes.byref(ctx)), "ctx_create")
+    e2e_steps = max(3, min(args.steps, 30))
+    for _ in range(3):
+        _lib.check(L.rdpn_pose_solve_host(ctx, ctypes.byref(inp), pin["hyp_idx"].data_ptr(), None, ctypes.byref(prm),
+                                          ctypes.byref(outs)), "pose_solve_host")
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        _lib.check(L.rdpn_pose_solve_host(ctx, ctypes.byref(inp), pin["hyp_idx"].data_ptr(), None, ctypes.byref(prm),
+                                          ctypes.byref(outs)), "pose_solve_host")
+    e2e_s = time.perf_counter() - t0
+    L.rdpn_ctx_destroy(ctx)
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t)
+    h2d = B * (BYTES_MAPS + H * 12 + R * 12 + 16 + 12)
+    d2h = B * (48 + 4 + 4)
+    # sanity: the host path produced the same poses as the device path
+    dev_pose = plans[0].launch().pose.reshape(B, 12)
+    torch.cuda.synchronize()
+    ok_frac = float((plans[0].result.status == 0).float().mean())
+
+    # ---- FP32 work actually issued by the scoring stage (valid hypotheses x gated points) ----
+    diag = pose_solver.PoseSolver(inlier_thr=INLIER_THR, want_hyp=True)
+    s0 = sets[0]
+    dres = diag(s0["depth"], s0["Kp"], s0["coor"][:, 0].contiguous(), s0["coor"][:, 1].contiguous(),
+                s0["coor"][:, 2].contiguous(), s0["mask"], s0["extent"], s0["hyp_idx"], s0["region_idx"], s0["anchors"])
+    valid = (dres.hyp_poses.reshape(B, H, 12).abs().sum(-1) > 0).sum(1).double()
+    pairs = float((valid * dres.n_sel.double()).sum())
+    mean_nsel = float(dres.n_sel.double().mean())
+    fp32_peak = ctypes.c_double(0.0)
+    L.rdpn_fp32_peak_probe(20000, ctypes.byref(fp32_peak))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        hbm_peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+    alg_bytes = B * bytes_per_roi(H, R)
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    flops = 27.0 * pairs
+    line = {
+        "metric": METRIC, "value": total * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+        "e2e": {"value": total * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "api": "rdpn_pose_solve_host (C ABI, pinned host buffers, chunked over 2 streams)",
+                "timer": "perf_counter around synchronous calls"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": None, "kernel": "rdpn::pose_solve_kernel<false>", "kernel_ms": kernel_ms,
+                     "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                     "note": "the fused solver is FP32-pipe bound (3x4 transforms x hypotheses x points), see fp32"},
+        "fp32": {"achieved_tflops": flops / (kernel_ms * 1e-3) / 1e12, "peak_tflops": fp32_peak.value / 1e12,
+                 "frac": (flops / (kernel_ms * 1e-3)) / max(fp32_peak.value, 1.0), "flop_per_pair": 27,
+                 "pairs_per_launch": pairs, "mean_gated_points_per_roi": mean_nsel,
+                 "peak_source": "rdpn_fp32_peak_probe (FFMA chains on all SMs, this run)"},
+        "solved_fraction": ok_frac,
+    }
+    if cpu_base is not None:
+        line["cpu_baseline"] = cpu_base
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--preheat", type=float, default=0.7, help="seconds of untimed load before the timed region")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return reference_arm(args)
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun
+        import subprocess
+
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29577", os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,147 @@
+#!/usr/bin/env python
+"""Per-kernel measurements that explain the headline number (run on the B200 box):
+
+  * FPS: 1M-point cloud -> 8/64/512 keypoints (BASELINE configs[3]) with the CPU reference beside it
+  * S1 standalone (rdpn_correspond): achieved HBM GB/s against the measured copy bandwidth
+  * fused solver at several batch sizes / hypothesis counts
+  * batched Kabsch, region arg-max
+
+Prints one JSON object per line.  CUDA events on the launching stream, >= 3 warm-ups, inputs rotated
+over sets larger than L2 where the kernel is HBM-bound.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from rdpn6d_b200 import _lib, fps_utils, geometry, pose_solver, synth  # noqa: E402
+
+
+def ev_time(fn, iters, warm=3):
+    for _ in range(warm):
+        fn(0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
+
+
+def bench_fps(cpu=True):
+    from oracle.fps import fps_indices_port, fps_indices_reference
+    from oracle import libfps_ref
+
+    cloud = synth.fps_cloud(1_000_000, seed=0)
+    t = torch.from_numpy(cloud).cuda()
+    for k in (8, 64, 512):
+        ms = ev_time(lambda i: fps_utils.fps_indices(t, k), 10)
+        idx = fps_utils.fps_indices(t, k).cpu().numpy()
+        rec = {"bench": "fps", "n": 1_000_000, "k": k, "gpu_ms": ms, "us_per_pick": 1e3 * ms / k,
+               "stream_model_GBps": 1_000_000 * k * 20 / (ms * 1e-3) / 1e9}
+        if cpu:
+            t0 = time.perf_counter()
+            ref = (fps_indices_reference if libfps_ref() is not None else fps_indices_port)(cloud, k)
+            rec["cpu_ms"] = 1e3 * (time.perf_counter() - t0)
+            rec["cpu_kind"] = "reference" if libfps_ref() is not None else "port"
+            rec["bit_exact"] = bool(np.array_equal(idx, ref))
+            rec["speedup"] = rec["cpu_ms"] / ms
+        print(json.dumps(rec), flush=True)
+    for n, k in ((5_000, 32), (50_000, 64), (200_000, 64)):
+        tt = torch.from_numpy(synth.fps_cloud(n, seed=1)).cuda()
+        ms = ev_time(lambda i: fps_utils.fps_indices(tt, k), 10)
+        print(json.dumps({"bench": "fps", "n": n, "k": k, "gpu_ms": ms, "us_per_pick": 1e3 * ms / k}), flush=True)
+
+
+def _sets(B, H, R, nsets, dense=False):
+    models = synth.make_models(8, R, seed=1)
+    base = synth.make_batch(min(B, 128), models=models, H=H, seed=20260101, occlusion_max=0.6, dense=dense)
+    b = synth.tile_batch(base, B)
+    out = []
+    for i in range(nsets):
+        out.append({k: (None if v is None else torch.from_numpy(np.roll(v, 37 * i, axis=0).copy()).cuda()) for k, v in b.items()})
+    return out
+
+
+def bench_s1():
+    B, R = 1024, 64
+    sets = _sets(B, 8, R, 4)
+    L = _lib.lib()
+    import ctypes
+    cam = torch.empty(B, 3, 4096, device="cuda")
+    obj = torch.empty(B, 3, 4096, device="cuda")
+    w = torch.empty(B, 4096, device="cuda")
+    sel = torch.empty(B, 4096, dtype=torch.uint8, device="cuda")
+    nsel = torch.empty(B, dtype=torch.int32, device="cuda")
+    inps = [pose_solver._Inputs(s["depth"], s["Kp"], s["coor"][:, 0].contiguous(), s["coor"][:, 1].contiguous(),
+                                s["coor"][:, 2].contiguous(), s["mask"], s["extent"], s["region_idx"], s["anchors"]) for s in sets]
+    st = torch.cuda.current_stream().cuda_stream
+    for name, objp in (("cam+w+sel (region id stays the object side)", None), ("cam+obj+w+sel", obj.data_ptr())):
+        def run(i):
+            rc = L.rdpn_correspond(ctypes.byref(inps[i % 4].struct), cam.data_ptr(), objp, w.data_ptr(), sel.data_ptr(), nsel.data_ptr(), st)
+            assert rc == 0
+        ms = ev_time(run, 50)
+        rd = 5 * 16384 + 4096 + R * 12 + 28
+        wr = 3 * 16384 + 16384 + 4096 + 4 + (3 * 16384 if objp else 0)
+        gbps = B * (rd + wr) / (ms * 1e-3) / 1e9
+        print(json.dumps({"bench": "s1_correspond", "variant": name, "B": B, "ms": ms, "read_B_per_roi": rd, "write_B_per_roi": wr,
+                          "achieved_GBps": gbps, "hbm_peak_GBps": peaks(), "frac": gbps / peaks()}), flush=True)
+
+
+def bench_solve():
+    for B, H, R in ((1024, 256, 64), (1024, 256, 32), (8192, 256, 32), (1024, 64, 32), (1024, 512, 32), (148, 256, 32), (296, 256, 32)):
+        sets = _sets(B, H, R, 4 if B <= 1024 else 1)
+        solver = pose_solver.PoseSolver(inlier_thr=0.005)
+        plans = [pose_solver.make_plan(solver, s["depth"], s["Kp"], s["coor"][:, 0].contiguous(), s["coor"][:, 1].contiguous(),
+                                       s["coor"][:, 2].contiguous(), s["mask"], s["extent"], s["hyp_idx"], s["region_idx"], s["anchors"]) for s in sets]
+        ms = ev_time(lambda i: plans[i % len(plans)].launch(), 50)
+        ns = float(plans[0].result.n_sel.double().mean())
+        print(json.dumps({"bench": "pose_solve", "B": B, "H": H, "R": R, "ms": ms, "rois_per_s": B / (ms * 1e-3), "mean_n_sel": ns}), flush=True)
+    sets = _sets(1024, 256, 32, 1, dense=True)
+    s = sets[0]
+    solver = pose_solver.PoseSolver(inlier_thr=0.005)
+    plan = pose_solver.make_plan(solver, s["depth"], s["Kp"], s["coor"][:, 0].contiguous(), s["coor"][:, 1].contiguous(),
+                                 s["coor"][:, 2].contiguous(), s["mask"], s["extent"], s["hyp_idx"])
+    ms = ev_time(lambda i: plan.launch(), 50)
+    print(json.dumps({"bench": "pose_solve_dense", "B": 1024, "H": 256, "ms": ms, "rois_per_s": 1024 / (ms * 1e-3)}), flush=True)
+
+
+def bench_misc():
+    B, N = 1024, 2000
+    a = torch.randn(B, N, 3, device="cuda")
+    c = torch.randn(B, N, 3, device="cuda")
+    ms = ev_time(lambda i: geometry.kabsch(a, c), 20)
+    print(json.dumps({"bench": "kabsch", "B": B, "N": N, "ms": ms, "GBps": B * N * 24 * 2 / (ms * 1e-3) / 1e9}), flush=True)
+    reg = [torch.randn(1024, 65, 64, 64, device="cuda") for _ in range(2)]
+    ms = ev_time(lambda i: geometry.region_argmax(reg[i % 2]), 20)
+    print(json.dumps({"bench": "region_argmax", "B": 1024, "R": 64, "ms": ms,
+                      "GBps": 1024 * (64 * 16384 + 4096) / (ms * 1e-3) / 1e9, "hbm_peak_GBps": peaks()}), flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    torch.cuda.set_device(0)
+    if a.only in ("", "fps"):
+        bench_fps(cpu=not a.no_cpu)
+    if a.only in ("", "s1"):
+        bench_s1()
+    if a.only in ("", "solve"):
+        bench_solve()
+    if a.only in ("", "misc"):
+        bench_misc()

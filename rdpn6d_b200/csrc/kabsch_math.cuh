@@ -4,8 +4,11 @@
 //    solution of lib/pysixd/transform.py:940-951 (R = U diag(1,1,det) V^T) reduces to: map plane
 //    normal to plane normal and rotate in-plane by atan2(sum cross, sum dot).  No iteration.
 //  * rotation_from_cov(): rotation maximising tr(R^T S) for a 3x3 cross-covariance via Horn's
-//    quaternion matrix (the reference's own non-SVD branch, transform.py:953-969) solved with a
-//    cyclic Jacobi sweep on the symmetric 4x4.  Equals the SVD branch incl. the det<0 fix (:945-948).
+//    quaternion matrix N (the reference's own non-SVD branch, transform.py:953-969).  Equals the SVD
+//    branch incl. the det<0 fix (:945-948).  The largest eigenvalue of N is found by Newton's method
+//    on the quartic characteristic polynomial started from the upper bound (Ga+Gb)/2 (monotone
+//    convergence; Theobald's QCP), its eigenvector from the adjugate of N - lambda I; a cyclic
+//    Jacobi sweep on the 4x4 is the fallback when that eigenvalue is (numerically) repeated.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -85,7 +88,94 @@ __device__ __forceinline__ void kabsch3(const double (*a)[3], const double (*c)[
 
 // S[i*3+j] = sum_w c_i a_j (camera row, object column), i.e. v1 . v0^T of transform.py:942.
 // R (row-major) maximises sum c^T R a over SO(3).
-__device__ __noinline__ void rotation_from_cov(const double* S, double* R) {
+__device__ __forceinline__ void quat_to_rot(double q0, double q1, double q2, double q3, double* R) {
+    const double inv = 1.0 / sqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+    q0 *= inv; q1 *= inv; q2 *= inv; q3 *= inv;
+    R[0] = 1.0 - 2.0 * (q2 * q2 + q3 * q3); R[1] = 2.0 * (q1 * q2 - q3 * q0);       R[2] = 2.0 * (q1 * q3 + q2 * q0);
+    R[3] = 2.0 * (q1 * q2 + q3 * q0);       R[4] = 1.0 - 2.0 * (q1 * q1 + q3 * q3); R[5] = 2.0 * (q2 * q3 - q1 * q0);
+    R[6] = 2.0 * (q1 * q3 - q2 * q0);       R[7] = 2.0 * (q2 * q3 + q1 * q0);       R[8] = 1.0 - 2.0 * (q1 * q1 + q2 * q2);
+}
+
+__device__ __forceinline__ double det3(double a, double b, double c, double d, double e, double f, double g, double h,
+                                       double i) {
+    return a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+}
+
+__device__ __noinline__ void rotation_from_cov_jacobi(const double* S, double* R);
+
+// Ga = sum_w |a - a_mean|^2, Gb = sum_w |c - c_mean|^2 (only used as the Newton start: any upper bound of
+// the largest eigenvalue works).
+__device__ __forceinline__ void rotation_from_cov(const double* S, double Ga, double Gb, double* R) {
+    const double Sxx = S[0], Sxy = S[3], Sxz = S[6];
+    const double Syx = S[1], Syy = S[4], Syz = S[7];
+    const double Szx = S[2], Szy = S[5], Szz = S[8];
+    // symmetric traceless N (upper triangle)
+    const double n00 = Sxx + Syy + Szz, n01 = Syz - Szy, n02 = Szx - Sxz, n03 = Sxy - Syx;
+    const double n11 = Sxx - Syy - Szz, n12 = Sxy + Syx, n13 = Szx + Sxz;
+    const double n22 = -Sxx + Syy - Szz, n23 = Syz + Szy;
+    const double n33 = -Sxx - Syy + Szz;
+    // characteristic polynomial  l^4 + C2 l^2 + C1 l + C0
+    double ss = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) ss += S[i] * S[i];
+    const double C2 = -2.0 * ss;
+    const double C1 = -8.0 * det3(S[0], S[1], S[2], S[3], S[4], S[5], S[6], S[7], S[8]);
+    const double C0 = n00 * det3(n11, n12, n13, n12, n22, n23, n13, n23, n33) -
+                      n01 * det3(n01, n12, n13, n02, n22, n23, n03, n23, n33) +
+                      n02 * det3(n01, n11, n13, n02, n12, n23, n03, n13, n33) -
+                      n03 * det3(n01, n11, n12, n02, n12, n22, n03, n13, n23);
+    double lam = 0.5 * (Ga + Gb);
+    const double scale = lam;
+    bool converged = false;
+    for (int it = 0; it < 64; ++it) {
+        const double x2 = lam * lam;
+        const double b = (x2 + C2) * lam;
+        const double a = b + C1;
+        const double fp = 2.0 * x2 * lam + b + a;
+        if (fp == 0.0) break;
+        const double delta = (a * lam + C0) / fp;
+        lam -= delta;
+        if (fabs(delta) <= 1e-15 * fabs(lam)) { converged = true; break; }
+    }
+    // eigenvector: column of adj(N - lam I) with the largest diagonal cofactor
+    const double m00 = n00 - lam, m11 = n11 - lam, m22 = n22 - lam, m33 = n33 - lam;
+    const double c00 = det3(m11, n12, n13, n12, m22, n23, n13, n23, m33);
+    const double c11 = det3(m00, n02, n03, n02, m22, n23, n03, n23, m33);
+    const double c22 = det3(m00, n01, n03, n01, m11, n13, n03, n13, m33);
+    const double c33 = det3(m00, n01, n02, n01, m11, n12, n02, n12, m22);
+    const double a00 = fabs(c00), a11 = fabs(c11), a22 = fabs(c22), a33 = fabs(c33);
+    const double big = fmax(fmax(a00, a11), fmax(a22, a33));
+    // |cofactor| ~ product of the three eigenvalue gaps: tiny relative to scale^3 => repeated eigenvalue
+    if (!converged || !(big > 1e-18 * scale * scale * scale)) {
+        rotation_from_cov_jacobi(S, R);
+        return;
+    }
+    double q0, q1, q2, q3;
+    if (big == a00) {
+        q0 = c00;
+        q1 = -det3(n01, n12, n13, n02, m22, n23, n03, n23, m33);
+        q2 = det3(n01, m11, n13, n02, n12, n23, n03, n13, m33);
+        q3 = -det3(n01, m11, n12, n02, n12, m22, n03, n13, n23);
+    } else if (big == a11) {
+        q0 = -det3(n01, n02, n03, n12, m22, n23, n13, n23, m33);
+        q1 = c11;
+        q2 = -det3(m00, n02, n03, n01, n12, n13, n03, n23, m33);
+        q3 = det3(m00, n02, n03, n01, n12, n13, n02, m22, n23);
+    } else if (big == a22) {
+        q0 = det3(n01, n02, n03, m11, n12, n13, n13, n23, m33);
+        q1 = -det3(m00, n02, n03, n01, n12, n13, n03, n23, m33);
+        q2 = c22;
+        q3 = -det3(m00, n01, n03, n01, m11, n13, n02, n12, n23);
+    } else {
+        q0 = -det3(n01, n02, n03, m11, n12, n13, n12, m22, n23);
+        q1 = det3(m00, n02, n03, n01, n12, n13, n02, m22, n23);
+        q2 = -det3(m00, n01, n03, n01, m11, n13, n02, n12, n23);
+        q3 = c33;
+    }
+    quat_to_rot(q0, q1, q2, q3, R);
+}
+
+__device__ __noinline__ void rotation_from_cov_jacobi(const double* S, double* R) {
     // Horn's N with Sh_ij = sum a_i c_j = S[j*3+i]
     const double Sxx = S[0], Sxy = S[3], Sxz = S[6];
     const double Syx = S[1], Syy = S[4], Syz = S[7];
@@ -147,11 +237,7 @@ __device__ __noinline__ void rotation_from_cov(const double* S, double* R) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
         if (i == best) { q0 = V[0][i]; q1 = V[1][i]; q2 = V[2][i]; q3 = V[3][i]; }
-    const double inv = 1.0 / sqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
-    q0 *= inv; q1 *= inv; q2 *= inv; q3 *= inv;
-    R[0] = 1.0 - 2.0 * (q2 * q2 + q3 * q3); R[1] = 2.0 * (q1 * q2 - q3 * q0);       R[2] = 2.0 * (q1 * q3 + q2 * q0);
-    R[3] = 2.0 * (q1 * q2 + q3 * q0);       R[4] = 1.0 - 2.0 * (q1 * q1 + q3 * q3); R[5] = 2.0 * (q2 * q3 - q1 * q0);
-    R[6] = 2.0 * (q1 * q3 - q2 * q0);       R[7] = 2.0 * (q2 * q3 + q1 * q0);       R[8] = 1.0 - 2.0 * (q1 * q1 + q2 * q2);
+    quat_to_rot(q0, q1, q2, q3, R);
 }
 
 }  // namespace rdpn

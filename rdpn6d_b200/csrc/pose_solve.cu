@@ -612,7 +612,7 @@ __global__ void __launch_bounds__(ST, 2) pose_solve_kernel(SolveArgs a, int smem
         block_sum<DENSE, 11>(s, cov);
         if (t == 0) {
             double R[9];
-            rotation_from_cov(cov, R);
+            rotation_from_cov(cov, cov[10], cov[9], R);
             double sc = 1.0;
             if (a.prm.with_scale) sc = sqrt(cov[9] / cov[10]);  // transform.py:971-975
 #pragma unroll
@@ -715,7 +715,7 @@ __global__ void __launch_bounds__(256) kabsch_kernel(const float* __restrict__ s
     bsum(cov, 11);
     if (t == 0) {
         double R[9];
-        rotation_from_cov(cov, R);
+        rotation_from_cov(cov, cov[10], cov[9], R);
         const double sc = with_scale ? sqrt(cov[9] / cov[10]) : 1.0;
         for (int r = 0; r < 3; ++r) {
             outM[(size_t)b * 12 + 4 * r + 0] = (float)(sc * R[3 * r + 0]);

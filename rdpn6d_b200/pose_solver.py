@@ -188,6 +188,50 @@ class PoseSolver:
                                hyp_counts=o.get("hyp_counts"), hyp_poses=o.get("hyp_poses"), scale=o["scale"])
 
 
+class SolvePlan:
+    """A fully prepared launch (C structs built once): `launch()` is a single ctypes call, so a
+    benchmark or serving loop pays no per-step Python tensor bookkeeping."""
+
+    def __init__(self, solver, inp, hyp, tn, prm, outs, result):
+        self._solver, self._inp, self._hyp, self._tn, self._prm, self._outs = solver, inp, hyp, tn, prm, outs
+        self.result = result
+        self._fn = _lib.lib().rdpn_pose_solve
+        self._args = (ctypes.byref(inp.struct), hyp.data_ptr(), tn.data_ptr() if tn is not None else None,
+                      ctypes.byref(prm), ctypes.byref(outs))
+        self._dev = inp.dev
+
+    def launch(self, stream=None):
+        st = (stream or torch.cuda.current_stream(self._dev)).cuda_stream
+        rc = self._fn(*self._args, st)
+        if rc:
+            _lib.check(rc, "pose_solve")
+        return self.result
+
+
+def make_plan(solver, depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx, region_idx=None, anchors=None,
+              depth_div=None, t_net=None):
+    """Prepare a reusable launch of `solver` on fixed device buffers (private output buffers)."""
+    inp = _Inputs(depth, Kp, coor_x, coor_y, coor_z, mask, extent, region_idx, anchors, depth_div,
+                  solver.mask_mode, solver.mask_thr)
+    B, dev = inp.B, inp.dev
+    H = hyp_idx.shape[1]
+    hyp = _vec(hyp_idx, (B, H, 3), "hyp_idx", torch.int32)
+    tn = _vec(t_net, (B, 3), "t_net") if t_net is not None else None
+    prm = _lib.SolveParams(num_hyp=H, **solver.prm)
+    solver._out.pop((B, H, str(dev)), None)
+    o = solver._buffers(B, H, dev)
+    solver._out.pop((B, H, str(dev)), None)  # the plan owns these buffers
+    outs = _lib.SolveOutputs()
+    for k in ("pose", "n_inliers", "status", "best_h", "n_sel", "inlier_mask", "hyp_counts", "hyp_poses", "scale"):
+        setattr(outs, k, o[k].data_ptr() if k in o else None)
+    res = PoseSolveResult(pose=o["pose"].view(B, 3, 4), n_inliers=o["n_inliers"], status=o["status"],
+                          best_h=o["best_h"], n_sel=o["n_sel"], inlier_mask=o.get("inlier_mask"),
+                          hyp_counts=o.get("hyp_counts"), hyp_poses=o.get("hyp_poses"), scale=o["scale"])
+    with torch.cuda.device(dev):
+        pass
+    return SolvePlan(solver, inp, hyp, tn, prm, outs, res)
+
+
 def pose_solve(depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx, region_idx=None, anchors=None,
                depth_div=None, t_net=None, stream=None, **kw):
     """One-shot functional form of PoseSolver (see its constructor for the keyword arguments)."""

@@ -157,13 +157,18 @@ def make_batch(B, models=None, H=256, num_regions=32, K=K_LM, seed=20260101, im_
         tt = np.where(hit, tt, 0.0)
         xo = o[None, :] + tt[:, None] * d  # object coordinates of the visible surface
         z = tt  # camera depth (dirs has z = 1)
-        if occlusion_max > 0:  # rectangular occluder
+        if occlusion_max > 0 and hit.any():  # rectangular occluder over U(0, occlusion_max) of the object's box
             frac = rng.uniform(0, occlusion_max)
-            side = int(round(ROI * np.sqrt(frac)))
-            if side > 0:
-                oy, ox = rng.integers(0, ROI - side + 1, 2)
+            hh = hit.reshape(ROI, ROI)
+            rows, cols = np.nonzero(hh.any(1))[0], np.nonzero(hh.any(0))[0]
+            r0, r1, c0, c1 = rows[0], rows[-1] + 1, cols[0], cols[-1] + 1
+            oh = int(round((r1 - r0) * np.sqrt(frac)))
+            ow = int(round((c1 - c0) * np.sqrt(frac)))
+            if oh > 0 and ow > 0:
+                oy = r0 if rng.random() < 0.5 else r1 - oh  # slides in from a random corner of the box
+                ox = c0 if rng.random() < 0.5 else c1 - ow
                 occ = np.zeros((ROI, ROI), bool)
-                occ[oy:oy + side, ox:ox + side] = True
+                occ[oy:oy + oh, ox:ox + ow] = True
                 hit = hit & ~occ.reshape(-1)
         fg = hit
         if dense:

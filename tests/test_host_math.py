@@ -23,7 +23,8 @@ static inline double __dmul_rn(double a,double b){return a*b;}
 #include "kabsch_math_host.cuh"
 extern "C" {
 void host_kabsch3(const double* a, const double* c, double* Rt){ rdpn::kabsch3((const double(*)[3])a,(const double(*)[3])c,Rt);}
-void host_rot_from_cov(const double* S, double* R){ rdpn::rotation_from_cov(S,R);}
+void host_rot_from_cov(const double* S, double ga, double gb, double* R){ rdpn::rotation_from_cov(S,ga,gb,R);}
+void host_rot_from_cov_jacobi(const double* S, double* R){ rdpn::rotation_from_cov_jacobi(S,R);}
 int host_triangle_ok(const double* p0,const double*p1,const double*p2){return rdpn::triangle_ok(p0,p1,p2);}
 }
 """
@@ -77,9 +78,13 @@ def test_rotation_from_cov_matches_reference_golden(hm, golden_dir):
         ac = a - a.mean(1, keepdims=True)
         cc = c - c.mean(1, keepdims=True)
         S = np.ascontiguousarray(cc @ ac.T)
-        R = np.zeros(9)
-        hm.host_rot_from_cov(_p(S), _p(R))
-        np.testing.assert_allclose(R.reshape(3, 3), M[:3, :3], atol=1e-10, err_msg=str(name))
+        for fn in ("qcp", "jacobi"):
+            R = np.zeros(9)
+            if fn == "qcp":
+                hm.host_rot_from_cov(_p(S), ctypes.c_double((ac * ac).sum()), ctypes.c_double((cc * cc).sum()), _p(R))
+            else:
+                hm.host_rot_from_cov_jacobi(_p(S), _p(R))
+            np.testing.assert_allclose(R.reshape(3, 3), M[:3, :3], atol=1e-10, err_msg=str(name) + fn)
 
 
 def test_rotation_from_cov_random_incl_reflection_and_planar(hm):
@@ -96,11 +101,40 @@ def test_rotation_from_cov_random_incl_reflection_and_planar(hm):
             a[2] = 0
             c = po.kabsch(rng.uniform(-1, 1, (3, 5)), rng.uniform(-1, 1, (3, 5)))[:3, :3] @ a + 0.3
         M = po.kabsch(a, c)
-        S = np.ascontiguousarray((c - c.mean(1, keepdims=True)) @ (a - a.mean(1, keepdims=True)).T)
+        ac, cc = a - a.mean(1, keepdims=True), c - c.mean(1, keepdims=True)
+        S = np.ascontiguousarray(cc @ ac.T)
         R = np.zeros(9)
-        hm.host_rot_from_cov(_p(S), _p(R))
+        hm.host_rot_from_cov(_p(S), ctypes.c_double((ac * ac).sum()), ctypes.c_double((cc * cc).sum()), _p(R))
         worst = max(worst, np.abs(R.reshape(3, 3) - M[:3, :3]).max())
-    assert worst < 1e-10
+        R2 = np.zeros(9)
+        hm.host_rot_from_cov_jacobi(_p(S), _p(R2))
+        worst = max(worst, np.abs(R2.reshape(3, 3) - M[:3, :3]).max())
+    assert worst < 1e-9
+
+
+def test_rotation_from_cov_degenerate_inputs_do_not_produce_nan(hm):
+    """Collinear points / zero covariance: the rotation is not unique, but the result must be a finite
+    proper rotation (Jacobi fallback)."""
+    rng = np.random.default_rng(4)
+    for kind in ("collinear", "zero", "identical"):
+        if kind == "collinear":
+            tt = rng.uniform(-1, 1, 20)
+            a = np.outer([0.3, -0.2, 0.9], tt)
+            c = np.outer([0.1, 0.8, 0.2], tt)
+        elif kind == "zero":
+            a = np.zeros((3, 5)); c = np.zeros((3, 5))
+        else:
+            a = rng.uniform(-1, 1, (3, 10)); c = a.copy()
+        ac, cc = a - a.mean(1, keepdims=True), c - c.mean(1, keepdims=True)
+        S = np.ascontiguousarray(cc @ ac.T)
+        R = np.zeros(9)
+        hm.host_rot_from_cov(_p(S), ctypes.c_double((ac * ac).sum()), ctypes.c_double((cc * cc).sum()), _p(R))
+        R = R.reshape(3, 3)
+        assert np.isfinite(R).all()
+        np.testing.assert_allclose(R @ R.T, np.eye(3), atol=1e-9)
+        assert abs(np.linalg.det(R) - 1) < 1e-9
+        if kind == "identical":
+            np.testing.assert_allclose(R, np.eye(3), atol=1e-9)
 
 
 def test_triangle_rule_is_bitwise_the_oracles(hm):
