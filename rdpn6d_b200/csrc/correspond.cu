@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(C_NT, 1)
         const float e0 = in.extent[3 * b + 0], e1 = in.extent[3 * b + 1], e2 = in.extent[3 * b + 2];
         const float g0 = (float)(0.0001 * (double)e0), g1 = (float)(0.0001 * (double)e1), g2 = (float)(0.0001 * (double)e2);
         const float div = in.depth_div ? in.depth_div[b] : 0.f;
+        const float sgx = copysignf(1.f, fx), sgy = copysignf(1.f, fy);
         mbar_wait(&s.full[stg], (i >> 1) & 1);
         const S1Stage& d = s.st[stg];
         float4 mq[C_QPT];
@@ -141,9 +142,19 @@ __global__ void __launch_bounds__(C_NT, 1)
             for (int j = 0; j < 4; ++j) {
                 const float u = (float)(4 * ((p0 + j) & 63));
                 float dz0 = dd[j];
-                if (div != 0.f) dz0 = __fdiv_rn(dz0, div);                               // data_loader.py:563
-                const float X = __fdiv_rn(__fmul_rn(__fsub_rn(u, cxp), dz0), fx);        // :573
-                const float Y = __fdiv_rn(__fmul_rn(__fsub_rn(v, cyp), dz0), fy);        // :574
+                if (div != 0.f) {                                                        // data_loader.py:563
+                    const float q = __fdiv_rn(dz0 == 0.f ? 1.f : dz0, div);
+                    dz0 = dz0 == 0.f ? __fmul_rn(dz0, copysignf(1.f, div)) : q;
+                }
+                // (u - cx') * d / fx' (:573-574).  Background pixels have d = 0, i.e. a zero numerator, which
+                // would send the whole warp through div.rn's special-operand slow path; 0 / f is +-0 with the
+                // sign of numerator * sign(f), so those lanes divide 1 / f instead and select the signed zero.
+                const float nx = __fmul_rn(__fsub_rn(u, cxp), dz0);
+                const float ny = __fmul_rn(__fsub_rn(v, cyp), dz0);
+                const float qx = __fdiv_rn(nx == 0.f ? 1.f : nx, fx);
+                const float qy = __fdiv_rn(ny == 0.f ? 1.f : ny, fy);
+                const float X = nx == 0.f ? __fmul_rn(nx, sgx) : qx;
+                const float Y = ny == 0.f ? __fmul_rn(ny, sgy) : qy;
                 const float dx = __fmul_rn(__fsub_rn(cxn[j], 0.5f), e0);                 // gdrn_evaluator.py:103-105
                 const float dy = __fmul_rn(__fsub_rn(cyn[j], 0.5f), e1);
                 const float dz = __fmul_rn(__fsub_rn(czn[j], 0.5f), e2);

@@ -44,8 +44,11 @@ __global__ void backproject_kernel(const float* __restrict__ depth, const float*
         const int b = (int)(i / ((size_t)W * H));
         const float* k = K + (size_t)k_stride * b;
         const float d = depth[i];
-        const float X = __fdiv_rn(__fmul_rn(__fsub_rn((float)w, k[2]), d), k[0]);
-        const float Y = __fdiv_rn(__fmul_rn(__fsub_rn((float)h, k[5]), d), k[4]);
+        // zero numerators (no depth) bypass div.rn's special-operand slow path: 0 / f = +-0
+        const float nx = __fmul_rn(__fsub_rn((float)w, k[2]), d), ny = __fmul_rn(__fsub_rn((float)h, k[5]), d);
+        const float qx = __fdiv_rn(nx == 0.f ? 1.f : nx, k[0]), qy = __fdiv_rn(ny == 0.f ? 1.f : ny, k[4]);
+        const float X = nx == 0.f ? __fmul_rn(nx, copysignf(1.f, k[0])) : qx;
+        const float Y = ny == 0.f ? __fmul_rn(ny, copysignf(1.f, k[4])) : qy;
         out[3 * i + 0] = X;
         out[3 * i + 1] = Y;
         out[3 * i + 2] = d;

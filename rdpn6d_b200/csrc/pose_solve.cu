@@ -310,7 +310,10 @@ __global__ void __launch_bounds__(ST, 2) pose_solve_kernel(SolveArgs a, FusedLay
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float d = dd[j];
-            if (rc.div != 0.f) d = __fdiv_rn(d, rc.div);
+            if (rc.div != 0.f) {  // zero lanes would drag the warp through div.rn's slow path: 0 / f = +-0
+                const float q = __fdiv_rn(d == 0.f ? 1.f : d, rc.div);
+                d = d == 0.f ? __fmul_rn(d, copysignf(1.f, rc.div)) : q;
+            }
             const float dx = __fmul_rn(__fsub_rn(cxn[j], 0.5f), rc.ext[0]);
             const float dy = __fmul_rn(__fsub_rn(cyn[j], 0.5f), rc.ext[1]);
             const float dz = __fmul_rn(__fsub_rn(czn[j], 0.5f), rc.ext[2]);
