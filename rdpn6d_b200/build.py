@@ -56,7 +56,8 @@ def _build_locked(ptxas, verbose):
     procs = []
     for s in srcs:
         o = os.path.join(CSRC, os.path.basename(s)[:-3] + ".o")
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas else []) + ["-c", s, "-o", o]
+        extra = os.environ.get("RDPN_NVCC_EXTRA", "").split()  # e.g. -DRDPN_SOLVE_CTAS=3 for tuning runs
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if ptxas else []) + ["-c", s, "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)
     for cmd, p in procs:

@@ -2,11 +2,11 @@
 // H x n inlier scoring + best selection + weighted Kabsch/Umeyama refit) and the batched Kabsch entry.
 // (The materialising S1 kernel lives in correspond.cu.)
 //
-// One CTA owns one ROI.  Its five 16 KB planes (depth, coor_x/y/z, mask) and the 4 KB region-index
-// plane are contiguous in HBM, so they are staged with 1-D bulk TMA copies (cp.async.bulk +
-// mbarrier, no tensor map) issued by one thread; two CTAs are resident per SM so the copies of one
-// ROI overlap the arithmetic of the other.  Everything after the copy stays in shared memory:
-// nothing but the 12-float pose (and optional diagnostics) goes back to HBM.
+// One CTA owns one ROI and four CTAs share an SM.  The ROI's planes are read once with coalesced
+// 16-byte loads for the gate (after an L2 prefetch); only the gated ~10 % of the pixels are gathered
+// again and turned into correspondences, which then live in shared memory.  Nothing but the 12-float
+// pose (and optional diagnostics) goes back to HBM.  (The bulk-TMA ring lives in correspond.cu, where
+// the whole ROI has to be materialised.)
 //
 // Arithmetic contracts (oracle/pose_oracle.py, oracle/pose_oracle.c):
 //   S1       FP32, one IEEE op per step: X = ((u - cx') * d) / fx'   (data_loader.py:563-576),
@@ -60,16 +60,20 @@ __device__ __forceinline__ float mask_prob(float m, int mode, float mn, float mx
 // ---------------------------------------------------------------------------------------------
 // fused solver
 // ---------------------------------------------------------------------------------------------
-// Per ROI (one CTA, 256 threads, two CTAs resident per SM):
-//   1  bulk-TMA stage of the raw planes                      (stage_roi)
-//   2  mask min/max, then the GATE only (no divisions): 16 pixels per thread -> selection bits
+// One CTA (256 threads) per ROI, FOUR CTAs resident per SM (<= 64 registers, ~48 KB shared memory):
+// every phase below is short and latency-bound on its own (global gathers, IEEE divisions, FP64
+// chains, barriers), so the SM is kept busy by thread-level parallelism across ROIs rather than by
+// staging whole ROIs in shared memory (the first version did: 112 KB and 126 registers per CTA capped
+// the SM at 16 warps and 57 % issue utilisation).
+//   1  L2 prefetch of this ROI's planes; mask min/max straight from global (coalesced float4)
+//   2  GATE only (no divisions): 16 pixels per thread from coalesced float4 loads -> selection bits
 //   3  deterministic counting sort of the gated pixels by region id (warp match_any ranks + per-warp
-//      bucket cursors) -> pix[slot]; bucket r occupies slots [bstart[r], bstart[r+1])
-//   4  hypothesis generation straight from the raw planes (3 pixels each, FP64 closed form)
-//   5  correspondence STAGING: one thread per gated slot computes (cam xyz, w) with the exact S1
-//      arithmetic and the list is written in place over the raw planes as float4 AoS
-//   6  scoring: one thread per hypothesis; per region bucket the transformed anchor R a + t is
-//      computed once (9 FMA) and every point of the bucket costs 1 LDS.128 + 6 FP32 + compare
+//      bucket cursors) -> pix[slot], srid[slot]; run table of the non-empty buckets
+//   4  hypothesis generation: 3 gathered pixels each, FP64 closed form, rounded once to FP32
+//   5  per chunk of <= 1024 gated slots: STAGING (one thread per slot gathers the raw pixel and computes
+//      (cam xyz, w) with the exact S1 arithmetic into a float4 list in shared memory), then
+//   6  SCORING: one thread per hypothesis; per run the transformed anchor R a + t is computed once
+//      (9 FMA) and every point costs 1 LDS.128 + 3 FADD + FMUL + 2 FFMA + FSETP + predicated IADD
 //   7  best hypothesis, FP64 refit sums, closed-form rotation, outputs
 struct RoiGate {
     float hi, lo;     // fast mask filter: a > hi -> in, a < lo -> out, else exact test
@@ -78,21 +82,11 @@ struct RoiGate {
     int incl;         // 1: >= (odd mantissa of the threshold), 0: >
 };
 
-template <bool DENSE>
-struct __align__(128) FusedSmem {
-    float tile[5][RDPN_P];                 // raw depth, coor_x, coor_y, coor_z, mask; later tile[0..3] = float4 camw[n]
-    float4 objS[DENSE ? RDPN_P : 1];       // dense: object-side AoS (x,y,z,-)
-    uint8_t rid[DENSE ? 16 : RDPN_P];
-    uint16_t pix[RDPN_P];                  // slot -> pixel
-    uint32_t selmap[RDPN_P / 32];          // gate bitmap by pixel
-    uint64_t bar;
-    RoiConst rc;
-    RoiGate gate;
-    float red_f[2][SW];
+constexpr int CHUNK = 1024;  // gated slots staged in shared memory at a time (dense mode: CHUNK / 2)
+
+struct FinishSmem {  // scratch of the select + refit tail
     double red_d[SW][12];
     double bc_d[16];
-    int n_sel;
-    int n_runs;
     int best_h;
     int n_best;
     int h_eff;
@@ -101,7 +95,20 @@ struct __align__(128) FusedSmem {
     int red_i[SW];
 };
 
-// one pixel of S1 with the exact oracle arithmetic; returns cam (and obj in dense mode), d = depth used
+struct __align__(128) FusedSmem {
+    float4 chunk[CHUNK];            // (cam xyz, w) by slot of the current chunk; dense: second half = obj xyz
+    uint16_t pix[RDPN_P];           // slot -> pixel
+    uint8_t srid[RDPN_P];           // slot -> region id (non-decreasing)
+    uint32_t selmap[RDPN_P / 32];   // gate bitmap by pixel
+    RoiConst rc;
+    RoiGate gate;
+    float red_f[2][SW];
+    int n_sel;
+    int n_runs;
+    FinishSmem fin;
+};
+
+// one pixel of S1 with the exact oracle arithmetic; cam (and obj in dense mode)
 template <bool DENSE>
 __device__ __forceinline__ void pixel_s1(const RoiConst& rc, int pix, float d_raw, float cxn, float cyn, float czn,
                                          float (&cam)[3], float (&obj)[3]) {
@@ -119,7 +126,29 @@ __device__ __forceinline__ void pixel_s1(const RoiConst& rc, int pix, float d_ra
         obj[0] = dx; obj[1] = dy; obj[2] = dz;
     } else {
         cam[0] = __fsub_rn(X, dx); cam[1] = __fsub_rn(Y, dy); cam[2] = __fsub_rn(d, dz);
+        obj[0] = obj[1] = obj[2] = 0.f;
     }
+}
+
+// the raw planes of one ROI in global memory
+struct RoiPlanes {
+    const float* depth;
+    const float* cx;
+    const float* cy;
+    const float* cz;
+    const float* mask;
+    const uint8_t* rid;
+};
+
+// gather one gated pixel and run S1 on it (cam xyz, w | obj xyz)
+template <bool DENSE>
+__device__ __forceinline__ void gather_s1(const RoiPlanes& pl, const RoiConst& rc, int p, bool weighted, int mask_mode,
+                                          float4& camw, float4& objv) {
+    float cam[3], obj[3];
+    pixel_s1<DENSE>(rc, p, __ldg(pl.depth + p), __ldg(pl.cx + p), __ldg(pl.cy + p), __ldg(pl.cz + p), cam, obj);
+    const float w = weighted ? mask_prob(__ldg(pl.mask + p), mask_mode, rc.mn, rc.mx) : 1.f;
+    camw = make_float4(cam[0], cam[1], cam[2], w);
+    objv = make_float4(obj[0], obj[1], obj[2], 0.f);
 }
 
 // (mask_prob(m) > mask_thr) without the division for the L1 mode: fl(a/b) > thr  <=>  a/b > (>=) cut
@@ -131,7 +160,7 @@ __device__ __forceinline__ bool mask_pass(float m, int mode, float thr, const Ro
         if (a > g.hi) return true;
         if (a < g.lo) return false;
         const double l = (double)a, r = __dmul_rn((double)g.b, g.cut);
-        return g.incl ? (l >= r) : (l > r);  // NaN (flat mask: 0/0) -> false
+        return g.incl ? (l >= r) : (l > r);  // NaN -> false
     }
     return mask_prob(m, mode, 0.f, 0.f) > thr;
 }
@@ -165,44 +194,46 @@ __device__ __forceinline__ float resid2(const float* P, float ax, float ay, floa
     return resid2_pt(x, y, z, cx, cy, cz);
 }
 
-// block-wide sum of NV doubles; result valid in every thread (via s.bc_d[0..NV)).
-template <typename SM, int NV>
-__device__ __forceinline__ void block_sum(SM& s, double (&v)[NV]) {
+// block-wide sum of NV doubles; result valid in every thread (via f.bc_d[0..NV)).
+template <int NV>
+__device__ __forceinline__ void block_sum(FinishSmem& f, double (&v)[NV]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         v[i] = warp_sum(v[i]);
-        if (lane == 0) s.red_d[warp][i] = v[i];
+        if (lane == 0) f.red_d[warp][i] = v[i];
     }
     __syncthreads();
     if (threadIdx.x < NV) {
         double a = 0.0;
-        for (int w = 0; w < SW; ++w) a += s.red_d[w][threadIdx.x];
-        s.bc_d[threadIdx.x] = a;
+        for (int w = 0; w < SW; ++w) a += f.red_d[w][threadIdx.x];
+        f.bc_d[threadIdx.x] = a;
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = s.bc_d[i];
+    for (int i = 0; i < NV; ++i) v[i] = f.bc_d[i];
     __syncthreads();
 }
 
 struct FusedLayout {  // byte offsets of the dynamic tail behind FusedSmem
     int anchors;      // float4[R]
     int runtab;       // float4[R]: non-empty buckets (anchor xyz, start | end << 16)
-    int bstart;       // int[RB + 1]
     int wrun;         // uint16[SW][RB]     (RB = R + 1: last bucket collects the unselected lanes)
     int hyp;          // float[H][12]
     int hcnt;         // int[H]
     int total;
 };
 
+#ifndef RDPN_SOLVE_CTAS
+#define RDPN_SOLVE_CTAS 4
+#endif
 template <bool DENSE>
-__global__ void __launch_bounds__(ST, 2) pose_solve_kernel(SolveArgs a, FusedLayout lay) {
+__global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveArgs a, FusedLayout lay) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    FusedSmem<DENSE>& s = *reinterpret_cast<FusedSmem<DENSE>*>(smem_raw);
+    FusedSmem& s = *reinterpret_cast<FusedSmem*>(smem_raw);
+    FinishSmem& f = s.fin;
     float4* anchors = reinterpret_cast<float4*>(smem_raw + lay.anchors);
     float4* runtab = reinterpret_cast<float4*>(smem_raw + lay.runtab);
-    int* bstart = reinterpret_cast<int*>(smem_raw + lay.bstart);
     uint16_t* wrun = reinterpret_cast<uint16_t*>(smem_raw + lay.wrun);
     float* hyp = reinterpret_cast<float*>(smem_raw + lay.hyp);  // [H][12]
     int* hcnt = reinterpret_cast<int*>(smem_raw + lay.hcnt);    // [H] counts, -1 = invalid
@@ -211,26 +242,26 @@ __global__ void __launch_bounds__(ST, 2) pose_solve_kernel(SolveArgs a, FusedLay
     const int RB = R + 1;
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const rdpn_roi_inputs& in = a.in;
+    const size_t po = (size_t)b * RDPN_P;
+    RoiPlanes pl;
+    pl.depth = in.depth + po;
+    pl.cx = in.coor_x + po;
+    pl.cy = in.coor_y + po;
+    pl.cz = in.coor_z + po;
+    pl.mask = in.mask + po;
+    pl.rid = DENSE ? nullptr : in.region_idx + po;
 
-    // first hypothesis triplet of this thread: issue the global loads before anything waits
-    int pre_ii[3] = {-1, -1, -1};
-    if (t < H) {
-        const int32_t* ip = a.hyp_idx + ((size_t)b * H + t) * 3;
-        pre_ii[0] = ip[0]; pre_ii[1] = ip[1]; pre_ii[2] = ip[2];
+    // ---- 1: prefetch this ROI's planes into L2 (one 64-byte line per thread and plane), constants, zeroing
+    {
+        const int o = t * 16;  // 256 threads x 16 floats = one plane
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pl.mask + o));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pl.depth + o));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pl.cx + o));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pl.cy + o));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pl.cz + o));
+        if (!DENSE && t < 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(pl.rid + t * 64));
     }
-    // ---- 1: stage ----
     if (t == 0) {
-        mbar_init(&s.bar, 1);
-        mbar_fence_init();
-        const size_t o = (size_t)b * RDPN_P;
-        const uint32_t plane = RDPN_P * sizeof(float);
-        mbar_expect_tx(&s.bar, 5 * plane + (DENSE ? 0 : RDPN_P));
-        bulk_g2s(s.tile[4], in.mask + o, plane, &s.bar);
-        bulk_g2s(s.tile[0], in.depth + o, plane, &s.bar);
-        bulk_g2s(s.tile[1], in.coor_x + o, plane, &s.bar);
-        bulk_g2s(s.tile[2], in.coor_y + o, plane, &s.bar);
-        bulk_g2s(s.tile[3], in.coor_z + o, plane, &s.bar);
-        if (!DENSE) bulk_g2s(s.rid, in.region_idx + o, RDPN_P, &s.bar);
         RoiConst& rc = s.rc;
         rc.fx = in.Kp[4 * b + 0];
         rc.fy = in.Kp[4 * b + 1];
@@ -242,9 +273,10 @@ __global__ void __launch_bounds__(ST, 2) pose_solve_kernel(SolveArgs a, FusedLay
             rc.gthr[c] = (float)(0.0001 * (double)e);  // gdrn_evaluator.py:112-114 under numpy-1.23 promotion
         }
         rc.div = in.depth_div ? in.depth_div[b] : 0.f;
-        s.best_h = -1;
-        s.n_best = 0;
-        s.h_eff = H;
+        rc.mn = rc.mx = 0.f;
+        f.best_h = -1;
+        f.n_best = 0;
+        f.h_eff = H;
     }
     if (!DENSE)
         for (int r = t; r < R; r += ST) {
@@ -252,28 +284,26 @@ __global__ void __launch_bounds__(ST, 2) pose_solve_kernel(SolveArgs a, FusedLay
             anchors[r] = make_float4(ap[0], ap[1], ap[2], 0.f);
         }
     for (int i = t; i < SW * RB; i += ST) wrun[i] = 0;
-    if (t < RDPN_P / 32) s.selmap[t] = 0u;
     if (a.out.inlier_mask) {  // zero-fill; inliers are scattered in after the last refit
         uint4* im = reinterpret_cast<uint4*>(a.out.inlier_mask + (size_t)b * RDPN_P);
         im[t] = make_uint4(0u, 0u, 0u, 0u);
     }
-    __syncthreads();
-    mbar_wait(&s.bar, 0);
-
-    // ---- 2: mask min/max + gate.  Thread owns quads q = 32*(SW*k + warp) + lane (k = 0..3): every warp gets
-    //         two image rows out of each 16, so the rows the object covers are spread over all warps ----
+    // mask min / max (engine_utils.py:123-124).  Thread owns quads q = 32*(SW*k + warp) + lane (k = 0..3):
+    // every warp gets two image rows out of each 16, so the rows the object covers are spread over all warps.
     if (in.mask_mode == RDPN_MASK_L1) {
         float mn = FLT_MAX, mx = -FLT_MAX;
 #pragma unroll
         for (int k = 0; k < QPT; ++k) {
-            const float4 m4 = reinterpret_cast<const float4*>(s.tile[4])[32 * (SW * k + warp) + lane];
+            const float4 m4 = __ldg(reinterpret_cast<const float4*>(pl.mask) + 32 * (SW * k + warp) + lane);
             mn = fminf(fminf(fminf(mn, m4.x), fminf(m4.y, m4.z)), m4.w);
             mx = fmaxf(fmaxf(fmaxf(mx, m4.x), fmaxf(m4.y, m4.z)), m4.w);
         }
         mn = warp_min(mn);
         mx = warp_max(mx);
         if (lane == 0) { s.red_f[0][warp] = mn; s.red_f[1][warp] = mx; }
-        __syncthreads();
+    }
+    __syncthreads();
+    if (in.mask_mode == RDPN_MASK_L1) {
         if (t == 0) {
             float lo = s.red_f[0][0], hi = s.red_f[1][0];
             for (int w = 1; w < SW; ++w) { lo = fminf(lo, s.red_f[0][w]); hi = fmaxf(hi, s.red_f[1][w]); }
@@ -291,43 +321,47 @@ __global__ void __launch_bounds__(ST, 2) pose_solve_kernel(SolveArgs a, FusedLay
         __syncthreads();
     }
     const RoiConst rc = s.rc;
-    const RoiGate gate = s.gate;
+
+    // ---- 2: gate (gdrn_evaluator.py:110-117 + depth validity), no divisions ----
     unsigned selbits = 0u;
+    {
+        const RoiGate gate = s.gate;
 #pragma unroll 1
-    for (int k = 0; k < QPT; ++k) {
-        const int q = 32 * (SW * k + warp) + lane;
-        const float4 dq = reinterpret_cast<const float4*>(s.tile[0])[q];
-        const float4 xq = reinterpret_cast<const float4*>(s.tile[1])[q];
-        const float4 yq = reinterpret_cast<const float4*>(s.tile[2])[q];
-        const float4 zq = reinterpret_cast<const float4*>(s.tile[3])[q];
-        const float4 m4 = reinterpret_cast<const float4*>(s.tile[4])[q];
-        const float dd[4] = {dq.x, dq.y, dq.z, dq.w};
-        const float cxn[4] = {xq.x, xq.y, xq.z, xq.w};
-        const float cyn[4] = {yq.x, yq.y, yq.z, yq.w};
-        const float czn[4] = {zq.x, zq.y, zq.z, zq.w};
-        const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
-        unsigned nib = 0u;
+        for (int k = 0; k < QPT; ++k) {
+            const int q = 32 * (SW * k + warp) + lane;
+            const float4 dq = __ldg(reinterpret_cast<const float4*>(pl.depth) + q);
+            const float4 xq = __ldg(reinterpret_cast<const float4*>(pl.cx) + q);
+            const float4 yq = __ldg(reinterpret_cast<const float4*>(pl.cy) + q);
+            const float4 zq = __ldg(reinterpret_cast<const float4*>(pl.cz) + q);
+            const float4 m4 = __ldg(reinterpret_cast<const float4*>(pl.mask) + q);
+            const float dd[4] = {dq.x, dq.y, dq.z, dq.w};
+            const float cxn[4] = {xq.x, xq.y, xq.z, xq.w};
+            const float cyn[4] = {yq.x, yq.y, yq.z, yq.w};
+            const float czn[4] = {zq.x, zq.y, zq.z, zq.w};
+            const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+            unsigned nib = 0u;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float d = dd[j];
-            if (rc.div != 0.f) {  // zero lanes would drag the warp through div.rn's slow path: 0 / f = +-0
-                const float q = __fdiv_rn(d == 0.f ? 1.f : d, rc.div);
-                d = d == 0.f ? __fmul_rn(d, copysignf(1.f, rc.div)) : q;
+            for (int j = 0; j < 4; ++j) {
+                float d = dd[j];
+                if (rc.div != 0.f) {  // zero lanes would drag the warp through div.rn's slow path: 0 / f = +-0
+                    const float qd = __fdiv_rn(d == 0.f ? 1.f : d, rc.div);
+                    d = d == 0.f ? __fmul_rn(d, copysignf(1.f, rc.div)) : qd;
+                }
+                const float dx = __fmul_rn(__fsub_rn(cxn[j], 0.5f), rc.ext[0]);
+                const float dy = __fmul_rn(__fsub_rn(cyn[j], 0.5f), rc.ext[1]);
+                const float dz = __fmul_rn(__fsub_rn(czn[j], 0.5f), rc.ext[2]);
+                bool sel = (fabsf(dx) > rc.gthr[0]) && (fabsf(dy) > rc.gthr[1]) && (fabsf(dz) > rc.gthr[2]) && (d > 0.f);
+                if (sel) sel = mask_pass(mm[j], in.mask_mode, in.mask_thr, rc, gate);
+                nib |= (sel ? 1u : 0u) << j;
             }
-            const float dx = __fmul_rn(__fsub_rn(cxn[j], 0.5f), rc.ext[0]);
-            const float dy = __fmul_rn(__fsub_rn(cyn[j], 0.5f), rc.ext[1]);
-            const float dz = __fmul_rn(__fsub_rn(czn[j], 0.5f), rc.ext[2]);
-            bool sel = (fabsf(dx) > rc.gthr[0]) && (fabsf(dy) > rc.gthr[1]) && (fabsf(dz) > rc.gthr[2]) && (d > 0.f);
-            if (sel) sel = mask_pass(mm[j], in.mask_mode, in.mask_thr, rc, gate);  // gdrn_evaluator.py:110-117 (+ depth)
-            nib |= (sel ? 1u : 0u) << j;
+            selbits |= nib << (4 * k);
+            // publish the gate bitmap (4 bits per quad, 8 quads per word)
+            unsigned wbits = nib << (4 * (lane & 7));
+            wbits |= __shfl_xor_sync(0xffffffffu, wbits, 1);
+            wbits |= __shfl_xor_sync(0xffffffffu, wbits, 2);
+            wbits |= __shfl_xor_sync(0xffffffffu, wbits, 4);
+            if ((lane & 7) == 0) s.selmap[q >> 3] = wbits;
         }
-        selbits |= nib << (4 * k);
-        // publish the gate bitmap (4 bits per quad, 8 quads per word)
-        unsigned wbits = nib << (4 * (lane & 7));
-        wbits |= __shfl_xor_sync(0xffffffffu, wbits, 1);
-        wbits |= __shfl_xor_sync(0xffffffffu, wbits, 2);
-        wbits |= __shfl_xor_sync(0xffffffffu, wbits, 4);
-        if ((lane & 7) == 0) s.selmap[q >> 3] = wbits;
     }
 
     // ---- 3: counting sort by region, deterministic order (warp, k, j, lane) ----
@@ -337,7 +371,7 @@ __global__ void __launch_bounds__(ST, 2) pose_solve_kernel(SolveArgs a, FusedLay
     for (int k = 0; k < QPT; ++k) {
         const unsigned nib = (selbits >> (4 * k)) & 0xFu;
         if (__ballot_sync(0xffffffffu, nib != 0u) == 0u) continue;
-        const uchar4 r4 = DENSE ? make_uchar4(0, 0, 0, 0) : reinterpret_cast<const uchar4*>(s.rid)[32 * (SW * k + warp) + lane];
+        const uchar4 r4 = DENSE ? make_uchar4(0, 0, 0, 0) : __ldg(reinterpret_cast<const uchar4*>(pl.rid) + 32 * (SW * k + warp) + lane);
         const uint8_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -350,58 +384,44 @@ __global__ void __launch_bounds__(ST, 2) pose_solve_kernel(SolveArgs a, FusedLay
         }
     }
     __syncthreads();
-    // bucket starts and per-warp cursors: warp 0, RPL consecutive buckets per lane, one warp scan
+    // bucket starts, per-warp cursors and the run table: warp 0, RPL consecutive buckets per lane
     if (warp == 0) {
         const int RPL = (R + 31) / 32;
-        int loc = 0;
-        for (int u = 0; u < RPL; ++u) {
-            const int r = lane * RPL + u;
-            if (r < R)
-                for (int w = 0; w < SW; ++w) loc += wrun[w * RB + r];
-        }
-        int x = loc;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
-        }
-        int run = x - loc;
-        // run table: one entry per NON-EMPTY bucket = (anchor xyz, start | end << 16), in bucket order
-        int ne = 0;
+        int loc = 0, ne = 0;
         for (int u = 0; u < RPL; ++u) {
             const int r = lane * RPL + u;
             if (r < R) {
                 int tot = 0;
                 for (int w = 0; w < SW; ++w) tot += wrun[w * RB + r];
+                loc += tot;
                 ne += tot > 0 ? 1 : 0;
             }
         }
-        int kx = ne;
+        int x = loc, kx = ne;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int y = __shfl_up_sync(0xffffffffu, kx, o);
-            if (lane >= o) kx += y;
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            const int ky = __shfl_up_sync(0xffffffffu, kx, o);
+            if (lane >= o) { x += y; kx += ky; }
         }
-        int kk = kx - ne;
+        int run = x - loc, kk = kx - ne;
         for (int u = 0; u < RPL; ++u) {
             const int r = lane * RPL + u;
             if (r < R) {
-                bstart[r] = run;
                 const int start = run;
                 for (int w = 0; w < SW; ++w) {
                     const int c = wrun[w * RB + r];
                     wrun[w * RB + r] = (uint16_t)run;
                     run += c;
                 }
-                if (run > start) {
+                if (run > start) {  // one entry per NON-EMPTY bucket = (anchor xyz, start | end << 16)
                     float4 hd = DENSE ? make_float4(0.f, 0.f, 0.f, 0.f) : anchors[r];
                     hd.w = __uint_as_float((unsigned)start | ((unsigned)run << 16));
                     runtab[kk++] = hd;
                 }
             }
         }
-        if (lane == 31) s.n_runs = kx;
-        if (lane == 31) { bstart[R] = x; s.n_sel = x; }
+        if (lane == 31) { s.n_sel = x; s.n_runs = kx; }
     }
     __syncthreads();
     // pass B: assign slots
@@ -409,7 +429,7 @@ __global__ void __launch_bounds__(ST, 2) pose_solve_kernel(SolveArgs a, FusedLay
     for (int k = 0; k < QPT; ++k) {
         const unsigned nib = (selbits >> (4 * k)) & 0xFu;
         if (__ballot_sync(0xffffffffu, nib != 0u) == 0u) continue;
-        const uchar4 r4 = DENSE ? make_uchar4(0, 0, 0, 0) : reinterpret_cast<const uchar4*>(s.rid)[32 * (SW * k + warp) + lane];
+        const uchar4 r4 = DENSE ? make_uchar4(0, 0, 0, 0) : __ldg(reinterpret_cast<const uchar4*>(pl.rid) + 32 * (SW * k + warp) + lane);
         const uint8_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -424,18 +444,19 @@ __global__ void __launch_bounds__(ST, 2) pose_solve_kernel(SolveArgs a, FusedLay
                 myrun[key] = (uint16_t)(cur + __popc(m));
             }
             cur = __shfl_sync(0xffffffffu, cur, leader);
-            if (sel) s.pix[cur + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(4 * (32 * (SW * k + warp) + lane) + j);
+            if (sel) {
+                const int sl = cur + __popc(m & ((1u << lane) - 1u));
+                s.pix[sl] = (uint16_t)(4 * (32 * (SW * k + warp) + lane) + j);
+                s.srid[sl] = (uint8_t)key;
+            }
             __syncwarp();
         }
     }
 
-    // ---- 4: hypothesis generation from the raw planes (FP64 closed form), one hypothesis per thread ----
+    // ---- 4: hypothesis generation (FP64 closed form), one hypothesis per thread, pixels gathered ----
     for (int h = t; h < H; h += ST) {
-        int ii[3] = {pre_ii[0], pre_ii[1], pre_ii[2]};
-        if (h != t) {
-            const int32_t* ip = a.hyp_idx + ((size_t)b * H + h) * 3;
-            ii[0] = ip[0]; ii[1] = ip[1]; ii[2] = ip[2];
-        }
+        const int32_t* ip = a.hyp_idx + ((size_t)b * H + h) * 3;
+        const int ii[3] = {ip[0], ip[1], ip[2]};
         bool ok = ((unsigned)ii[0] < RDPN_P) && ((unsigned)ii[1] < RDPN_P) && ((unsigned)ii[2] < RDPN_P);
         float* P = hyp + (size_t)h * 12;
         if (ok) {
@@ -447,13 +468,13 @@ __global__ void __launch_bounds__(ST, 2) pose_solve_kernel(SolveArgs a, FusedLay
 #pragma unroll
             for (int v = 0; v < 3; ++v) {
                 const int p = ii[v];
-                float cam[3], obj[3];
-                pixel_s1<DENSE>(rc, p, s.tile[0][p], s.tile[1][p], s.tile[2][p], s.tile[3][p], cam, obj);
-                C[v][0] = (double)cam[0]; C[v][1] = (double)cam[1]; C[v][2] = (double)cam[2];
+                float4 cw, ob;
+                gather_s1<DENSE>(pl, rc, p, false, in.mask_mode, cw, ob);
+                C[v][0] = (double)cw.x; C[v][1] = (double)cw.y; C[v][2] = (double)cw.z;
                 if (DENSE) {
-                    A[v][0] = (double)obj[0]; A[v][1] = (double)obj[1]; A[v][2] = (double)obj[2];
+                    A[v][0] = (double)ob.x; A[v][1] = (double)ob.y; A[v][2] = (double)ob.z;
                 } else {
-                    const float4 an = anchors[s.rid[p]];
+                    const float4 an = anchors[__ldg(pl.rid + p)];
                     A[v][0] = (double)an.x; A[v][1] = (double)an.y; A[v][2] = (double)an.z;
                 }
             }
@@ -471,120 +492,94 @@ __global__ void __launch_bounds__(ST, 2) pose_solve_kernel(SolveArgs a, FusedLay
         }
         hcnt[h] = ok ? 0 : -1;
     }
-    __syncthreads();  // slots, hypotheses visible; raw planes may be overwritten after the next barrier
+    __syncthreads();  // slots, run table, hypotheses visible
     const int n = s.n_sel;
-
-    // ---- 5: staging: thread per slot computes (cam xyz, w) with the exact S1 arithmetic; the AoS list then
-    //         replaces raw planes (n <= 1024: the mask plane; larger: the depth/coor planes) and the
-    //         region-id plane is rewritten in slot order.  All raw reads precede the barrier.
-    const bool small_n = n <= 4 * ST;
-    float4* camw_w = reinterpret_cast<float4*>(small_n ? s.tile[4] : s.tile[0]);
-    if (small_n) {
-        float4 cw[4];
-        uint8_t rb[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int sl = u * ST + t;
-            if (sl < n) {
-                const int p = s.pix[sl];
-                float cam[3], obj[3];
-                pixel_s1<DENSE>(rc, p, s.tile[0][p], s.tile[1][p], s.tile[2][p], s.tile[3][p], cam, obj);
-                const float w = a.prm.weighted ? mask_prob(s.tile[4][p], in.mask_mode, rc.mn, rc.mx) : 1.f;
-                cw[u] = make_float4(cam[0], cam[1], cam[2], w);
-                rb[u] = DENSE ? (uint8_t)0 : s.rid[p];
-                if (DENSE) s.objS[sl] = make_float4(obj[0], obj[1], obj[2], 0.f);
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int sl = u * ST + t;
-            if (sl < n) {
-                camw_w[sl] = cw[u];
-                if (!DENSE) s.rid[sl] = rb[u];
-            }
-        }
-    } else {  // rare: more than a quarter of the ROI is gated; same arithmetic, results parked in local memory
-        float4 cwl[RDPN_P / ST];
-        uint8_t rbl[RDPN_P / ST];
-#pragma unroll 1
-        for (int u = 0; u < RDPN_P / ST; ++u) {
-            const int sl = u * ST + t;
-            if (sl < n) {
-                const int p = s.pix[sl];
-                float cam[3], obj[3];
-                pixel_s1<DENSE>(rc, p, s.tile[0][p], s.tile[1][p], s.tile[2][p], s.tile[3][p], cam, obj);
-                const float w = a.prm.weighted ? mask_prob(s.tile[4][p], in.mask_mode, rc.mn, rc.mx) : 1.f;
-                cwl[u] = make_float4(cam[0], cam[1], cam[2], w);
-                rbl[u] = DENSE ? (uint8_t)0 : s.rid[p];
-                if (DENSE) s.objS[sl] = make_float4(obj[0], obj[1], obj[2], 0.f);
-            }
-        }
-        __syncthreads();
-#pragma unroll 1
-        for (int u = 0; u < RDPN_P / ST; ++u) {
-            const int sl = u * ST + t;
-            if (sl < n) {
-                camw_w[sl] = cwl[u];
-                if (!DENSE) s.rid[sl] = rbl[u];
-            }
-        }
-    }
-    __syncthreads();
-    const float4* camw = camw_w;
-    const uint8_t* srid = s.rid;  // region id by slot (non-decreasing)
-
+    const int nruns = s.n_runs;
     if (a.out.n_sel && t == 0) a.out.n_sel[b] = n;
     const bool enough = n >= a.prm.min_pts;
+    constexpr int CH = DENSE ? CHUNK / 2 : CHUNK;
+    float4* camw_s = s.chunk;
+    float4* obj_s = s.chunk + CH;  // dense only
 
-    // ---- 6: inlier scoring ----
+    // ---- 5 + 6: per chunk of gated slots: staging, then inlier scoring ----
     if (enough) {
-        const int S = (H >= ST) ? 1 : (ST / H);
         const float cut = a.sq_cut;
-        for (int item = t; item < H * S; item += ST) {
-            const int h = item % H, seg = item / H;
-            if (hcnt[h] < 0) continue;
-            float P[12];
-#pragma unroll
-            for (int i = 0; i < 12; ++i) P[i] = hyp[(size_t)h * 12 + i];
-            int c = 0;
-            if (DENSE) {
-                const int i0 = (int)(((long long)n * seg) / S), i1 = (int)(((long long)n * (seg + 1)) / S);
-#pragma unroll 4
-                for (int i = i0; i < i1; ++i) {
-                    const float4 cp = camw[i];
-                    const float4 ap = s.objS[i];
-                    count_if_lt(c, resid2(P, ap.x, ap.y, ap.z, cp.x, cp.y, cp.z), cut);
-                }
-            } else {
-                // slots are sorted by region: per run (non-empty bucket) the transformed anchor R a + t is
-                // computed once; every point then costs 1 LDS.128 + 6 FP32 + compare + predicated add.
-                const int nruns = s.n_runs;
-                for (int k = seg; k < nruns; k += S) {  // runs interleaved over the segments
-                    const float4 hd = runtab[k];
-                    const unsigned se = __float_as_uint(hd.w);
-                    int i = (int)(se & 0xFFFFu);
-                    const int e = (int)(se >> 16);
-                    float tx, ty, tz;
-                    xform(P, hd.x, hd.y, hd.z, tx, ty, tz);
-                    for (; i + 4 <= e; i += 4) {
-                        const float4 c0 = camw[i], c1 = camw[i + 1], c2 = camw[i + 2], c3 = camw[i + 3];
-                        count_if_lt(c, resid2_pt(tx, ty, tz, c0.x, c0.y, c0.z), cut);
-                        count_if_lt(c, resid2_pt(tx, ty, tz, c1.x, c1.y, c1.z), cut);
-                        count_if_lt(c, resid2_pt(tx, ty, tz, c2.x, c2.y, c2.z), cut);
-                        count_if_lt(c, resid2_pt(tx, ty, tz, c3.x, c3.y, c3.z), cut);
-                    }
-                    for (; i < e; ++i) {
-                        const float4 c0 = camw[i];
-                        count_if_lt(c, resid2_pt(tx, ty, tz, c0.x, c0.y, c0.z), cut);
-                    }
-                }
+        const int S = (H >= ST) ? 1 : (ST / H);
+        for (int c0 = 0; c0 < n; c0 += CH) {
+            const int c1 = min(n, c0 + CH);
+            if (c0 > 0) __syncthreads();  // previous chunk fully scored
+            for (int sl = c0 + t; sl < c1; sl += ST) {
+                float4 cw, ob;
+                gather_s1<DENSE>(pl, rc, s.pix[sl], a.prm.weighted != 0, in.mask_mode, cw, ob);
+                camw_s[sl - c0] = cw;
+                if (DENSE) obj_s[sl - c0] = ob;
             }
-            if (S == 1) hcnt[h] = c;
-            else atomicAdd(&hcnt[h], c);
+            __syncthreads();
+            for (int item = t; item < H * S; item += ST) {
+                const int h = item % H, seg = item / H;
+                if (hcnt[h] < 0) continue;
+                float P[12];
+#pragma unroll
+                for (int i = 0; i < 12; ++i) P[i] = hyp[(size_t)h * 12 + i];
+                int c = 0;
+                if (DENSE) {
+                    const int m = c1 - c0;
+                    const int i0 = (int)(((long long)m * seg) / S), i1 = (int)(((long long)m * (seg + 1)) / S);
+#pragma unroll 4
+                    for (int i = i0; i < i1; ++i) {
+                        const float4 cp = camw_s[i];
+                        const float4 ap = obj_s[i];
+                        count_if_lt(c, resid2(P, ap.x, ap.y, ap.z, cp.x, cp.y, cp.z), cut);
+                    }
+                } else {
+                    // slots are sorted by region: per run (non-empty bucket) the transformed anchor R a + t is
+                    // computed once; every point then costs 1 LDS.128 + 6 FP32 + compare + predicated add.
+                    const bool whole = (c0 == 0 && c1 == n);  // the usual case: everything in one chunk, no clipping
+                    for (int k = seg; k < nruns; k += S) {  // runs interleaved over the segments
+                        const float4 hd = runtab[k];
+                        const unsigned se = __float_as_uint(hd.w);
+                        int i = (int)(se & 0xFFFFu);
+                        int e = (int)(se >> 16);
+                        if (!whole) {
+                            i = max(i, c0) - c0;
+                            e = min(e, c1) - c0;
+                            if (i >= e) continue;
+                        }
+                        float tx, ty, tz;
+                        xform(P, hd.x, hd.y, hd.z, tx, ty, tz);
+#pragma unroll 1
+                        for (; i + 4 <= e; i += 4) {
+                            const float4 q0 = camw_s[i], q1 = camw_s[i + 1], q2 = camw_s[i + 2], q3 = camw_s[i + 3];
+                            count_if_lt(c, resid2_pt(tx, ty, tz, q0.x, q0.y, q0.z), cut);
+                            count_if_lt(c, resid2_pt(tx, ty, tz, q1.x, q1.y, q1.z), cut);
+                            count_if_lt(c, resid2_pt(tx, ty, tz, q2.x, q2.y, q2.z), cut);
+                            count_if_lt(c, resid2_pt(tx, ty, tz, q3.x, q3.y, q3.z), cut);
+                        }
+                        if (i < e) {  // 1..3 left: one masked batch (warp-uniform predicates), indices clamped into the run
+                            const float4 q0 = camw_s[i], q1 = camw_s[min(i + 1, e - 1)], q2 = camw_s[min(i + 2, e - 1)];
+                            count_if_lt(c, resid2_pt(tx, ty, tz, q0.x, q0.y, q0.z), cut);
+                            if (i + 1 < e) count_if_lt(c, resid2_pt(tx, ty, tz, q1.x, q1.y, q1.z), cut);
+                            if (i + 2 < e) count_if_lt(c, resid2_pt(tx, ty, tz, q2.x, q2.y, q2.z), cut);
+                        }
+                    }
+                }
+                if (S == 1) hcnt[h] += c;
+                else atomicAdd(&hcnt[h], c);
+            }
         }
     }
     __syncthreads();
+    // slot accessor of the refit: the staged chunk when everything fitted into one, else re-gathered
+    const bool one_chunk = n <= CH;
+    auto get_slot = [&](int i, float4& cp, float4& ap) {
+        if (one_chunk) {
+            cp = camw_s[i];
+            if (DENSE) ap = obj_s[i];
+        } else {
+            gather_s1<DENSE>(pl, rc, s.pix[i], a.prm.weighted != 0, in.mask_mode, cp, ap);
+        }
+        if (!DENSE) ap = anchors[s.srid[i]];
+    };
 
     // ---- 7a: best hypothesis (misc.py:121) with optional adaptive stop (misc.py:134-138) ----
     if (enough) {
@@ -602,24 +597,24 @@ __global__ void __launch_bounds__(ST, 2) pose_solve_kernel(SolveArgs a, FusedLay
                     const int y = __shfl_up_sync(0xffffffffu, x, o);
                     if (lane >= o) x += y;
                 }
-                if (lane == 31) s.red_i[warp] = x;
+                if (lane == 31) f.red_i[warp] = x;
                 __syncthreads();
                 int wbase = 0;
-                for (int w = 0; w < warp; ++w) wbase += s.red_i[w];
+                for (int w = 0; w < warp; ++w) wbase += f.red_i[w];
                 int tot = 0;
-                for (int w = 0; w < SW; ++w) tot += s.red_i[w];
+                for (int w = 0; w < SW; ++w) tot += f.red_i[w];
                 const int i_ransac = running + wbase + x;
                 if (v) {
                     const double wr = (double)hcnt[h] / (double)n;
                     const double k = lc / log10(1.0 - pow(wr, 10.0));
                     const double lim = fmax(k, (double)a.prm.min_iter);
-                    if ((double)i_ransac > lim) atomicMin(&s.h_eff, h + 1);
+                    if ((double)i_ransac > lim) atomicMin(&f.h_eff, h + 1);
                 }
                 running += tot;
                 __syncthreads();
             }
         }
-        const int heff = s.h_eff;
+        const int heff = f.h_eff;
         unsigned long long key = 0ull;
         for (int h = t; h < heff; h += ST) {
             const int c = hcnt[h];
@@ -629,19 +624,19 @@ __global__ void __launch_bounds__(ST, 2) pose_solve_kernel(SolveArgs a, FusedLay
             }
         }
         key = warp_max_u64(key);
-        if (lane == 0) s.red_k[warp] = key;
+        if (lane == 0) f.red_k[warp] = key;
         __syncthreads();
         if (t == 0) {
             unsigned long long k = 0ull;
-            for (int w = 0; w < SW; ++w) k = s.red_k[w] > k ? s.red_k[w] : k;
+            for (int w = 0; w < SW; ++w) k = f.red_k[w] > k ? f.red_k[w] : k;
             if (k) {
-                s.best_h = 0x7FFFFFFF - (int)(k & 0xFFFFFFFFull);
-                s.n_best = (int)(k >> 32);
+                f.best_h = 0x7FFFFFFF - (int)(k & 0xFFFFFFFFull);
+                f.n_best = (int)(k >> 32);
             }
         }
         __syncthreads();
     }
-    const int best = s.best_h;
+    const int best = f.best_h;
 
     // optional diagnostics
     if (a.out.hyp_counts)
@@ -661,7 +656,7 @@ __global__ void __launch_bounds__(ST, 2) pose_solve_kernel(SolveArgs a, FusedLay
     }
 
     // ---- 7b: refit on the inliers (misc.py:123-126 -> transform.py:913-980), FP64 accumulation ----
-    if (t < 12) s.pose[t] = hyp[(size_t)best * 12 + t];
+    if (t < 12) f.pose[t] = hyp[(size_t)best * 12 + t];
     __syncthreads();
     const float cut = a.sq_cut;
     float out_scale = 1.f;
@@ -669,16 +664,14 @@ __global__ void __launch_bounds__(ST, 2) pose_solve_kernel(SolveArgs a, FusedLay
     for (int it = 0; it < iters; ++it) {
         float P[12];
 #pragma unroll
-        for (int i = 0; i < 12; ++i) P[i] = s.pose[i];
+        for (int i = 0; i < 12; ++i) P[i] = f.pose[i];
         // pass 1: weighted centroids; thread handles slots t, t+ST, ... (<= 16 of them)
         double acc[7] = {0, 0, 0, 0, 0, 0, 0};
         unsigned inl_bits = 0u;
         int slot = 0;
         for (int i = t; i < n; i += ST, ++slot) {
-            const float4 cp = camw[i];
-            float4 ap;
-            if (DENSE) ap = s.objS[i];
-            else ap = anchors[srid[i]];
+            float4 cp, ap;
+            get_slot(i, cp, ap);
             if (resid2(P, ap.x, ap.y, ap.z, cp.x, cp.y, cp.z) < cut) {
                 inl_bits |= 1u << slot;
                 const double w = a.prm.weighted ? (double)cp.w : 1.0;
@@ -688,10 +681,10 @@ __global__ void __launch_bounds__(ST, 2) pose_solve_kernel(SolveArgs a, FusedLay
             }
         }
         int tot_inl = warp_sum(__popc(inl_bits));
-        if (lane == 0) s.red_i[warp] = tot_inl;
-        block_sum<FusedSmem<DENSE>, 7>(s, acc);  // contains the barriers that publish red_i
+        if (lane == 0) f.red_i[warp] = tot_inl;
+        block_sum<7>(f, acc);  // contains the barriers that publish red_i
         tot_inl = 0;
-        for (int w = 0; w < SW; ++w) tot_inl += s.red_i[w];
+        for (int w = 0; w < SW; ++w) tot_inl += f.red_i[w];
         if (tot_inl < 3) break;  // uniform across the block
         const double isw = 1.0 / acc[0];
         const double mc[3] = {acc[1] * isw, acc[2] * isw, acc[3] * isw};
@@ -701,10 +694,8 @@ __global__ void __launch_bounds__(ST, 2) pose_solve_kernel(SolveArgs a, FusedLay
         slot = 0;
         for (int i = t; i < n; i += ST, ++slot) {
             if (inl_bits & (1u << slot)) {
-                const float4 cp = camw[i];
-                float4 ap;
-                if (DENSE) ap = s.objS[i];
-                else ap = anchors[srid[i]];
+                float4 cp, ap;
+                get_slot(i, cp, ap);
                 const double w = a.prm.weighted ? (double)cp.w : 1.0;
                 const double c0 = cp.x - mc[0], c1 = cp.y - mc[1], c2 = cp.z - mc[2];
                 const double a0 = ap.x - ma[0], a1 = ap.y - ma[1], a2 = ap.z - ma[2];
@@ -715,7 +706,7 @@ __global__ void __launch_bounds__(ST, 2) pose_solve_kernel(SolveArgs a, FusedLay
                 cov[10] += w * (a0 * a0 + a1 * a1 + a2 * a2);
             }
         }
-        block_sum<FusedSmem<DENSE>, 11>(s, cov);
+        block_sum<11>(f, cov);
         if (t == 0) {
             double Rm[9];
             rotation_from_cov(cov, cov[10], cov[9], Rm);
@@ -724,12 +715,12 @@ __global__ void __launch_bounds__(ST, 2) pose_solve_kernel(SolveArgs a, FusedLay
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 const double tr = mc[r] - sc * (Rm[3 * r] * ma[0] + Rm[3 * r + 1] * ma[1] + Rm[3 * r + 2] * ma[2]);
-                s.pose[4 * r + 0] = (float)(sc * Rm[3 * r + 0]);
-                s.pose[4 * r + 1] = (float)(sc * Rm[3 * r + 1]);
-                s.pose[4 * r + 2] = (float)(sc * Rm[3 * r + 2]);
-                s.pose[4 * r + 3] = (float)tr;
+                f.pose[4 * r + 0] = (float)(sc * Rm[3 * r + 0]);
+                f.pose[4 * r + 1] = (float)(sc * Rm[3 * r + 1]);
+                f.pose[4 * r + 2] = (float)(sc * Rm[3 * r + 2]);
+                f.pose[4 * r + 3] = (float)tr;
             }
-            s.bc_d[15] = sc;
+            f.bc_d[15] = sc;
         }
         if (a.out.inlier_mask && it == iters - 1) {  // the inlier set used by the last refit
             slot = 0;
@@ -737,30 +728,30 @@ __global__ void __launch_bounds__(ST, 2) pose_solve_kernel(SolveArgs a, FusedLay
                 if (inl_bits & (1u << slot)) a.out.inlier_mask[(size_t)b * RDPN_P + s.pix[i]] = 1;
         }
         __syncthreads();
-        out_scale = (float)s.bc_d[15];
+        out_scale = (float)f.bc_d[15];
     }
 
     // ---- outputs (+ translation sanity, gdrn_evaluator.py:293-296) ----
     if (t == 0) {
         int status = RDPN_STATUS_OK;
-        const float tx = s.pose[3], ty = s.pose[7], tz = s.pose[11];
+        const float tx = f.pose[3], ty = f.pose[7], tz = f.pose[11];
         if (a.t_net) {
             const double d0 = (double)a.t_net[3 * b] - tx, d1 = (double)a.t_net[3 * b + 1] - ty,
                          d2 = (double)a.t_net[3 * b + 2] - tz;
             if (sqrt(d0 * d0 + d1 * d1 + d2 * d2) > 1.0) {
                 status = RDPN_STATUS_T_SANITY;
-                s.pose[3] = a.t_net[3 * b];
-                s.pose[7] = a.t_net[3 * b + 1];
-                s.pose[11] = a.t_net[3 * b + 2];
+                f.pose[3] = a.t_net[3 * b];
+                f.pose[7] = a.t_net[3 * b + 1];
+                f.pose[11] = a.t_net[3 * b + 2];
             }
         }
-        a.out.n_inliers[b] = s.n_best;
+        a.out.n_inliers[b] = f.n_best;
         a.out.status[b] = status;
         if (a.out.best_h) a.out.best_h[b] = best;
         if (a.out.scale) a.out.scale[b] = out_scale;
     }
     __syncthreads();
-    if (t < 12) a.out.pose[(size_t)b * 12 + t] = s.pose[t];
+    if (t < 12) a.out.pose[(size_t)b * 12 + t] = f.pose[t];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -860,10 +851,9 @@ static int launch_solve(const SolveArgs& a, cudaStream_t st) {
     const int RB = R + 1;
     auto al = [](size_t x) { return (x + 127) & ~(size_t)127; };
     FusedLayout lay;
-    size_t off = al(sizeof(FusedSmem<DENSE>));
+    size_t off = al(sizeof(FusedSmem));
     lay.anchors = (int)off; off = al(off + (size_t)R * sizeof(float4));
     lay.runtab = (int)off;  off = al(off + (size_t)R * sizeof(float4));
-    lay.bstart = (int)off;  off = al(off + (size_t)(RB + 1) * sizeof(int));
     lay.wrun = (int)off;    off = al(off + (size_t)SW * RB * sizeof(uint16_t));
     lay.hyp = (int)off;     off = al(off + (size_t)H * 12 * sizeof(float));
     lay.hcnt = (int)off;    off = al(off + (size_t)H * sizeof(int));
