@@ -55,6 +55,7 @@ def workload_config(n_gpus):
         "rois_per_gpu": ROIS_PER_GPU, "global_rois_per_step": ROIS_PER_GPU * n_gpus, "hypotheses": NUM_HYP,
         "num_regions": NUM_REGIONS, "inlier_thr_m": INLIER_THR, "refit": "unweighted Kabsch on inliers, 1 iteration",
         "l2": "%d rotating input sets (%.0f MB) > 126 MB L2" % (N_INPUT_SETS, N_INPUT_SETS * ROIS_PER_GPU * BYTES_MAPS / 1e6),
+        "streams": "steps alternate over 2 CUDA streams (launch tails overlap); timed with events on the parent stream",
         "parallelism": "roi-shard x%d + NCCL all-gather of [shard,16] rows" % n_gpus if n_gpus > 1 else "single GPU",
     }
 
@@ -109,8 +110,9 @@ def _cpu_as_run_range(rng):
         sel = po.gate(mp_, delta, c["extent"][b], q[2])
         if sel.sum() < 4:
             continue
-        # 2D-3D pairs as the evaluator builds them: model point = anchor + R^T-free residual is not
-        # available to EPnP, so use the dense object coordinate (anchor + object-frame delta surrogate)
+        # timing-only stand-in for the evaluator's 2D-3D pairs (gdrn_evaluator.py:89-126): one 3-D model point
+        # (the pixel's anchor) and its crop pixel per gated pixel -- the same number of correspondences the
+        # reference would hand to cv2.solvePnPRansac for this ROI
         p3 = (c["anchors"][b][c["region_idx"][b].astype(np.int64)][sel]).astype(np.float64)
         fx, fy, cx, cy = [float(v) for v in c["Kp"][b]]
         p2 = np.stack([4.0 * ii[sel], 4.0 * jj[sel]], 1).astype(np.float64)
@@ -308,15 +310,32 @@ def gpu_arm(args):
     total = B * world
     gather_out = [torch.empty(total, 16, dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
 
+    # consecutive steps alternate over two streams so that the tail of one launch (the last CTAs of a
+    # 1024-ROI grid leave most SMs idle) overlaps the head of the next -- a continuous ROI stream does the same
+    streams = [torch.cuda.Stream(dev) for _ in range(2)]
+
     def step(i, pending):
-        p = plans[i % N_INPUT_SETS]
-        res = p.launch()
-        if world > 1:
-            rows = res.rows16()
-            if pending[i % 2] is not None:
-                pending[i % 2].wait()
-            pending[i % 2] = dist.all_gather_into_tensor(gather_out[i % 2], rows, async_op=True)
+        with torch.cuda.stream(streams[i % 2]):
+            p = plans[i % N_INPUT_SETS]
+            res = p.launch()
+            if world > 1:
+                rows = res.rows16()
+                if pending[i % 2] is not None:
+                    pending[i % 2].wait()
+                pending[i % 2] = dist.all_gather_into_tensor(gather_out[i % 2], rows, async_op=True)
         return res
+
+    def fork():  # both streams start after everything already queued on the current stream
+        ev = torch.cuda.Event()
+        ev.record()
+        for st in streams:
+            st.wait_event(ev)
+
+    def join():  # the current stream continues after both streams
+        for st in streams:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            torch.cuda.current_stream().wait_event(ev)
 
     def drain(pending):
         for j in range(2):
@@ -325,9 +344,11 @@ def gpu_arm(args):
                 pending[j] = None
 
     pending = [None, None]
+    fork()
     for i in range(max(args.warmup, 3)):
         step(i, pending)
     drain(pending)
+    join()
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank if os.environ.get("CUDA_VISIBLE_DEVICES") is None else
@@ -337,10 +358,12 @@ def gpu_arm(args):
     t_heat = time.perf_counter()
     i = 0
     while time.perf_counter() - t_heat < args.preheat:
+        fork()
         for _ in range(50):
             step(i, pending)
             i += 1
         drain(pending)
+        join()
         torch.cuda.synchronize()
 
     if world > 1:
@@ -349,9 +372,11 @@ def gpu_arm(args):
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    fork()
     for i in range(args.steps):
         step(i, pending)
     drain(pending)
+    join()
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -452,6 +477,7 @@ def gpu_arm(args):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": None, "kernel": "rdpn::pose_solve_kernel<false>", "kernel_ms": kernel_ms,
+                     "kernel_ms_note": "average duration of back-to-back launches on ONE stream (no overlap)",
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                      "note": "the fused solver is FP32-pipe bound (3x4 transforms x hypotheses x points), see fp32"},
         "fp32": {"achieved_tflops": flops / (kernel_ms * 1e-3) / 1e12, "peak_tflops": fp32_peak.value / 1e12,
