@@ -190,6 +190,16 @@ int rdpn_centroid_z_to_pose(const float* d_rot_in, int rot_is_6d, const float* d
 int rdpn_region_argmax(const float* d_region, int R, uint8_t* d_region_idx, int B, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * f1  ROI depth crop from the full frame -- cv2.warpAffine(depth, A, (256,256), INTER_LINEAR)[::4, ::4]
+ *     of core/gdrn_modeling/data_loader.py:532-535, 625 (core/utils/data_utils.py:81-96), sampled
+ *     directly at the 64 x 64 kept positions.  depth_imgs [N,H,W] metres; img_idx [B] (NULL: image 0);
+ *     center [B,2], scale [B] as in rdpn_roi_intrinsics; out [B,out_res,out_res].  The result feeds
+ *     rdpn_correspond / rdpn_pose_solve as `depth` (depth_div = resize_ratio reproduces :563).
+ * ---------------------------------------------------------------------------------------------- */
+int rdpn_roi_crop_depth(const float* d_depth_imgs, int H, int W, const int32_t* d_img_idx, const float* d_center,
+                        const float* d_scale, int crop_res, int out_res, float* d_out, int B, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Host-buffer plugin call (what a CPU caller of the reference's evaluator binds): every pointer in
  * `in`, hyp_idx, t_net and `out` is a HOST pointer.  The context owns device scratch and streams;
  * ROIs are pipelined in chunks so host->device copies overlap the kernels.

@@ -579,3 +579,59 @@ def xyz_to_region(xyz_crop, fps_points):
     region_ids = np.argmin(dists, axis=1).reshape(bh, bw) + 1
     delta = xyz_crop - fps_points[region_ids - 1]
     return mask_crop * region_ids, delta
+
+
+# --------------------------------------------------------------------------------------------
+# f1: ROI depth crop as the loader does it (data_loader.py:532-535 -> data_utils.py:81-96), via OpenCV
+# --------------------------------------------------------------------------------------------
+def roi_crop_depth_cv2(depth_img, center, scale, crop_res=256, stride=4):
+    """cv2.warpAffine(depth, A, (crop,crop), INTER_LINEAR)[::stride, ::stride] with A = roi_affine().
+    Third-party arithmetic (OpenCV): a cross-check for rdpn_roi_crop_depth, not a pinned oracle."""
+    import cv2
+
+    A = roi_affine(center, scale, crop_res)
+    crop = cv2.warpAffine(np.asarray(depth_img, F32), A, (int(crop_res), int(crop_res)), flags=cv2.INTER_LINEAR)
+    return crop[::stride, ::stride]
+
+
+def roi_crop_depth(depth_img, center, scale, crop_res=256, out_res=64):
+    """numpy restatement of OpenCV's warpAffine + remap for CV_32F / INTER_LINEAR / BORDER_CONSTANT(0)
+    (modules/imgproc/src/imgwarp.cpp; third-party: opencv-python 4.5.5.62 pinned by the reference), evaluated
+    only at the pixels the loader keeps (data_loader.py:625).  Bit-identical to cv2 4.13 in this container
+    (tests/test_oracle_pose.py); slow Python loops, small cases only."""
+    depth = np.asarray(depth_img, F32)
+    M = roi_affine(center, scale, crop_res).flatten().copy()
+    D = M[0] * M[4] - M[1] * M[3]
+    D = 1.0 / D if D != 0 else 0.0
+    A11, A22 = M[4] * D, M[0] * D
+    M[0] = A11
+    M[1] *= -D
+    M[3] *= -D
+    M[4] = A22
+    b1 = -M[0] * M[2] - M[1] * M[5]
+    b2 = -M[3] * M[2] - M[4] * M[5]
+    M[2], M[5] = b1, b2
+    H, W = depth.shape
+    st = crop_res // out_res
+    res = np.zeros((out_res, out_res), F32)
+    one = F32(1)
+
+    def tap(yy, xx):
+        return depth[yy, xx] if 0 <= xx < W and 0 <= yy < H else F32(0)
+
+    for j in range(out_res):
+        y = st * j
+        X0 = int(np.rint((M[1] * y + M[2]) * 1024)) + 16
+        Y0 = int(np.rint((M[4] * y + M[5]) * 1024)) + 16
+        for i in range(out_res):
+            x = st * i
+            X = (X0 + int(np.rint(M[0] * x * 1024))) >> 5
+            Y = (Y0 + int(np.rint(M[3] * x * 1024))) >> 5
+            sx, sy = X >> 5, Y >> 5
+            fx, fy = F32((X & 31) / 32.0), F32((Y & 31) / 32.0)
+            r = F32(tap(sy, sx) * F32((one - fy) * (one - fx)))
+            r = F32(r + F32(tap(sy, sx + 1) * F32((one - fy) * fx)))
+            r = F32(r + F32(tap(sy + 1, sx) * F32(fy * (one - fx))))
+            r = F32(r + F32(tap(sy + 1, sx + 1) * F32(fy * fx)))
+            res[j, i] = r
+    return res

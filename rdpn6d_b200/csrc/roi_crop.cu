@@ -1,0 +1,89 @@
+// f1: ROI crop of the full-frame depth on the GPU.
+//
+// The reference crops every detection out of the 480x640 depth image on the CPU with
+// cv2.warpAffine(depth, A, (256,256), INTER_LINEAR) (core/gdrn_modeling/data_loader.py:532-535 ->
+// core/utils/data_utils.py:81-96) and keeps pixels (4i,4j) of the result (:625).  This kernel samples
+// exactly those 64x64 positions straight from the full frame, so the loader ships one depth image per
+// frame instead of n 256x256 crops and the H2D of roi_coord_2d disappears.
+//
+// Arithmetic follows OpenCV's warpAffine/remap for CV_32F + INTER_LINEAR + BORDER_CONSTANT(0)
+// (third-party, opencv-python 4.5.5.62 pinned by the reference; checked against 4.13 here to float
+// rounding -- parity unpinned by any reference test):
+//   * the 2x3 matrix (same float32-point closed form as rdpn_roi_intrinsics) is inverted in double,
+//   * source coordinates are fixed point: X = (round((M1*y + M2)*1024) + 16 + round(M0*x*1024)) >> 5,
+//     integer part X >> 5, fraction (X & 31)/32 (INTER_BITS = 5, AB_BITS = 10),
+//   * the four taps are blended with float weights (1-fy)(1-fx), (1-fy)fx, fy(1-fx), fy*fx; taps
+//     outside the image contribute the border value 0.
+#include "common.cuh"
+
+namespace rdpn {
+extern unsigned long long g_launch_count;
+
+__global__ void roi_crop_depth_kernel(const float* __restrict__ imgs, int H, int W, const int32_t* __restrict__ img_idx,
+                                      const float* __restrict__ center, const float* __restrict__ scale, int crop_res,
+                                      int out_res, float* __restrict__ out, int B) {
+    const int b = blockIdx.x;
+    if (b >= B) return;
+    __shared__ double Minv[6];
+    if (threadIdx.x == 0) {
+        // forward affine (crop <- image), float32-point closed form of data_utils.get_affine_transform (rot = 0)
+        const double x0 = (double)center[2 * b], y0 = (double)center[2 * b + 1];
+        const double h = __dmul_rn(0.5, (double)scale[b]);
+        const double y1 = (double)__double2float_rn(__dsub_rn(y0, h));
+        const double e1 = __dsub_rn(y0, y1);
+        const double e = (double)__double2float_rn(e1);
+        const double x2 = (double)__double2float_rn(__dsub_rn(x0, e));
+        const double e2 = __dsub_rn(x0, x2);
+        const double half = 0.5 * (double)crop_res;
+        double M[6];
+        M[0] = __ddiv_rn(half, e2); M[1] = 0.0; M[2] = __dsub_rn(half, __dmul_rn(M[0], x0));
+        M[3] = 0.0; M[4] = __ddiv_rn(half, e1); M[5] = __dsub_rn(half, __dmul_rn(M[4], y0));
+        // cv::warpAffine inverts the matrix (imgwarp.cpp): D = 1/det, then the usual 2x2 inverse and offsets
+        double D = __dsub_rn(__dmul_rn(M[0], M[4]), __dmul_rn(M[1], M[3]));
+        D = D != 0.0 ? __ddiv_rn(1.0, D) : 0.0;
+        const double A11 = __dmul_rn(M[4], D), A22 = __dmul_rn(M[0], D);
+        M[0] = A11; M[1] = __dmul_rn(M[1], -D);
+        M[3] = __dmul_rn(M[3], -D); M[4] = A22;
+        const double b1 = __dsub_rn(__dmul_rn(-M[0], M[2]), __dmul_rn(M[1], M[5]));
+        const double b2 = __dsub_rn(__dmul_rn(-M[3], M[2]), __dmul_rn(M[4], M[5]));
+        M[2] = b1; M[5] = b2;
+        for (int i = 0; i < 6; ++i) Minv[i] = M[i];
+    }
+    __syncthreads();
+    const float* img = imgs + (size_t)(img_idx ? img_idx[b] : 0) * H * W;
+    const int stride = crop_res / out_res;
+    const double AB = 1024.0;
+    for (int p = threadIdx.x; p < out_res * out_res; p += blockDim.x) {
+        const int x = stride * (p % out_res), y = stride * (p / out_res);  // crop pixel kept by [::4, ::4]
+        const int adelta = __double2int_rn(__dmul_rn(__dmul_rn(Minv[0], (double)x), AB));
+        const int bdelta = __double2int_rn(__dmul_rn(__dmul_rn(Minv[3], (double)x), AB));
+        const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(Minv[1], (double)y), Minv[2]), AB)) + 16;
+        const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(Minv[4], (double)y), Minv[5]), AB)) + 16;
+        const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
+        const int sx = X >> 5, sy = Y >> 5;
+        const float fx = (float)(X & 31) * (1.f / 32.f), fy = (float)(Y & 31) * (1.f / 32.f);
+        const float wx0 = 1.f - fx, wy0 = 1.f - fy;
+        auto tap = [&](int yy, int xx) -> float {
+            return ((unsigned)xx < (unsigned)W && (unsigned)yy < (unsigned)H) ? __ldg(img + (size_t)yy * W + xx) : 0.f;
+        };
+        const float v00 = tap(sy, sx), v01 = tap(sy, sx + 1), v10 = tap(sy + 1, sx), v11 = tap(sy + 1, sx + 1);
+        float r = __fmul_rn(v00, __fmul_rn(wy0, wx0));
+        r = __fadd_rn(r, __fmul_rn(v01, __fmul_rn(wy0, fx)));
+        r = __fadd_rn(r, __fmul_rn(v10, __fmul_rn(fy, wx0)));
+        r = __fadd_rn(r, __fmul_rn(v11, __fmul_rn(fy, fx)));
+        out[(size_t)b * out_res * out_res + p] = r;
+    }
+}
+
+}  // namespace rdpn
+
+extern "C" int rdpn_roi_crop_depth(const float* d_depth_imgs, int H, int W, const int32_t* d_img_idx, const float* d_center,
+                                   const float* d_scale, int crop_res, int out_res, float* d_out, int B, void* stream) {
+    if (!d_depth_imgs || !d_center || !d_scale || !d_out || B <= 0 || H <= 0 || W <= 0) return RDPN_E_BADARG;
+    if (crop_res <= 0 || out_res <= 0 || crop_res % out_res != 0) return RDPN_E_BADARG;
+    rdpn::roi_crop_depth_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(d_depth_imgs, H, W, d_img_idx, d_center, d_scale, crop_res,
+                                                                      out_res, d_out, B);
+    ++rdpn::g_launch_count;
+    RDPN_LAUNCH_CHECK();
+    return 0;
+}

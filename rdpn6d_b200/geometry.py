@@ -88,6 +88,28 @@ def roi_intrinsics(K, center, scale, crop_res=256):
     return out
 
 
+def roi_crop_depth(depth_imgs, center, scale, img_idx=None, crop_res=256, out_res=64):
+    """Full-frame depth [N,H,W] (or [H,W]) -> ROI depth maps [B,64,64]: the pixels (4i,4j) of
+    cv2.warpAffine(depth, A, (256,256), INTER_LINEAR) (data_loader.py:532-535, 625) without the 256x256 crop."""
+    d = _cuda_f32(depth_imgs, "depth_imgs")
+    if d.dim() == 2:
+        d = d[None]
+    N, H, W = d.shape
+    c = _cuda_f32(center, "center")
+    B = c.shape[0]
+    s = _cuda_f32(scale.reshape(B), "scale")
+    idx = None
+    if img_idx is not None:
+        idx = img_idx.detach().to(torch.int32).contiguous()
+        assert idx.shape == (B,) and idx.is_cuda
+    out = torch.empty(B, out_res, out_res, dtype=torch.float32, device=d.device)
+    with torch.cuda.device(d.device):
+        rc = _lib.lib().rdpn_roi_crop_depth(d.data_ptr(), H, W, idx.data_ptr() if idx is not None else None, c.data_ptr(),
+                                            s.data_ptr(), int(crop_res), int(out_res), out.data_ptr(), B, _stream(d.device))
+    _lib.check(rc, "roi_crop_depth")
+    return out
+
+
 def region_argmax(region):
     """GDRN.py:206-209: region [B,R+1,64,64] logits -> uint8 [B,64,64] index in [0,R) (bg channel 0 skipped)."""
     r = _cuda_f32(region, "region")

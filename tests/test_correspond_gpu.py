@@ -108,3 +108,26 @@ def test_region_argmax_matches_torch_and_oracle(cuda):
     assert torch.equal(idx.long(), ref_logit)
     assert (idx.long() == ref).float().mean() > 0.999  # softmax rounding can merge near-ties
     assert np.array_equal(idx[0].cpu().numpy(), po.region_argmax(reg[0].cpu().numpy()))
+
+
+def test_roi_crop_depth_matches_cv2_warpaffine(cuda):
+    """f1: GPU ROI crop sampled at the kept pixels vs the loader's cv2.warpAffine(...)[::4, ::4]
+    (data_loader.py:532-535, 625).  OpenCV's fixed-point coordinates are reproduced, so the only slack is
+    float rounding of the 4-tap blend (OpenCV's SIMD path may fuse multiply-adds)."""
+    pytest.importorskip("cv2")
+    rng = np.random.default_rng(4)
+    depth = rng.uniform(0.4, 1.6, (2, 480, 640)).astype(np.float32)
+    depth[:, 100:200, 300:400] = 0.0  # holes
+    B = 24
+    centers = np.stack([rng.uniform(40, 600, B), rng.uniform(40, 440, B)], 1).astype(np.float32)
+    scales = rng.uniform(40, 640, B).astype(np.float32)
+    centers[0] = [5, 5]  # crop hangs over the image border -> zero taps
+    scales[0] = 200
+    idx = (np.arange(B) % 2).astype(np.int32)
+    out = geometry.roi_crop_depth(torch.from_numpy(depth).cuda(), torch.from_numpy(centers).cuda(), torch.from_numpy(scales).cuda(),
+                                  torch.from_numpy(idx).cuda()).cpu().numpy()
+    for b in range(B):
+        ref = po.roi_crop_depth_cv2(depth[idx[b]], centers[b], scales[b])
+        assert ref.shape == (64, 64)
+        assert np.array_equal(out[b].view(np.uint32), ref.view(np.uint32)), b  # bit-identical to cv2 4.13
+    assert np.array_equal(out[3], po.roi_crop_depth(depth[idx[3]], centers[3], scales[3]))  # and to the restatement

@@ -154,3 +154,18 @@ def test_pose_assembly_allo_ego_roundtrip():
                                                 np.array([0.5, 0.4], np.float32), np.array([[50, 60], [70, 80]], np.float32))
     assert rot.shape == (2, 3, 3) and tr.shape == (2, 3)
     np.testing.assert_allclose(tr[:, 2], [0.75, 0.8], rtol=1e-6)
+
+
+def test_roi_crop_restatement_matches_cv2():
+    """f1: the numpy restatement of OpenCV's fixed-point bilinear warpAffine equals cv2 bit for bit at the
+    pixels the loader keeps (incl. a crop hanging over the image border)."""
+    pytest.importorskip("cv2")
+    rng = np.random.default_rng(4)
+    depth = rng.uniform(0.4, 1.6, (120, 160)).astype(np.float32)
+    depth[30:60, 70:110] = 0
+    for t in range(4):
+        c = np.array([rng.uniform(10, 150), rng.uniform(10, 110)], np.float32)
+        s = np.float32(rng.uniform(20, 160))
+        if t == 0:
+            c, s = np.array([3, 3], np.float32), np.float32(80)
+        assert np.array_equal(po.roi_crop_depth(depth, c, s), po.roi_crop_depth_cv2(depth, c, s))

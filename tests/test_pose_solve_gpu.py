@@ -198,6 +198,41 @@ def test_full_size_lmo_1024_properties(cuda):
             assert po.te(pose[i][:, 3], ores[i]["pose"][:, 3]) <= TRANS_TOL_M
 
 
+def test_full_size_ycbv_8192_incl_symmetric(cuda):
+    """BASELINE configs[2]: 21 objects (5 with symmetric geometry), 8192 ROIs, YCB-V intrinsics.  Properties at
+    full size + oracle parity on a slice that covers every object."""
+    models = synth.make_models(21, 32, seed=7, n_symmetric=5)
+    base = synth.make_batch(84, models=models, H=256, seed=777, K=synth.K_YCBV, occlusion_max=0.5)
+    b = synth.tile_batch(base, 8192)
+    g = _to_cuda(b)
+    r = _solve(g)
+    assert torch.equal(r.pose[:84], r.pose[84 * 96:84 * 97])  # any slot, same bits
+    assert float((r.status == 0).float().mean()) > 0.95
+    ores = po.pose_solve_batch({k: (None if v is None else v[:42]) for k, v in base.items()}, base["hyp_idx"][:42], THR)
+    pose = r.pose.cpu().numpy()
+    for i in range(42):
+        assert int(r.n_inliers[i]) == ores[i]["n_inl"] and int(r.best_h[i]) == ores[i]["best_h"], i
+        assert np.array_equal(r.inlier_mask[i].reshape(-1).cpu().numpy(), ores[i]["inlier_mask"]), i
+        if ores[i]["status"] == 0:
+            assert po.re_rad_small(pose[i][:, :3], ores[i]["pose"][:, :3]) <= ROT_TOL_RAD, i
+            assert po.te(pose[i][:, 3], ores[i]["pose"][:, 3]) <= TRANS_TOL_M, i
+
+
+def test_many_gated_points_multi_chunk(cuda):
+    """More than 1024 gated pixels per ROI: the staging/scoring loop runs several chunks and the refit
+    re-gathers its slots.  Big objects filling the crop, no dropout, no outliers."""
+    models = [synth.ObjectModel("box", [0.12, 0.12, 0.12], 32, np.random.default_rng(0)),
+              synth.ObjectModel("ellipsoid", [0.125, 0.125, 0.12], 32, np.random.default_rng(1))]
+    b = synth.make_batch(6, models=models, H=64, seed=3, dzi_pad_scale=1.0, mask_dropout=0.0, outlier_frac=0.02)
+    ores = po.pose_solve_batch(b, b["hyp_idx"], THR)
+    assert max(o["n_sel"] for o in ores) > 1024
+    _compare(_solve(_to_cuda(b)), ores, b)
+    bd = synth.make_batch(4, models=models, H=64, seed=4, dzi_pad_scale=1.0, mask_dropout=0.0, outlier_frac=0.02, dense=True)
+    od = po.pose_solve_batch(bd, bd["hyp_idx"], THR)
+    assert max(o["n_sel"] for o in od) > 512
+    _compare(_solve(_to_cuda(bd)), od, bd)
+
+
 def test_host_buffer_plugin_call_matches_device_call(cuda):
     """rdpn_pose_solve_host: HOST pointers in/out through the C ABI (chunked, two streams)."""
     L = _lib.lib()
