@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""Small driver for compute-sanitizer runs (memcheck / racecheck / synccheck) over every kernel:
+    compute-sanitizer --tool racecheck python benchmarks/sanitize.py
+Keeps problem sizes tiny (the tools slow kernels down by 10-100x)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from rdpn6d_b200 import fps_utils, geometry, pose_from_pred, pose_solver, synth  # noqa: E402
+
+
+def main():
+    torch.cuda.set_device(0)
+    tc = lambda x: torch.from_numpy(x).cuda()
+    # FPS (multi-block cooperative + single block)
+    for n, k in ((3000, 16), (40000, 12)):
+        fps_utils.fps_indices(tc(synth.fps_cloud(n, seed=1)), k)
+    # S1 + fused solver, anchor and dense mode, multi-chunk case included
+    big = [synth.ObjectModel("box", [0.12, 0.12, 0.12], 32, np.random.default_rng(0))]
+    for kw in (dict(), dict(dense=True), dict(models=big, dzi_pad_scale=1.0, mask_dropout=0.0)):
+        b = synth.make_batch(5, H=64, seed=11, **kw)
+        g = {k: (None if v is None else tc(v)) for k, v in b.items()}
+        pose_solver.correspond(g["depth"], g["Kp"], g["coor"][:, 0], g["coor"][:, 1], g["coor"][:, 2], g["mask"], g["extent"],
+                               g["region_idx"], g["anchors"])
+        for opts in (dict(), dict(weighted=True, refit_iters=2, adaptive=True)):
+            pose_solver.pose_solve(g["depth"], g["Kp"], g["coor"][:, 0], g["coor"][:, 1], g["coor"][:, 2], g["mask"], g["extent"],
+                                   g["hyp_idx"], g["region_idx"], g["anchors"], want_inlier_mask=True, want_hyp=True, **opts)
+    # geometry
+    geometry.kabsch(torch.randn(3, 100, 3, device="cuda"), torch.randn(3, 100, 3, device="cuda"))
+    geometry.region_argmax(torch.randn(2, 33, 64, 64, device="cuda"))
+    geometry.backproject_th(torch.rand(2, 30, 40, device="cuda"), torch.eye(3, device="cuda"))
+    geometry.roi_intrinsics(torch.eye(3, device="cuda")[None].repeat(4, 1, 1), torch.rand(4, 2, device="cuda") * 100, torch.rand(4, device="cuda") * 100 + 20)
+    geometry.roi_crop_depth(torch.rand(1, 120, 160, device="cuda"), torch.rand(4, 2, device="cuda") * 100, torch.rand(4, device="cuda") * 100 + 20)
+    pose_from_pred.pose_from_pred_centroid_z(torch.randn(4, 6, device="cuda"), torch.rand(4, 2, device="cuda"), torch.rand(4, 1, device="cuda") + 0.5,
+                                             torch.eye(3, device="cuda")[None].repeat(4, 1, 1) * 500, torch.rand(4, 2, device="cuda") * 100,
+                                             torch.rand(4, device="cuda") + 0.2, torch.rand(4, 2, device="cuda") * 50 + 10)
+    torch.cuda.synchronize()
+    print("sanitize driver done")
+
+
+if __name__ == "__main__":
+    main()

@@ -157,6 +157,8 @@ typedef struct rdpn_solve_outputs {
     int32_t* hyp_counts;   /* [B,H] inlier count per hypothesis (0 = invalid) (may be NULL)          */
     float* hyp_poses;      /* [B,H,12] FP32 hypothesis poses                (may be NULL)            */
     float* scale;          /* [B] Umeyama scale                             (may be NULL)            */
+    float* rows16;         /* [B,16] pose(12) | n_inliers | status | n_sel | best_h as FP32: the dense row
+                              block that is all-gathered across GPUs          (may be NULL)            */
 } rdpn_solve_outputs;
 
 /* hyp_idx [B,H,3] int32 absolute pixel indices (0..4095); t_net [B,3] or NULL (translation sanity). */

@@ -40,7 +40,7 @@ class SolveOutputs(ctypes.Structure):
     """struct rdpn_solve_outputs"""
     _fields_ = [
         ("pose", c_vp), ("n_inliers", c_vp), ("status", c_vp), ("best_h", c_vp), ("n_sel", c_vp),
-        ("inlier_mask", c_vp), ("hyp_counts", c_vp), ("hyp_poses", c_vp), ("scale", c_vp),
+        ("inlier_mask", c_vp), ("hyp_counts", c_vp), ("hyp_poses", c_vp), ("scale", c_vp), ("rows16", c_vp),
     ]
 
 

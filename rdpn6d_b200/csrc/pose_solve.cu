@@ -646,6 +646,10 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
 
     if (!enough || best < 0) {
         if (t < 12) a.out.pose[(size_t)b * 12 + t] = -100.f;  // gdrn_evaluator.py:395
+        if (a.out.rows16 && t < 16) {
+            const float st = enough ? (float)RDPN_STATUS_NO_CONSENSUS : (float)RDPN_STATUS_FEW_POINTS;
+            a.out.rows16[(size_t)b * 16 + t] = t < 12 ? -100.f : (t == 12 ? 0.f : (t == 13 ? st : (t == 14 ? (float)n : -1.f)));
+        }
         if (t == 0) {
             a.out.n_inliers[b] = 0;
             a.out.status[b] = enough ? RDPN_STATUS_NO_CONSENSUS : RDPN_STATUS_FEW_POINTS;
@@ -747,11 +751,15 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
         }
         a.out.n_inliers[b] = f.n_best;
         a.out.status[b] = status;
+        f.red_i[0] = status;
         if (a.out.best_h) a.out.best_h[b] = best;
         if (a.out.scale) a.out.scale[b] = out_scale;
     }
     __syncthreads();
     if (t < 12) a.out.pose[(size_t)b * 12 + t] = f.pose[t];
+    if (a.out.rows16 && t < 16)  // gather row: pose(12) | n_inliers | status | n_sel | best_h
+        a.out.rows16[(size_t)b * 16 + t] =
+            t < 12 ? f.pose[t] : (t == 12 ? (float)f.n_best : (t == 13 ? (float)f.red_i[0] : (t == 14 ? (float)n : (float)best)));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -122,9 +122,12 @@ class PoseSolveResult:
     hyp_counts: Optional[torch.Tensor] = None  # [B,H] int32
     hyp_poses: Optional[torch.Tensor] = None  # [B,H,3,4] float32
     scale: Optional[torch.Tensor] = None  # [B] float32
+    rows: Optional[torch.Tensor] = None  # [B,16] float32 written by the kernel (see rows16)
 
     def rows16(self):
         """[B,16] float32 rows for the multi-GPU gather: pose(12) | n_inliers | status | n_sel | best_h."""
+        if self.rows is not None:
+            return self.rows
         B = self.pose.shape[0]
         return torch.cat([self.pose.reshape(B, 12), self.n_inliers.float()[:, None], self.status.float()[:, None],
                           self.n_sel.float()[:, None], self.best_h.float()[:, None]], dim=1)
@@ -153,7 +156,8 @@ class PoseSolver:
                      status=torch.empty(B, dtype=torch.int32, device=dev),
                      best_h=torch.empty(B, dtype=torch.int32, device=dev),
                      n_sel=torch.empty(B, dtype=torch.int32, device=dev),
-                     scale=torch.empty(B, dtype=torch.float32, device=dev))
+                     scale=torch.empty(B, dtype=torch.float32, device=dev),
+                     rows16=torch.empty(B, 16, dtype=torch.float32, device=dev))
             if self.want_inlier_mask:
                 o["inlier_mask"] = torch.empty(B, 64, 64, dtype=torch.uint8, device=dev)
             if self.want_hyp:
@@ -175,7 +179,7 @@ class PoseSolver:
         prm = _lib.SolveParams(num_hyp=H, **self.prm)
         o = self._buffers(B, H, dev)
         outs = _lib.SolveOutputs()
-        for k in ("pose", "n_inliers", "status", "best_h", "n_sel", "inlier_mask", "hyp_counts", "hyp_poses", "scale"):
+        for k in ("pose", "n_inliers", "status", "best_h", "n_sel", "inlier_mask", "hyp_counts", "hyp_poses", "scale", "rows16"):
             setattr(outs, k, o[k].data_ptr() if k in o else None)
         st = (stream or torch.cuda.current_stream(dev)).cuda_stream
         with torch.cuda.device(dev):
@@ -185,7 +189,7 @@ class PoseSolver:
         self._keep = (inp, hyp, tn)  # keep inputs alive until the next call (stream-ordered use)
         return PoseSolveResult(pose=o["pose"].view(B, 3, 4), n_inliers=o["n_inliers"], status=o["status"],
                                best_h=o["best_h"], n_sel=o["n_sel"], inlier_mask=o.get("inlier_mask"),
-                               hyp_counts=o.get("hyp_counts"), hyp_poses=o.get("hyp_poses"), scale=o["scale"])
+                               hyp_counts=o.get("hyp_counts"), hyp_poses=o.get("hyp_poses"), scale=o["scale"], rows=o["rows16"])
 
 
 class SolvePlan:
@@ -222,11 +226,11 @@ def make_plan(solver, depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx, 
     o = solver._buffers(B, H, dev)
     solver._out.pop((B, H, str(dev)), None)  # the plan owns these buffers
     outs = _lib.SolveOutputs()
-    for k in ("pose", "n_inliers", "status", "best_h", "n_sel", "inlier_mask", "hyp_counts", "hyp_poses", "scale"):
+    for k in ("pose", "n_inliers", "status", "best_h", "n_sel", "inlier_mask", "hyp_counts", "hyp_poses", "scale", "rows16"):
         setattr(outs, k, o[k].data_ptr() if k in o else None)
     res = PoseSolveResult(pose=o["pose"].view(B, 3, 4), n_inliers=o["n_inliers"], status=o["status"],
                           best_h=o["best_h"], n_sel=o["n_sel"], inlier_mask=o.get("inlier_mask"),
-                          hyp_counts=o.get("hyp_counts"), hyp_poses=o.get("hyp_poses"), scale=o["scale"])
+                          hyp_counts=o.get("hyp_counts"), hyp_poses=o.get("hyp_poses"), scale=o["scale"], rows=o["rows16"])
     with torch.cuda.device(dev):
         pass
     return SolvePlan(solver, inp, hyp, tn, prm, outs, res)

@@ -40,7 +40,7 @@ def test_struct_layouts_match_header_sizes():
     # x86-64 SysV: 10 pointers + 4 x 4-byte scalars; 10 x 4-byte; 9 pointers
     assert ctypes.sizeof(_lib.RoiInputs) == 10 * 8 + 16
     assert ctypes.sizeof(_lib.SolveParams) == 40
-    assert ctypes.sizeof(_lib.SolveOutputs) == 9 * 8
+    assert ctypes.sizeof(_lib.SolveOutputs) == 10 * 8
 
 
 def test_version_and_error_strings():

@@ -65,6 +65,11 @@ def _compare(res, ores, b, check_counts=True):
             assert (pose[i] == -100).all()
     if stats["hyp"]:
         assert stats["pose_mismatch"] <= 0.001 * stats["hyp"] + 1  # FP32 hypothesis poses are ~always bit-identical
+    # the kernel-written gather rows are exactly the individual outputs
+    rows = res.rows16()
+    expect = torch.cat([res.pose.reshape(B, 12), res.n_inliers.float()[:, None], res.status.float()[:, None],
+                        res.n_sel.float()[:, None], res.best_h.float()[:, None]], dim=1)
+    assert rows.shape == (B, 16) and torch.equal(rows, expect)
     return stats
 
 
