@@ -221,6 +221,7 @@ struct FusedLayout {  // byte offsets of the dynamic tail behind FusedSmem
     int wrun;         // uint16[SW][RB]     (RB = R + 1: last bucket collects the unselected lanes)
     int hyp;          // float[H][12]
     int hcnt;         // int[H]
+    int vlist;        // uint16[H] indices of the valid hypotheses
     int total;
 };
 
@@ -237,6 +238,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
     uint16_t* wrun = reinterpret_cast<uint16_t*>(smem_raw + lay.wrun);
     float* hyp = reinterpret_cast<float*>(smem_raw + lay.hyp);  // [H][12]
     int* hcnt = reinterpret_cast<int*>(smem_raw + lay.hcnt);    // [H] counts, -1 = invalid
+    uint16_t* vlist = reinterpret_cast<uint16_t*>(smem_raw + lay.vlist);
     const int H = a.prm.num_hyp;
     const int R = DENSE ? 1 : a.in.num_regions;
     const int RB = R + 1;
@@ -493,6 +495,24 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
         hcnt[h] = ok ? 0 : -1;
     }
     __syncthreads();  // slots, run table, hypotheses visible
+    // compact the indices of the valid hypotheses (ascending) so that the scoring warps are densely filled
+    int nvalid = 0;
+    for (int h0 = 0; h0 < H; h0 += ST) {
+        const int h = h0 + t;
+        const bool v = h < H && hcnt[h] >= 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, v);
+        if (lane == 0) f.red_i[warp] = __popc(bal);
+        __syncthreads();
+        int base = nvalid, tot = 0;
+        for (int w = 0; w < SW; ++w) {
+            const int c = f.red_i[w];
+            if (w < warp) base += c;
+            tot += c;
+        }
+        if (v) vlist[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)h;
+        nvalid += tot;
+        __syncthreads();
+    }
     const int n = s.n_sel;
     const int nruns = s.n_runs;
     if (a.out.n_sel && t == 0) a.out.n_sel[b] = n;
@@ -504,7 +524,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
     // ---- 5 + 6: per chunk of gated slots: staging, then inlier scoring ----
     if (enough) {
         const float cut = a.sq_cut;
-        const int S = (H >= ST) ? 1 : (ST / H);
+        const int S = (nvalid >= ST || nvalid == 0) ? 1 : (ST / nvalid);
         for (int c0 = 0; c0 < n; c0 += CH) {
             const int c1 = min(n, c0 + CH);
             if (c0 > 0) __syncthreads();  // previous chunk fully scored
@@ -515,9 +535,8 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
                 if (DENSE) obj_s[sl - c0] = ob;
             }
             __syncthreads();
-            for (int item = t; item < H * S; item += ST) {
-                const int h = item % H, seg = item / H;
-                if (hcnt[h] < 0) continue;
+            for (int item = t; item < nvalid * S; item += ST) {
+                const int h = vlist[item % nvalid], seg = item / nvalid;
                 float P[12];
 #pragma unroll
                 for (int i = 0; i < 12; ++i) P[i] = hyp[(size_t)h * 12 + i];
@@ -865,6 +884,7 @@ static int launch_solve(const SolveArgs& a, cudaStream_t st) {
     lay.wrun = (int)off;    off = al(off + (size_t)SW * RB * sizeof(uint16_t));
     lay.hyp = (int)off;     off = al(off + (size_t)H * 12 * sizeof(float));
     lay.hcnt = (int)off;    off = al(off + (size_t)H * sizeof(int));
+    lay.vlist = (int)off;   off = al(off + (size_t)H * sizeof(uint16_t));
     lay.total = (int)off;
     const size_t smem = off;
     if (smem > 227 * 1024) return RDPN_E_TOOLARGE;
