@@ -125,6 +125,18 @@ def bench_misc():
     c = torch.randn(B, N, 3, device="cuda")
     ms = ev_time(lambda i: geometry.kabsch(a, c), 20)
     print(json.dumps({"bench": "kabsch", "B": B, "N": N, "ms": ms, "GBps": B * N * 24 * 2 / (ms * 1e-3) / 1e9}), flush=True)
+    for R in (32, 64):
+        B = 512
+        reg2 = [torch.randn(B, R + 1, 64, 64, device="cuda") for _ in range(2)]
+        cx = torch.rand(B, 1, 64, 64, device="cuda")
+        c2d = torch.randn(B, 5, 64, 64, device="cuda")
+        fps = torch.randn(B, R, 3, device="cuda")
+        mk = torch.randn(B, 1, 64, 64, device="cuda")
+        ms = ev_time(lambda i: geometry.coor_feat(cx, cx, cx, c2d, reg2[i % 2], fps, mk), 20)
+        byts = B * 16384 * ((R + 1 + 3 + 5 + 1) + (11 + R))
+        print(json.dumps({"bench": "coor_feat", "B": B, "R": R, "ms": ms, "GBps": byts / (ms * 1e-3) / 1e9, "hbm_peak_GBps": peaks(),
+                          "frac": byts / (ms * 1e-3) / 1e9 / peaks()}), flush=True)
+        del reg2
     reg = [torch.randn(1024, 65, 64, 64, device="cuda") for _ in range(2)]
     ms = ev_time(lambda i: geometry.region_argmax(reg[i % 2]), 20)
     print(json.dumps({"bench": "region_argmax", "B": 1024, "R": 64, "ms": ms,

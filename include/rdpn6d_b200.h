@@ -192,6 +192,17 @@ int rdpn_centroid_z_to_pose(const float* d_rot_in, int rot_is_6d, const float* d
 int rdpn_region_argmax(const float* d_region, int R, uint8_t* d_region_idx, int B, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * f2  Correspondence-feature assembly for the unchanged ConvPnPNet -- GDRN.py:199-222 +
+ *     conv_pnp_net.py:128-136 + model_utils.py:24-42 in one pass over the region logits:
+ *     out [B,C,P] = [coor_x,y,z | roi_coord_2d (5) | fps[argmax softmax(region[:,1:])] (3) | softmax (R, when
+ *     region_attention) ] * mask_prob (mask_attention 1 = "mul") [| mask_prob (2 = "concat")];  0 = "none".
+ *     C = 11 + (region_attention ? R : 0) + (mask_attention == 2).  R <= 64.
+ * ---------------------------------------------------------------------------------------------- */
+int rdpn_coor_feat(const float* d_coor_x, const float* d_coor_y, const float* d_coor_z, const float* d_roi_coord_2d,
+                   const float* d_region, const float* d_fps, const float* d_mask, int R, int mask_mode,
+                   int region_attention, int mask_attention, float* d_out, int B, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * f1  ROI depth crop from the full frame -- cv2.warpAffine(depth, A, (256,256), INTER_LINEAR)[::4, ::4]
  *     of core/gdrn_modeling/data_loader.py:532-535, 625 (core/utils/data_utils.py:81-96), sampled
  *     directly at the 64 x 64 kept positions.  depth_imgs [N,H,W] metres; img_idx [B] (NULL: image 0);

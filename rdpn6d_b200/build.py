@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librdpn6d_b200.so")
-SOURCES = ["fps.cu", "correspond.cu", "pose_solve.cu", "geometry.cu", "roi_crop.cu", "host_api.cu"]
+SOURCES = ["fps.cu", "correspond.cu", "pose_solve.cu", "geometry.cu", "roi_crop.cu", "coor_feat.cu", "host_api.cu"]
 HEADERS = ["common.cuh", "kabsch_math.cuh", os.path.join("..", "..", "include", "rdpn6d_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

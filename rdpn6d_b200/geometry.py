@@ -110,6 +110,35 @@ def roi_crop_depth(depth_imgs, center, scale, img_idx=None, crop_res=256, out_re
     return out
 
 
+def coor_feat(coor_x, coor_y, coor_z, roi_coord_2d, region, fps, mask=None, mask_mode="l1", region_attention=True,
+              mask_attention="mul"):
+    """The tensor ConvPnPNet's conv stack consumes, in one fused pass (GDRN.py:199-222, conv_pnp_net.py:128-136):
+    cat(coor_x, coor_y, coor_z, roi_coord_2d, fps[argmax softmax(region[:,1:])], softmax(region[:,1:]))
+    multiplied by (or concatenated with) get_mask_prob(mask).  Returns [B, C, 64, 64]."""
+    B = coor_x.shape[0]
+    f = lambda x, shp, n: _cuda_f32(x, n).reshape(shp)
+    cx, cy, cz = f(coor_x, (B, 4096), "coor_x"), f(coor_y, (B, 4096), "coor_y"), f(coor_z, (B, 4096), "coor_z")
+    c2d = f(roi_coord_2d, (B, 5, 4096), "roi_coord_2d")
+    reg = _cuda_f32(region, "region")
+    R = reg.shape[1] - 1
+    reg = reg.reshape(B, R + 1, 4096)
+    anc = _cuda_f32(fps, "fps")
+    if anc.dim() == 2:
+        anc = anc[None].expand(B, -1, -1).contiguous()
+    assert anc.shape == (B, R, 3), tuple(anc.shape)
+    ma = {"none": 0, "mul": 1, "concat": 2}[mask_attention]
+    mm = {"raw": 0, "l1": 1, "bce": 2}[mask_mode.lower()] if isinstance(mask_mode, str) else int(mask_mode)
+    mk = f(mask, (B, 4096), "mask") if ma else None
+    C = 11 + (R if region_attention else 0) + (1 if ma == 2 else 0)
+    out = torch.empty(B, C, 64, 64, dtype=torch.float32, device=cx.device)
+    with torch.cuda.device(cx.device):
+        rc = _lib.lib().rdpn_coor_feat(cx.data_ptr(), cy.data_ptr(), cz.data_ptr(), c2d.data_ptr(), reg.data_ptr(), anc.data_ptr(),
+                                       mk.data_ptr() if mk is not None else None, R, mm, int(bool(region_attention)), ma,
+                                       out.data_ptr(), B, _stream(cx.device))
+    _lib.check(rc, "coor_feat")
+    return out
+
+
 def region_argmax(region):
     """GDRN.py:206-209: region [B,R+1,64,64] logits -> uint8 [B,64,64] index in [0,R) (bg channel 0 skipped)."""
     r = _cuda_f32(region, "region")

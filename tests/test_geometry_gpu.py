@@ -129,3 +129,52 @@ def test_nccl_sharded_solve_two_gpus(cuda):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "NCCL_GATHER_OK" in r.stdout
+
+
+def _coor_feat_torch(coor_x, coor_y, coor_z, roi_coord_2d, region, fps, mask, region_attention, mask_attention, mask_mode):
+    """The reference's own op sequence: GDRN.py:199-222 + conv_pnp_net.py:128-136 + model_utils.py:24-42."""
+    import torch.nn.functional as F
+
+    coor_feat = torch.cat([coor_x, coor_y, coor_z], dim=1)
+    coor_feat = torch.cat([coor_feat, roi_coord_2d], dim=1)
+    region_softmax = F.softmax(region[:, 1:, :, :], dim=1)
+    am = torch.argmax(region_softmax.reshape(region_softmax.shape[0], region_softmax.shape[1], -1), dim=1).unsqueeze(2)
+    region_fps = torch.gather(fps.unsqueeze(1).expand(-1, am.shape[1], -1, -1), 2, am.unsqueeze(3).expand(-1, -1, -1, 3))
+    region_fps = region_fps.squeeze(2).reshape(region_fps.shape[0], 64, 64, 3).permute(0, 3, 1, 2)
+    coor_feat = torch.cat([coor_feat, region_fps], dim=1)
+    x = torch.cat([coor_feat, region_softmax], dim=1) if region_attention else coor_feat
+    if mask_attention != "none":
+        bs = mask.shape[0]
+        if mask_mode == "l1":
+            mmax = torch.max(mask.view(bs, -1), dim=-1)[0].view(bs, 1, 1, 1)
+            mmin = torch.min(mask.view(bs, -1), dim=-1)[0].view(bs, 1, 1, 1)
+            mp = (mask - mmin) / (mmax - mmin)
+        else:
+            mp = torch.sigmoid(mask)
+        x = x * mp if mask_attention == "mul" else torch.cat([x, mp], dim=1)
+    return x
+
+
+@pytest.mark.parametrize("R,ra,ma,mm", [(32, True, "mul", "l1"), (64, True, "mul", "l1"), (32, False, "none", "l1"),
+                                        (20, True, "concat", "bce"), (32, True, "mul", "bce")])
+def test_coor_feat_matches_reference_ops(cuda, R, ra, ma, mm):
+    """f2: fused correspondence-feature assembly vs the reference's torch op sequence (43 channels at R=32)."""
+    g = torch.Generator(device="cuda").manual_seed(R)
+    B = 6
+    rnd = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    cx, cy, cz = torch.rand(B, 1, 64, 64, device="cuda", generator=g), torch.rand(B, 1, 64, 64, device="cuda", generator=g), torch.rand(B, 1, 64, 64, device="cuda", generator=g)
+    c2d, region, fps, mask = rnd(B, 5, 64, 64), 3 * rnd(B, R + 1, 64, 64), 0.1 * rnd(B, R, 3), rnd(B, 1, 64, 64)
+    region[:, 7] = region[:, 3]  # exact ties between two regions: the first maximum must win
+    out = geometry.coor_feat(cx, cy, cz, c2d, region, fps, mask, mask_mode=mm, region_attention=ra, mask_attention=ma)
+    ref = _coor_feat_torch(cx, cy, cz, c2d, region, fps, mask, ra, ma, mm)
+    assert out.shape == ref.shape
+    if R == 32 and ra and ma == "mul":
+        assert out.shape[1] == 43  # nIn of ConvPnPNet (conv_pnp_net.py:73)
+    # the anchor channels must be bit-identical except where the reference's softmax rounding merged a near-tie
+    agree = (out[:, 8:11] == ref[:, 8:11]).all(dim=1).float().mean()
+    assert agree > 0.999
+    torch.testing.assert_close(out[:, :8], ref[:, :8], rtol=2e-6, atol=1e-7)
+    if ra:
+        torch.testing.assert_close(out[:, 11:11 + R], ref[:, 11:11 + R], rtol=1e-5, atol=2e-7)
+    if ma == "concat":
+        torch.testing.assert_close(out[:, -1], ref[:, -1], rtol=2e-6, atol=1e-7)
