@@ -203,6 +203,14 @@ int rdpn_coor_feat(const float* d_coor_x, const float* d_coor_y, const float* d_
                    int region_attention, int mask_attention, float* d_out, int B, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * f4  Region / residual targets -- core/utils/data_utils.py:229-244 (xyz_to_region): nearest FPS anchor per
+ *     pixel (float64 distances as scipy cdist, first minimum), region ids 1..R (0 = background where
+ *     xyz == 0) and delta = xyz - anchor.  xyz [B,P,3] (HWC), fps [B,R,3] -> region [B,P] u8, delta [B,P,3].
+ * ---------------------------------------------------------------------------------------------- */
+int rdpn_xyz_to_region(const float* d_xyz, const float* d_fps, int R, int P, uint8_t* d_region, float* d_delta, int B,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * f1  ROI depth crop from the full frame -- cv2.warpAffine(depth, A, (256,256), INTER_LINEAR)[::4, ::4]
  *     of core/gdrn_modeling/data_loader.py:532-535, 625 (core/utils/data_utils.py:81-96), sampled
  *     directly at the 64 x 64 kept positions.  depth_imgs [N,H,W] metres; img_idx [B] (NULL: image 0);

@@ -65,6 +65,7 @@ SIGNATURES = {
     "rdpn_region_argmax": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, ctypes.c_int, c_vp]),
     "rdpn_coor_feat": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                       ctypes.c_int, c_vp, ctypes.c_int, c_vp]),
+    "rdpn_xyz_to_region": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_vp, ctypes.c_int, c_vp]),
     "rdpn_roi_crop_depth": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp, ctypes.c_int,
                                            ctypes.c_int, c_vp, ctypes.c_int, c_vp]),
     "rdpn_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(c_vp)]),

@@ -229,3 +229,47 @@ int rdpn_fp32_peak_probe(int iters, double* out_flops) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// f4: region / residual targets -- core/utils/data_utils.py:229-244 (xyz_to_region).
+//   region id = 1 + argmin_r ||xyz - fps_r||  (scipy cdist: float64, sqrt(sum of squares), first minimum),
+//   0 where xyz == (0,0,0) (background); delta = xyz - fps[region-1] for every pixel (also background).
+// xyz [B,P,3] (HWC as the loader holds it), fps [B,R,3]; out region [B,P] uint8, delta [B,P,3].
+// ------------------------------------------------------------------------------------------------
+namespace rdpn {
+__global__ void xyz_to_region_kernel(const float* __restrict__ xyz, const float* __restrict__ fps, int R, int P,
+                                     uint8_t* __restrict__ region, float* __restrict__ delta, int B) {
+    extern __shared__ float sfps[];  // [R*3]
+    const int b = blockIdx.y;
+    for (int i = threadIdx.x; i < R * 3; i += blockDim.x) sfps[i] = fps[(size_t)b * R * 3 + i];
+    __syncthreads();
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const float* v = xyz + ((size_t)b * P + p) * 3;
+    const float x = v[0], y = v[1], z = v[2];
+    int best = 0;
+    double bd = 1e300;
+    for (int r = 0; r < R; ++r) {
+        const double dx = __dsub_rn((double)x, (double)sfps[3 * r]), dy = __dsub_rn((double)y, (double)sfps[3 * r + 1]),
+                     dz = __dsub_rn((double)z, (double)sfps[3 * r + 2]);
+        const double d = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+        if (d < bd) { bd = d; best = r; }
+    }
+    const bool fg = (x != 0.f) || (y != 0.f) || (z != 0.f);  // data_utils.py:232-233
+    region[(size_t)b * P + p] = fg ? (uint8_t)(best + 1) : (uint8_t)0;
+    float* o = delta + ((size_t)b * P + p) * 3;
+    o[0] = __fsub_rn(x, sfps[3 * best]);
+    o[1] = __fsub_rn(y, sfps[3 * best + 1]);
+    o[2] = __fsub_rn(z, sfps[3 * best + 2]);
+}
+}  // namespace rdpn
+
+extern "C" int rdpn_xyz_to_region(const float* d_xyz, const float* d_fps, int R, int P, uint8_t* d_region, float* d_delta, int B,
+                                  void* stream) {
+    if (!d_xyz || !d_fps || !d_region || !d_delta || B <= 0 || P <= 0 || R <= 0 || R > 254) return RDPN_E_BADARG;
+    dim3 grid((P + 255) / 256, B);
+    rdpn::xyz_to_region_kernel<<<grid, 256, (size_t)R * 3 * sizeof(float), (cudaStream_t)stream>>>(d_xyz, d_fps, R, P, d_region, d_delta, B);
+    ++rdpn::g_launch_count;
+    RDPN_LAUNCH_CHECK();
+    return 0;
+}

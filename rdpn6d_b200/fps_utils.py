@@ -79,3 +79,21 @@ def get_fps_and_center(pts, num_fps=8, init_center=True):
                                center.data_ptr(), torch.cuda.current_stream(p32.device).cuda_stream)
     _lib.check(rc, "fps_gather")
     return torch.cat([out.to(torch.float64), center[None]], dim=0)
+
+
+def fps_and_center_for_models(clouds, nums_fps=(2, 4, 8, 12, 16, 20, 32, 64, 128, 256)):
+    """The loop of tools/*/..._compute_fps.py (e.g. tools/lm/1_compute_fps.py:26-35): for every object cloud and
+    every sample count, `get_fps_and_center(pts, n, init_center=True)`.  clouds: dict obj_id -> [N,3] numpy array.
+    Returns {str(obj_id): {"fps{n}_and_center": [n+1,3] array}} ready for mmcv.dump(fps_points.pkl).  Each cloud
+    is uploaded once; the K-step kernel runs per sample count (FPS prefixes differ per count only in length,
+    so the largest count is computed and shorter ones are prefixes of it)."""
+    _require_cuda()
+    out = {}
+    kmax = max(nums_fps)
+    for obj_id, pts in clouds.items():
+        pts = np.asarray(pts)
+        p32 = np.ascontiguousarray(pts, np.float32)
+        idx = fps_indices(torch.from_numpy(p32).cuda(), kmax, init_center=True).cpu().numpy()
+        avg = np.array([[np.average(pts[:, 0]), np.average(pts[:, 1]), np.average(pts[:, 2])]])
+        out[str(obj_id)] = {f"fps{n}_and_center": np.concatenate([p32[idx[:n]], avg], axis=0) for n in nums_fps}
+    return out

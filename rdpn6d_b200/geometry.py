@@ -139,6 +139,27 @@ def coor_feat(coor_x, coor_y, coor_z, roi_coord_2d, region, fps, mask=None, mask
     return out
 
 
+def xyz_to_region(xyz_crop, fps_points):
+    """data_utils.py:229-244 batched: xyz_crop [B,h,w,3] (or [h,w,3]), fps_points [B,R,3] (or [R,3]) ->
+    (region ids uint8 [B,h,w] with 0 = background, delta float32 [B,h,w,3])."""
+    x = _cuda_f32(xyz_crop, "xyz_crop")
+    single = x.dim() == 3
+    if single:
+        x = x[None]
+    B, h, w, _ = x.shape
+    fp = _cuda_f32(fps_points, "fps_points")
+    if fp.dim() == 2:
+        fp = fp[None].expand(B, -1, -1).contiguous()
+    R = fp.shape[1]
+    region = torch.empty(B, h, w, dtype=torch.uint8, device=x.device)
+    delta = torch.empty(B, h, w, 3, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().rdpn_xyz_to_region(x.data_ptr(), fp.data_ptr(), R, h * w, region.data_ptr(), delta.data_ptr(), B,
+                                           _stream(x.device))
+    _lib.check(rc, "xyz_to_region")
+    return (region[0], delta[0]) if single else (region, delta)
+
+
 def region_argmax(region):
     """GDRN.py:206-209: region [B,R+1,64,64] logits -> uint8 [B,64,64] index in [0,R) (bg channel 0 skipped)."""
     r = _cuda_f32(region, "region")

@@ -178,3 +178,33 @@ def test_coor_feat_matches_reference_ops(cuda, R, ra, ma, mm):
         torch.testing.assert_close(out[:, 11:11 + R], ref[:, 11:11 + R], rtol=1e-5, atol=2e-7)
     if ma == "concat":
         torch.testing.assert_close(out[:, -1], ref[:, -1], rtol=2e-6, atol=1e-7)
+
+
+def test_xyz_to_region_vs_reference_golden(cuda, golden_dir):
+    """f4: nearest-anchor region ids and residuals against golden outputs of the reference's
+    core/utils/data_utils.xyz_to_region (scipy cdist + argmin)."""
+    g = np.load(os.path.join(golden_dir, "region_golden.npz"))
+    xyz32 = g["xyz"].astype(np.float32)
+    fps32 = g["fps"].astype(np.float32)
+    reg, delta = geometry.xyz_to_region(torch.from_numpy(xyz32).cuda(), torch.from_numpy(fps32).cuda())
+    for i in range(xyz32.shape[0]):
+        r_o, d_o = po.xyz_to_region(xyz32[i], fps32[i])  # oracle on the float32 inputs the kernel sees
+        assert np.array_equal(reg[i].cpu().numpy(), r_o)
+        assert np.array_equal(delta[i].cpu().numpy(), d_o)
+        # and against the reference's own float64 run: ids identical except float32-rounding near-ties
+        assert (reg[i].cpu().numpy() == g["region"][i]).mean() > 0.999
+        np.testing.assert_allclose(delta[i].cpu().numpy()[reg[i].cpu().numpy() == g["region"][i]],
+                                   g["delta"][i][reg[i].cpu().numpy() == g["region"][i]], atol=1e-7)
+    assert (reg[:, :10] == 0).all()  # background rows
+
+
+def test_fps_for_models_prefix_property(cuda):
+    """tools/*/..._compute_fps.py loop: FPS(n) is a prefix of FPS(n_max), so one run serves every sample count."""
+    from oracle.fps import get_fps_and_center
+    from rdpn6d_b200 import fps_utils
+
+    clouds = {1: synth.fps_cloud(4000, seed=1).astype(np.float64), 5: synth.fps_cloud(9000, seed=2).astype(np.float64)}
+    out = fps_utils.fps_and_center_for_models(clouds, nums_fps=(2, 8, 32))
+    for oid, pts in clouds.items():
+        for n in (2, 8, 32):
+            np.testing.assert_array_equal(out[str(oid)][f"fps{n}_and_center"], get_fps_and_center(pts, n))
