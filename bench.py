@@ -401,6 +401,35 @@ def gpu_arm(args):
     torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1) / nk
 
+    # ---- stage S1 alone (rdpn_correspond, the materialising HBM-bound kernel): its own roofline line ----
+    s1_ms = None
+    try:
+        s1_in = [pose_solver._Inputs(s["depth"], s["Kp"], s["coor"][:, 0].contiguous(), s["coor"][:, 1].contiguous(),
+                                     s["coor"][:, 2].contiguous(), s["mask"], s["extent"], s["region_idx"], s["anchors"]) for s in sets]
+        s1_cam = torch.empty(ROIS_PER_GPU, 3, 4096, device=dev)
+        s1_w = torch.empty(ROIS_PER_GPU, 4096, device=dev)
+        s1_sel = torch.empty(ROIS_PER_GPU, 4096, dtype=torch.uint8, device=dev)
+        s1_n = torch.empty(ROIS_PER_GPU, dtype=torch.int32, device=dev)
+        cs = torch.cuda.current_stream(dev).cuda_stream
+
+        def s1_launch(i):
+            _lib.check(L.rdpn_correspond(ctypes.byref(s1_in[i % N_INPUT_SETS].struct), s1_cam.data_ptr(), None, s1_w.data_ptr(),
+                                         s1_sel.data_ptr(), s1_n.data_ptr(), cs), "correspond")
+
+        for i in range(5):
+            s1_launch(i)
+        torch.cuda.synchronize()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for i in range(50):
+            s1_launch(i)
+        q1.record()
+        torch.cuda.synchronize()
+        s1_ms = q0.elapsed_time(q1) / 50
+    except Exception as e:  # the headline does not depend on this leg
+        s1_ms = None
+        print("s1 leg failed: %r" % (e,), file=sys.stderr)
+
     # ---- end to end through the host-buffer C-ABI call (pinned host buffers) ----
     pin = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in batch.items()
            if v is not None and k in ("depth", "Kp", "mask", "extent", "region_idx", "anchors", "hyp_idx")}
@@ -520,6 +549,11 @@ def gpu_arm(args):
                  "pairs_per_launch": pairs, "mean_gated_points_per_roi": mean_nsel,
                  "peak_source": "rdpn_fp32_peak_probe (FFMA chains on all SMs, this run)"},
         "solved_fraction": ok_frac,
+        "s1_roofline": None if s1_ms is None else {
+            "kernel": "rdpn::correspond_kernel<false> (S1 materialised: cam xyz + w + sel for every pixel)", "bound": "hbm",
+            "kernel_ms": s1_ms, "algorithmic_bytes_per_launch": ROIS_PER_GPU * (BYTES_MAPS + NUM_REGIONS * 12 + 28 + 69636),
+            "achieved": ROIS_PER_GPU * (BYTES_MAPS + NUM_REGIONS * 12 + 28 + 69636) / (s1_ms * 1e-3) / 1e9, "peak": hbm_peak,
+            "unit": "GB/s", "frac": ROIS_PER_GPU * (BYTES_MAPS + NUM_REGIONS * 12 + 28 + 69636) / (s1_ms * 1e-3) / 1e9 / hbm_peak},
     }
     if cpu_base is not None:
         line["cpu_baseline"] = cpu_base

@@ -35,8 +35,8 @@ __device__ __forceinline__ void plane_basis(const double* p0, const double* p1, 
     double ax = p1[0] - p0[0], ay = p1[1] - p0[1], az = p1[2] - p0[2];
     const double bx = p2[0] - p0[0], by = p2[1] - p0[1], bz = p2[2] - p0[2];
     double nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
-    const double il = 1.0 / sqrt(ax * ax + ay * ay + az * az);
-    const double in = 1.0 / sqrt(nx * nx + ny * ny + nz * nz);
+    const double il = rsqrt(ax * ax + ay * ay + az * az);  // ~1 ulp; the result is rounded to FP32 anyway
+    const double in = rsqrt(nx * nx + ny * ny + nz * nz);
     ax *= il; ay *= il; az *= il;
     nx *= in; ny *= in; nz *= in;
     e1[0] = ax; e1[1] = ay; e1[2] = az;
@@ -69,7 +69,7 @@ __device__ __forceinline__ void kabsch3(const double (*a)[3], const double (*c)[
         sdot += xc * xa + yc * ya;
         scross += yc * xa - xc * ya;
     }
-    const double ih = 1.0 / sqrt(sdot * sdot + scross * scross);
+    const double ih = rsqrt(sdot * sdot + scross * scross);
     const double cs = sdot * ih, sn = scross * ih;
     double f1[3], f2[3];  // images of e1a, e2a
 #pragma unroll

@@ -85,8 +85,8 @@ struct RoiGate {
 constexpr int CHUNK = 1024;  // gated slots staged in shared memory at a time (dense mode: CHUNK / 2)
 
 struct FinishSmem {  // scratch of the select + refit tail
-    double red_d[SW][12];
-    double bc_d[16];
+    double red_d[SW][18];
+    double bc_d[20];
     int best_h;
     int n_best;
     int h_eff;
@@ -197,6 +197,7 @@ __device__ __forceinline__ float resid2(const float* P, float ax, float ay, floa
 // block-wide sum of NV doubles; result valid in every thread (via f.bc_d[0..NV)).
 template <int NV>
 __device__ __forceinline__ void block_sum(FinishSmem& f, double (&v)[NV]) {
+    static_assert(NV <= 18, "red_d / bc_d hold 18 values");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -688,8 +689,14 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
         float P[12];
 #pragma unroll
         for (int i = 0; i < 12; ++i) P[i] = f.pose[i];
-        // pass 1: weighted centroids; thread handles slots t, t+ST, ... (<= 16 of them)
-        double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+        // ONE pass over the slots (thread handles t, t+ST, ...: <= 16 of them): FP64 raw moments about a pivot
+        // (slot 0, exact FP32 differences), from which centroids, cross-covariance and spreads follow; the
+        // residual cancellation is ~1e2 on 1e-16, far below the FP32 rounding of the result.
+        float4 cp0, ap0;
+        get_slot(0, cp0, ap0);
+        double mom[18];
+#pragma unroll
+        for (int i = 0; i < 18; ++i) mom[i] = 0.0;
         unsigned inl_bits = 0u;
         int slot = 0;
         for (int i = t; i < n; i += ST, ++slot) {
@@ -698,38 +705,36 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
             if (resid2(P, ap.x, ap.y, ap.z, cp.x, cp.y, cp.z) < cut) {
                 inl_bits |= 1u << slot;
                 const double w = a.prm.weighted ? (double)cp.w : 1.0;
-                acc[0] += w;
-                acc[1] += w * cp.x; acc[2] += w * cp.y; acc[3] += w * cp.z;
-                acc[4] += w * ap.x; acc[5] += w * ap.y; acc[6] += w * ap.z;
+                const double c0 = (double)cp.x - (double)cp0.x, c1 = (double)cp.y - (double)cp0.y, c2 = (double)cp.z - (double)cp0.z;
+                const double a0 = (double)ap.x - (double)ap0.x, a1 = (double)ap.y - (double)ap0.y, a2 = (double)ap.z - (double)ap0.z;
+                mom[0] += w;
+                mom[1] += w * c0; mom[2] += w * c1; mom[3] += w * c2;
+                mom[4] += w * a0; mom[5] += w * a1; mom[6] += w * a2;
+                mom[7] += w * c0 * a0; mom[8] += w * c0 * a1; mom[9] += w * c0 * a2;
+                mom[10] += w * c1 * a0; mom[11] += w * c1 * a1; mom[12] += w * c1 * a2;
+                mom[13] += w * c2 * a0; mom[14] += w * c2 * a1; mom[15] += w * c2 * a2;
+                mom[16] += w * (c0 * c0 + c1 * c1 + c2 * c2);
+                mom[17] += w * (a0 * a0 + a1 * a1 + a2 * a2);
             }
         }
         int tot_inl = warp_sum(__popc(inl_bits));
         if (lane == 0) f.red_i[warp] = tot_inl;
-        block_sum<7>(f, acc);  // contains the barriers that publish red_i
+        block_sum<18>(f, mom);  // contains the barriers that publish red_i
         tot_inl = 0;
         for (int w = 0; w < SW; ++w) tot_inl += f.red_i[w];
         if (tot_inl < 3) break;  // uniform across the block
-        const double isw = 1.0 / acc[0];
-        const double mc[3] = {acc[1] * isw, acc[2] * isw, acc[3] * isw};
-        const double ma[3] = {acc[4] * isw, acc[5] * isw, acc[6] * isw};
-        // pass 2: cross-covariance about the centroids (+ spreads for the Umeyama scale)
-        double cov[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-        slot = 0;
-        for (int i = t; i < n; i += ST, ++slot) {
-            if (inl_bits & (1u << slot)) {
-                float4 cp, ap;
-                get_slot(i, cp, ap);
-                const double w = a.prm.weighted ? (double)cp.w : 1.0;
-                const double c0 = cp.x - mc[0], c1 = cp.y - mc[1], c2 = cp.z - mc[2];
-                const double a0 = ap.x - ma[0], a1 = ap.y - ma[1], a2 = ap.z - ma[2];
-                cov[0] += w * c0 * a0; cov[1] += w * c0 * a1; cov[2] += w * c0 * a2;
-                cov[3] += w * c1 * a0; cov[4] += w * c1 * a1; cov[5] += w * c1 * a2;
-                cov[6] += w * c2 * a0; cov[7] += w * c2 * a1; cov[8] += w * c2 * a2;
-                cov[9] += w * (c0 * c0 + c1 * c1 + c2 * c2);
-                cov[10] += w * (a0 * a0 + a1 * a1 + a2 * a2);
-            }
-        }
-        block_sum<11>(f, cov);
+        const double isw = 1.0 / mom[0];
+        const double mcp[3] = {mom[1] * isw, mom[2] * isw, mom[3] * isw};  // centroids relative to the pivot
+        const double map[3] = {mom[4] * isw, mom[5] * isw, mom[6] * isw};
+        const double mc[3] = {mcp[0] + (double)cp0.x, mcp[1] + (double)cp0.y, mcp[2] + (double)cp0.z};
+        const double ma[3] = {map[0] + (double)ap0.x, map[1] + (double)ap0.y, map[2] + (double)ap0.z};
+        double cov[11];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) cov[3 * r + c] = mom[7 + 3 * r + c] - mom[1 + r] * map[c];  // sum w c a^T - (sum w c)(mean a)^T
+        cov[9] = mom[16] - (mom[1] * mcp[0] + mom[2] * mcp[1] + mom[3] * mcp[2]);
+        cov[10] = mom[17] - (mom[4] * map[0] + mom[5] * map[1] + mom[6] * map[2]);
         if (t == 0) {
             double Rm[9];
             rotation_from_cov(cov, cov[10], cov[9], Rm);
@@ -743,7 +748,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
                 f.pose[4 * r + 2] = (float)(sc * Rm[3 * r + 2]);
                 f.pose[4 * r + 3] = (float)tr;
             }
-            f.bc_d[15] = sc;
+            f.bc_d[19] = sc;
         }
         if (a.out.inlier_mask && it == iters - 1) {  // the inlier set used by the last refit
             slot = 0;
@@ -751,7 +756,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
                 if (inl_bits & (1u << slot)) a.out.inlier_mask[(size_t)b * RDPN_P + s.pix[i]] = 1;
         }
         __syncthreads();
-        out_scale = (float)f.bc_d[15];
+        out_scale = (float)f.bc_d[19];
     }
 
     // ---- outputs (+ translation sanity, gdrn_evaluator.py:293-296) ----

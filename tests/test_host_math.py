@@ -20,6 +20,7 @@ SHIM = r"""
 static inline double __dsub_rn(double a,double b){return a-b;}
 static inline double __dadd_rn(double a,double b){return a+b;}
 static inline double __dmul_rn(double a,double b){return a*b;}
+static inline double rsqrt(double x){return 1.0/std::sqrt(x);}
 #include "kabsch_math_host.cuh"
 extern "C" {
 void host_kabsch3(const double* a, const double* c, double* Rt){ rdpn::kabsch3((const double(*)[3])a,(const double(*)[3])c,Rt);}
