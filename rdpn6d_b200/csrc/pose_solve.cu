@@ -194,6 +194,14 @@ __device__ __forceinline__ float resid2(const float* P, float ax, float ay, floa
     return resid2_pt(x, y, z, cx, cy, cz);
 }
 
+// misc.py:134-138: k = log10(1-conf) / log10(1 - w^10), stop once i_ransac > max(k, min_iter).  Kept out of line:
+// double pow/log10 are ~1500 instructions that only the (non-default) adaptive mode needs.
+__device__ __noinline__ bool adaptive_stop(int count, int n, int i_ransac, double log_1m_conf, int min_iter) {
+    const double wr = (double)count / (double)n;
+    const double k = log_1m_conf / log10(1.0 - pow(wr, 10.0));
+    return (double)i_ransac > fmax(k, (double)min_iter);
+}
+
 // block-wide sum of NV doubles; result valid in every thread (via f.bc_d[0..NV)).
 template <int NV>
 __device__ __forceinline__ void block_sum(FinishSmem& f, double (&v)[NV]) {
@@ -228,6 +236,9 @@ struct FusedLayout {  // byte offsets of the dynamic tail behind FusedSmem
 
 #ifndef RDPN_SOLVE_CTAS
 #define RDPN_SOLVE_CTAS 4
+#endif
+#ifndef RDPN_SCORE_PAIRS
+#define RDPN_SCORE_PAIRS 1
 #endif
 template <bool DENSE>
 __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveArgs a, FusedLayout lay) {
@@ -536,6 +547,63 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
                 if (DENSE) obj_s[sl - c0] = ob;
             }
             __syncthreads();
+            if (!DENSE && RDPN_SCORE_PAIRS) {
+                // anchor mode, TWO hypotheses per thread: every staged point (one LDS.128) and every run header is
+                // shared by both, which removes ~12 % of the scoring instructions (the loop is issue-bound)
+                const int npairs = (nvalid + 1) >> 1;
+                const int S2 = (npairs >= ST || npairs == 0) ? 1 : (ST / npairs);
+                const bool whole = (c0 == 0 && c1 == n);
+                for (int item = t; item < npairs * S2; item += ST) {
+                    const int j = item % npairs, seg = item / npairs;
+                    const int hA = vlist[2 * j];
+                    const bool hasB = 2 * j + 1 < nvalid;
+                    const int hB = hasB ? vlist[2 * j + 1] : hA;
+                    float PA[12], PB[12];
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) { PA[i] = hyp[(size_t)hA * 12 + i]; PB[i] = hyp[(size_t)hB * 12 + i]; }
+                    int cA = 0, cB = 0;
+                    for (int k = seg; k < nruns; k += S2) {
+                        const float4 hd = runtab[k];
+                        const unsigned se = __float_as_uint(hd.w);
+                        int i = (int)(se & 0xFFFFu);
+                        int e = (int)(se >> 16);
+                        if (!whole) {
+                            i = max(i, c0) - c0;
+                            e = min(e, c1) - c0;
+                            if (i >= e) continue;
+                        }
+                        float ax, ay, az, bx, by, bz;
+                        xform(PA, hd.x, hd.y, hd.z, ax, ay, az);
+                        xform(PB, hd.x, hd.y, hd.z, bx, by, bz);
+#pragma unroll 1
+                        for (; i + 4 <= e; i += 4) {
+                            const float4 q0 = camw_s[i], q1 = camw_s[i + 1], q2 = camw_s[i + 2], q3 = camw_s[i + 3];
+                            count_if_lt(cA, resid2_pt(ax, ay, az, q0.x, q0.y, q0.z), cut);
+                            count_if_lt(cB, resid2_pt(bx, by, bz, q0.x, q0.y, q0.z), cut);
+                            count_if_lt(cA, resid2_pt(ax, ay, az, q1.x, q1.y, q1.z), cut);
+                            count_if_lt(cB, resid2_pt(bx, by, bz, q1.x, q1.y, q1.z), cut);
+                            count_if_lt(cA, resid2_pt(ax, ay, az, q2.x, q2.y, q2.z), cut);
+                            count_if_lt(cB, resid2_pt(bx, by, bz, q2.x, q2.y, q2.z), cut);
+                            count_if_lt(cA, resid2_pt(ax, ay, az, q3.x, q3.y, q3.z), cut);
+                            count_if_lt(cB, resid2_pt(bx, by, bz, q3.x, q3.y, q3.z), cut);
+                        }
+#pragma unroll 1
+                        for (; i < e; ++i) {
+                            const float4 q0 = camw_s[i];
+                            count_if_lt(cA, resid2_pt(ax, ay, az, q0.x, q0.y, q0.z), cut);
+                            count_if_lt(cB, resid2_pt(bx, by, bz, q0.x, q0.y, q0.z), cut);
+                        }
+                    }
+                    if (S2 == 1) {
+                        hcnt[hA] += cA;
+                        if (hasB) hcnt[hB] += cB;
+                    } else {
+                        atomicAdd(&hcnt[hA], cA);
+                        if (hasB) atomicAdd(&hcnt[hB], cB);
+                    }
+                }
+                continue;
+            }
             for (int item = t; item < nvalid * S; item += ST) {
                 const int h = vlist[item % nvalid], seg = item / nvalid;
                 float P[12];
@@ -624,12 +692,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
                 int tot = 0;
                 for (int w = 0; w < SW; ++w) tot += f.red_i[w];
                 const int i_ransac = running + wbase + x;
-                if (v) {
-                    const double wr = (double)hcnt[h] / (double)n;
-                    const double k = lc / log10(1.0 - pow(wr, 10.0));
-                    const double lim = fmax(k, (double)a.prm.min_iter);
-                    if ((double)i_ransac > lim) atomicMin(&f.h_eff, h + 1);
-                }
+                if (v && adaptive_stop(hcnt[h], n, i_ransac, lc, a.prm.min_iter)) atomicMin(&f.h_eff, h + 1);
                 running += tot;
                 __syncthreads();
             }
