@@ -506,10 +506,26 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
         }
         hcnt[h] = ok ? 0 : -1;
     }
-    __syncthreads();  // slots, run table, hypotheses visible
-    // compact the indices of the valid hypotheses (ascending) so that the scoring warps are densely filled
+    // compact the indices of the valid hypotheses (ascending) so that the scoring warps are densely filled.
+    // Round 0 (h = t) publishes its per-warp counts BEFORE the barrier that ends hypothesis generation and the
+    // list itself is only needed after the staging barrier, so the usual H <= 256 case costs no extra barrier.
+    const bool v0 = t < H && hcnt[t] >= 0;
+    const unsigned bal0 = __ballot_sync(0xffffffffu, v0);
+    if (lane == 0) f.red_i[warp] = __popc(bal0);
+    __syncthreads();  // slots, run table, hypotheses, round-0 counts visible
     int nvalid = 0;
-    for (int h0 = 0; h0 < H; h0 += ST) {
+    {
+        int base = 0, tot = 0;
+        for (int w = 0; w < SW; ++w) {
+            const int c = f.red_i[w];
+            if (w < warp) base += c;
+            tot += c;
+        }
+        if (v0) vlist[base + __popc(bal0 & ((1u << lane) - 1u))] = (uint16_t)t;
+        nvalid = tot;
+    }
+    for (int h0 = ST; h0 < H; h0 += ST) {  // H > 256: further rounds, two barriers each
+        __syncthreads();
         const int h = h0 + t;
         const bool v = h < H && hcnt[h] >= 0;
         const unsigned bal = __ballot_sync(0xffffffffu, v);
@@ -523,7 +539,6 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
         }
         if (v) vlist[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)h;
         nvalid += tot;
-        __syncthreads();
     }
     const int n = s.n_sel;
     const int nruns = s.n_runs;
@@ -670,6 +685,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
     };
 
     // ---- 7a: best hypothesis (misc.py:121) with optional adaptive stop (misc.py:134-138) ----
+    int best_r = -1, nbest_r = 0;
     if (enough) {
         if (a.prm.adaptive) {
             // i_ransac(h) = number of valid hypotheses in [0,h]; stop after the first h with
@@ -709,17 +725,15 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
         key = warp_max_u64(key);
         if (lane == 0) f.red_k[warp] = key;
         __syncthreads();
-        if (t == 0) {
-            unsigned long long k = 0ull;
-            for (int w = 0; w < SW; ++w) k = f.red_k[w] > k ? f.red_k[w] : k;
-            if (k) {
-                f.best_h = 0x7FFFFFFF - (int)(k & 0xFFFFFFFFull);
-                f.n_best = (int)(k >> 32);
-            }
+        unsigned long long kb = 0ull;
+#pragma unroll
+        for (int w = 0; w < SW; ++w) kb = f.red_k[w] > kb ? f.red_k[w] : kb;  // every thread: no second barrier
+        if (kb) {
+            best_r = 0x7FFFFFFF - (int)(kb & 0xFFFFFFFFull);
+            nbest_r = (int)(kb >> 32);
         }
-        __syncthreads();
     }
-    const int best = f.best_h;
+    const int best = best_r;
 
     // optional diagnostics
     if (a.out.hyp_counts)
@@ -743,15 +757,14 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
     }
 
     // ---- 7b: refit on the inliers (misc.py:123-126 -> transform.py:913-980), FP64 accumulation ----
-    if (t < 12) f.pose[t] = hyp[(size_t)best * 12 + t];
-    __syncthreads();
+    if (t < 12) f.pose[t] = hyp[(size_t)best * 12 + t];  // stays if the refit bails out (< 3 inliers)
     const float cut = a.sq_cut;
     float out_scale = 1.f;
     const int iters = a.prm.refit_iters < 1 ? 1 : a.prm.refit_iters;
     for (int it = 0; it < iters; ++it) {
         float P[12];
 #pragma unroll
-        for (int i = 0; i < 12; ++i) P[i] = f.pose[i];
+        for (int i = 0; i < 12; ++i) P[i] = it == 0 ? hyp[(size_t)best * 12 + i] : f.pose[i];
         // ONE pass over the slots (thread handles t, t+ST, ...: <= 16 of them): FP64 raw moments about a pivot
         // (slot 0, exact FP32 differences), from which centroids, cross-covariance and spreads follow; the
         // residual cancellation is ~1e2 on 1e-16, far below the FP32 rounding of the result.
@@ -780,46 +793,70 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
                 mom[17] += w * (a0 * a0 + a1 * a1 + a2 * a2);
             }
         }
-        int tot_inl = warp_sum(__popc(inl_bits));
-        if (lane == 0) f.red_i[warp] = tot_inl;
-        block_sum<18>(f, mom);  // contains the barriers that publish red_i
-        tot_inl = 0;
-        for (int w = 0; w < SW; ++w) tot_inl += f.red_i[w];
-        if (tot_inl < 3) break;  // uniform across the block
-        const double isw = 1.0 / mom[0];
-        const double mcp[3] = {mom[1] * isw, mom[2] * isw, mom[3] * isw};  // centroids relative to the pivot
-        const double map[3] = {mom[4] * isw, mom[5] * isw, mom[6] * isw};
-        const double mc[3] = {mcp[0] + (double)cp0.x, mcp[1] + (double)cp0.y, mcp[2] + (double)cp0.z};
-        const double ma[3] = {map[0] + (double)ap0.x, map[1] + (double)ap0.y, map[2] + (double)ap0.z};
-        double cov[11];
+        // reduction: warp shuffles -> per-warp partials -> warp 0 (lane i sums value i) -> lane 0 solves.
+        // Only the solving thread needs the moments, so two barriers suffice.
+        const int winl = warp_sum(__popc(inl_bits));
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) cov[3 * r + c] = mom[7 + 3 * r + c] - mom[1 + r] * map[c];  // sum w c a^T - (sum w c)(mean a)^T
-        cov[9] = mom[16] - (mom[1] * mcp[0] + mom[2] * mcp[1] + mom[3] * mcp[2]);
-        cov[10] = mom[17] - (mom[4] * map[0] + mom[5] * map[1] + mom[6] * map[2]);
-        if (t == 0) {
-            double Rm[9];
-            rotation_from_cov(cov, cov[10], cov[9], Rm);
-            double sc = 1.0;
-            if (a.prm.with_scale) sc = sqrt(cov[9] / cov[10]);  // transform.py:971-975
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const double tr = mc[r] - sc * (Rm[3 * r] * ma[0] + Rm[3 * r + 1] * ma[1] + Rm[3 * r + 2] * ma[2]);
-                f.pose[4 * r + 0] = (float)(sc * Rm[3 * r + 0]);
-                f.pose[4 * r + 1] = (float)(sc * Rm[3 * r + 1]);
-                f.pose[4 * r + 2] = (float)(sc * Rm[3 * r + 2]);
-                f.pose[4 * r + 3] = (float)tr;
-            }
-            f.bc_d[19] = sc;
+        for (int i = 0; i < 18; ++i) {
+            const double v = warp_sum(mom[i]);
+            if (lane == 0) f.red_d[warp][i] = v;
         }
+        if (lane == 0) f.red_i[warp] = winl;
+        __syncthreads();
+        if (warp == 0) {
+            if (lane < 18) {
+                double acc = 0.0;
+#pragma unroll
+                for (int w = 0; w < SW; ++w) acc += f.red_d[w][lane];
+                f.bc_d[lane] = acc;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                int tot_inl = 0;
+#pragma unroll
+                for (int w = 0; w < SW; ++w) tot_inl += f.red_i[w];
+                f.h_eff = tot_inl;  // h_eff is free after the best selection: reuse as the broadcast slot
+                if (tot_inl >= 3) {
+                    double m[18];
+#pragma unroll
+                    for (int i = 0; i < 18; ++i) m[i] = f.bc_d[i];
+                    const double isw = 1.0 / m[0];
+                    const double mcp[3] = {m[1] * isw, m[2] * isw, m[3] * isw};  // centroids relative to the pivot
+                    const double map[3] = {m[4] * isw, m[5] * isw, m[6] * isw};
+                    const double mc[3] = {mcp[0] + (double)cp0.x, mcp[1] + (double)cp0.y, mcp[2] + (double)cp0.z};
+                    const double ma[3] = {map[0] + (double)ap0.x, map[1] + (double)ap0.y, map[2] + (double)ap0.z};
+                    double cov[9];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) cov[3 * r + c] = m[7 + 3 * r + c] - m[1 + r] * map[c];  // sum w c a^T - (sum w c)(mean a)^T
+                    const double gb = m[16] - (m[1] * mcp[0] + m[2] * mcp[1] + m[3] * mcp[2]);
+                    const double ga = m[17] - (m[4] * map[0] + m[5] * map[1] + m[6] * map[2]);
+                    double Rm[9];
+                    rotation_from_cov(cov, ga, gb, Rm);
+                    double sc = 1.0;
+                    if (a.prm.with_scale) sc = sqrt(gb / ga);  // transform.py:971-975
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        const double tr = mc[r] - sc * (Rm[3 * r] * ma[0] + Rm[3 * r + 1] * ma[1] + Rm[3 * r + 2] * ma[2]);
+                        f.pose[4 * r + 0] = (float)(sc * Rm[3 * r + 0]);
+                        f.pose[4 * r + 1] = (float)(sc * Rm[3 * r + 1]);
+                        f.pose[4 * r + 2] = (float)(sc * Rm[3 * r + 2]);
+                        f.pose[4 * r + 3] = (float)tr;
+                    }
+                    f.bc_d[19] = sc;
+                }
+            }
+        }
+        __syncthreads();
+        if (f.h_eff < 3) break;  // uniform across the block
         if (a.out.inlier_mask && it == iters - 1) {  // the inlier set used by the last refit
             slot = 0;
             for (int i = t; i < n; i += ST, ++slot)
                 if (inl_bits & (1u << slot)) a.out.inlier_mask[(size_t)b * RDPN_P + s.pix[i]] = 1;
         }
-        __syncthreads();
         out_scale = (float)f.bc_d[19];
+        if (it + 1 < iters) __syncthreads();  // next iteration overwrites the reduction scratch
     }
 
     // ---- outputs (+ translation sanity, gdrn_evaluator.py:293-296) ----
@@ -836,7 +873,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
                 f.pose[11] = a.t_net[3 * b + 2];
             }
         }
-        a.out.n_inliers[b] = f.n_best;
+        a.out.n_inliers[b] = nbest_r;
         a.out.status[b] = status;
         f.red_i[0] = status;
         if (a.out.best_h) a.out.best_h[b] = best;
@@ -846,7 +883,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
     if (t < 12) a.out.pose[(size_t)b * 12 + t] = f.pose[t];
     if (a.out.rows16 && t < 16)  // gather row: pose(12) | n_inliers | status | n_sel | best_h
         a.out.rows16[(size_t)b * 16 + t] =
-            t < 12 ? f.pose[t] : (t == 12 ? (float)f.n_best : (t == 13 ? (float)f.red_i[0] : (t == 14 ? (float)n : (float)best)));
+            t < 12 ? f.pose[t] : (t == 12 ? (float)nbest_r : (t == 13 ? (float)f.red_i[0] : (t == 14 ? (float)n : (float)best)));
 }
 
 // ---------------------------------------------------------------------------------------------
