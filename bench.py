@@ -449,22 +449,39 @@ def gpu_arm(args):
     ctx = ctypes.c_void_p()
     _lib.check(L.rdpn_ctx_create(local_rank, ctypes.byref(ctx)), "ctx_create")
     e2e_steps = max(3, min(args.steps, 30))
-    for _ in range(3):
+
+    def host_call():
         _lib.check(L.rdpn_pose_solve_host(ctx, ctypes.byref(inp), pin["hyp_idx"].data_ptr(), None, ctypes.byref(prm),
                                           ctypes.byref(outs)), "pose_solve_host")
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        _lib.check(L.rdpn_pose_solve_host(ctx, ctypes.byref(inp), pin["hyp_idx"].data_ptr(), None, ctypes.byref(prm),
-                                          ctypes.byref(outs)), "pose_solve_host")
-    e2e_s = time.perf_counter() - t0
+
+    def time_host_calls(transfer):
+        """(seconds for e2e_steps calls, bytes that crossed the bus per call, strategy used)"""
+        _lib.check(L.rdpn_ctx_set_option(ctx, _lib.OPT_TRANSFER, transfer), "set_option")
+        _lib.check(L.rdpn_ctx_set_option(ctx, _lib.OPT_COUNT_BYTES, 1), "set_option")
+        host_call()  # untimed: measures the bytes (copied tensors + sectors fetched by the gated pull)
+        nbytes = int(L.rdpn_ctx_last_h2d_bytes(ctx))
+        used = int(L.rdpn_ctx_last_transfer(ctx))
+        _lib.check(L.rdpn_ctx_set_option(ctx, _lib.OPT_COUNT_BYTES, 0), "set_option")
+        for _ in range(3):
+            host_call()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            host_call()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t)
+        return dt, nbytes, used
+
+    copy_s, copy_bytes, _ = time_host_calls(_lib.TRANSFER_COPY)
+    copy_pose = h_pose.clone()
+    e2e_s, h2d, e2e_used = time_host_calls(_lib.TRANSFER_AUTO)  # pinned buffers -> gated pull
+    transfers_identical = bool(torch.equal(copy_pose, h_pose))
     L.rdpn_ctx_destroy(ctx)
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t)
-    h2d = B * (BYTES_MAPS + H * 12 + R * 12 + 16 + 12)
+    host_input_bytes = B * (BYTES_MAPS + H * 12 + R * 12 + 16 + 12)
     d2h = B * (48 + 4 + 4)
     # sanity: the host path produced the same poses as the device path
     dev_pose = plans[0].launch().pose.reshape(B, 12)
@@ -529,8 +546,17 @@ def gpu_arm(args):
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
         "e2e": {"value": total * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": "rdpn_pose_solve_host (C ABI, pinned host buffers, chunked over 2 streams)",
+                "host_input_bytes_per_step": host_input_bytes, "steps": e2e_steps,
+                "transfer": "gated pull" if e2e_used == _lib.TRANSFER_PULL else "full copy",
+                "api": "rdpn_pose_solve_host (C ABI, every input and output in pinned host memory; 4-stage pipeline)",
+                "note": "h2d_bytes_per_step is MEASURED: the mask planes (copy engine) + the per-ROI arrays, hypothesis "
+                        "triplets and the 32-byte sectors of depth/coor/region-id planes that the pull kernel fetched over "
+                        "PCIe for pixel groups whose mask test passes; host_input_bytes_per_step is the size of all input "
+                        "tensors.  Results are bit-identical to the full copy (transfers_identical).",
                 "timer": "perf_counter around synchronous calls"},
+        "e2e_full_copy": {"value": total * e2e_steps / copy_s, "unit": UNIT, "h2d_bytes_per_step": copy_bytes,
+                          "d2h_bytes_per_step": d2h, "note": "same call with RDPN_TRANSFER_COPY: every input tensor copied"},
+        "transfers_identical": transfers_identical,
         "e2e_head_on_device": {"value": total * mixed_steps / mixed_s, "unit": UNIT,
                                "h2d_bytes_per_step": B * (16384 + H * 12 + 16 + 12), "d2h_bytes_per_step": B * 64,
                                "note": "supplementary: depth maps + per-ROI scalars + hypothesis triplets from pinned host memory, "

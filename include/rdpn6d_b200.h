@@ -223,13 +223,37 @@ int rdpn_roi_crop_depth(const float* d_depth_imgs, int H, int W, const int32_t* 
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer plugin call (what a CPU caller of the reference's evaluator binds): every pointer in
  * `in`, hyp_idx, t_net and `out` is a HOST pointer.  The context owns device scratch and streams;
- * ROIs are pipelined in chunks so host->device copies overlap the kernels.
+ * ROIs are pipelined in chunks over two streams so that transfers overlap the kernels.
+ *
+ * Transfer strategies (results are bit-identical):
+ *   RDPN_TRANSFER_COPY  every input tensor is copied host -> device by the copy engine.
+ *   RDPN_TRANSFER_PULL  "gated pull": only the mask plane (+ the small per-ROI arrays and the hypothesis
+ *                       triplets) is copied; a kernel evaluates the mask test of the gate
+ *                       (gdrn_evaluator.py:110-117, engine_utils.py:118-136) and reads depth / coor_x/y/z /
+ *                       region_idx straight from the caller's buffers over PCIe, only where a pixel can
+ *                       pass (typically 10-20 % of a ROI).  Needs depth, coor_*, region_idx in pinned or
+ *                       cudaHostRegister'ed memory, 16-byte aligned.
+ *   RDPN_TRANSFER_AUTO  (default) PULL when those buffers are device-mapped, else COPY.
  * ---------------------------------------------------------------------------------------------- */
+#define RDPN_TRANSFER_AUTO 0
+#define RDPN_TRANSFER_COPY 1
+#define RDPN_TRANSFER_PULL 2
+
+#define RDPN_OPT_TRANSFER 1          /* RDPN_TRANSFER_*                                                 */
+#define RDPN_OPT_PULL_GRANULARITY 2  /* 16-byte quads fetched together per plane: 1, 2, 4, 8 or 16      */
+#define RDPN_OPT_CHUNK_ROIS 3        /* ROIs per pipeline stage (1..1024, default 256)                  */
+#define RDPN_OPT_COUNT_BYTES 4       /* 1: measure the bytes that cross the bus (one 8-byte read-back)  */
+
 typedef struct rdpn_ctx rdpn_ctx;
 int rdpn_ctx_create(int device, rdpn_ctx** out_ctx);
 void rdpn_ctx_destroy(rdpn_ctx* ctx);
+int rdpn_ctx_set_option(rdpn_ctx* ctx, int key, int value);
 int rdpn_pose_solve_host(rdpn_ctx* ctx, const rdpn_roi_inputs* h_in, const int32_t* h_hyp_idx, const float* h_t_net,
                          const rdpn_solve_params* prm, const rdpn_solve_outputs* h_out);
+/* Host -> device bytes of the last rdpn_pose_solve_host call: copied tensors, plus the fetched sectors of
+ * the gated pull when RDPN_OPT_COUNT_BYTES is on.  rdpn_ctx_last_transfer: the strategy that call used. */
+unsigned long long rdpn_ctx_last_h2d_bytes(const rdpn_ctx* ctx);
+int rdpn_ctx_last_transfer(const rdpn_ctx* ctx);
 /* Number of kernel launches issued by this library in this process (bench.py's gpu_launches). */
 unsigned long long rdpn_launch_count(void);
 

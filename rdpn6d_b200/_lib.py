@@ -70,11 +70,18 @@ SIGNATURES = {
                                            ctypes.c_int, c_vp, ctypes.c_int, c_vp]),
     "rdpn_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(c_vp)]),
     "rdpn_ctx_destroy": (None, [c_vp]),
+    "rdpn_ctx_set_option": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int]),
+    "rdpn_ctx_last_h2d_bytes": (ctypes.c_ulonglong, [c_vp]),
+    "rdpn_ctx_last_transfer": (ctypes.c_int, [c_vp]),
     "rdpn_pose_solve_host": (ctypes.c_int, [c_vp, ctypes.POINTER(RoiInputs), c_vp, c_vp, ctypes.POINTER(SolveParams),
                                             ctypes.POINTER(SolveOutputs)]),
     "rdpn_launch_count": (ctypes.c_ulonglong, []),
     "rdpn_fp32_peak_probe": (ctypes.c_int, [ctypes.c_int, c_f64p]),
 }
+
+# rdpn_ctx_set_option keys / transfer strategies (include/rdpn6d_b200.h)
+TRANSFER_AUTO, TRANSFER_COPY, TRANSFER_PULL = 0, 1, 2
+OPT_TRANSFER, OPT_PULL_GRANULARITY, OPT_CHUNK_ROIS, OPT_COUNT_BYTES = 1, 2, 3, 4
 
 _lib = None
 

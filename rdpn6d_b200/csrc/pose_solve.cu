@@ -19,6 +19,7 @@
 //   refit    FP64 accumulation of centroids / cross-covariance over the inliers, Horn rotation,
 //            Umeyama scale (transform.py:921-928, 942-948, 971-979).
 #include "common.cuh"
+#include "gate.cuh"
 #include "kabsch_math.cuh"
 
 #include <float.h>
@@ -32,14 +33,6 @@ constexpr int ST = 256;              // threads per CTA
 constexpr int SW = ST / 32;          // warps
 constexpr int QPT = RDPN_P / 4 / ST;  // pixel quads per thread (4)
 
-struct RoiConst {
-    float fx, fy, cx, cy;
-    float ext[3];
-    float gthr[3];
-    float div;  // depth divisor or 0 (= none)
-    float mn, mx;
-};
-
 struct SolveArgs {
     rdpn_roi_inputs in;
     const int32_t* hyp_idx;
@@ -50,12 +43,6 @@ struct SolveArgs {
     double mask_cut;    // midpoint between mask_thr and its FP32 successor
     int mask_cut_incl;  // ties-to-even: 1 when the quotient may equal the midpoint
 };
-
-__device__ __forceinline__ float mask_prob(float m, int mode, float mn, float mx) {
-    if (mode == RDPN_MASK_L1) return __fdiv_rn(__fsub_rn(m, mn), __fsub_rn(mx, mn));
-    if (mode == RDPN_MASK_BCE) return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-m)));
-    return m;
-}
 
 // ---------------------------------------------------------------------------------------------
 // fused solver
@@ -75,13 +62,6 @@ __device__ __forceinline__ float mask_prob(float m, int mode, float mn, float mx
 //   6  SCORING: one thread per hypothesis; per run the transformed anchor R a + t is computed once
 //      (9 FMA) and every point costs 1 LDS.128 + 3 FADD + FMUL + 2 FFMA + FSETP + predicated IADD
 //   7  best hypothesis, FP64 refit sums, closed-form rotation, outputs
-struct RoiGate {
-    float hi, lo;     // fast mask filter: a > hi -> in, a < lo -> out, else exact test
-    double cut;       // exact: (double)a > / >= (double)b * cut
-    float b;          // max - min
-    int incl;         // 1: >= (odd mantissa of the threshold), 0: >
-};
-
 constexpr int CHUNK = 1024;  // gated slots staged in shared memory at a time (dense mode: CHUNK / 2)
 
 struct FinishSmem {  // scratch of the select + refit tail
@@ -149,20 +129,6 @@ __device__ __forceinline__ void gather_s1(const RoiPlanes& pl, const RoiConst& r
     const float w = weighted ? mask_prob(__ldg(pl.mask + p), mask_mode, rc.mn, rc.mx) : 1.f;
     camw = make_float4(cam[0], cam[1], cam[2], w);
     objv = make_float4(obj[0], obj[1], obj[2], 0.f);
-}
-
-// (mask_prob(m) > mask_thr) without the division for the L1 mode: fl(a/b) > thr  <=>  a/b > (>=) cut
-// where cut is the midpoint between thr and its FP32 successor (ties-to-even decides the inclusivity).
-__device__ __forceinline__ bool mask_pass(float m, int mode, float thr, const RoiConst& rc, const RoiGate& g) {
-    if (mode == RDPN_MASK_L1) {
-        if (!(g.b > 0.f)) return false;  // flat mask: 0/0 = NaN never passes (engine_utils.py:128 has no eps)
-        const float a = __fsub_rn(m, rc.mn);
-        if (a > g.hi) return true;
-        if (a < g.lo) return false;
-        const double l = (double)a, r = __dmul_rn((double)g.b, g.cut);
-        return g.incl ? (l >= r) : (l > r);  // NaN -> false
-    }
-    return mask_prob(m, mode, 0.f, 0.f) > thr;
 }
 
 __device__ __forceinline__ float resid2_pt(float tx, float ty, float tz, float cx, float cy, float cz) {
@@ -309,8 +275,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
 #pragma unroll
         for (int k = 0; k < QPT; ++k) {
             const float4 m4 = __ldg(reinterpret_cast<const float4*>(pl.mask) + 32 * (SW * k + warp) + lane);
-            mn = fminf(fminf(fminf(mn, m4.x), fminf(m4.y, m4.z)), m4.w);
-            mx = fmaxf(fmaxf(fmaxf(mx, m4.x), fmaxf(m4.y, m4.z)), m4.w);
+            minmax4(m4, mn, mx);
         }
         mn = warp_min(mn);
         mx = warp_max(mx);
@@ -323,14 +288,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
             for (int w = 1; w < SW; ++w) { lo = fminf(lo, s.red_f[0][w]); hi = fmaxf(hi, s.red_f[1][w]); }
             s.rc.mn = lo;
             s.rc.mx = hi;
-            RoiGate& g = s.gate;
-            g.b = __fsub_rn(hi, lo);
-            g.cut = a.mask_cut;
-            g.incl = a.mask_cut_incl;
-            const float bt = g.b * in.mask_thr;
-            const bool filt = in.mask_thr > 1e-30f && in.mask_thr < 1e30f;
-            g.hi = filt ? bt * 1.000002f : INFINITY;
-            g.lo = filt ? bt * 0.999998f : -INFINITY;
+            make_gate(s.gate, lo, hi, in.mask_thr, a.mask_cut, a.mask_cut_incl);
         }
         __syncthreads();
     }
@@ -365,7 +323,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
                 const float dy = __fmul_rn(__fsub_rn(cyn[j], 0.5f), rc.ext[1]);
                 const float dz = __fmul_rn(__fsub_rn(czn[j], 0.5f), rc.ext[2]);
                 bool sel = (fabsf(dx) > rc.gthr[0]) && (fabsf(dy) > rc.gthr[1]) && (fabsf(dz) > rc.gthr[2]) && (d > 0.f);
-                if (sel) sel = mask_pass(mm[j], in.mask_mode, in.mask_thr, rc, gate);
+                if (sel) sel = mask_pass(mm[j], in.mask_mode, in.mask_thr, rc.mn, gate);
                 nib |= (sel ? 1u : 0u) << j;
             }
             selbits |= nib << (4 * k);
@@ -1023,13 +981,7 @@ int rdpn_pose_solve(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, const f
     a.prm = *prm;
     a.out = *out;
     a.sq_cut = rdpn::host_sq_cut(prm->inlier_thr);
-    {
-        const float thr = in->mask_thr;
-        uint32_t bits;
-        memcpy(&bits, &thr, sizeof(bits));
-        a.mask_cut = 0.5 * ((double)thr + (double)nextafterf(thr, INFINITY));
-        a.mask_cut_incl = (int)(bits & 1u);
-    }
+    rdpn::host_mask_cut(in->mask_thr, &a.mask_cut, &a.mask_cut_incl);
     return dense ? rdpn::launch_solve<true>(a, (cudaStream_t)stream) : rdpn::launch_solve<false>(a, (cudaStream_t)stream);
 }
 

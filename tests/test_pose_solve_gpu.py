@@ -272,6 +272,101 @@ def test_host_buffer_plugin_call_matches_device_call(cuda):
     assert np.array_equal(imask, dev.inlier_mask.reshape(B, -1).cpu().numpy())
 
 
+def _host_call(L, ctx, t, B, H, R, mask_mode=1, dense=False, pinned_out=False):
+    """rdpn_pose_solve_host on a dict of (pinned or pageable) torch CPU tensors; returns numpy outputs."""
+    inp = _lib.RoiInputs(depth=t["depth"].data_ptr(), Kp=t["Kp"].data_ptr(), depth_div=None, coor_x=t["cx"].data_ptr(),
+                         coor_y=t["cy"].data_ptr(), coor_z=t["cz"].data_ptr(), mask=t["mask"].data_ptr(),
+                         extent=t["extent"].data_ptr(), region_idx=None if dense else t["region_idx"].data_ptr(),
+                         anchors=None if dense else t["anchors"].data_ptr(), num_regions=R, mask_mode=mask_mode,
+                         mask_thr=0.5, B=B)
+    prm = _lib.SolveParams(inlier_thr=THR, num_hyp=H, min_pts=4, min_inliers=4, weighted=0, refit_iters=1,
+                           with_scale=0, adaptive=0, confidence=0.995, min_iter=10)
+    o = {"pose": np.zeros((B, 12), np.float32), "ninl": np.zeros(B, np.int32), "status": np.zeros(B, np.int32),
+         "best": np.zeros(B, np.int32), "nsel": np.zeros(B, np.int32), "imask": np.zeros((B, 4096), np.uint8)}
+    keep = None
+    if pinned_out:  # mapped result buffers and no per-pixel diagnostics: the kernel writes them directly
+        keep = {k: torch.from_numpy(v).pin_memory() for k, v in o.items() if k != "imask"}
+        o = {k: v.numpy() for k, v in keep.items()}
+    out = _lib.SolveOutputs(pose=o["pose"].ctypes.data, n_inliers=o["ninl"].ctypes.data, status=o["status"].ctypes.data,
+                            best_h=o["best"].ctypes.data, n_sel=o["nsel"].ctypes.data,
+                            inlier_mask=None if pinned_out else o["imask"].ctypes.data)
+    _lib.check(L.rdpn_pose_solve_host(ctx, ctypes.byref(inp), t["hyp_idx"].data_ptr(), None, ctypes.byref(prm),
+                                      ctypes.byref(out)), "pose_solve_host")
+    return {k: v.copy() for k, v in o.items()}
+
+
+def _host_tensors(b, pinned):
+    t = {k: torch.from_numpy(np.ascontiguousarray(b[k])) for k in ("depth", "Kp", "mask", "extent", "region_idx", "anchors",
+                                                                   "hyp_idx") if b.get(k) is not None}
+    for c, name in enumerate(("cx", "cy", "cz")):
+        t[name] = torch.from_numpy(np.ascontiguousarray(b["coor"][:, c]))
+    return {k: v.pin_memory() for k, v in t.items()} if pinned else t
+
+
+@pytest.mark.parametrize("mask_mode", [1, 2, 0])
+def test_gated_pull_transfer_is_bit_identical_to_full_copy(cuda, mask_mode):
+    """Pinned host buffers: only the mask plane is copied, depth / coor / region ids are fetched over PCIe for
+    the pixel groups whose mask test passes.  Every output must equal the full-copy strategy bit for bit, for
+    every fetch granularity, and fewer bytes must cross the bus."""
+    L = _lib.lib()
+    B, H = 300, 64
+    b = synth.tile_batch(synth.make_batch(30, H=H, seed=11, occlusion_max=0.5), B)
+    if mask_mode == 2:  # logits: sigmoid(m) > 0.5 <=> m > 0
+        b["mask"] = ((b["mask"] - 0.5) * 8).astype(np.float32)
+    t = _host_tensors(b, pinned=True)
+    ctx = ctypes.c_void_p()
+    _lib.check(L.rdpn_ctx_create(0, ctypes.byref(ctx)), "ctx_create")
+    try:
+        _lib.check(L.rdpn_ctx_set_option(ctx, _lib.OPT_COUNT_BYTES, 1), "opt")
+        _lib.check(L.rdpn_ctx_set_option(ctx, _lib.OPT_CHUNK_ROIS, 128), "opt")
+        _lib.check(L.rdpn_ctx_set_option(ctx, _lib.OPT_TRANSFER, _lib.TRANSFER_COPY), "opt")
+        ref = _host_call(L, ctx, t, B, H, 32, mask_mode)
+        assert L.rdpn_ctx_last_transfer(ctx) == _lib.TRANSFER_COPY
+        full_bytes = L.rdpn_ctx_last_h2d_bytes(ctx)
+        assert full_bytes >= B * (5 * 16384 + 4096)
+        assert (ref["status"] == 0).mean() > 0.8
+        _lib.check(L.rdpn_ctx_set_option(ctx, _lib.OPT_TRANSFER, _lib.TRANSFER_AUTO), "opt")
+        for gran in (1, 2, 8, 16):
+            _lib.check(L.rdpn_ctx_set_option(ctx, _lib.OPT_PULL_GRANULARITY, gran), "opt")
+            got = _host_call(L, ctx, t, B, H, 32, mask_mode)
+            assert L.rdpn_ctx_last_transfer(ctx) == _lib.TRANSFER_PULL
+            for k in ref:
+                assert np.array_equal(got[k].view(np.uint8), ref[k].view(np.uint8)), (gran, k)
+            pulled = L.rdpn_ctx_last_h2d_bytes(ctx)
+            assert pulled < 0.75 * full_bytes, (gran, pulled, full_bytes)
+            direct = _host_call(L, ctx, t, B, H, 32, mask_mode, pinned_out=True)
+            for k in direct:
+                assert np.array_equal(direct[k].view(np.uint8), ref[k].view(np.uint8)), (gran, k, "direct")
+        # pageable buffers cannot be pulled: AUTO copies, an explicit PULL is refused
+        tp = _host_tensors(b, pinned=False)
+        got = _host_call(L, ctx, tp, B, H, 32, mask_mode)
+        assert L.rdpn_ctx_last_transfer(ctx) == _lib.TRANSFER_COPY
+        assert np.array_equal(got["pose"].view(np.uint32), ref["pose"].view(np.uint32))
+        _lib.check(L.rdpn_ctx_set_option(ctx, _lib.OPT_TRANSFER, _lib.TRANSFER_PULL), "opt")
+        with pytest.raises(RuntimeError):
+            _host_call(L, ctx, tp, B, H, 32, mask_mode)
+    finally:
+        L.rdpn_ctx_destroy(ctx)
+
+
+def test_gated_pull_dense_mode(cuda):
+    L = _lib.lib()
+    B, H = 64, 32
+    b = synth.make_batch(B, H=H, seed=5, dense=True)
+    t = _host_tensors(b, True)
+    ctx = ctypes.c_void_p()
+    _lib.check(L.rdpn_ctx_create(0, ctypes.byref(ctx)), "ctx_create")
+    try:
+        _lib.check(L.rdpn_ctx_set_option(ctx, _lib.OPT_TRANSFER, _lib.TRANSFER_COPY), "opt")
+        ref = _host_call(L, ctx, t, B, H, 0, 1, dense=True)
+        _lib.check(L.rdpn_ctx_set_option(ctx, _lib.OPT_TRANSFER, _lib.TRANSFER_PULL), "opt")
+        got = _host_call(L, ctx, t, B, H, 0, 1, dense=True)
+        for k in ref:
+            assert np.array_equal(got[k].view(np.uint8), ref[k].view(np.uint8)), k
+    finally:
+        L.rdpn_ctx_destroy(ctx)
+
+
 def test_cpu_tensors_are_rejected_loudly(cuda):
     b = synth.make_batch(2, H=8, seed=1)
     t = {k: (None if v is None else torch.from_numpy(v)) for k, v in b.items()}
