@@ -12,6 +12,9 @@ __device__ __forceinline__ float hi(u64 v) { return __uint_as_float((unsigned)(v
 __device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ void count_if_ltu(int& c, float d2, float cut) {  // d2 >= +0 or NaN: unsigned bit order == float order
+    asm("{\n.reg .pred p;\nsetp.lt.u32 p, %1, %2;\n@p add.s32 %0, %0, 1;\n}" : "+r"(c) : "r"(__float_as_uint(d2)), "r"(__float_as_uint(cut)));
+}
 __device__ __forceinline__ void count_if_lt(int& c, float d2, float cut) {
     asm("{\n.reg .pred p;\nsetp.lt.f32 p, %1, %2;\n@p add.s32 %0, %0, 1;\n}" : "+r"(c) : "f"(d2), "f"(cut));
 }
@@ -89,11 +92,13 @@ __global__ void __launch_bounds__(256, 4) k_score_packed(int* out, int iters, fl
                 const u64 xx = h ? X.y : X.x, yy = h ? Y.y : Y.x, zz = h ? Z.y : Z.x;
                 u64 d = sub2(Ax, xx), e = sub2(Ay, yy), f = sub2(Az, zz);
                 u64 s = fma2(f, f, fma2(e, e, mul2(d, d)));
-                if (MODE == 0) { count_if_lt(cA, lo(s), cut); count_if_lt(cA, hi(s), cut); }
+                if (MODE == 2) { count_if_ltu(cA, lo(s), cut); count_if_ltu(cA, hi(s), cut); }
+                else if (MODE == 0) { count_if_lt(cA, lo(s), cut); count_if_lt(cA, hi(s), cut); }
                 else { cA -= (int)(lo(s) < cut ? -1 : 0) ; int m0, m1; asm("set.lt.s32.f32 %0, %1, %2;" : "=r"(m0) : "f"(lo(s)), "f"(cut)); asm("set.lt.s32.f32 %0, %1, %2;" : "=r"(m1) : "f"(hi(s)), "f"(cut)); cA = cA - m0 - m1; }
                 d = sub2(Bx, xx); e = sub2(By, yy); f = sub2(Bz, zz);
                 s = fma2(f, f, fma2(e, e, mul2(d, d)));
-                if (MODE == 0) { count_if_lt(cB, lo(s), cut); count_if_lt(cB, hi(s), cut); }
+                if (MODE == 2) { count_if_ltu(cB, lo(s), cut); count_if_ltu(cB, hi(s), cut); }
+                else if (MODE == 0) { count_if_lt(cB, lo(s), cut); count_if_lt(cB, hi(s), cut); }
                 else { int m0, m1; asm("set.lt.s32.f32 %0, %1, %2;" : "=r"(m0) : "f"(lo(s)), "f"(cut)); asm("set.lt.s32.f32 %0, %1, %2;" : "=r"(m1) : "f"(hi(s)), "f"(cut)); cB = cB - m0 - m1; }
             }
         }
@@ -133,6 +138,9 @@ int main() {
            (ms * 1e-3) * p.clockRate * 1e3 / (pairs / 32 / (sms * 4)));
     ms = timeit([&] { k_score_packed<1><<<grid2, 256>>>((int*)out, it2, 0.01f); });
     printf("{\"probe\":\"score_packed_set_iadd3\",\"Gpairs_s\":%.1f,\"clk_per_warp_pair_per_smsp\":%.2f}\n", pairs / (ms * 1e-3) / 1e9,
+           (ms * 1e-3) * p.clockRate * 1e3 / (pairs / 32 / (sms * 4)));
+    ms = timeit([&] { k_score_packed<2><<<grid2, 256>>>((int*)out, it2, 0.01f); });
+    printf("{\"probe\":\"score_packed_isetp\",\"Gpairs_s\":%.1f,\"clk_per_warp_pair_per_smsp\":%.2f}\n", pairs / (ms * 1e-3) / 1e9,
            (ms * 1e-3) * p.clockRate * 1e3 / (pairs / 32 / (sms * 4)));
     return 0;
 }

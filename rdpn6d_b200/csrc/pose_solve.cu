@@ -29,6 +29,17 @@
 namespace rdpn {
 extern unsigned long long g_launch_count;
 
+// Optional per-phase cycle stamps (tuning builds only: RDPN_NVCC_EXTRA=-DRDPN_PHASE_CLOCKS, benchmarks/phase_clocks.py)
+#ifdef RDPN_PHASE_CLOCKS
+__device__ long long* g_phase_clk = nullptr;  // [B][16]
+#define PHASE_MARK(i)                                                                    \
+    do {                                                                                 \
+        if (threadIdx.x == 0 && g_phase_clk) g_phase_clk[(size_t)blockIdx.x * 16 + (i)] = clock64(); \
+    } while (0)
+#else
+#define PHASE_MARK(i) do { } while (0)
+#endif
+
 constexpr int ST = 256;              // threads per CTA
 constexpr int SW = ST / 32;          // warps
 constexpr int QPT = RDPN_P / 4 / ST;  // pixel quads per thread (4)
@@ -206,6 +217,10 @@ struct FusedLayout {  // byte offsets of the dynamic tail behind FusedSmem
 #ifndef RDPN_SCORE_PAIRS
 #define RDPN_SCORE_PAIRS 1
 #endif
+// the warp that runs the single-warp sections (bucket cursors, refit solve)
+#ifndef RDPN_SERIAL_WARP
+#define RDPN_SERIAL_WARP (SW - 1)
+#endif
 template <bool DENSE>
 __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveArgs a, FusedLayout lay) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -231,6 +246,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
     pl.mask = in.mask + po;
     pl.rid = DENSE ? nullptr : in.region_idx + po;
 
+    PHASE_MARK(0);
     // ---- 1: prefetch this ROI's planes into L2 (one 64-byte line per thread and plane), constants, zeroing
     {
         const int o = t * 16;  // 256 threads x 16 floats = one plane
@@ -293,38 +309,49 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
         __syncthreads();
     }
     const RoiConst rc = s.rc;
+    PHASE_MARK(1);
 
     // ---- 2: gate (gdrn_evaluator.py:110-117 + depth validity), no divisions ----
     unsigned selbits = 0u;
     {
         const RoiGate gate = s.gate;
+        // mask test first (the gate is a conjunction): ~85 % of the quads have no passing pixel and never touch the
+        // other four planes -- no L2 -> SM traffic and no arithmetic for them
+        unsigned mbits = 0u;
+#pragma unroll
+        for (int k = 0; k < QPT; ++k) {
+            const float4 m4 = __ldg(reinterpret_cast<const float4*>(pl.mask) + 32 * (SW * k + warp) + lane);
+            const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                mbits |= (mask_pass(mm[j], in.mask_mode, in.mask_thr, rc.mn, gate) ? 1u : 0u) << (4 * k + j);
+        }
 #pragma unroll 1
         for (int k = 0; k < QPT; ++k) {
             const int q = 32 * (SW * k + warp) + lane;
-            const float4 dq = __ldg(reinterpret_cast<const float4*>(pl.depth) + q);
-            const float4 xq = __ldg(reinterpret_cast<const float4*>(pl.cx) + q);
-            const float4 yq = __ldg(reinterpret_cast<const float4*>(pl.cy) + q);
-            const float4 zq = __ldg(reinterpret_cast<const float4*>(pl.cz) + q);
-            const float4 m4 = __ldg(reinterpret_cast<const float4*>(pl.mask) + q);
-            const float dd[4] = {dq.x, dq.y, dq.z, dq.w};
-            const float cxn[4] = {xq.x, xq.y, xq.z, xq.w};
-            const float cyn[4] = {yq.x, yq.y, yq.z, yq.w};
-            const float czn[4] = {zq.x, zq.y, zq.z, zq.w};
-            const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
-            unsigned nib = 0u;
+            unsigned nib = (mbits >> (4 * k)) & 0xFu;
+            if (nib) {
+                const float4 dq = __ldg(reinterpret_cast<const float4*>(pl.depth) + q);
+                const float4 xq = __ldg(reinterpret_cast<const float4*>(pl.cx) + q);
+                const float4 yq = __ldg(reinterpret_cast<const float4*>(pl.cy) + q);
+                const float4 zq = __ldg(reinterpret_cast<const float4*>(pl.cz) + q);
+                const float dd[4] = {dq.x, dq.y, dq.z, dq.w};
+                const float cxn[4] = {xq.x, xq.y, xq.z, xq.w};
+                const float cyn[4] = {yq.x, yq.y, yq.z, yq.w};
+                const float czn[4] = {zq.x, zq.y, zq.z, zq.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float d = dd[j];
-                if (rc.div != 0.f) {  // zero lanes would drag the warp through div.rn's slow path: 0 / f = +-0
-                    const float qd = __fdiv_rn(d == 0.f ? 1.f : d, rc.div);
-                    d = d == 0.f ? __fmul_rn(d, copysignf(1.f, rc.div)) : qd;
+                for (int j = 0; j < 4; ++j) {
+                    float d = dd[j];
+                    if (rc.div != 0.f) {  // zero lanes would drag the warp through div.rn's slow path: 0 / f = +-0
+                        const float qd = __fdiv_rn(d == 0.f ? 1.f : d, rc.div);
+                        d = d == 0.f ? __fmul_rn(d, copysignf(1.f, rc.div)) : qd;
+                    }
+                    const float dx = __fmul_rn(__fsub_rn(cxn[j], 0.5f), rc.ext[0]);
+                    const float dy = __fmul_rn(__fsub_rn(cyn[j], 0.5f), rc.ext[1]);
+                    const float dz = __fmul_rn(__fsub_rn(czn[j], 0.5f), rc.ext[2]);
+                    const bool sel = (fabsf(dx) > rc.gthr[0]) && (fabsf(dy) > rc.gthr[1]) && (fabsf(dz) > rc.gthr[2]) && (d > 0.f);
+                    if (!sel) nib &= ~(1u << j);
                 }
-                const float dx = __fmul_rn(__fsub_rn(cxn[j], 0.5f), rc.ext[0]);
-                const float dy = __fmul_rn(__fsub_rn(cyn[j], 0.5f), rc.ext[1]);
-                const float dz = __fmul_rn(__fsub_rn(czn[j], 0.5f), rc.ext[2]);
-                bool sel = (fabsf(dx) > rc.gthr[0]) && (fabsf(dy) > rc.gthr[1]) && (fabsf(dz) > rc.gthr[2]) && (d > 0.f);
-                if (sel) sel = mask_pass(mm[j], in.mask_mode, in.mask_thr, rc.mn, gate);
-                nib |= (sel ? 1u : 0u) << j;
             }
             selbits |= nib << (4 * k);
             // publish the gate bitmap (4 bits per quad, 8 quads per word)
@@ -336,6 +363,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
         }
     }
 
+    PHASE_MARK(2);
     // ---- 3: counting sort by region, deterministic order (warp, k, j, lane) ----
     // pass A: per-warp bucket histogram
     uint16_t* myrun = wrun + warp * RB;
@@ -356,8 +384,9 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
         }
     }
     __syncthreads();
-    // bucket starts, per-warp cursors and the run table: warp 0, RPL consecutive buckets per lane
-    if (warp == 0) {
+    PHASE_MARK(3);
+    // bucket starts, per-warp cursors and the run table: one warp, RPL consecutive buckets per lane
+    if (warp == RDPN_SERIAL_WARP) {
         const int RPL = (R + 31) / 32;
         int loc = 0, ne = 0;
         for (int u = 0; u < RPL; ++u) {
@@ -396,6 +425,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
         if (lane == 31) { s.n_sel = x; s.n_runs = kx; }
     }
     __syncthreads();
+    PHASE_MARK(4);
     // pass B: assign slots
 #pragma unroll 1
     for (int k = 0; k < QPT; ++k) {
@@ -425,6 +455,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
         }
     }
 
+    PHASE_MARK(5);
     // ---- 4: hypothesis generation (FP64 closed form), one hypothesis per thread, pixels gathered ----
     for (int h = t; h < H; h += ST) {
         const int32_t* ip = a.hyp_idx + ((size_t)b * H + h) * 3;
@@ -471,6 +502,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
     const unsigned bal0 = __ballot_sync(0xffffffffu, v0);
     if (lane == 0) f.red_i[warp] = __popc(bal0);
     __syncthreads();  // slots, run table, hypotheses, round-0 counts visible
+    PHASE_MARK(6);
     int nvalid = 0;
     {
         int base = 0, tot = 0;
@@ -520,14 +552,21 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
                 if (DENSE) obj_s[sl - c0] = ob;
             }
             __syncthreads();
+            PHASE_MARK(7);
             if (!DENSE && RDPN_SCORE_PAIRS) {
                 // anchor mode, TWO hypotheses per thread: every staged point (one LDS.128) and every run header is
                 // shared by both, which removes ~12 % of the scoring instructions (the loop is issue-bound)
+                // Segments are WARP-ALIGNED: W warps cover all pairs once, the SW / W groups of W warps split the runs
+                // between them (a warp straddling two segments would execute both halves one after the other and
+                // hold the whole CTA at the barrier for twice as long).
                 const int npairs = (nvalid + 1) >> 1;
-                const int S2 = (npairs >= ST || npairs == 0) ? 1 : (ST / npairs);
+                const int W = max(1, (npairs + 31) >> 5);
+                const bool wide = W >= SW;  // H > 512: every thread loops over several pairs, no run split
+                const int S2 = wide ? 1 : SW / W;
+                const int seg = wide ? 0 : warp / W;
+                const int j0 = wide ? t : (warp % W) * 32 + lane;
                 const bool whole = (c0 == 0 && c1 == n);
-                for (int item = t; item < npairs * S2; item += ST) {
-                    const int j = item % npairs, seg = item / npairs;
+                for (int j = j0; j < npairs && seg < S2; j += wide ? ST : npairs) {
                     const int hA = vlist[2 * j];
                     const bool hasB = 2 * j + 1 < nvalid;
                     const int hB = hasB ? vlist[2 * j + 1] : hA;
@@ -630,6 +669,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
         }
     }
     __syncthreads();
+    PHASE_MARK(8);
     // slot accessor of the refit: the staged chunk when everything fitted into one, else re-gathered
     const bool one_chunk = n <= CH;
     auto get_slot = [&](int i, float4& cp, float4& ap) {
@@ -692,6 +732,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
         }
     }
     const int best = best_r;
+    PHASE_MARK(9);
 
     // optional diagnostics
     if (a.out.hyp_counts)
@@ -751,7 +792,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
                 mom[17] += w * (a0 * a0 + a1 * a1 + a2 * a2);
             }
         }
-        // reduction: warp shuffles -> per-warp partials -> warp 0 (lane i sums value i) -> lane 0 solves.
+        // reduction: warp shuffles -> per-warp partials -> one warp (lane i sums value i) -> its lane 0 solves.
         // Only the solving thread needs the moments, so two barriers suffice.
         const int winl = warp_sum(__popc(inl_bits));
 #pragma unroll
@@ -761,7 +802,8 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
         }
         if (lane == 0) f.red_i[warp] = winl;
         __syncthreads();
-        if (warp == 0) {
+        PHASE_MARK(10);
+        if (warp == RDPN_SERIAL_WARP) {
             if (lane < 18) {
                 double acc = 0.0;
 #pragma unroll
@@ -817,6 +859,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
         if (it + 1 < iters) __syncthreads();  // next iteration overwrites the reduction scratch
     }
 
+    PHASE_MARK(11);
     // ---- outputs (+ translation sanity, gdrn_evaluator.py:293-296) ----
     if (t == 0) {
         int status = RDPN_STATUS_OK;
@@ -842,6 +885,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
     if (a.out.rows16 && t < 16)  // gather row: pose(12) | n_inliers | status | n_sel | best_h
         a.out.rows16[(size_t)b * 16 + t] =
             t < 12 ? f.pose[t] : (t == 12 ? (float)nbest_r : (t == 13 ? (float)f.red_i[0] : (t == 14 ? (float)n : (float)best)));
+    PHASE_MARK(12);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -965,6 +1009,12 @@ static int launch_solve(const SolveArgs& a, cudaStream_t st) {
 }  // namespace rdpn
 
 extern "C" {
+
+#ifdef RDPN_PHASE_CLOCKS
+int rdpn_debug_set_phase_clocks(long long* d_buf) {
+    return (int)cudaMemcpyToSymbol(rdpn::g_phase_clk, &d_buf, sizeof(d_buf));
+}
+#endif
 
 int rdpn_pose_solve(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, const float* d_t_net,
                     const rdpn_solve_params* prm, const rdpn_solve_outputs* out, void* stream) {
