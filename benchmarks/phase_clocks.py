@@ -37,3 +37,23 @@ lo, hi = int(0.15 * B), int(0.85 * B)
 out = {n: round(float(d[lo:hi, i].mean())) for i, n in enumerate(NAMES)}
 out["total_cycles_per_cta"] = round(float(tot[lo:hi].mean()))
 print(json.dumps(out, indent=1))
+# phase overlap per SM: how many resident CTAs are inside the scoring phase at the same time?
+import numpy as np
+cn = c.numpy()
+smid = cn[:, 15].astype(int)
+s0, s1 = cn[:, 7], cn[:, 8]      # scoring interval
+b0, b1 = cn[:, 0], cn[:, 12]     # CTA lifetime
+hist = np.zeros(8)
+res_hist = np.zeros(8)
+for sm in np.unique(smid):
+    idx = np.nonzero(smid == sm)[0]
+    t0, t1 = np.quantile(b0[idx], 0.2), np.quantile(b1[idx], 0.8)
+    ts = np.linspace(t0, t1, 400)
+    k = ((s0[idx][None, :] <= ts[:, None]) & (ts[:, None] < s1[idx][None, :])).sum(1)
+    r = ((b0[idx][None, :] <= ts[:, None]) & (ts[:, None] < b1[idx][None, :])).sum(1)
+    hist += np.bincount(np.minimum(k, 7), minlength=8)
+    res_hist += np.bincount(np.minimum(r, 7), minlength=8)
+print("CTAs resident per SM (time share):", (res_hist / res_hist.sum()).round(3).tolist())
+print("CTAs in the scoring phase per SM (time share):", (hist / hist.sum()).round(3).tolist())
+lt = (b1 - b0)[lo:hi]
+print("lifetime mean %.0f std %.0f min %.0f max %.0f" % (lt.mean(), lt.std(), lt.min(), lt.max()))

@@ -34,13 +34,23 @@ extern unsigned long long g_launch_count;
 __device__ long long* g_phase_clk = nullptr;  // [B][16]
 #define PHASE_MARK(i)                                                                    \
     do {                                                                                 \
-        if (threadIdx.x == 0 && g_phase_clk) g_phase_clk[(size_t)blockIdx.x * 16 + (i)] = clock64(); \
+        if (threadIdx.x == 0 && g_phase_clk) {                                           \
+            g_phase_clk[(size_t)blockIdx.x * 16 + (i)] = clock64();                      \
+            if ((i) == 0) {                                                              \
+                unsigned smid_;                                                          \
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid_));                       \
+                g_phase_clk[(size_t)blockIdx.x * 16 + 15] = smid_;                       \
+            }                                                                            \
+        }                                                                                \
     } while (0)
 #else
 #define PHASE_MARK(i) do { } while (0)
 #endif
 
-constexpr int ST = 256;              // threads per CTA
+#ifndef RDPN_SOLVE_THREADS
+#define RDPN_SOLVE_THREADS 256
+#endif
+constexpr int ST = RDPN_SOLVE_THREADS;  // threads per CTA (256; 128 works too: benchmarks show no gain)
 constexpr int SW = ST / 32;          // warps
 constexpr int QPT = RDPN_P / 4 / ST;  // pixel quads per thread (4)
 
@@ -73,7 +83,10 @@ struct SolveArgs {
 //   6  SCORING: one thread per hypothesis; per run the transformed anchor R a + t is computed once
 //      (9 FMA) and every point costs 1 LDS.128 + 3 FADD + FMUL + 2 FFMA + FSETP + predicated IADD
 //   7  best hypothesis, FP64 refit sums, closed-form rotation, outputs
-constexpr int CHUNK = 1024;  // gated slots staged in shared memory at a time (dense mode: CHUNK / 2)
+#ifndef RDPN_CHUNK_SLOTS
+#define RDPN_CHUNK_SLOTS 1024
+#endif
+constexpr int CHUNK = RDPN_CHUNK_SLOTS;  // gated slots staged in shared memory at a time (dense mode: CHUNK / 2)
 
 struct FinishSmem {  // scratch of the select + refit tail
     double red_d[SW][18];
@@ -249,12 +262,14 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
     PHASE_MARK(0);
     // ---- 1: prefetch this ROI's planes into L2 (one 64-byte line per thread and plane), constants, zeroing
     {
-        const int o = t * 16;  // 256 threads x 16 floats = one plane
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pl.mask + o));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pl.depth + o));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pl.cx + o));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pl.cy + o));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pl.cz + o));
+#pragma unroll
+        for (int o = t * 16; o < RDPN_P; o += ST * 16) {  // one 64-byte line per request
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pl.mask + o));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pl.depth + o));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pl.cx + o));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pl.cy + o));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pl.cz + o));
+        }
         if (!DENSE && t < 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(pl.rid + t * 64));
     }
     if (t == 0) {
@@ -282,7 +297,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
     for (int i = t; i < SW * RB; i += ST) wrun[i] = 0;
     if (a.out.inlier_mask) {  // zero-fill; inliers are scattered in after the last refit
         uint4* im = reinterpret_cast<uint4*>(a.out.inlier_mask + (size_t)b * RDPN_P);
-        im[t] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = t; i < RDPN_P / 16; i += ST) im[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     // mask min / max (engine_utils.py:123-124).  Thread owns quads q = 32*(SW*k + warp) + lane (k = 0..3):
     // every warp gets two image rows out of each 16, so the rows the object covers are spread over all warps.

@@ -32,9 +32,16 @@ def _to_cuda(b):
 
 def _solve(g, **kw):
     kw.setdefault("inlier_thr", THR)
-    solver = pose_solver.PoseSolver(want_inlier_mask=True, want_hyp=True, **kw)
-    return solver(g["depth"], g["Kp"], g["coor"][:, 0], g["coor"][:, 1], g["coor"][:, 2], g["mask"], g["extent"],
-                  g["hyp_idx"], region_idx=g.get("region_idx"), anchors=g.get("anchors"), t_net=g.get("t_net"))
+    args = (g["depth"], g["Kp"], g["coor"][:, 0], g["coor"][:, 1], g["coor"][:, 2], g["mask"], g["extent"], g["hyp_idx"])
+    kwargs = dict(region_idx=g.get("region_idx"), anchors=g.get("anchors"), t_net=g.get("t_net"))
+    res = pose_solver.PoseSolver(want_inlier_mask=True, want_hyp=True, **kw)(*args, **kwargs)
+    # The production call (no per-hypothesis diagnostics) must give bit-identical results to the diagnostic call.
+    fast = pose_solver.PoseSolver(want_inlier_mask=True, want_hyp=False, **kw)(*args, **kwargs)
+    assert torch.equal(fast.pose.view(torch.int32), res.pose.view(torch.int32))
+    assert torch.equal(fast.best_h, res.best_h) and torch.equal(fast.n_inliers, res.n_inliers)
+    assert torch.equal(fast.status, res.status) and torch.equal(fast.n_sel, res.n_sel)
+    assert torch.equal(fast.inlier_mask, res.inlier_mask)
+    return res
 
 
 def _compare(res, ores, b, check_counts=True):
