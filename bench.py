@@ -12,7 +12,10 @@ all-gathered over NCCL each step (pipelined behind the next step's kernel).
 
 One JSON line is printed by rank 0 (see the keys at the bottom).  `value` is device-resident
 throughput (inputs already in HBM), `e2e` is the same metric through the host-buffer C-ABI plugin call
-rdpn_pose_solve_host with pinned host buffers (H2D + kernel + D2H inside the timed region).
+rdpn_pose_solve_host with every input and output in pinned host memory (transfers + kernels + results inside the
+timed region).  With pinned buffers the library uses its gated-pull transfer: the mask planes are copied, depth /
+coor / region ids are fetched over PCIe only where the mask test passes; `e2e_full_copy` is the same call with every
+tensor copied, `h2d_bytes_per_step` is measured by the library.
 
 --impl reference times the CPU implementation of the same path (the oracle port of the reference's
 functions, oracle/pose_oracle.py + oracle/pose_oracle.c) on all host cores.
@@ -46,6 +49,25 @@ BYTES_MAPS = 5 * 16384 + 4096
 
 def bytes_per_roi(H, R):
     return BYTES_MAPS + H * 12 + R * 12 + 16 + 12 + 48 + 20
+
+
+def ncu_traffic_bytes(path=None):
+    """DRAM bytes (read + write) of ONE launch of the fused solver on this workload, from the committed
+    `ncu --set full` capture (profiles/r1/ncu_pose_solve_summary.csv); None when the summary is absent."""
+    import csv
+
+    path = path or os.path.join(ROOT, "profiles", "r1", "ncu_pose_solve_summary.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units, vals = rows[0], rows[1], rows[2]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(name)
+            tot += float(vals[i]) * scale[units[i]]
+        return tot
+    except Exception:
+        return None
 
 
 def workload_config(n_gpus):
@@ -490,28 +512,30 @@ def gpu_arm(args):
     host_matches_device = bool(torch.equal(dev_pose.cpu(), h_pose))
 
     # ---- supplementary: the deployment split of the reference -- the CNN head's outputs (coor, mask, region)
-    # are already on the GPU (models/GDRN.py:291-297); only the loader's depth maps, per-ROI scalars and the
-    # hypothesis triplets come from the host, and the [B,16] rows go back.  Public Python API.
+    # are already on the GPU (models/GDRN.py:291-297); only the loader's depth maps, per-ROI scalars, anchors and
+    # the hypothesis triplets sit in (pinned) host memory, and the results go back to pinned host tensors.  Same
+    # plugin call: it takes device pointers in place, buffer by buffer (rdpn6d_b200.pose_solver.HostPoseSolver).
     s0 = sets[0]
-    mixed_solver = pose_solver.PoseSolver(inlier_thr=INLIER_THR)
     d_cx, d_cy, d_cz = [s0["coor"][:, c].contiguous() for c in range(3)]
+    mixed = pose_solver.HostPoseSolver(device=local_rank, inlier_thr=INLIER_THR, count_bytes=True)
+    mixed_args = (pin["depth"], pin["Kp"], d_cx, d_cy, d_cz, s0["mask"], pin["extent"], pin["hyp_idx"], s0["region_idx"],
+                  pin["anchors"])
+    # pin[] holds the unrolled workload, set 0 on the device is the same data rolled by 0 ROIs
+    mixed_call = mixed.plan(*mixed_args)  # C structs built once, like the e2e leg above
+    mixed_res = mixed_call()
+    mixed_bytes = mixed.last_h2d_bytes
+    mixed.set_option(_lib.OPT_COUNT_BYTES, 0)
+    mixed_ok = bool(torch.equal(mixed_res.pose.reshape(B, 12), h_pose))
     mixed_steps = max(3, min(args.steps, 30))
-
-    def mixed_step():
-        depth_d = pin["depth"].to(dev, non_blocking=True)
-        kp_d = pin["Kp"].to(dev, non_blocking=True)
-        ext_d = pin["extent"].to(dev, non_blocking=True)
-        hyp_d = pin["hyp_idx"].to(dev, non_blocking=True)
-        r = mixed_solver(depth_d, kp_d, d_cx, d_cy, d_cz, s0["mask"], ext_d, hyp_d, s0["region_idx"], s0["anchors"])
-        return r.rows16().to("cpu", non_blocking=False)
-
     for _ in range(3):
-        mixed_step()
-    torch.cuda.synchronize()
+        mixed_call()
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     for _ in range(mixed_steps):
-        mixed_step()
+        mixed_call()
     mixed_s = time.perf_counter() - t0
+    mixed.close()
     if world > 1:
         t = torch.tensor([mixed_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -558,15 +582,18 @@ def gpu_arm(args):
                           "d2h_bytes_per_step": d2h, "note": "same call with RDPN_TRANSFER_COPY: every input tensor copied"},
         "transfers_identical": transfers_identical,
         "e2e_head_on_device": {"value": total * mixed_steps / mixed_s, "unit": UNIT,
-                               "h2d_bytes_per_step": B * (16384 + H * 12 + 16 + 12), "d2h_bytes_per_step": B * 64,
-                               "note": "supplementary: depth maps + per-ROI scalars + hypothesis triplets from pinned host memory, "
-                                       "CNN-head outputs (coor/mask/region) already device-resident as in the reference's flow; "
-                                       "rdpn6d_b200.pose_solver.PoseSolver + rows16().cpu()"},
+                               "h2d_bytes_per_step": mixed_bytes, "d2h_bytes_per_step": d2h, "matches_e2e": mixed_ok,
+                               "note": "supplementary, the reference's deployment split: CNN-head outputs (coor / mask / region ids) "
+                                       "already device-resident and used in place; depth maps, per-ROI scalars, anchors and hypothesis "
+                                       "triplets in pinned host memory (depth fetched only where the mask passes); results to pinned "
+                                       "host tensors.  Same rdpn_pose_solve_host call via rdpn6d_b200.pose_solver.HostPoseSolver."},
         "host_path_matches_device_path": host_matches_device,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": None, "kernel": "rdpn::pose_solve_kernel<false>", "kernel_ms": kernel_ms,
+                     "traffic": ncu_traffic_bytes(), "traffic_source": "profiles/r1/ncu_pose_solve_summary.csv (ncu --set full, "
+                     "dram__bytes_read.sum + dram__bytes_write.sum of one launch of this workload)",
+                     "kernel": "rdpn::pose_solve_kernel<false>", "kernel_ms": kernel_ms,
                      "kernel_ms_note": "average duration of back-to-back launches on ONE stream (no overlap)",
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                      "note": "the fused solver is FP32-pipe bound (3x4 transforms x hypotheses x points), see fp32"},

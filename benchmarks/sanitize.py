@@ -28,6 +28,22 @@ def main():
         for opts in (dict(), dict(weighted=True, refit_iters=2, adaptive=True)):
             pose_solver.pose_solve(g["depth"], g["Kp"], g["coor"][:, 0], g["coor"][:, 1], g["coor"][:, 2], g["mask"], g["extent"],
                                    g["hyp_idx"], g["region_idx"], g["anchors"], want_inlier_mask=True, want_hyp=True, **opts)
+    # host-buffer plugin call: gated pull (pinned) and full copy (pageable)
+    b = synth.make_batch(6, H=32, seed=12)
+    for pinned in (True, False):
+        t = {k: (None if v is None else (torch.from_numpy(np.ascontiguousarray(v)).pin_memory() if pinned else
+                                         torch.from_numpy(np.ascontiguousarray(v)))) for k, v in b.items()}
+        cx, cy, cz = [t["coor"][:, c].contiguous() for c in range(3)]
+        if pinned:
+            cx, cy, cz = cx.pin_memory(), cy.pin_memory(), cz.pin_memory()
+        hs = pose_solver.HostPoseSolver(inlier_thr=0.005, chunk_rois=4, count_bytes=True)
+        hs(t["depth"], t["Kp"], cx, cy, cz, t["mask"], t["extent"], t["hyp_idx"], t["region_idx"], t["anchors"])
+        hs.close()
+    # correspondence features / region targets
+    geometry.coor_feat(torch.rand(2, 1, 64, 64, device="cuda"), torch.rand(2, 1, 64, 64, device="cuda"), torch.rand(2, 1, 64, 64, device="cuda"),
+                       torch.randn(2, 5, 64, 64, device="cuda"), torch.randn(2, 33, 64, 64, device="cuda"), torch.randn(2, 32, 3, device="cuda"),
+                       torch.randn(2, 1, 64, 64, device="cuda"))
+    geometry.xyz_to_region(torch.randn(2, 64, 64, 3, device="cuda"), torch.randn(2, 32, 3, device="cuda"))
     # geometry
     geometry.kabsch(torch.randn(3, 100, 3, device="cuda"), torch.randn(3, 100, 3, device="cuda"))
     geometry.region_argmax(torch.randn(2, 33, 64, 64, device="cuda"))

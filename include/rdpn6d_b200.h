@@ -221,9 +221,11 @@ int rdpn_roi_crop_depth(const float* d_depth_imgs, int H, int W, const int32_t* 
                         const float* d_scale, int crop_res, int out_res, float* d_out, int B, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Host-buffer plugin call (what a CPU caller of the reference's evaluator binds): every pointer in
- * `in`, hyp_idx, t_net and `out` is a HOST pointer.  The context owns device scratch and streams;
- * ROIs are pipelined in chunks over two streams so that transfers overlap the kernels.
+ * Host-buffer plugin call (what a CPU caller of the reference's evaluator binds): the pointers in `in`,
+ * hyp_idx, t_net and `out` may be HOST pointers -- or, buffer by buffer, device pointers, which are then used
+ * in place (the deployment split of the reference: head outputs already on the GPU, models/GDRN.py:291-297,
+ * loader tensors on the host, data_loader.py:417-421).  Synchronous.  The context owns device scratch and
+ * streams; ROIs are pipelined in chunks over four stages so that transfers overlap the kernels.
  *
  * Transfer strategies (results are bit-identical):
  *   RDPN_TRANSFER_COPY  every input tensor is copied host -> device by the copy engine.
@@ -233,7 +235,8 @@ int rdpn_roi_crop_depth(const float* d_depth_imgs, int H, int W, const int32_t* 
  *                       region_idx straight from the caller's buffers over PCIe, only where a pixel can
  *                       pass (typically 10-20 % of a ROI).  Needs depth, coor_*, region_idx in pinned or
  *                       cudaHostRegister'ed memory, 16-byte aligned.
- *   RDPN_TRANSFER_AUTO  (default) PULL when those buffers are device-mapped, else COPY.
+ *   RDPN_TRANSFER_AUTO  (default) decided per buffer: device memory in place, pinned memory pulled (results:
+ *                       written by the kernel directly), pageable memory copied.
  * ---------------------------------------------------------------------------------------------- */
 #define RDPN_TRANSFER_AUTO 0
 #define RDPN_TRANSFER_COPY 1

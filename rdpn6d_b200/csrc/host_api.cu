@@ -107,33 +107,45 @@ __global__ void __launch_bounds__(256) pull_gated_kernel(PullArgs a) {
 #pragma unroll
     for (int k = 0; k < QPT; ++k) {
         const int q = 32 * (SW * k + warp) + lane;
-        if (need[k]) {
-            dq[k] = __ldcs(reinterpret_cast<const float4*>(a.h_depth + po) + q);
-            xq[k] = __ldcs(reinterpret_cast<const float4*>(a.h_cx + po) + q);
-            yq[k] = __ldcs(reinterpret_cast<const float4*>(a.h_cy + po) + q);
-            zq[k] = __ldcs(reinterpret_cast<const float4*>(a.h_cz + po) + q);
+        if (need[k]) {  // each plane is optional: planes that already live on the device are used in place
+            if (a.h_depth) dq[k] = __ldcs(reinterpret_cast<const float4*>(a.h_depth + po) + q);
+            if (a.h_cx) xq[k] = __ldcs(reinterpret_cast<const float4*>(a.h_cx + po) + q);
+            if (a.h_cy) yq[k] = __ldcs(reinterpret_cast<const float4*>(a.h_cy + po) + q);
+            if (a.h_cz) zq[k] = __ldcs(reinterpret_cast<const float4*>(a.h_cz + po) + q);
             if (a.h_rid) rq[k] = __ldcs(reinterpret_cast<const uchar4*>(a.h_rid + po) + q);
         }
     }
-    if (a.h_hyp) {  // hypothesis triplets, anchors and scalars ride along while the plane requests are in flight
+    // hypothesis triplets, anchors and scalars ride along while the plane requests are in flight (each optional)
+    if (a.h_hyp) {
         const int32_t* hs = a.h_hyp + (size_t)b * a.H3;
         int32_t* hd = a.d_hyp + (size_t)b * a.H3;
-        for (int i = t; i < a.H3; i += 256) hd[i] = __ldcs(hs + i);
-        if (a.h_anchors)
-            for (int i = t; i < a.R3; i += 256) a.d_anchors[(size_t)b * a.R3 + i] = __ldcs(a.h_anchors + (size_t)b * a.R3 + i);
-        if (t < 4) a.d_kp[4 * b + t] = __ldcs(a.h_kp + 4 * b + t);
-        else if (t < 7) a.d_ext[3 * b + t - 4] = __ldcs(a.h_ext + 3 * b + t - 4);
-        else if (t < 10) { if (a.h_tnet) a.d_tnet[3 * b + t - 7] = __ldcs(a.h_tnet + 3 * b + t - 7); }
-        else if (t == 10) { if (a.h_div) a.d_div[b] = __ldcs(a.h_div + b); }
+        if (((a.H3 & 3) | (int)(((uintptr_t)hs | (uintptr_t)hd) & 15)) == 0) {  // 16 bytes per request
+            for (int i = t; i < a.H3 / 4; i += 256) reinterpret_cast<int4*>(hd)[i] = __ldcs(reinterpret_cast<const int4*>(hs) + i);
+        } else {
+            for (int i = t; i < a.H3; i += 256) hd[i] = __ldcs(hs + i);
+        }
     }
+    if (a.h_anchors) {
+        const float* as = a.h_anchors + (size_t)b * a.R3;
+        float* ad = a.d_anchors + (size_t)b * a.R3;
+        if (((a.R3 & 3) | (int)(((uintptr_t)as | (uintptr_t)ad) & 15)) == 0) {
+            for (int i = t; i < a.R3 / 4; i += 256) reinterpret_cast<float4*>(ad)[i] = __ldcs(reinterpret_cast<const float4*>(as) + i);
+        } else {
+            for (int i = t; i < a.R3; i += 256) ad[i] = __ldcs(as + i);
+        }
+    }
+    if (t < 4) { if (a.h_kp) a.d_kp[4 * b + t] = __ldcs(a.h_kp + 4 * b + t); }
+    else if (t < 7) { if (a.h_ext) a.d_ext[3 * b + t - 4] = __ldcs(a.h_ext + 3 * b + t - 4); }
+    else if (t < 10) { if (a.h_tnet) a.d_tnet[3 * b + t - 7] = __ldcs(a.h_tnet + 3 * b + t - 7); }
+    else if (t == 10) { if (a.h_div) a.d_div[b] = __ldcs(a.h_div + b); }
 #pragma unroll
     for (int k = 0; k < QPT; ++k) {
         const int q = 32 * (SW * k + warp) + lane;
         if (need[k]) {
-            reinterpret_cast<float4*>(a.d_depth + po)[q] = dq[k];
-            reinterpret_cast<float4*>(a.d_cx + po)[q] = xq[k];
-            reinterpret_cast<float4*>(a.d_cy + po)[q] = yq[k];
-            reinterpret_cast<float4*>(a.d_cz + po)[q] = zq[k];
+            if (a.h_depth) reinterpret_cast<float4*>(a.d_depth + po)[q] = dq[k];
+            if (a.h_cx) reinterpret_cast<float4*>(a.d_cx + po)[q] = xq[k];
+            if (a.h_cy) reinterpret_cast<float4*>(a.d_cy + po)[q] = yq[k];
+            if (a.h_cz) reinterpret_cast<float4*>(a.d_cz + po)[q] = zq[k];
             if (a.h_rid) reinterpret_cast<uchar4*>(a.d_rid + po)[q] = rq[k];
         }
     }
@@ -163,21 +175,37 @@ static int launch_pull(const PullArgs& a, int nb, int gran, cudaStream_t st) {
     return 0;
 }
 
-// pinned / registered host memory is addressable from the device under UVA
-static bool device_can_read_host(const void* p) {
-    if (!p) return true;
+// Where a caller's buffer lives decides how it reaches the solver.
+enum Loc { LOC_NULL = 0, LOC_DEVICE, LOC_MAPPED, LOC_PAGEABLE };
+enum Move { MOVE_NONE = 0, MOVE_IN_PLACE, MOVE_PULL, MOVE_COPY };
+struct Buf {
+    const void* host;  // the caller's pointer
+    const void* dev;   // device-usable address (device memory, or pinned / registered host memory under UVA)
+    Loc loc;
+    Move move;
+};
+static Buf classify(const void* p) {
+    Buf b = {p, nullptr, LOC_NULL, MOVE_NONE};
+    if (!p) return b;
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
         cudaGetLastError();
-        return false;
+        b.loc = LOC_PAGEABLE;
+    } else if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) {
+        b.loc = LOC_DEVICE;
+        b.dev = at.devicePointer ? at.devicePointer : p;
+    } else if (at.type == cudaMemoryTypeHost && at.devicePointer) {
+        b.loc = LOC_MAPPED;
+        b.dev = at.devicePointer;
+    } else {
+        b.loc = LOC_PAGEABLE;
     }
-    return at.type == cudaMemoryTypeHost && at.devicePointer != nullptr;
+    return b;
 }
-static const void* device_view(const void* p) {
-    if (!p) return nullptr;
-    cudaPointerAttributes at;
-    cudaPointerGetAttributes(&at, p);
-    return at.devicePointer;
+static void plan(Buf& b, bool may_pull) {
+    b.move = b.loc == LOC_NULL ? MOVE_NONE
+             : b.loc == LOC_DEVICE ? MOVE_IN_PLACE
+             : (b.loc == LOC_MAPPED && may_pull) ? MOVE_PULL : MOVE_COPY;
 }
 }  // namespace rdpn
 
@@ -319,6 +347,7 @@ static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 int rdpn_pose_solve_host(rdpn_ctx* c, const rdpn_roi_inputs* h, const int32_t* h_hyp, const float* h_tnet,
                          const rdpn_solve_params* prm, const rdpn_solve_outputs* ho) {
+    using namespace rdpn;
     if (!c || !h || !h_hyp || !prm || !ho || h->B <= 0 || prm->num_hyp <= 0) return RDPN_E_BADARG;
     if (!ho->pose || !ho->n_inliers || !ho->status) return RDPN_E_BADARG;
     if (!h->depth || !h->coor_x || !h->coor_y || !h->coor_z || !h->mask || !h->Kp || !h->extent) return RDPN_E_BADARG;
@@ -327,15 +356,32 @@ int rdpn_pose_solve_host(rdpn_ctx* c, const rdpn_roi_inputs* h, const int32_t* h
     const bool dense = h->region_idx == nullptr;
     const int H = prm->num_hyp, R = dense ? 0 : h->num_regions;
     const size_t P = RDPN_P, CH = (size_t)c->chunk;
-    // transfer strategy: gated pull needs the big planes in device-mapped (pinned / registered) host memory
-    const bool mapped = rdpn::device_can_read_host(h->depth) && rdpn::device_can_read_host(h->coor_x) &&
-                        rdpn::device_can_read_host(h->coor_y) && rdpn::device_can_read_host(h->coor_z) &&
-                        rdpn::device_can_read_host(h->region_idx);
-    if (c->transfer == RDPN_TRANSFER_PULL && !mapped) return RDPN_E_BADARG;
-    const bool pull = c->transfer == RDPN_TRANSFER_PULL || (c->transfer == RDPN_TRANSFER_AUTO && mapped);
-    const bool aligned = !(((uintptr_t)h->depth | (uintptr_t)h->coor_x | (uintptr_t)h->coor_y | (uintptr_t)h->coor_z |
-                            (uintptr_t)h->region_idx) & 15);
-    if (pull && !aligned) return RDPN_E_ALIGN;
+    const bool may_pull = c->transfer != RDPN_TRANSFER_COPY;
+
+    // every buffer is classified on its own: device memory is used in place, pinned memory is pulled (planes: only
+    // where the mask passes) or written directly (results), pageable memory goes through the stage buffers
+    enum { I_DEPTH, I_CX, I_CY, I_CZ, I_RID, I_MASK, I_ANC, I_KP, I_EXT, I_DIV, I_HYP, I_TNET, NIN };
+    Buf in[NIN] = {classify(h->depth), classify(h->coor_x), classify(h->coor_y), classify(h->coor_z),
+                   classify(h->region_idx), classify(h->mask), classify(h->anchors), classify(h->Kp),
+                   classify(h->extent), classify(h->depth_div), classify(h_hyp), classify(h_tnet)};
+    for (int i = 0; i < NIN; ++i) plan(in[i], may_pull);
+    if (in[I_MASK].move == MOVE_PULL) in[I_MASK].move = MOVE_COPY;  // the whole mask plane is needed (min / max)
+    bool any_pull = false, pull_planes = false;
+    for (int i = 0; i < NIN; ++i) any_pull = any_pull || in[i].move == MOVE_PULL;
+    for (int i = I_DEPTH; i <= I_RID; ++i) {
+        pull_planes = pull_planes || in[i].move == MOVE_PULL;
+        if (c->transfer == RDPN_TRANSFER_PULL && in[i].loc == LOC_PAGEABLE) return RDPN_E_BADARG;
+        if (in[i].move != MOVE_COPY && ((uintptr_t)in[i].dev & 15)) return RDPN_E_ALIGN;
+    }
+    enum { O_POSE, O_NINL, O_STAT, O_BEST, O_NSEL, O_SCALE, O_IMASK, O_HCNT, O_HPOSE, NOUT };
+    Buf out[NOUT] = {classify(ho->pose), classify(ho->n_inliers), classify(ho->status), classify(ho->best_h),
+                     classify(ho->n_sel), classify(ho->scale), classify(ho->inlier_mask), classify(ho->hyp_counts),
+                     classify(ho->hyp_poses)};
+    for (int i = 0; i < NOUT; ++i) {
+        plan(out[i], may_pull && i <= O_SCALE);  // MOVE_PULL on an output = the kernel writes it directly
+        if (i == O_IMASK && out[i].move == MOVE_IN_PLACE && ((uintptr_t)out[i].dev & 15)) return RDPN_E_ALIGN;
+    }
+
     // device layout of one stage
     size_t off = 0;
     const size_t o_depth = off; off += al256(CH * P * 4);
@@ -368,140 +414,112 @@ int rdpn_pose_solve_host(rdpn_ctx* c, const rdpn_roi_inputs* h, const int32_t* h
         }
         c->buf_bytes = off;
     }
+    const size_t in_off[NIN] = {o_depth, o_cx, o_cy, o_cz, o_rid, o_mask, o_anc, o_kp, o_ext, o_div, o_hyp, o_tnet};
+    const size_t in_roi_bytes[NIN] = {P * 4, P * 4, P * 4, P * 4, P, P * 4, (size_t)R * 12, 16, 12, 4, (size_t)H * 12, 12};
+    const size_t out_off[NOUT] = {o_pose, o_ninl, o_stat, o_best, o_nsel, o_scale, o_imask, o_hcnt, o_hpose};
+    const size_t out_roi_bytes[NOUT] = {48, 4, 4, 4, 4, 4, P, (size_t)H * 4, (size_t)H * 48};
+
     const int B = h->B;
     int rc = 0;
-    unsigned long long copied = 0;
-    const float* hv_depth = pull ? (const float*)rdpn::device_view(h->depth) : nullptr;
-    const float* hv_cx = pull ? (const float*)rdpn::device_view(h->coor_x) : nullptr;
-    const float* hv_cy = pull ? (const float*)rdpn::device_view(h->coor_y) : nullptr;
-    const float* hv_cz = pull ? (const float*)rdpn::device_view(h->coor_z) : nullptr;
-    const uint8_t* hv_rid = pull && !dense ? (const uint8_t*)rdpn::device_view(h->region_idx) : nullptr;
-    // the small per-ROI arrays ride along in the pull kernel when they are mapped too (saves 6 copies per chunk)
-    const bool pull_small = pull && rdpn::device_can_read_host(h_hyp) && rdpn::device_can_read_host(h->anchors) &&
-                            rdpn::device_can_read_host(h->Kp) && rdpn::device_can_read_host(h->extent) &&
-                            rdpn::device_can_read_host(h->depth_div) && rdpn::device_can_read_host(h_tnet);
-    const int32_t* hv_hyp = pull_small ? (const int32_t*)rdpn::device_view(h_hyp) : nullptr;
-    const float* hv_anc = pull_small ? (const float*)rdpn::device_view(h->anchors) : nullptr;
-    const float* hv_kp = pull_small ? (const float*)rdpn::device_view(h->Kp) : nullptr;
-    const float* hv_ext = pull_small ? (const float*)rdpn::device_view(h->extent) : nullptr;
-    const float* hv_div = pull_small ? (const float*)rdpn::device_view(h->depth_div) : nullptr;
-    const float* hv_tnet = pull_small ? (const float*)rdpn::device_view(h_tnet) : nullptr;
-    // results are written straight into the caller's buffers when those are mapped (no device -> host copies)
-    const bool direct_out = pull && rdpn::device_can_read_host(ho->pose) && rdpn::device_can_read_host(ho->n_inliers) &&
-                            rdpn::device_can_read_host(ho->status) && rdpn::device_can_read_host(ho->best_h) &&
-                            rdpn::device_can_read_host(ho->n_sel) && rdpn::device_can_read_host(ho->scale) &&
-                            !ho->inlier_mask && !ho->hyp_counts && !ho->hyp_poses;
+    unsigned long long moved = 0;
     for (int b0 = 0, stage = 0; b0 < B && rc == 0; b0 += c->chunk, stage = (stage + 1) % RDPN_STAGES) {
         const size_t nb = (size_t)((B - b0) < c->chunk ? (B - b0) : c->chunk);
         cudaStream_t st = c->st[stage];
         unsigned char* d = c->buf[stage];
-        const size_t po = (size_t)b0 * P;
-#define H2D(dst_off, src, bytes)                                                                           \
-    do {                                                                                                   \
-        RDPN_CUDA_TRY(cudaMemcpyAsync(d + (dst_off), (src), (bytes), cudaMemcpyHostToDevice, st));         \
-        copied += (bytes);                                                                                 \
-    } while (0)
-        H2D(o_mask, h->mask + po, nb * P * 4);
-        if (!pull) {
-            H2D(o_depth, h->depth + po, nb * P * 4);
-            H2D(o_cx, h->coor_x + po, nb * P * 4);
-            H2D(o_cy, h->coor_y + po, nb * P * 4);
-            H2D(o_cz, h->coor_z + po, nb * P * 4);
-            if (!dense) H2D(o_rid, h->region_idx + po, nb * P);
+        // where the solver finds input i of this chunk, and the copies
+        const void* src[NIN];
+        for (int i = 0; i < NIN; ++i) {
+            const size_t skip = (size_t)b0 * in_roi_bytes[i];
+            if (in[i].move == MOVE_IN_PLACE) {
+                src[i] = (const unsigned char*)in[i].dev + skip;
+            } else if (in[i].move == MOVE_NONE) {
+                src[i] = nullptr;
+            } else {
+                src[i] = d + in_off[i];
+                if (in[i].move == MOVE_COPY) {
+                    RDPN_CUDA_TRY(cudaMemcpyAsync(d + in_off[i], (const unsigned char*)in[i].host + skip, nb * in_roi_bytes[i],
+                                                  cudaMemcpyHostToDevice, st));
+                    moved += nb * in_roi_bytes[i];
+                } else if (i > I_RID) {
+                    moved += nb * in_roi_bytes[i];  // small array fetched whole by the pull kernel
+                }
+            }
         }
-        if (!pull_small) {
-            if (!dense) H2D(o_anc, h->anchors + (size_t)b0 * R * 3, nb * R * 12);
-            H2D(o_kp, h->Kp + (size_t)b0 * 4, nb * 16);
-            H2D(o_ext, h->extent + (size_t)b0 * 3, nb * 12);
-            if (h->depth_div) H2D(o_div, h->depth_div + b0, nb * 4);
-            H2D(o_hyp, h_hyp + (size_t)b0 * H * 3, nb * H * 12);
-            if (h_tnet) H2D(o_tnet, h_tnet + (size_t)b0 * 3, nb * 12);
-        } else {
-            copied += nb * ((size_t)R * 12 + 16 + 12 + (h->depth_div ? 4 : 0) + (size_t)H * 12 + (h_tnet ? 12 : 0));
-        }
-#undef H2D
-        if (pull) {
-            rdpn::PullArgs pa;
-            pa.d_mask = (const float*)(d + o_mask);
-            pa.h_depth = hv_depth + po;
-            pa.h_cx = hv_cx + po;
-            pa.h_cy = hv_cy + po;
-            pa.h_cz = hv_cz + po;
-            pa.h_rid = dense ? nullptr : hv_rid + po;
+        if (any_pull) {
+            PullArgs pa;
+            memset(&pa, 0, sizeof(pa));
+            auto hsrc = [&](int i) -> const void* {
+                return in[i].move == MOVE_PULL ? (const unsigned char*)in[i].dev + (size_t)b0 * in_roi_bytes[i] : nullptr;
+            };
+            pa.d_mask = (const float*)src[I_MASK];
+            pa.h_depth = (const float*)hsrc(I_DEPTH);
+            pa.h_cx = (const float*)hsrc(I_CX);
+            pa.h_cy = (const float*)hsrc(I_CY);
+            pa.h_cz = (const float*)hsrc(I_CZ);
+            pa.h_rid = (const uint8_t*)hsrc(I_RID);
             pa.d_depth = (float*)(d + o_depth);
             pa.d_cx = (float*)(d + o_cx);
             pa.d_cy = (float*)(d + o_cy);
             pa.d_cz = (float*)(d + o_cz);
             pa.d_rid = (uint8_t*)(d + o_rid);
-            pa.pulled_quads = c->count ? c->d_pulled : nullptr;
-            memset(&pa.h_hyp, 0, (char*)&pa.H3 - (char*)&pa.h_hyp);
-            if (pull_small) {
-                pa.h_hyp = hv_hyp + (size_t)b0 * H * 3;
-                pa.h_anchors = dense ? nullptr : hv_anc + (size_t)b0 * R * 3;
-                pa.h_kp = hv_kp + (size_t)b0 * 4;
-                pa.h_ext = hv_ext + (size_t)b0 * 3;
-                pa.h_div = h->depth_div ? hv_div + b0 : nullptr;
-                pa.h_tnet = h_tnet ? hv_tnet + (size_t)b0 * 3 : nullptr;
-                pa.d_hyp = (int32_t*)(d + o_hyp);
-                pa.d_anchors = (float*)(d + o_anc);
-                pa.d_kp = (float*)(d + o_kp);
-                pa.d_ext = (float*)(d + o_ext);
-                pa.d_div = (float*)(d + o_div);
-                pa.d_tnet = (float*)(d + o_tnet);
-            }
+            pa.pulled_quads = (c->count && pull_planes) ? c->d_pulled : nullptr;
+            pa.h_hyp = (const int32_t*)hsrc(I_HYP);
+            pa.h_anchors = (const float*)hsrc(I_ANC);
+            pa.h_kp = (const float*)hsrc(I_KP);
+            pa.h_ext = (const float*)hsrc(I_EXT);
+            pa.h_div = (const float*)hsrc(I_DIV);
+            pa.h_tnet = (const float*)hsrc(I_TNET);
+            pa.d_hyp = (int32_t*)(d + o_hyp);
+            pa.d_anchors = (float*)(d + o_anc);
+            pa.d_kp = (float*)(d + o_kp);
+            pa.d_ext = (float*)(d + o_ext);
+            pa.d_div = (float*)(d + o_div);
+            pa.d_tnet = (float*)(d + o_tnet);
             pa.H3 = H * 3;
             pa.R3 = R * 3;
             pa.mask_mode = h->mask_mode;
             pa.mask_thr = h->mask_thr;
-            rdpn::host_mask_cut(h->mask_thr, &pa.mask_cut, &pa.mask_cut_incl);
-            rc = rdpn::launch_pull(pa, (int)nb, c->gran, st);
+            host_mask_cut(h->mask_thr, &pa.mask_cut, &pa.mask_cut_incl);
+            rc = launch_pull(pa, (int)nb, c->gran, st);
             if (rc) break;
         }
         rdpn_roi_inputs di = *h;
         di.B = (int)nb;
-        di.depth = (const float*)(d + o_depth);
-        di.coor_x = (const float*)(d + o_cx);
-        di.coor_y = (const float*)(d + o_cy);
-        di.coor_z = (const float*)(d + o_cz);
-        di.mask = (const float*)(d + o_mask);
-        di.region_idx = dense ? nullptr : (const uint8_t*)(d + o_rid);
-        di.anchors = dense ? nullptr : (const float*)(d + o_anc);
-        di.Kp = (const float*)(d + o_kp);
-        di.extent = (const float*)(d + o_ext);
-        di.depth_div = h->depth_div ? (const float*)(d + o_div) : nullptr;
+        di.depth = (const float*)src[I_DEPTH];
+        di.coor_x = (const float*)src[I_CX];
+        di.coor_y = (const float*)src[I_CY];
+        di.coor_z = (const float*)src[I_CZ];
+        di.mask = (const float*)src[I_MASK];
+        di.region_idx = (const uint8_t*)src[I_RID];
+        di.anchors = (const float*)src[I_ANC];
+        di.Kp = (const float*)src[I_KP];
+        di.extent = (const float*)src[I_EXT];
+        di.depth_div = (const float*)src[I_DIV];
+        // outputs: in place (device), direct (pinned) or staged + copied back
+        void* dst[NOUT];
+        for (int i = 0; i < NOUT; ++i) {
+            const size_t skip = (size_t)b0 * out_roi_bytes[i];
+            dst[i] = out[i].move == MOVE_NONE ? nullptr
+                     : (out[i].move == MOVE_IN_PLACE || out[i].move == MOVE_PULL) ? (void*)((unsigned char*)out[i].dev + skip)
+                     : (void*)(d + out_off[i]);
+        }
         rdpn_solve_outputs dout;
         memset(&dout, 0, sizeof(dout));
-        dout.pose = (float*)(d + o_pose);
-        dout.n_inliers = (int32_t*)(d + o_ninl);
-        dout.status = (int32_t*)(d + o_stat);
-        dout.best_h = ho->best_h ? (int32_t*)(d + o_best) : nullptr;
-        dout.n_sel = ho->n_sel ? (int32_t*)(d + o_nsel) : nullptr;
-        dout.scale = ho->scale ? (float*)(d + o_scale) : nullptr;
-        dout.inlier_mask = ho->inlier_mask ? (uint8_t*)(d + o_imask) : nullptr;
-        dout.hyp_counts = ho->hyp_counts ? (int32_t*)(d + o_hcnt) : nullptr;
-        dout.hyp_poses = ho->hyp_poses ? (float*)(d + o_hpose) : nullptr;
-        if (direct_out) {
-            dout.pose = (float*)rdpn::device_view(ho->pose) + (size_t)b0 * 12;
-            dout.n_inliers = (int32_t*)rdpn::device_view(ho->n_inliers) + b0;
-            dout.status = (int32_t*)rdpn::device_view(ho->status) + b0;
-            dout.best_h = ho->best_h ? (int32_t*)rdpn::device_view(ho->best_h) + b0 : nullptr;
-            dout.n_sel = ho->n_sel ? (int32_t*)rdpn::device_view(ho->n_sel) + b0 : nullptr;
-            dout.scale = ho->scale ? (float*)rdpn::device_view(ho->scale) + b0 : nullptr;
-        }
-        rc = rdpn_pose_solve(&di, (const int32_t*)(d + o_hyp), h_tnet ? (const float*)(d + o_tnet) : nullptr, prm, &dout, st);
+        dout.pose = (float*)dst[O_POSE];
+        dout.n_inliers = (int32_t*)dst[O_NINL];
+        dout.status = (int32_t*)dst[O_STAT];
+        dout.best_h = (int32_t*)dst[O_BEST];
+        dout.n_sel = (int32_t*)dst[O_NSEL];
+        dout.scale = (float*)dst[O_SCALE];
+        dout.inlier_mask = (uint8_t*)dst[O_IMASK];
+        dout.hyp_counts = (int32_t*)dst[O_HCNT];
+        dout.hyp_poses = (float*)dst[O_HPOSE];
+        rc = rdpn_pose_solve(&di, (const int32_t*)src[I_HYP], (const float*)src[I_TNET], prm, &dout, st);
         if (rc) break;
-        if (direct_out) continue;
-#define D2H(dst, src_off, bytes) RDPN_CUDA_TRY(cudaMemcpyAsync((dst), d + (src_off), (bytes), cudaMemcpyDeviceToHost, st))
-        D2H(ho->pose + (size_t)b0 * 12, o_pose, nb * 48);
-        D2H(ho->n_inliers + b0, o_ninl, nb * 4);
-        D2H(ho->status + b0, o_stat, nb * 4);
-        if (ho->best_h) D2H(ho->best_h + b0, o_best, nb * 4);
-        if (ho->n_sel) D2H(ho->n_sel + b0, o_nsel, nb * 4);
-        if (ho->scale) D2H(ho->scale + b0, o_scale, nb * 4);
-        if (ho->inlier_mask) D2H(ho->inlier_mask + po, o_imask, nb * P);
-        if (ho->hyp_counts) D2H(ho->hyp_counts + (size_t)b0 * H, o_hcnt, nb * H * 4);
-        if (ho->hyp_poses) D2H(ho->hyp_poses + (size_t)b0 * H * 12, o_hpose, nb * H * 48);
-#undef D2H
+        for (int i = 0; i < NOUT; ++i)
+            if (out[i].move == MOVE_COPY)
+                RDPN_CUDA_TRY(cudaMemcpyAsync((unsigned char*)out[i].host + (size_t)b0 * out_roi_bytes[i], d + out_off[i],
+                                              nb * out_roi_bytes[i], cudaMemcpyDeviceToHost, st));
     }
     cudaError_t es = cudaSuccess;
     for (int i = 0; i < RDPN_STAGES; ++i) {
@@ -510,14 +528,17 @@ int rdpn_pose_solve_host(rdpn_ctx* c, const rdpn_roi_inputs* h, const int32_t* h
     }
     if (rc) return rc;
     if (es != cudaSuccess) return (int)es;
-    c->last_transfer = pull ? RDPN_TRANSFER_PULL : RDPN_TRANSFER_COPY;
-    c->last_h2d_bytes = copied;
-    if (pull && c->count) {
+    c->last_transfer = any_pull ? RDPN_TRANSFER_PULL : RDPN_TRANSFER_COPY;
+    c->last_h2d_bytes = moved;
+    if (pull_planes && c->count) {
         unsigned long long tot = 0;
         RDPN_CUDA_TRY(cudaMemcpy(&tot, c->d_pulled, sizeof(tot), cudaMemcpyDeviceToHost));
         const unsigned long long quads = tot - c->pulled_seen;
         c->pulled_seen = tot;
-        c->last_h2d_bytes += quads * (unsigned long long)(4 * 16 + (dense ? 0 : 4));
+        unsigned long long per_quad = 0;
+        for (int i = I_DEPTH; i <= I_CZ; ++i) per_quad += in[i].move == MOVE_PULL ? 16 : 0;
+        per_quad += in[I_RID].move == MOVE_PULL ? 4 : 0;
+        c->last_h2d_bytes += quads * per_quad;
     }
     return 0;
 }

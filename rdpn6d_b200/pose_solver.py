@@ -14,7 +14,8 @@ Inputs follow the reference's tensors at the evaluator boundary
   extent       [B,3]       roi_extent
   region_idx   [B,64,64] uint8 (geometry.region_argmax of out_dict["region"]) + anchors [B,R,3] (fps)
   hyp_idx      [B,H,3] int32 absolute pixel indices of each hypothesis' three correspondences
-There is no CPU path: tensors must live on a CUDA device.
+PoseSolver / correspond take CUDA tensors; HostPoseSolver takes CPU tensors and moves them itself (host-buffer
+plugin call).  Either way the arithmetic runs in the CUDA kernels: there is no CPU compute path.
 """
 import ctypes
 from dataclasses import dataclass
@@ -257,3 +258,133 @@ def sample_hypotheses(sel, H, generator=None):
     w[empty, 0] = 1.0
     idx = torch.multinomial(w, H * 3, replacement=True, generator=generator)
     return idx.view(B, H, 3).to(torch.int32)
+
+
+class HostPoseSolver:
+    """Plugin call for buffers that are not (all) on the GPU yet (rdpn_pose_solve_host): results come back in CPU
+    tensors.  Every input may be a CUDA tensor (used in place -- the head outputs of models/GDRN.py:291-297), a
+    PINNED CPU tensor (the loader's roi_coord_2d / cam / roi_extent, data_loader.py:417-421) or a pageable one.
+    The library moves what has to move and launches the fused solver in a 4-stage pipeline; pinned planes are not
+    copied but fetched over PCIe only where the mask test passes ("gated pull", include/rdpn6d_b200.h), pinned
+    outputs are written by the kernel directly.  There is still no CPU compute path.
+
+    transfer: "auto" (pull when the buffers are pinned), "copy", "pull".
+    """
+
+    _TRANSFER = {"auto": _lib.TRANSFER_AUTO, "copy": _lib.TRANSFER_COPY, "pull": _lib.TRANSFER_PULL}
+
+    def __init__(self, device=0, transfer="auto", chunk_rois=None, pull_granularity=None, count_bytes=False, pin_outputs=True,
+                 **solver_kw):
+        self._L = _lib.lib()
+        self._ctx = ctypes.c_void_p()
+        self.device = int(device)
+        _lib.check(self._L.rdpn_ctx_create(int(device), ctypes.byref(self._ctx)), "ctx_create")
+        self.set_option(_lib.OPT_TRANSFER, self._TRANSFER[transfer])
+        if chunk_rois is not None:
+            self.set_option(_lib.OPT_CHUNK_ROIS, int(chunk_rois))
+        if pull_granularity is not None:
+            self.set_option(_lib.OPT_PULL_GRANULARITY, int(pull_granularity))
+        self.set_option(_lib.OPT_COUNT_BYTES, int(bool(count_bytes)))
+        self.pin_outputs = pin_outputs
+        s = PoseSolver(**solver_kw)
+        self.prm, self.mask_mode, self.mask_thr = s.prm, s.mask_mode, s.mask_thr
+        self.want_inlier_mask, self.want_hyp = s.want_inlier_mask, s.want_hyp
+        self._out = {}
+
+    def set_option(self, key, value):
+        _lib.check(self._L.rdpn_ctx_set_option(self._ctx, key, value), "ctx_set_option")
+
+    @property
+    def last_h2d_bytes(self):
+        return int(self._L.rdpn_ctx_last_h2d_bytes(self._ctx))
+
+    @property
+    def last_transfer(self):
+        return {_lib.TRANSFER_COPY: "copy", _lib.TRANSFER_PULL: "pull"}.get(int(self._L.rdpn_ctx_last_transfer(self._ctx)))
+
+    def close(self):
+        if self._ctx:
+            self._L.rdpn_ctx_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _cpu(self, x, shape, dtype, name):
+        """Any mix of CPU and CUDA tensors is accepted: the library classifies every buffer on its own (device memory is
+        used in place, pinned memory is pulled / written directly, pageable memory is copied)."""
+        if x.is_cuda and x.device.index != self.device:
+            raise RuntimeError("rdpn6d_b200: %s is on %s, the context is on cuda:%d" % (name, x.device, self.device))
+        x = x.detach()
+        if x.dtype != dtype or not x.is_contiguous():
+            x = x.to(dtype).contiguous()  # note: loses pinning; pass float32 / uint8 / int32 contiguous tensors to pull
+        return x.reshape(shape)
+
+    def _buffers(self, B, H):
+        key = (B, H)
+        if key not in self._out:
+            mk = (lambda *s, dtype: torch.empty(*s, dtype=dtype).pin_memory()) if self.pin_outputs else \
+                 (lambda *s, dtype: torch.empty(*s, dtype=dtype))
+            o = dict(pose=mk(B, 12, dtype=torch.float32), n_inliers=mk(B, dtype=torch.int32), status=mk(B, dtype=torch.int32),
+                     best_h=mk(B, dtype=torch.int32), n_sel=mk(B, dtype=torch.int32), scale=mk(B, dtype=torch.float32))
+            if self.want_inlier_mask:
+                o["inlier_mask"] = mk(B, 64, 64, dtype=torch.uint8)
+            if self.want_hyp:
+                o["hyp_counts"] = mk(B, H, dtype=torch.int32)
+                o["hyp_poses"] = mk(B, H, 3, 4, dtype=torch.float32)
+            self._out[key] = o
+        return self._out[key]
+
+    def plan(self, depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx, region_idx=None, anchors=None,
+             depth_div=None, t_net=None):
+        """Prepare a call on fixed buffers: returns a zero-argument callable that is one ctypes call (a serving loop
+        that refills the same pinned buffers pays no per-step Python bookkeeping) and yields the PoseSolveResult."""
+        B = depth.shape[0]
+        H = hyp_idx.shape[1]
+        f32, t = torch.float32, {}
+        for name, x in (("depth", depth), ("coor_x", coor_x), ("coor_y", coor_y), ("coor_z", coor_z), ("mask", mask)):
+            t[name] = self._cpu(x, (B, P), f32, name)
+        t["Kp"] = self._cpu(Kp, (B, 4), f32, "Kp")
+        t["extent"] = self._cpu(extent, (B, 3), f32, "extent")
+        if (region_idx is None) != (anchors is None):
+            raise ValueError("region_idx and anchors must be given together (anchor mode) or both None (dense mode)")
+        R = 0
+        if region_idx is not None:
+            R = anchors.shape[1]
+            t["region_idx"] = self._cpu(region_idx, (B, P), torch.uint8, "region_idx")
+            t["anchors"] = self._cpu(anchors, (B, R, 3), f32, "anchors")
+        if depth_div is not None:
+            t["depth_div"] = self._cpu(depth_div, (B,), f32, "depth_div")
+        hyp = self._cpu(hyp_idx, (B, H, 3), torch.int32, "hyp_idx")
+        tn = self._cpu(t_net, (B, 3), f32, "t_net") if t_net is not None else None
+        s = _lib.RoiInputs()
+        for k in ("depth", "Kp", "depth_div", "coor_x", "coor_y", "coor_z", "mask", "extent", "region_idx", "anchors"):
+            setattr(s, k, t[k].data_ptr() if k in t else None)
+        s.num_regions, s.mask_mode, s.mask_thr, s.B = R, _mask_mode(self.mask_mode), float(self.mask_thr), B
+        prm = _lib.SolveParams(num_hyp=H, **self.prm)
+        o = self._buffers(B, H)
+        outs = _lib.SolveOutputs()
+        for k in ("pose", "n_inliers", "status", "best_h", "n_sel", "inlier_mask", "hyp_counts", "hyp_poses", "scale"):
+            setattr(outs, k, o[k].data_ptr() if k in o else None)
+        res = PoseSolveResult(pose=o["pose"].view(B, 3, 4), n_inliers=o["n_inliers"], status=o["status"], best_h=o["best_h"],
+                              n_sel=o["n_sel"], inlier_mask=o.get("inlier_mask"), hyp_counts=o.get("hyp_counts"),
+                              hyp_poses=o.get("hyp_poses"), scale=o["scale"], rows=None)
+        fn, ctx = self._L.rdpn_pose_solve_host, self._ctx
+        cargs = (ctx, ctypes.byref(s), hyp.data_ptr(), tn.data_ptr() if tn is not None else None, ctypes.byref(prm),
+                 ctypes.byref(outs))
+        keep = (t, hyp, tn, s, prm, outs)  # the C structs point into these
+
+        def run(_keep=keep):
+            rc = fn(*cargs)
+            if rc:
+                _lib.check(rc, "pose_solve_host")
+            return res
+
+        return run
+
+    def __call__(self, depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx, region_idx=None, anchors=None,
+                 depth_div=None, t_net=None):
+        return self.plan(depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx, region_idx, anchors, depth_div, t_net)()

@@ -374,6 +374,44 @@ def test_gated_pull_dense_mode(cuda):
         L.rdpn_ctx_destroy(ctx)
 
 
+def test_host_pose_solver_wrapper(cuda):
+    """Python face of the host-buffer call: pinned CPU tensors in, pinned CPU tensors out, gated pull underneath."""
+    B, H = 96, 64
+    b = synth.make_batch(B, H=H, seed=21, occlusion_max=0.4)
+    dev = _solve(_to_cuda(b))
+    t = {k: (None if v is None else torch.from_numpy(np.ascontiguousarray(v)).pin_memory()) for k, v in b.items()}
+    cx, cy, cz = [t["coor"][:, c].contiguous().pin_memory() for c in range(3)]
+    hs = pose_solver.HostPoseSolver(inlier_thr=THR, count_bytes=True)
+    res = hs(t["depth"], t["Kp"], cx, cy, cz, t["mask"], t["extent"], t["hyp_idx"], t["region_idx"], t["anchors"])
+    assert hs.last_transfer == "pull" and 0 < hs.last_h2d_bytes < B * (5 * 16384 + 4096)
+    assert torch.equal(res.pose.view(torch.int32), dev.pose.cpu().view(torch.int32))
+    assert torch.equal(res.n_inliers, dev.n_inliers.cpu()) and torch.equal(res.status, dev.status.cpu())
+    assert torch.equal(res.best_h, dev.best_h.cpu()) and torch.equal(res.n_sel, dev.n_sel.cpu())
+    # pageable tensors: same results through the full copy
+    hc = pose_solver.HostPoseSolver(inlier_thr=THR, pin_outputs=False, want_inlier_mask=True)
+    u = {k: (None if v is None else torch.from_numpy(np.ascontiguousarray(v))) for k, v in b.items()}
+    res2 = hc(u["depth"], u["Kp"], u["coor"][:, 0], u["coor"][:, 1], u["coor"][:, 2], u["mask"], u["extent"], u["hyp_idx"],
+              u["region_idx"], u["anchors"])
+    assert hc.last_transfer == "copy"
+    assert torch.equal(res2.pose.view(torch.int32), dev.pose.cpu().view(torch.int32))
+    assert torch.equal(res2.inlier_mask, dev.inlier_mask.cpu())
+    # the deployment split of the reference: head outputs (coor, mask, region ids) already on the GPU, the loader's
+    # depth / intrinsics / extents / anchors and the hypothesis triplets in pinned host memory
+    g = _to_cuda(b)
+    res3 = hs(t["depth"], t["Kp"], g["coor"][:, 0].contiguous(), g["coor"][:, 1].contiguous(), g["coor"][:, 2].contiguous(),
+              g["mask"], t["extent"], t["hyp_idx"], g["region_idx"], t["anchors"])
+    assert hs.last_transfer == "pull" and 0 < hs.last_h2d_bytes < B * (16384 + H * 12 + 32 * 12 + 28 + 1)
+    assert torch.equal(res3.pose.view(torch.int32), dev.pose.cpu().view(torch.int32))
+    assert torch.equal(res3.n_inliers, dev.n_inliers.cpu()) and torch.equal(res3.best_h, dev.best_h.cpu())
+    # everything on the device: nothing moves, results still land in the pinned CPU tensors
+    res4 = hs(g["depth"], g["Kp"], g["coor"][:, 0].contiguous(), g["coor"][:, 1].contiguous(), g["coor"][:, 2].contiguous(),
+              g["mask"], g["extent"], g["hyp_idx"], g["region_idx"], g["anchors"])
+    assert hs.last_h2d_bytes == 0
+    assert torch.equal(res4.pose.view(torch.int32), dev.pose.cpu().view(torch.int32))
+    hs.close()
+    hc.close()
+
+
 def test_cpu_tensors_are_rejected_loudly(cuda):
     b = synth.make_batch(2, H=8, seed=1)
     t = {k: (None if v is None else torch.from_numpy(v)) for k, v in b.items()}
