@@ -217,7 +217,7 @@ __device__ __forceinline__ void block_sum(FinishSmem& f, double (&v)[NV]) {
 struct FusedLayout {  // byte offsets of the dynamic tail behind FusedSmem
     int anchors;      // float4[R]
     int runtab;       // float4[R]: non-empty buckets (anchor xyz, start | end << 16)
-    int wrun;         // uint16[SW][RB]     (RB = R + 1: last bucket collects the unselected lanes)
+    int wrun;         // uint32[SW][RB]     per-warp bucket counts, then cursors (RB = R + 1)
     int hyp;          // float[H][12]
     int hcnt;         // int[H]
     int vlist;        // uint16[H] indices of the valid hypotheses
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
     FinishSmem& f = s.fin;
     float4* anchors = reinterpret_cast<float4*>(smem_raw + lay.anchors);
     float4* runtab = reinterpret_cast<float4*>(smem_raw + lay.runtab);
-    uint16_t* wrun = reinterpret_cast<uint16_t*>(smem_raw + lay.wrun);
+    uint32_t* wrun = reinterpret_cast<uint32_t*>(smem_raw + lay.wrun);
     float* hyp = reinterpret_cast<float*>(smem_raw + lay.hyp);  // [H][12]
     int* hcnt = reinterpret_cast<int*>(smem_raw + lay.hcnt);    // [H] counts, -1 = invalid
     uint16_t* vlist = reinterpret_cast<uint16_t*>(smem_raw + lay.vlist);
@@ -271,6 +271,14 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
             asm volatile("prefetch.global.L2 [%0];" ::"l"(pl.cz + o));
         }
         if (!DENSE && t < 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(pl.rid + t * 64));
+    }
+    // the thread's first hypothesis triplet is requested now (DRAM) and consumed in phase 4
+    int pre0 = -1, pre1 = -1, pre2 = -1;
+    if (t < H) {
+        const int32_t* ip = a.hyp_idx + ((size_t)b * H + t) * 3;
+        pre0 = __ldg(ip);
+        pre1 = __ldg(ip + 1);
+        pre2 = __ldg(ip + 2);
     }
     if (t == 0) {
         RoiConst& rc = s.rc;
@@ -380,22 +388,19 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
 
     PHASE_MARK(2);
     // ---- 3: counting sort by region, deterministic order (warp, k, j, lane) ----
-    // pass A: per-warp bucket histogram
-    uint16_t* myrun = wrun + warp * RB;
+    // pass A: per-warp bucket histogram.  Counts do not depend on the order, so plain shared-memory atomics on the
+    // warp's private row do (the deterministic ranks are only needed when the slots are handed out, pass B).
+    uint32_t* myrun = wrun + warp * RB;
+    if (selbits) {
 #pragma unroll 1
-    for (int k = 0; k < QPT; ++k) {
-        const unsigned nib = (selbits >> (4 * k)) & 0xFu;
-        if (__ballot_sync(0xffffffffu, nib != 0u) == 0u) continue;
-        const uchar4 r4 = DENSE ? make_uchar4(0, 0, 0, 0) : __ldg(reinterpret_cast<const uchar4*>(pl.rid) + 32 * (SW * k + warp) + lane);
-        const uint8_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const bool sel = (nib >> j) & 1u;
-            if (__ballot_sync(0xffffffffu, sel) == 0u) continue;
-            const unsigned key = sel ? (unsigned)rr[j] : (unsigned)R;
-            const unsigned m = __match_any_sync(0xffffffffu, key);
-            if (sel && lane == __ffs(m) - 1) myrun[key] += (uint16_t)__popc(m);
-            __syncwarp();
+        for (int k = 0; k < QPT; ++k) {
+            const unsigned nib = (selbits >> (4 * k)) & 0xFu;
+            if (nib == 0u) continue;
+            const uchar4 r4 = DENSE ? make_uchar4(0, 0, 0, 0) : __ldg(reinterpret_cast<const uchar4*>(pl.rid) + 32 * (SW * k + warp) + lane);
+            if (nib & 1u) atomicAdd(&myrun[r4.x], 1u);
+            if (nib & 2u) atomicAdd(&myrun[r4.y], 1u);
+            if (nib & 4u) atomicAdd(&myrun[r4.z], 1u);
+            if (nib & 8u) atomicAdd(&myrun[r4.w], 1u);
         }
     }
     __syncthreads();
@@ -427,7 +432,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
                 const int start = run;
                 for (int w = 0; w < SW; ++w) {
                     const int c = wrun[w * RB + r];
-                    wrun[w * RB + r] = (uint16_t)run;
+                    wrun[w * RB + r] = (uint32_t)run;
                     run += c;
                 }
                 if (run > start) {  // one entry per NON-EMPTY bucket = (anchor xyz, start | end << 16)
@@ -458,7 +463,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
             int cur = 0;
             if (sel && lane == leader) {
                 cur = myrun[key];
-                myrun[key] = (uint16_t)(cur + __popc(m));
+                myrun[key] = (uint32_t)(cur + __popc(m));
             }
             cur = __shfl_sync(0xffffffffu, cur, leader);
             if (sel) {
@@ -474,7 +479,8 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
     // ---- 4: hypothesis generation (FP64 closed form), one hypothesis per thread, pixels gathered ----
     for (int h = t; h < H; h += ST) {
         const int32_t* ip = a.hyp_idx + ((size_t)b * H + h) * 3;
-        const int ii[3] = {ip[0], ip[1], ip[2]};
+        const bool first = h == t;
+        const int ii[3] = {first ? pre0 : ip[0], first ? pre1 : ip[1], first ? pre2 : ip[2]};
         bool ok = ((unsigned)ii[0] < RDPN_P) && ((unsigned)ii[1] < RDPN_P) && ((unsigned)ii[2] < RDPN_P);
         float* P = hyp + (size_t)h * 12;
         if (ok) {
@@ -779,42 +785,64 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
         float P[12];
 #pragma unroll
         for (int i = 0; i < 12; ++i) P[i] = it == 0 ? hyp[(size_t)best * 12 + i] : f.pose[i];
-        // ONE pass over the slots (thread handles t, t+ST, ...: <= 16 of them): FP64 raw moments about a pivot
-        // (slot 0, exact FP32 differences), from which centroids, cross-covariance and spreads follow; the
-        // residual cancellation is ~1e2 on 1e-16, far below the FP32 rounding of the result.
+        // FP64 raw moments about a pivot (slot 0, exact FP32 differences) over the slots t, t+ST, ... (<= 16 per
+        // thread), from which centroids, cross-covariance and spreads follow; the residual cancellation is ~1e2 on
+        // 1e-16, far below the FP32 rounding of the result.
         float4 cp0, ap0;
         get_slot(0, cp0, ap0);
-        double mom[18];
-#pragma unroll
-        for (int i = 0; i < 18; ++i) mom[i] = 0.0;
+        // Two sweeps of nine moments each keep the live FP64 state at 18 registers (one sweep of 18 spills at the
+        // 64-register cap of four CTAs per SM); the second sweep re-reads the inliers found by the first.
         unsigned inl_bits = 0u;
-        int slot = 0;
-        for (int i = t; i < n; i += ST, ++slot) {
-            float4 cp, ap;
-            get_slot(i, cp, ap);
-            if (resid2(P, ap.x, ap.y, ap.z, cp.x, cp.y, cp.z) < cut) {
-                inl_bits |= 1u << slot;
-                const double w = a.prm.weighted ? (double)cp.w : 1.0;
-                const double c0 = (double)cp.x - (double)cp0.x, c1 = (double)cp.y - (double)cp0.y, c2 = (double)cp.z - (double)cp0.z;
-                const double a0 = (double)ap.x - (double)ap0.x, a1 = (double)ap.y - (double)ap0.y, a2 = (double)ap.z - (double)ap0.z;
-                mom[0] += w;
-                mom[1] += w * c0; mom[2] += w * c1; mom[3] += w * c2;
-                mom[4] += w * a0; mom[5] += w * a1; mom[6] += w * a2;
-                mom[7] += w * c0 * a0; mom[8] += w * c0 * a1; mom[9] += w * c0 * a2;
-                mom[10] += w * c1 * a0; mom[11] += w * c1 * a1; mom[12] += w * c1 * a2;
-                mom[13] += w * c2 * a0; mom[14] += w * c2 * a1; mom[15] += w * c2 * a2;
-                mom[16] += w * (c0 * c0 + c1 * c1 + c2 * c2);
-                mom[17] += w * (a0 * a0 + a1 * a1 + a2 * a2);
+        {
+            double m[9];  // sum w | w c (3) | w a (3) | w |c|^2 | w |a|^2
+#pragma unroll
+            for (int i = 0; i < 9; ++i) m[i] = 0.0;
+            int slot = 0;
+            for (int i = t; i < n; i += ST, ++slot) {
+                float4 cp, ap;
+                get_slot(i, cp, ap);
+                if (resid2(P, ap.x, ap.y, ap.z, cp.x, cp.y, cp.z) < cut) {
+                    inl_bits |= 1u << slot;
+                    const double w = a.prm.weighted ? (double)cp.w : 1.0;
+                    const double c0 = (double)cp.x - (double)cp0.x, c1 = (double)cp.y - (double)cp0.y, c2 = (double)cp.z - (double)cp0.z;
+                    const double a0 = (double)ap.x - (double)ap0.x, a1 = (double)ap.y - (double)ap0.y, a2 = (double)ap.z - (double)ap0.z;
+                    m[0] += w;
+                    m[1] += w * c0; m[2] += w * c1; m[3] += w * c2;
+                    m[4] += w * a0; m[5] += w * a1; m[6] += w * a2;
+                    m[7] += w * (c0 * c0 + c1 * c1 + c2 * c2);
+                    m[8] += w * (a0 * a0 + a1 * a1 + a2 * a2);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                const double v = warp_sum(m[i]);
+                if (lane == 0) f.red_d[warp][i < 7 ? i : i + 9] = v;  // slots 0..6, 16, 17
             }
         }
-        // reduction: warp shuffles -> per-warp partials -> one warp (lane i sums value i) -> its lane 0 solves.
-        // Only the solving thread needs the moments, so two barriers suffice.
-        const int winl = warp_sum(__popc(inl_bits));
+        {
+            double m[9];  // sum w c a^T
 #pragma unroll
-        for (int i = 0; i < 18; ++i) {
-            const double v = warp_sum(mom[i]);
-            if (lane == 0) f.red_d[warp][i] = v;
+            for (int i = 0; i < 9; ++i) m[i] = 0.0;
+            int slot = 0;
+            for (int i = t; i < n; i += ST, ++slot) {
+                if (!(inl_bits & (1u << slot))) continue;
+                float4 cp, ap;
+                get_slot(i, cp, ap);
+                const double w = a.prm.weighted ? (double)cp.w : 1.0;
+                const double c0 = w * ((double)cp.x - (double)cp0.x), c1 = w * ((double)cp.y - (double)cp0.y),
+                             c2 = w * ((double)cp.z - (double)cp0.z);
+                const double a0 = (double)ap.x - (double)ap0.x, a1 = (double)ap.y - (double)ap0.y, a2 = (double)ap.z - (double)ap0.z;
+                m[0] += c0 * a0; m[1] += c0 * a1; m[2] += c0 * a2;
+                m[3] += c1 * a0; m[4] += c1 * a1; m[5] += c1 * a2;
+                m[6] += c2 * a0; m[7] += c2 * a1; m[8] += c2 * a2;
+            }
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                const double v = warp_sum(m[i]);
+                if (lane == 0) f.red_d[warp][7 + i] = v;
+            }
         }
+        const int winl = warp_sum(__popc(inl_bits));
         if (lane == 0) f.red_i[warp] = winl;
         __syncthreads();
         PHASE_MARK(10);
@@ -866,7 +894,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
         __syncthreads();
         if (f.h_eff < 3) break;  // uniform across the block
         if (a.out.inlier_mask && it == iters - 1) {  // the inlier set used by the last refit
-            slot = 0;
+            int slot = 0;
             for (int i = t; i < n; i += ST, ++slot)
                 if (inl_bits & (1u << slot)) a.out.inlier_mask[(size_t)b * RDPN_P + s.pix[i]] = 1;
         }
@@ -1003,7 +1031,7 @@ static int launch_solve(const SolveArgs& a, cudaStream_t st) {
     size_t off = al(sizeof(FusedSmem));
     lay.anchors = (int)off; off = al(off + (size_t)R * sizeof(float4));
     lay.runtab = (int)off;  off = al(off + (size_t)R * sizeof(float4));
-    lay.wrun = (int)off;    off = al(off + (size_t)SW * RB * sizeof(uint16_t));
+    lay.wrun = (int)off;    off = al(off + (size_t)SW * RB * sizeof(uint32_t));
     lay.hyp = (int)off;     off = al(off + (size_t)H * 12 * sizeof(float));
     lay.hcnt = (int)off;    off = al(off + (size_t)H * sizeof(int));
     lay.vlist = (int)off;   off = al(off + (size_t)H * sizeof(uint16_t));
