@@ -309,46 +309,82 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
     }
     // mask min / max (engine_utils.py:123-124).  Thread owns quads q = 32*(SW*k + warp) + lane (k = 0..3):
     // every warp gets two image rows out of each 16, so the rows the object covers are spread over all warps.
+    float4 mq[QPT];  // the thread's mask quads stay in registers for the gate
+#pragma unroll
+    for (int k = 0; k < QPT; ++k) mq[k] = __ldg(reinterpret_cast<const float4*>(pl.mask) + 32 * (SW * k + warp) + lane);
     if (in.mask_mode == RDPN_MASK_L1) {
         float mn = FLT_MAX, mx = -FLT_MAX;
 #pragma unroll
-        for (int k = 0; k < QPT; ++k) {
-            const float4 m4 = __ldg(reinterpret_cast<const float4*>(pl.mask) + 32 * (SW * k + warp) + lane);
-            minmax4(m4, mn, mx);
-        }
+        for (int k = 0; k < QPT; ++k) minmax4(mq[k], mn, mx);
         mn = warp_min(mn);
         mx = warp_max(mx);
         if (lane == 0) { s.red_f[0][warp] = mn; s.red_f[1][warp] = mx; }
     }
     __syncthreads();
-    if (in.mask_mode == RDPN_MASK_L1) {
-        if (t == 0) {
-            float lo = s.red_f[0][0], hi = s.red_f[1][0];
-            for (int w = 1; w < SW; ++w) { lo = fminf(lo, s.red_f[0][w]); hi = fmaxf(hi, s.red_f[1][w]); }
-            s.rc.mn = lo;
-            s.rc.mx = hi;
-            make_gate(s.gate, lo, hi, in.mask_thr, a.mask_cut, a.mask_cut_incl);
-        }
-        __syncthreads();
+    RoiConst rc = s.rc;
+    RoiGate gate;
+    gate.hi = gate.lo = gate.b = 0.f;
+    gate.cut = 0.0;
+    gate.incl = 0;
+    if (in.mask_mode == RDPN_MASK_L1) {  // every thread folds the eight partials itself: no second barrier
+        float lo = s.red_f[0][0], hi = s.red_f[1][0];
+#pragma unroll
+        for (int w = 1; w < SW; ++w) { lo = fminf(lo, s.red_f[0][w]); hi = fmaxf(hi, s.red_f[1][w]); }
+        rc.mn = lo;
+        rc.mx = hi;
+        make_gate(gate, lo, hi, in.mask_thr, a.mask_cut, a.mask_cut_incl);
     }
-    const RoiConst rc = s.rc;
     PHASE_MARK(1);
 
     // ---- 2: gate (gdrn_evaluator.py:110-117 + depth validity), no divisions ----
     unsigned selbits = 0u;
     {
-        const RoiGate gate = s.gate;
         // mask test first (the gate is a conjunction): ~85 % of the quads have no passing pixel and never touch the
         // other four planes -- no L2 -> SM traffic and no arithmetic for them
         unsigned mbits = 0u;
 #pragma unroll
         for (int k = 0; k < QPT; ++k) {
-            const float4 m4 = __ldg(reinterpret_cast<const float4*>(pl.mask) + 32 * (SW * k + warp) + lane);
-            const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+            const float mm[4] = {mq[k].x, mq[k].y, mq[k].z, mq[k].w};
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 mbits |= (mask_pass(mm[j], in.mask_mode, in.mask_thr, rc.mn, gate) ? 1u : 0u) << (4 * k + j);
         }
+        // the rest of the gate for one quad whose planes have been loaded; also sort pass A: the per-warp bucket
+        // histogram (counts do not depend on the order, so shared-memory atomics on the warp's private row do;
+        // deterministic ranks are only needed in pass B)
+        uint32_t* hrow = wrun + warp * RB;
+        auto gate_quad = [&](unsigned nib, const float4& dq, const float4& xq, const float4& yq, const float4& zq,
+                             const uchar4& r4) -> unsigned {
+            const float dd[4] = {dq.x, dq.y, dq.z, dq.w};
+            const float cxn[4] = {xq.x, xq.y, xq.z, xq.w};
+            const float cyn[4] = {yq.x, yq.y, yq.z, yq.w};
+            const float czn[4] = {zq.x, zq.y, zq.z, zq.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float d = dd[j];
+                if (rc.div != 0.f) {  // zero lanes would drag the warp through div.rn's slow path: 0 / f = +-0
+                    const float qd = __fdiv_rn(d == 0.f ? 1.f : d, rc.div);
+                    d = d == 0.f ? __fmul_rn(d, copysignf(1.f, rc.div)) : qd;
+                }
+                const float dx = __fmul_rn(__fsub_rn(cxn[j], 0.5f), rc.ext[0]);
+                const float dy = __fmul_rn(__fsub_rn(cyn[j], 0.5f), rc.ext[1]);
+                const float dz = __fmul_rn(__fsub_rn(czn[j], 0.5f), rc.ext[2]);
+                const bool sel = (fabsf(dx) > rc.gthr[0]) && (fabsf(dy) > rc.gthr[1]) && (fabsf(dz) > rc.gthr[2]) && (d > 0.f);
+                if (!sel) nib &= ~(1u << j);
+            }
+            if (nib & 1u) atomicAdd(&hrow[r4.x], 1u);
+            if (nib & 2u) atomicAdd(&hrow[r4.y], 1u);
+            if (nib & 4u) atomicAdd(&hrow[r4.z], 1u);
+            if (nib & 8u) atomicAdd(&hrow[r4.w], 1u);
+            return nib;
+        };
+        auto publish = [&](int q, unsigned nib) {  // gate bitmap: 4 bits per quad, 8 quads per word
+            unsigned wbits = nib << (4 * (lane & 7));
+            wbits |= __shfl_xor_sync(0xffffffffu, wbits, 1);
+            wbits |= __shfl_xor_sync(0xffffffffu, wbits, 2);
+            wbits |= __shfl_xor_sync(0xffffffffu, wbits, 4);
+            if ((lane & 7) == 0) s.selmap[q >> 3] = wbits;
+        };
 #pragma unroll 1
         for (int k = 0; k < QPT; ++k) {
             const int q = 32 * (SW * k + warp) + lane;
@@ -358,54 +394,62 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
                 const float4 xq = __ldg(reinterpret_cast<const float4*>(pl.cx) + q);
                 const float4 yq = __ldg(reinterpret_cast<const float4*>(pl.cy) + q);
                 const float4 zq = __ldg(reinterpret_cast<const float4*>(pl.cz) + q);
-                const float dd[4] = {dq.x, dq.y, dq.z, dq.w};
-                const float cxn[4] = {xq.x, xq.y, xq.z, xq.w};
-                const float cyn[4] = {yq.x, yq.y, yq.z, yq.w};
-                const float czn[4] = {zq.x, zq.y, zq.z, zq.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float d = dd[j];
-                    if (rc.div != 0.f) {  // zero lanes would drag the warp through div.rn's slow path: 0 / f = +-0
-                        const float qd = __fdiv_rn(d == 0.f ? 1.f : d, rc.div);
-                        d = d == 0.f ? __fmul_rn(d, copysignf(1.f, rc.div)) : qd;
-                    }
-                    const float dx = __fmul_rn(__fsub_rn(cxn[j], 0.5f), rc.ext[0]);
-                    const float dy = __fmul_rn(__fsub_rn(cyn[j], 0.5f), rc.ext[1]);
-                    const float dz = __fmul_rn(__fsub_rn(czn[j], 0.5f), rc.ext[2]);
-                    const bool sel = (fabsf(dx) > rc.gthr[0]) && (fabsf(dy) > rc.gthr[1]) && (fabsf(dz) > rc.gthr[2]) && (d > 0.f);
-                    if (!sel) nib &= ~(1u << j);
-                }
+                const uchar4 r4 = DENSE ? make_uchar4(0, 0, 0, 0) : __ldg(reinterpret_cast<const uchar4*>(pl.rid) + q);
+                nib = gate_quad(nib, dq, xq, yq, zq, r4);
             }
             selbits |= nib << (4 * k);
-            // publish the gate bitmap (4 bits per quad, 8 quads per word)
-            unsigned wbits = nib << (4 * (lane & 7));
-            wbits |= __shfl_xor_sync(0xffffffffu, wbits, 1);
-            wbits |= __shfl_xor_sync(0xffffffffu, wbits, 2);
-            wbits |= __shfl_xor_sync(0xffffffffu, wbits, 4);
-            if ((lane & 7) == 0) s.selmap[q >> 3] = wbits;
+            publish(q, nib);
         }
     }
 
     PHASE_MARK(2);
     // ---- 3: counting sort by region, deterministic order (warp, k, j, lane) ----
-    // pass A: per-warp bucket histogram.  Counts do not depend on the order, so plain shared-memory atomics on the
-    // warp's private row do (the deterministic ranks are only needed when the slots are handed out, pass B).
     uint32_t* myrun = wrun + warp * RB;
-    if (selbits) {
-#pragma unroll 1
-        for (int k = 0; k < QPT; ++k) {
-            const unsigned nib = (selbits >> (4 * k)) & 0xFu;
-            if (nib == 0u) continue;
-            const uchar4 r4 = DENSE ? make_uchar4(0, 0, 0, 0) : __ldg(reinterpret_cast<const uchar4*>(pl.rid) + 32 * (SW * k + warp) + lane);
-            if (nib & 1u) atomicAdd(&myrun[r4.x], 1u);
-            if (nib & 2u) atomicAdd(&myrun[r4.y], 1u);
-            if (nib & 4u) atomicAdd(&myrun[r4.z], 1u);
-            if (nib & 8u) atomicAdd(&myrun[r4.w], 1u);
-        }
-    }
     __syncthreads();
     PHASE_MARK(3);
-    // bucket starts, per-warp cursors and the run table: one warp, RPL consecutive buckets per lane
+    // bucket starts, per-warp cursors and the run table
+    if (R <= ST) {
+        // one thread per bucket: its eight per-warp counts in registers, a block-wide exclusive scan of
+        // (points | non-empty << 16) over the buckets, then the cursors -- no single-warp stretch
+        const bool mine = t < R;
+        int c[SW];
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < SW; ++w) {
+            c[w] = mine ? (int)wrun[w * RB + t] : 0;
+            tot += c[w];
+        }
+        const int packed = tot | ((tot > 0 ? 1 : 0) << 16);
+        int x = packed;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) f.red_i[warp] = x;
+        __syncthreads();
+        int base = 0;
+#pragma unroll
+        for (int w = 0; w < SW; ++w)
+            if (w < warp) base += f.red_i[w];
+        const int excl = base + x - packed;
+        int run = excl & 0xFFFF;
+        const int kk = excl >> 16;
+        if (mine) {
+            const int start = run;
+#pragma unroll
+            for (int w = 0; w < SW; ++w) {
+                wrun[w * RB + t] = (uint32_t)run;
+                run += c[w];
+            }
+            if (tot > 0) {  // one entry per NON-EMPTY bucket = (anchor xyz, start | end << 16)
+                float4 hd = DENSE ? make_float4(0.f, 0.f, 0.f, 0.f) : anchors[t];
+                hd.w = __uint_as_float((unsigned)start | ((unsigned)run << 16));
+                runtab[kk] = hd;
+            }
+            if (t == R - 1) { s.n_sel = run; s.n_runs = kk + (tot > 0 ? 1 : 0); }
+        }
+    } else
     if (warp == RDPN_SERIAL_WARP) {
         const int RPL = (R + 31) / 32;
         int loc = 0, ne = 0;
