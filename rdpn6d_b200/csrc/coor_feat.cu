@@ -8,58 +8,58 @@
 // Output: x [B, C, 64, 64], C = 3 + 5 + 3 (+ R when REGION_ATTENTION) (+ 1 when MASK_ATTENTION == "concat"),
 // exactly the tensor ConvPnPNet.features consumes (C = 43 for R = 32, conv_pnp_net.py:73).
 //
-// The region logits [B, R+1, 64, 64] are the widest tensor on the path (132-260 B/px); they are read
-// from HBM exactly once: a thread keeps the R logits of one pixel in registers (lanes = consecutive
-// pixels, so every channel access is a coalesced 128-byte line), does max / arg-max, exp, sum and the
-// normalisation there, and streams the C output planes out.  Algorithmic bytes per ROI:
-// (R + 1 + 3 + 5 + 1) * 16 KB in, C * 16 KB out.
+// The region logits [B, R+1, 64, 64] are the widest tensor on the path (132-260 B/px); they cross HBM exactly
+// once (bulk TMA into shared memory, see the kernel), the soft-max planes leave by bulk-TMA stores.
+// Algorithmic bytes per ROI: (R + 1 + 3 + 5 + 1) * 16 KB in, C * 16 KB out.
 #include "common.cuh"
 
 #include <float.h>
+#include <stdlib.h>
 
 namespace rdpn {
 extern unsigned long long g_launch_count;
 
-constexpr int CF_T = 256;
 
-template <int VEC> struct VecT;
-template <> struct VecT<4> { typedef float4 type; };
-template <> struct VecT<2> { typedef float2 type; };
 
-template <int VEC>
-__device__ __forceinline__ void ld_vec(const float* p, float (&v)[VEC]) {
-    typename VecT<VEC>::type x = __ldcs(reinterpret_cast<const typename VecT<VEC>::type*>(p));
-    const float* xp = reinterpret_cast<const float*>(&x);
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) v[j] = xp[j];
-}
-template <int VEC>
-__device__ __forceinline__ void st_vec(float* p, const float (&v)[VEC]) {
-    typename VecT<VEC>::type x;
-    float* xp = reinterpret_cast<float*>(&x);
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) xp[j] = v[j];
-    __stcs(reinterpret_cast<typename VecT<VEC>::type*>(p), x);
-}
+// One CTA owns a TILE of CF_TP (= threads per CTA) consecutive pixels of one ROI: the R logit rows of the tile (R x 1 KB,
+// contiguous in every plane) are staged in shared memory by R bulk-TMA copies behind one mbarrier, a thread owns one
+// pixel (conflict-free column access) and sweeps its column three times in shared memory -- max / arg-max,
+// exp(l - max) written back in place + its sum in channel order, normalisation in place -- and the finished
+// rows leave by bulk-TMA stores.  The logits cross HBM exactly once in each direction and never sit in
+// registers (the register-resident version held R x 4 logits in 180 registers: one CTA per SM, load / exp /
+// store phases serialised, 54 % of the copy bandwidth at R = 32 and 41 % at R = 64).
+// Shared memory: R KB per CTA (3 CTAs per SM at R = 64, 7 at R = 32).
 
-// A thread owns VEC consecutive pixels (VEC = 4 for R <= 32, 2 for R <= 64) and keeps their R logits in
-// registers: every channel access of a warp is then VEC*128 contiguous bytes and a CTA touches
-// VEC*1 KB per channel at a time (DRAM-page friendly; with scalar accesses the same kernel ran at 30 %).
-template <int RMAX, int VEC>
-__global__ void __launch_bounds__(CF_T)
+template <int CF_TP>  // pixels per tile = threads per CTA: 512 for R <= 32 (79 % of the copy bandwidth), 256 above (66 %)
+__global__ void __launch_bounds__(CF_TP)
     coor_feat_kernel(const float* __restrict__ cx, const float* __restrict__ cy, const float* __restrict__ cz,
                      const float* __restrict__ coord2d, const float* __restrict__ region, const float* __restrict__ fps,
                      const float* __restrict__ mask, int R, int mask_mode, int region_attention, int mask_attention,
                      float* __restrict__ out, int C) {
+    extern __shared__ __align__(128) unsigned char cf_smem[];
+    float* tile = reinterpret_cast<float*>(cf_smem);  // [R][CF_TP]
+    constexpr int CF_T = CF_TP;
     __shared__ float red[2][CF_T / 32];
-    __shared__ float4 anchors[RMAX];
-    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    __shared__ float4 anchors[64];
+    __shared__ __align__(8) uint64_t bar;
+    constexpr int TILES = RDPN_P / CF_TP;
+    const int b = blockIdx.x / TILES, p0 = (blockIdx.x % TILES) * CF_TP;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const size_t po = (size_t)b * RDPN_P;
+    const float* reg = region + ((size_t)b * (R + 1) + 1) * RDPN_P + p0;  // channel 0 is background (GDRN.py:206)
+    float* ob = out + (size_t)b * C * RDPN_P + p0;
+    if (t == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&bar, (uint32_t)R * CF_TP * 4);
+        for (int r = 0; r < R; ++r) bulk_g2s(tile + r * CF_TP, reg + (size_t)r * RDPN_P, CF_TP * 4, &bar);
+    }
     for (int r = t; r < R; r += CF_T) {
         const float* ap = fps + ((size_t)b * R + r) * 3;
         anchors[r] = make_float4(ap[0], ap[1], ap[2], 0.f);
     }
-    // mask probability parameters (model_utils.py:29-34): per-ROI min / max for the L1 mode
+    // mask probability parameters (model_utils.py:29-34): per-ROI min / max for the L1 mode (the 16 KB plane is
+    // re-read by the 16 tiles of the ROI out of L2)
     float mn = 0.f, mden = 1.f;
     if (mask_attention != 0 && mask_mode == RDPN_MASK_L1) {
         float lo = FLT_MAX, hi = -FLT_MAX;
@@ -78,91 +78,66 @@ __global__ void __launch_bounds__(CF_T)
         mn = lo;
         mden = __fsub_rn(hi, lo);
     }
-    __syncthreads();
-    const float* reg = region + ((size_t)b * (R + 1) + 1) * RDPN_P;  // channel 0 is background (GDRN.py:206)
-    float* ob = out + (size_t)b * C * RDPN_P;
-    for (int p = VEC * t; p < RDPN_P; p += VEC * CF_T) {
-        float scale[VEC], mp[VEC];
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) mp[j] = 1.f;
-        if (mask_attention != 0) {
-            float m[VEC];
-            ld_vec<VEC>(mask + po + p, m);
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                if (mask_mode == RDPN_MASK_L1) mp[j] = __fdiv_rn(__fsub_rn(m[j], mn), mden);
-                else if (mask_mode == RDPN_MASK_BCE) mp[j] = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-m[j])));
-                else mp[j] = m[j];
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) scale[j] = mask_attention == 1 ? mp[j] : 1.f;  // "mul" (conv_pnp_net.py:134-135)
-        float lg[RMAX][VEC];
-        float mx[VEC];
-        int am[VEC];
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) { mx[j] = -FLT_MAX; am[j] = 0; }
-#pragma unroll
-        for (int r = 0; r < RMAX; ++r)
-            if (r < R) ld_vec<VEC>(reg + (size_t)r * RDPN_P + p, lg[r]);
-#pragma unroll
-        for (int r = 0; r < RMAX; ++r)
-            if (r < R) {
-#pragma unroll
-                for (int j = 0; j < VEC; ++j)
-                    if (lg[r][j] > mx[j]) { mx[j] = lg[r][j]; am[j] = r; }  // first maximum wins (torch.argmax)
-            }
-        float sum[VEC];
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) sum[j] = 0.f;
-#pragma unroll
-        for (int r = 0; r < RMAX; ++r)
-            if (r < R) {
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) {
-                    lg[r][j] = expf(__fsub_rn(lg[r][j], mx[j]));
-                    sum[j] = __fadd_rn(sum[j], lg[r][j]);
-                }
-            }
-        // channels 0-2: coor, 3-7: roi_coord_2d, 8-10: anchor of the arg-max region
-        float v[VEC];
-        const float* srcs[8] = {cx + po, cy + po, cz + po, coord2d + ((size_t)b * 5 + 0) * RDPN_P, coord2d + ((size_t)b * 5 + 1) * RDPN_P,
-                                coord2d + ((size_t)b * 5 + 2) * RDPN_P, coord2d + ((size_t)b * 5 + 3) * RDPN_P,
-                                coord2d + ((size_t)b * 5 + 4) * RDPN_P};
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            ld_vec<VEC>(srcs[c] + p, v);
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) v[j] *= scale[j];
-            st_vec<VEC>(ob + (size_t)c * RDPN_P + p, v);
-        }
-        float ax[VEC], ay[VEC], az[VEC];
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            const float4 an = anchors[am[j]];
-            ax[j] = an.x * scale[j]; ay[j] = an.y * scale[j]; az[j] = an.z * scale[j];
-        }
-        st_vec<VEC>(ob + (size_t)8 * RDPN_P + p, ax);
-        st_vec<VEC>(ob + (size_t)9 * RDPN_P + p, ay);
-        st_vec<VEC>(ob + (size_t)10 * RDPN_P + p, az);
-        int c = 11;
-        if (region_attention) {
-            // exp(x - max) / sum, then * mask_prob: one IEEE division per pixel (scale / sum) instead of one per
-            // channel -- within 1 ulp of the reference's per-element division (tolerance stated in the test)
-            float k[VEC];
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) k[j] = __fdiv_rn(scale[j], sum[j]);
-#pragma unroll
-            for (int r = 0; r < RMAX; ++r)
-                if (r < R) {
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) lg[r][j] *= k[j];
-                    st_vec<VEC>(ob + (size_t)(11 + r) * RDPN_P + p, lg[r]);
-                }
-            c += R;
-        }
-        if (mask_attention == 2) st_vec<VEC>(ob + (size_t)c * RDPN_P + p, mp);  // "concat"
+    __syncthreads();  // anchors, barrier initialisation
+    const int p = p0 + t;
+    float mp = 1.f;
+    if (mask_attention != 0) {
+        const float m = __ldcs(mask + po + p);
+        if (mask_mode == RDPN_MASK_L1) mp = __fdiv_rn(__fsub_rn(m, mn), mden);
+        else if (mask_mode == RDPN_MASK_BCE) mp = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-m)));
+        else mp = m;
     }
+    const float scale = mask_attention == 1 ? mp : 1.f;  // "mul" (conv_pnp_net.py:134-135)
+    // channels 0-2: coor, 3-7: roi_coord_2d -- while the tile is in flight
+    {
+        const float* srcs[8] = {cx + po, cy + po, cz + po, coord2d + ((size_t)b * 5 + 0) * RDPN_P,
+                                coord2d + ((size_t)b * 5 + 1) * RDPN_P, coord2d + ((size_t)b * 5 + 2) * RDPN_P,
+                                coord2d + ((size_t)b * 5 + 3) * RDPN_P, coord2d + ((size_t)b * 5 + 4) * RDPN_P};
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = __ldcs(srcs[c] + p);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) __stcs(ob + (size_t)c * RDPN_P + t, v[c] * scale);
+    }
+    mbar_wait(&bar, 0);
+    // sweep 1: max / arg-max (first maximum wins, torch.argmax)
+    float mx = -FLT_MAX;
+    int am = 0;
+#pragma unroll 8
+    for (int r = 0; r < R; ++r) {
+        const float l = tile[r * CF_TP + t];
+        if (l > mx) { mx = l; am = r; }
+    }
+    {   // channels 8-10: anchor of the arg-max region
+        const float4 an = anchors[am];
+        __stcs(ob + (size_t)8 * RDPN_P + t, an.x * scale);
+        __stcs(ob + (size_t)9 * RDPN_P + t, an.y * scale);
+        __stcs(ob + (size_t)10 * RDPN_P + t, an.z * scale);
+    }
+    int c = 11;
+    if (region_attention) {
+        // sweep 2: e = exp(l - max) in place, sum in channel order
+        float sum = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < R; ++r) {
+            const float e = expf(__fsub_rn(tile[r * CF_TP + t], mx));
+            tile[r * CF_TP + t] = e;
+            sum = __fadd_rn(sum, e);
+        }
+        // exp(x - max) / sum, then * mask_prob: one IEEE division per pixel (scale / sum) instead of one per
+        // channel -- within 1 ulp of the reference's per-element division (tolerance stated in the test)
+        const float k = __fdiv_rn(scale, sum);
+        // sweep 3: normalise in place, then the rows leave by bulk stores
+#pragma unroll 8
+        for (int r = 0; r < R; ++r) tile[r * CF_TP + t] *= k;
+        fence_proxy_async();
+        __syncthreads();
+        for (int r = t; r < R; r += CF_T) bulk_s2g(ob + (size_t)(11 + r) * RDPN_P, tile + r * CF_TP, CF_TP * 4);
+        bulk_commit();
+        c += R;
+    }
+    if (mask_attention == 2) __stcs(ob + (size_t)c * RDPN_P + t, mp);  // "concat"
+    bulk_wait_read_all();  // the tile must stay intact until the bulk stores have read it
 }
 
 }  // namespace rdpn
@@ -179,12 +154,22 @@ extern "C" int rdpn_coor_feat(const float* d_coor_x, const float* d_coor_y, cons
         return RDPN_E_ALIGN;
     const int C = 11 + (region_attention ? R : 0) + (mask_attention == 2 ? 1 : 0);
     cudaStream_t st = (cudaStream_t)stream;
-    if (R <= 32)
-        rdpn::coor_feat_kernel<32, 4><<<B, rdpn::CF_T, 0, st>>>(d_coor_x, d_coor_y, d_coor_z, d_roi_coord_2d, d_region, d_fps, d_mask, R,
-                                                             mask_mode, region_attention, mask_attention, d_out, C);
+    const int tp = R <= 32 ? 512 : 256;
+    const int smem = R * tp * 4;
+    static int attr_smem[2] = {0, 0};
+    if (smem > attr_smem[tp == 512]) {
+        if (tp == 512)
+            RDPN_CUDA_TRY(cudaFuncSetAttribute(rdpn::coor_feat_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        else
+            RDPN_CUDA_TRY(cudaFuncSetAttribute(rdpn::coor_feat_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_smem[tp == 512] = smem;
+    }
+    if (tp == 512)
+        rdpn::coor_feat_kernel<512><<<B * (RDPN_P / 512), 512, smem, st>>>(d_coor_x, d_coor_y, d_coor_z, d_roi_coord_2d, d_region, d_fps,
+                                                                       d_mask, R, mask_mode, region_attention, mask_attention, d_out, C);
     else
-        rdpn::coor_feat_kernel<64, 2><<<B, rdpn::CF_T, 0, st>>>(d_coor_x, d_coor_y, d_coor_z, d_roi_coord_2d, d_region, d_fps, d_mask, R,
-                                                             mask_mode, region_attention, mask_attention, d_out, C);
+        rdpn::coor_feat_kernel<256><<<B * (RDPN_P / 256), 256, smem, st>>>(d_coor_x, d_coor_y, d_coor_z, d_roi_coord_2d, d_region, d_fps,
+                                                                       d_mask, R, mask_mode, region_attention, mask_attention, d_out, C);
     ++rdpn::g_launch_count;
     RDPN_LAUNCH_CHECK();
     return 0;
