@@ -7,8 +7,10 @@ gate + RANSAC scoring + Kabsch refit) on N B200s of one node.
 
 A "step" is one pass of the fused solver (one kernel launch) over one batch of synthetic ROIs.  The
 workload at N=1 is BASELINE.json configs[1]: LM-O, 8 objects, 1024 ROIs, 256 hypotheses/ROI; at N>1
-every rank processes its own 1024-ROI shard (weak scaling) and the [shard,16] result rows are
-all-gathered over NCCL each step (pipelined behind the next step's kernel).
+every rank processes its own 1024-ROI shard per step (weak scaling); the [shard,16] result rows of the timed
+steps are collected on the device and all-gathered over NCCL once, inside the timed region, as the reference
+gathers its predictions once per evaluation (gdrn_evaluator.py:439-442); --gather-every G gathers after every
+G steps instead (G = 1: every step, pipelined behind the next step's kernel).
 
 One JSON line is printed by rank 0 (see the keys at the bottom).  `value` is device-resident
 throughput (inputs already in HBM), `e2e` is the same metric through the host-buffer C-ABI plugin call
@@ -78,7 +80,9 @@ def workload_config(n_gpus):
         "num_regions": NUM_REGIONS, "inlier_thr_m": INLIER_THR, "refit": "unweighted Kabsch on inliers, 1 iteration",
         "l2": "%d rotating input sets (%.0f MB) > 126 MB L2" % (N_INPUT_SETS, N_INPUT_SETS * ROIS_PER_GPU * BYTES_MAPS / 1e6),
         "streams": "steps alternate over 2 CUDA streams (launch tails overlap); timed with events on the parent stream",
-        "parallelism": "roi-shard x%d + NCCL all-gather of [shard,16] rows" % n_gpus if n_gpus > 1 else "single GPU",
+        "parallelism": "roi-shard x%d, one NCCL all-gather of the [steps*shard,16] result rows inside the timed region "
+                       "(the reference gathers once per evaluation, gdrn_evaluator.py:439-442)" % n_gpus if n_gpus > 1
+                       else "single GPU",
     }
 
 
@@ -287,6 +291,14 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def step_noacc(plans, streams, i):
+    """Pre-heat step: the kernel only (no row collection, no collective)."""
+    import torch
+
+    with torch.cuda.stream(streams[i % 2]):
+        plans[i % N_INPUT_SETS].launch()
+
+
 def gpu_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -330,22 +342,38 @@ def gpu_arm(args):
                                    s["anchors"]) for s in sets]
     B, H, R = ROIS_PER_GPU, NUM_HYP, NUM_REGIONS
     total = B * world
-    gather_out = [torch.empty(total, 16, dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
+    G = args.gather_every if args.gather_every > 0 else max(args.steps, 1)  # steps per gather
+    acc = gathered = None
+    if world > 1:
+        acc = [torch.empty(G, B, 16, dtype=torch.float32, device=dev) for _ in range(2)]  # rows of the current / previous group
+        gathered = [torch.empty(world * G, B, 16, dtype=torch.float32, device=dev) for _ in range(2)]
 
     # consecutive steps alternate over two streams so that the tail of one launch (the last CTAs of a
     # 1024-ROI grid leave most SMs idle) overlaps the head of the next -- a continuous ROI stream does the same
     streams = [torch.cuda.Stream(dev) for _ in range(2)]
+    state = {"pending": None}
 
-    def step(i, pending):
+    def step(i):
         with torch.cuda.stream(streams[i % 2]):
             p = plans[i % N_INPUT_SETS]
             res = p.launch()
             if world > 1:
-                rows = res.rows16()
-                if pending[i % 2] is not None:
-                    pending[i % 2].wait()
-                pending[i % 2] = dist.all_gather_into_tensor(gather_out[i % 2], rows, async_op=True)
+                acc[(i // G) % 2][i % G].copy_(res.rows16(), non_blocking=True)
+        if world > 1 and (i % G) == G - 1:
+            gather_group((i // G) % 2)
         return res
+
+    def gather_group(g):
+        """All-gather the rows of group g (both compute streams must have finished writing them)."""
+        gs = torch.cuda.current_stream(dev)
+        for st in streams:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            gs.wait_event(ev)
+        if state["pending"] is not None:
+            state["pending"].wait()
+        state["pending"] = dist.all_gather_into_tensor(gathered[g].view(-1),
+                                                       acc[g].reshape(-1), async_op=True)
 
     def fork():  # both streams start after everything already queued on the current stream
         ev = torch.cuda.Event()
@@ -359,18 +387,21 @@ def gpu_arm(args):
             ev.record(st)
             torch.cuda.current_stream().wait_event(ev)
 
-    def drain(pending):
-        for j in range(2):
-            if pending[j] is not None:
-                pending[j].wait()
-                pending[j] = None
+    def drain(n_steps):
+        """Gather a trailing partial group and wait for the last collective."""
+        if world > 1:
+            if n_steps % G:
+                gather_group(((n_steps - 1) // G) % 2)
+            if state["pending"] is not None:
+                state["pending"].wait()
+                state["pending"] = None
 
-    pending = [None, None]
     fork()
-    for i in range(max(args.warmup, 3)):
-        step(i, pending)
-    drain(pending)
+    nw = max(args.warmup, 3)
+    for i in range(nw):
+        step(i)
     join()
+    drain(nw)
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank if os.environ.get("CUDA_VISIBLE_DEVICES") is None else
@@ -378,13 +409,10 @@ def gpu_arm(args):
     sampler.start()
     # pre-heat ~0.7 s under the same load so that the sampled clocks are the steady-state ones
     t_heat = time.perf_counter()
-    i = 0
     while time.perf_counter() - t_heat < args.preheat:
         fork()
-        for _ in range(50):
-            step(i, pending)
-            i += 1
-        drain(pending)
+        for i in range(50):
+            step_noacc(plans, streams, i)
         join()
         torch.cuda.synchronize()
 
@@ -396,9 +424,9 @@ def gpu_arm(args):
     e0.record()
     fork()
     for i in range(args.steps):
-        step(i, pending)
-    drain(pending)
+        step(i)
     join()
+    drain(args.steps)
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -411,6 +439,11 @@ def gpu_arm(args):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t)
+        # the gathered block of this rank holds every rank's rows of the last group, in rank order
+        last = gathered[((args.steps - 1) // G) % 2].view(world, G, B, 16)
+        gather_ok = bool(torch.equal(last[rank], acc[((args.steps - 1) // G) % 2]))
+    else:
+        gather_ok = None
 
     # ---- kernel-only duration of the dominant kernel (no gather), for the roofline ----
     torch.cuda.synchronize()
@@ -588,6 +621,7 @@ def gpu_arm(args):
                                        "triplets in pinned host memory (depth fetched only where the mask passes); results to pinned "
                                        "host tensors.  Same rdpn_pose_solve_host call via rdpn6d_b200.pose_solver.HostPoseSolver."},
         "host_path_matches_device_path": host_matches_device,
+        "gather_ok": gather_ok,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
@@ -624,6 +658,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--preheat", type=float, default=0.7, help="seconds of untimed load before the timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather-every", type=int, default=0,
+                    help="N>1: all-gather the result rows after every G steps (0 = once, after the last timed step)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
