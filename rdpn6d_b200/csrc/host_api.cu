@@ -422,7 +422,10 @@ int rdpn_pose_solve_host(rdpn_ctx* c, const rdpn_roi_inputs* h, const int32_t* h
     const int B = h->B;
     int rc = 0;
     unsigned long long moved = 0;
-    for (int b0 = 0, stage = 0; b0 < B && rc == 0; b0 += c->chunk, stage = (stage + 1) % RDPN_STAGES) {
+    // bulk copies of many tensors queue best over two streams (more only interleaves them on the copy engines); the
+    // pull pipeline (one bulk copy + two kernels per chunk) wants all four stages
+    const int nstages = any_pull ? RDPN_STAGES : 2;
+    for (int b0 = 0, stage = 0; b0 < B && rc == 0; b0 += c->chunk, stage = (stage + 1) % nstages) {
         const size_t nb = (size_t)((B - b0) < c->chunk ? (B - b0) : c->chunk);
         cudaStream_t st = c->st[stage];
         unsigned char* d = c->buf[stage];
