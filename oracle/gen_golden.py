@@ -15,6 +15,18 @@ Files written (small, committed):
   region_golden.npz   xyz crops + anchors + (region ids, delta) from data_utils.xyz_to_region (:229-244)
   pose_golden.npz     a 4-ROI synthetic batch + the composite's outputs where EVERY Kabsch call
                       (hypotheses and refit) went through the reference's affine_matrix_from_points
+  path_golden.npz     outputs of reference functions whose MODULES do not import here (mmcv / detectron2 /
+                      transforms3d are absent) but whose bodies are plain numpy / torch: the function source is cut
+                      out of the reference file with `ast` and executed as it stands (ref_functions below):
+                        gate + de-normalisation   gdrn_evaluator.py:89-126  get_img_model_points_with_coords2d
+                        mask post-processing      engine_utils.py:118-136   get_out_mask (L1, BCE)
+                        back-projection           misc.py:319-349           backproject, backproject_th
+                        rigid apply               misc.py:895-905           transform_pts_Rt
+                        re / te                   pose_error.py:400-436
+                        rot6d                     rot_reps.py:8-49          ortho6d_to_mat_batch (+ helpers)
+                        allo -> ego, pose assembly  utils.py:39-94, pose_from_pred_centroid_z.py:52-141, with the one
+                                                  missing third-party call (transforms3d.axangles.axangle2mat =
+                                                  Rodrigues' formula) supplied by the oracle
 """
 import importlib.util
 import os
@@ -32,6 +44,113 @@ def _load(name, rel):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+def ref_functions(rel, names, env=None):
+    """Compile the named top-level functions or methods of a reference file WITHOUT importing the module: their
+    source segments are taken verbatim from the file (ast) and executed in a namespace holding numpy / torch / math
+    and `env`.  Methods become plain functions (pass self=None).  Nothing is written anywhere."""
+    import ast
+    import math
+
+    import torch
+
+    src = open(os.path.join(REF, rel)).read()
+    tree = ast.parse(src)
+    found = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name in names and node.name not in found:
+            found[node.name] = node
+    ns = {"np": np, "torch": torch, "math": math, "random": __import__("random")}
+    ns.update(env or {})
+    for name in names:
+        seg = ast.get_source_segment(src, found[name])
+        import textwrap
+
+        exec(compile(textwrap.dedent(seg), os.path.join(REF, rel), "exec"), ns)
+    return {n: ns[n] for n in names}
+
+
+def gen_path():
+    """Reference functions executed from source (see the module docstring)."""
+    import types
+
+    import torch
+
+    from oracle import pose_oracle as po
+
+    rng = np.random.default_rng(23)
+    out = {}
+    # --- gate + de-normalisation (gdrn_evaluator.py:89-126)
+    f = ref_functions("core/gdrn_modeling/gdrn_evaluator.py", ["get_img_model_points_with_coords2d"])
+    gate_ref = f["get_img_model_points_with_coords2d"]
+    G = 6
+    maskp = rng.uniform(0, 1, (G, 64, 64)).astype(np.float32)
+    coor = rng.uniform(0, 1, (G, 64, 64, 3)).astype(np.float32)
+    coor[:, :8] = 0.5  # rows whose de-normalised residual is exactly 0: must be gated out
+    coor[:, 8:12, :, 1] = 0.5 + 5e-5  # |delta_y| = 5e-5 * extent < 1e-4 * extent: out as well
+    extent = rng.uniform(0.05, 0.3, (G, 3)).astype(np.float32)
+    c2d = rng.uniform(0, 1, (G, 64, 64, 2)).astype(np.float32)
+    npts, mpts, ipts = [], [], []
+    for i in range(G):
+        ip, mp_ = gate_ref(None, maskp[i].copy(), coor[i].copy(), c2d[i].copy(), 480, 640, extent[i], -1, 0.5)
+        npts.append(len(mp_))
+        mpts.append(mp_)
+        ipts.append(ip)
+    out.update(gate_mask=maskp, gate_coor=coor, gate_extent=extent, gate_c2d=c2d, gate_n=np.array(npts),
+               gate_model_points=np.concatenate(mpts), gate_image_points=np.concatenate(ipts))
+    # --- mask post-processing (engine_utils.py:118-136)
+    gm = ref_functions("core/gdrn_modeling/engine_utils.py", ["get_out_mask"])["get_out_mask"]
+    raw = rng.normal(0.3, 0.4, (5, 1, 64, 64)).astype(np.float32)
+    for mode in ("L1", "BCE"):
+        cfg = types.SimpleNamespace(MODEL=types.SimpleNamespace(CDPN=types.SimpleNamespace(
+            ROT_HEAD=types.SimpleNamespace(MASK_LOSS_TYPE=mode))))
+        out["mask_" + mode] = gm(cfg, torch.from_numpy(raw)).numpy()
+    out["mask_raw"] = raw
+    # --- back-projection, rigid apply (misc.py)
+    mf = ref_functions("lib/pysixd/misc.py", ["backproject", "backproject_th", "transform_pts_Rt"])
+    depth = rng.uniform(0.3, 1.5, (48, 64)).astype(np.float32)
+    depth[rng.random((48, 64)) < 0.2] = 0
+    K = np.array([[572.4114, 0, 325.2611], [0, 573.57043, 242.04899], [0, 0, 1]])
+    out.update(bp_depth=depth, bp_K=K, bp_np=mf["backproject"](depth, K),
+               bp_th=mf["backproject_th"](torch.from_numpy(depth), torch.from_numpy(K.astype(np.float32))).numpy())
+    pts = rng.uniform(-0.2, 0.2, (50, 3))
+    tf = _load("ref_transform", "lib/pysixd/transform.py")
+    R = tf.random_rotation_matrix(rng.random(3))[:3, :3]
+    t = rng.uniform(-1, 1, 3)
+    out.update(rt_pts=pts, rt_R=R, rt_t=t, rt_out=mf["transform_pts_Rt"](pts, R, t))
+    # --- re / te (pose_error.py:400-436)
+    ef = ref_functions("lib/pysixd/pose_error.py", ["re", "te"])
+    Rs = np.stack([tf.random_rotation_matrix(rng.random(3))[:3, :3] for _ in range(8)])
+    Rs[1] = Rs[0]  # identical rotations: trace 3 (clamp branch)
+    ts = rng.uniform(-1, 1, (8, 3))
+    out.update(err_R=Rs, err_t=ts, err_re=np.array([ef["re"](Rs[i], Rs[(i + 1) % 8]) for i in range(8)]),
+               err_te=np.array([ef["te"](ts[i], ts[(i + 1) % 8]) for i in range(8)]))
+    # --- rot6d (rot_reps.py)
+    rf = ref_functions("core/utils/rot_reps.py", ["normalize_vector", "cross_product", "ortho6d_to_mat_batch"],
+                       env={"F": torch.nn.functional})  # rot_reps.py:6 import torch.nn.functional as F
+    p6 = rng.normal(0, 1, (16, 6)).astype(np.float32)
+    out.update(rot6d_in=p6, rot6d_out=rf["ortho6d_to_mat_batch"](torch.from_numpy(p6)).numpy())
+    # --- allo -> ego and the test-time pose assembly; axangle2mat (transforms3d, absent) = Rodrigues from the oracle
+    uf = ref_functions("core/utils/utils.py", ["allocentric_to_egocentric"], env={"axangle2mat": po.axangle2mat})
+    pf = ref_functions("core/gdrn_modeling/models/pose_from_pred_centroid_z.py", ["pose_from_predictions_test"],
+                       env={"allocentric_to_egocentric": uf["allocentric_to_egocentric"]})
+    n = 12
+    rots = np.stack([tf.random_rotation_matrix(rng.random(3))[:3, :3] for _ in range(n)]).astype(np.float32)
+    cent = rng.uniform(-0.3, 0.3, (n, 2)).astype(np.float32)
+    zv = rng.uniform(0.5, 1.5, (n, 1)).astype(np.float32)
+    cams = np.tile(K.astype(np.float32)[None], (n, 1, 1))
+    ctr = rng.uniform(100, 500, (n, 2)).astype(np.float32)
+    rr = rng.uniform(0.2, 1.5, n).astype(np.float32)
+    whs = rng.uniform(40, 200, (n, 2)).astype(np.float32)
+    for zt in ("REL", "ABS"):
+        ego, tr = pf["pose_from_predictions_test"](torch.from_numpy(rots), torch.from_numpy(cent), torch.from_numpy(zv),
+                                                   torch.from_numpy(cams.copy()), torch.from_numpy(ctr), torch.from_numpy(rr),
+                                                   torch.from_numpy(whs), is_allo=True, z_type=zt)
+        out["assm_rot_" + zt], out["assm_trans_" + zt] = ego.numpy(), tr.numpy()
+    out.update(assm_rots=rots, assm_cent=cent, assm_z=zv, assm_cams=cams, assm_ctr=ctr, assm_rr=rr, assm_whs=whs)
+    np.savez_compressed(os.path.join(GOLD, "path_golden.npz"), **out)
+    print("path_golden.npz", len(out), "gate n:", npts)
 
 
 def gen_fps():
@@ -182,6 +301,7 @@ def main():
     gen_affine(du)
     gen_region(du)
     gen_pose(tf)
+    gen_path()
 
 
 if __name__ == "__main__":

@@ -510,13 +510,17 @@ def axangle2mat(axis, angle):
 
 
 def allocentric_to_egocentric_mat(R_allo, trans):
-    """utils.py:39-94 for src_type=dst_type='mat', cam_ray=(0,0,1): R_ego = Rodrigues(cam x obj, acos(obj_z)) R_allo."""
+    """utils.py:39-94 for src_type=dst_type='mat', cam_ray=(0,0,1): R_ego = Rodrigues(cam x obj, acos(obj_z)) R_allo.
+
+    dtype flow of the reference as called from pose_from_pred_centroid_z.py:127-136 (pinned by
+    tests/golden/path_golden.npz): the pose is float32, so the object ray is normalised in float32; angle, axis and the
+    Rodrigues matrix are float64; the product is rounded to float32 when stored into the float32 ego pose."""
     cam_ray = np.array([0, 0, 1.0])
-    trans = np.asarray(trans, F64)
-    obj_ray = trans / np.linalg.norm(trans)
+    trans = np.asarray(trans, F32)
+    obj_ray = trans.copy() / np.linalg.norm(trans)  # float32
     angle = math.acos(cam_ray.dot(obj_ray))
     if angle > 0:
-        return axangle2mat(np.cross(cam_ray, obj_ray), angle) @ np.asarray(R_allo, F64)
+        return np.dot(axangle2mat(np.cross(cam_ray, obj_ray), angle), np.asarray(R_allo, F32))
     return np.asarray(R_allo, F64).copy()
 
 

@@ -1,0 +1,69 @@
+"""CPU: the oracle's restatements of the path pieces whose reference MODULES cannot be imported here, checked
+against tests/golden/path_golden.npz -- outputs of the reference's own function bodies (cut out of the reference
+files with `ast` and executed by oracle/gen_golden.py:gen_path)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pose_oracle as po
+
+
+@pytest.fixture(scope="module")
+def g(golden_dir):
+    return np.load(os.path.join(golden_dir, "path_golden.npz"))
+
+
+def test_gate_and_denormalisation_match_reference(g):
+    """gdrn_evaluator.py:89-126: model points = de-normalised residual of the gated pixels, in raster order."""
+    off = 0
+    for i in range(len(g["gate_n"])):
+        coor = np.ascontiguousarray(g["gate_coor"][i].transpose(2, 0, 1))  # HWC -> 3HW
+        delta = po.denormalise_residual(coor, g["gate_extent"][i])
+        sel = po.gate(g["gate_mask"][i], delta, g["gate_extent"][i], np.ones((64, 64), np.float32), 0.5)
+        n = int(g["gate_n"][i])
+        assert int(sel.sum()) == n
+        mine = delta.transpose(1, 2, 0)[sel]
+        assert np.array_equal(mine.view(np.uint32), g["gate_model_points"][off:off + n].view(np.uint32))
+        # the rows constructed to sit exactly on / inside the |delta| > 1e-4 * extent rule are out
+        assert not sel[:12].any()
+        off += n
+
+
+def test_mask_postprocessing_matches_reference(g):
+    raw = g["mask_raw"]
+    for b in range(raw.shape[0]):
+        l1 = po.out_mask(raw[b, 0], po.MASK_L1)
+        assert np.array_equal(l1.view(np.uint32), g["mask_L1"][b, 0].view(np.uint32))
+        bce = po.out_mask(raw[b, 0], po.MASK_BCE)
+        np.testing.assert_allclose(bce, g["mask_BCE"][b, 0], rtol=3e-7, atol=0)  # torch.sigmoid vs 1/(1+exp(-m)): 2 ulp
+
+
+def test_backprojection_matches_reference(g):
+    mine = po.backproject(g["bp_depth"], g["bp_K"])
+    # torch float32 version (misc.py:334-349): same operation order -> bit-exact
+    assert np.array_equal(mine.view(np.uint32), g["bp_th"].view(np.uint32))
+    # numpy version computes in float64 (range() is int64, K float64): equal to float32 rounding
+    np.testing.assert_allclose(mine, g["bp_np"], rtol=2e-7, atol=1e-9)
+
+
+def test_rigid_apply_and_error_metrics_match_reference(g):
+    out = po.transform_pts_Rt(g["rt_pts"], g["rt_R"], g["rt_t"])
+    assert np.array_equal(out, g["rt_out"])
+    for i in range(8):
+        assert po.re(g["err_R"][i], g["err_R"][(i + 1) % 8]) == pytest.approx(float(g["err_re"][i]), abs=1e-12)
+        assert po.te(g["err_t"][i], g["err_t"][(i + 1) % 8]) == pytest.approx(float(g["err_te"][i]), abs=1e-15)
+    assert float(g["err_re"][0]) == 0.0  # identical rotations (clamp branch)
+
+
+def test_rot6d_matches_reference(g):
+    np.testing.assert_allclose(po.ortho6d_to_mat(g["rot6d_in"]), g["rot6d_out"], rtol=0, atol=3e-7)
+
+
+@pytest.mark.parametrize("zt", ["REL", "ABS"])
+def test_pose_assembly_matches_reference(g, zt):
+    """pose_from_pred_centroid_z.py:52-141 + utils.py:39-94 (allo -> ego)."""
+    rot, tr = po.pose_from_pred_centroid_z_test(g["assm_rots"], g["assm_cent"], g["assm_z"], g["assm_cams"], g["assm_ctr"],
+                                                g["assm_rr"], g["assm_whs"], is_allo=True, z_type=zt)
+    assert np.array_equal(tr.view(np.uint32), g["assm_trans_" + zt].view(np.uint32))
+    np.testing.assert_allclose(rot, g["assm_rot_" + zt], rtol=0, atol=1.5e-7)

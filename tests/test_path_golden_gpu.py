@@ -1,0 +1,83 @@
+"""GPU: the kernels against outputs of the REFERENCE's own function bodies (tests/golden/path_golden.npz, produced by
+oracle/gen_golden.py:gen_path): gate + de-normalisation, mask post-processing, back-projection, rot6d and the
+test-time pose assembly."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from rdpn6d_b200 import geometry, pose_from_pred, pose_solver
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def g(golden_dir):
+    return np.load(os.path.join(golden_dir, "path_golden.npz"))
+
+
+def _cu(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def test_s1_gate_matches_reference_gate(cuda, g):
+    """gdrn_evaluator.py:89-126 executed from source: same selected pixels, and the dense-mode object point of the
+    S1 kernel is exactly the reference's de-normalised model point."""
+    G = len(g["gate_n"])
+    coor = g["gate_coor"].transpose(0, 3, 1, 2)  # [G,3,64,64]
+    depth = np.ones((G, 64, 64), np.float32)  # the 3D-3D gate additionally wants a depth; give every pixel one
+    Kp = np.tile(np.array([[500.0, 500.0, 128.0, 128.0]], np.float32), (G, 1))
+    s1 = pose_solver.correspond(_cu(depth), _cu(Kp), _cu(coor[:, 0]), _cu(coor[:, 1]), _cu(coor[:, 2]), _cu(g["gate_mask"]),
+                                _cu(g["gate_extent"]), mask_mode="raw", want_obj=True)
+    sel = s1["sel"].reshape(G, 64, 64).cpu().numpy().astype(bool)
+    obj = s1["obj"].reshape(G, 3, 64, 64).cpu().numpy()
+    off = 0
+    for i in range(G):
+        n = int(g["gate_n"][i])
+        assert int(sel[i].sum()) == n == int(s1["n_sel"][i])
+        mine = obj[i].transpose(1, 2, 0)[sel[i]]
+        assert np.array_equal(mine.view(np.uint32), g["gate_model_points"][off:off + n].view(np.uint32))
+        off += n
+
+
+def test_s1_mask_probability_matches_reference_get_out_mask(cuda, g):
+    raw = g["mask_raw"][:, 0]
+    B = raw.shape[0]
+    depth = np.ones((B, 64, 64), np.float32)
+    Kp = np.tile(np.array([[500.0, 500.0, 128.0, 128.0]], np.float32), (B, 1))
+    half = np.full((B, 64, 64), 0.7, np.float32)
+    ext = np.full((B, 3), 0.1, np.float32)
+    for mode, key, exact in (("l1", "mask_L1", True), ("bce", "mask_BCE", False)):
+        s1 = pose_solver.correspond(_cu(depth), _cu(Kp), _cu(half), _cu(half), _cu(half), _cu(raw), _cu(ext), mask_mode=mode)
+        w = s1["w"].reshape(B, 64, 64).cpu().numpy()
+        if exact:
+            assert np.array_equal(w.view(np.uint32), g[key][:, 0].view(np.uint32))
+        else:
+            np.testing.assert_allclose(w, g[key][:, 0], rtol=3e-7, atol=0)  # torch.sigmoid vs 1 / (1 + expf(-m))
+        assert np.array_equal(s1["sel"].reshape(B, 64, 64).cpu().numpy().astype(bool), g[key][:, 0] > 0.5)
+
+
+def test_backproject_matches_reference_backproject_th(cuda, g):
+    out = geometry.backproject_th(_cu(g["bp_depth"]), _cu(g["bp_K"].astype(np.float32))).cpu().numpy()
+    assert np.array_equal(out.view(np.uint32), g["bp_th"].view(np.uint32))
+
+
+@pytest.mark.parametrize("zt", ["REL", "ABS"])
+def test_pose_assembly_matches_reference(cuda, g, zt):
+    rot, tr = pose_from_pred.pose_from_pred_centroid_z(_cu(g["assm_rots"]), _cu(g["assm_cent"]), _cu(g["assm_z"]),
+                                                       _cu(g["assm_cams"]), _cu(g["assm_ctr"]), _cu(g["assm_rr"]),
+                                                       _cu(g["assm_whs"]), is_allo=True, z_type=zt)
+    assert np.array_equal(tr.cpu().numpy().view(np.uint32), g["assm_trans_" + zt].view(np.uint32))
+    np.testing.assert_allclose(rot.cpu().numpy(), g["assm_rot_" + zt], rtol=0, atol=2e-6)
+
+
+def test_rot6d_matches_reference(cuda, g):
+    n = g["rot6d_in"].shape[0]
+    z = torch.ones(n, 1, device="cuda")
+    K = torch.eye(3, device="cuda")[None].repeat(n, 1, 1) * 500
+    K[:, 2, 2] = 1
+    rot, _ = pose_from_pred.pose_from_pred_centroid_z(_cu(g["rot6d_in"]), torch.zeros(n, 2, device="cuda"), z, K,
+                                                      torch.zeros(n, 2, device="cuda"), torch.ones(n, device="cuda"),
+                                                      torch.ones(n, 2, device="cuda"), is_allo=False, z_type="ABS")
+    np.testing.assert_allclose(rot.cpu().numpy(), g["rot6d_out"], rtol=0, atol=5e-7)
