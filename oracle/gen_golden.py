@@ -149,6 +149,36 @@ def gen_path():
                                                    torch.from_numpy(whs), is_allo=True, z_type=zt)
         out["assm_rot_" + zt], out["assm_trans_" + zt] = ego.numpy(), tr.numpy()
     out.update(assm_rots=rots, assm_cent=cent, assm_z=zv, assm_cams=cams, assm_ctr=ctr, assm_rr=rr, assm_whs=whs)
+    # --- the loader's depth back-projection, data_loader.py:530-576 + the [:, ::4, ::4] of :625: the statements are
+    # inline code of a detectron2-dependent method, so the source LINES are cut out and executed as they stand with
+    # the local variables they expect.  NOTE numpy here (2.x, NEP 50) evaluates float32-array (op) np.float64-scalar
+    # in float64, the reference's pinned numpy 1.23 in float32: the stored float32 result equals the float32-step
+    # arithmetic of the oracle / kernels to within 1-2 float32 ulps, not bit for bit.
+    import textwrap
+
+    import cv2
+
+    du = _load("ref_data_utils", "core/utils/data_utils.py")
+    lines = open(os.path.join(REF, "core/gdrn_modeling/data_loader.py")).read().splitlines()
+    block = textwrap.dedent("\n".join(lines[529:576]))  # 1-based lines 530..576
+    assert block.lstrip().startswith("resize_ratio = out_res / scale") and "depth_xyz = np.concatenate" in block
+    n = 6
+    dimg = rng.uniform(0.4, 1.6, (480, 640)).astype(np.float32)
+    dimg[rng.random((480, 640)) < 0.1] = 0
+    Kc = np.array([[572.4114, 0, 325.2611], [0, 573.57043, 242.04899], [0, 0, 1]], dtype=np.float32)
+    centers = rng.uniform(150, 450, (n, 2)).astype(np.float32)
+    scales = rng.uniform(60, 300, n).astype(np.float32)
+    coord_2d = du.get_2d_coord_np(640, 480, low=0, high=1).transpose(1, 2, 0)
+    xyz64, newK = [], []
+    for i in range(n):
+        env = dict(np=np, cv2=cv2, crop_resize_by_warp_affine=du.crop_resize_by_warp_affine, my_warp_affine=du.my_warp_affine,
+                   out_res=64, input_res=256, scale=float(scales[i]), bbox_center=centers[i], depth_img=dimg, K=Kc,
+                   coord_2d=coord_2d)
+        exec(compile(block, "data_loader.py:530-576", "exec"), env)
+        xyz64.append(env["depth_xyz"][:, ::4, ::4].astype("float32"))  # :624-627
+        newK.append(env["newCameraK"])
+    out.update(loader_depth_img=dimg, loader_K=Kc, loader_centers=centers, loader_scales=scales,
+               loader_depth_xyz=np.stack(xyz64), loader_newK=np.stack(newK))
     np.savez_compressed(os.path.join(GOLD, "path_golden.npz"), **out)
     print("path_golden.npz", len(out), "gate n:", npts)
 

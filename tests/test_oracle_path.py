@@ -67,3 +67,20 @@ def test_pose_assembly_matches_reference(g, zt):
                                                 g["assm_rr"], g["assm_whs"], is_allo=True, z_type=zt)
     assert np.array_equal(tr.view(np.uint32), g["assm_trans_" + zt].view(np.uint32))
     np.testing.assert_allclose(rot, g["assm_rot_" + zt], rtol=0, atol=1.5e-7)
+
+
+def test_loader_backprojection_matches_reference_lines(g):
+    """data_loader.py:530-576 + :625 executed from the source lines: crop intrinsics K' = A K, bilinear depth crop
+    / resize_ratio, (x - cx') * d / fx' at the kept pixels.  Depth is bit-exact; X / Y agree to one float32 ulp of
+    the coordinate (the reference evaluates this formula in float32 under its pinned numpy 1.23 -- as the oracle
+    and the kernels do -- but in float64 under the numpy 2 that generated the vectors)."""
+    for i in range(len(g["loader_scales"])):
+        c, sc = g["loader_centers"][i], float(g["loader_scales"][i])
+        Kp = po.roi_intrinsics(g["loader_K"], c, sc, 256)
+        nk = g["loader_newK"][i]
+        np.testing.assert_allclose(Kp, [nk[0, 0], nk[1, 1], nk[0, 2], nk[1, 2]], rtol=1e-12)
+        d64 = po.roi_crop_depth(g["loader_depth_img"], c, sc, 256, 64)
+        q = po.backproject_roi(d64, Kp, depth_div=np.float32(64 / sc), stride=4)
+        ref = g["loader_depth_xyz"][i]
+        assert np.array_equal(q[2].view(np.uint32), ref[2].view(np.uint32))
+        assert (np.abs(q[:2] - ref[:2]) <= 1.2e-7 * ref[2][None]).all()

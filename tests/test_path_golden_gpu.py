@@ -81,3 +81,21 @@ def test_rot6d_matches_reference(cuda, g):
                                                       torch.zeros(n, 2, device="cuda"), torch.ones(n, device="cuda"),
                                                       torch.ones(n, 2, device="cuda"), is_allo=False, z_type="ABS")
     np.testing.assert_allclose(rot.cpu().numpy(), g["rot6d_out"], rtol=0, atol=5e-7)
+
+
+def test_loader_backprojection_matches_reference_lines(cuda, g):
+    """data_loader.py:530-576 + :625 executed from the source lines vs rdpn_roi_intrinsics + rdpn_roi_crop_depth +
+    the S1 kernel (dense mode: cam = back-projected point).  Tolerance as in tests/test_oracle_path.py."""
+    n = len(g["loader_scales"])
+    K = _cu(np.tile(g["loader_K"][None], (n, 1, 1)))
+    ctr, sc = _cu(g["loader_centers"]), _cu(g["loader_scales"])
+    Kp = geometry.roi_intrinsics(K, ctr, sc)
+    d64 = geometry.roi_crop_depth(_cu(g["loader_depth_img"])[None], ctr, sc)
+    rr = 64.0 / sc
+    half = torch.full((n, 64, 64), 0.7, device="cuda")
+    s1 = pose_solver.correspond(d64, Kp, half, half, half, torch.ones(n, 64, 64, device="cuda"), torch.ones(n, 3, device="cuda"),
+                                depth_div=rr, mask_mode="raw")
+    cam = s1["cam"].reshape(n, 3, 64, 64).cpu().numpy()
+    ref = g["loader_depth_xyz"]
+    assert np.array_equal(cam[:, 2].view(np.uint32), ref[:, 2].view(np.uint32))
+    assert (np.abs(cam[:, :2] - ref[:, :2]) <= 1.2e-7 * ref[:, 2][:, None]).all()
