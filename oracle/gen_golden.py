@@ -179,8 +179,58 @@ def gen_path():
         newK.append(env["newCameraK"])
     out.update(loader_depth_img=dimg, loader_K=Kc, loader_centers=centers, loader_scales=scales,
                loader_depth_xyz=np.stack(xyz64), loader_newK=np.stack(newK))
+    # --- RANSAC loop rules: misc.pnp_ransac_custom (misc.py:58-142) executed from source with a cv2 SHIM that turns
+    # its 2D-3D solver calls into 3D-3D ones (solvePnP -> the reference's own Kabsch, projectPoints -> rigid apply,
+    # Rodrigues -> identity): the loop, its sampling, its strict '<' inlier rule and its adaptive stop run as written.
+    # Recorded: inlier count of every iteration and the number of iterations executed.  (The loop's SELECTION rule --
+    # lowest mean error over all points -- is deliberately not the composite's)
+    class Cv2Shim:
+        SOLVEPNP_ITERATIVE = 0
+
+        def __init__(self):
+            self.sample_solves, self.proj = 0, []
+
+        def solvePnP(self, mp_, ip_, K_, dist, flags=0):
+            if len(mp_) == 10:
+                self.sample_solves += 1
+            M = tf.affine_matrix_from_points(np.asarray(mp_, float).T, np.asarray(ip_, float).T, shear=False, scale=False,
+                                             usesvd=True)
+            return True, M[:3, :3].copy(), M[:3, 3].copy()
+
+        def projectPoints(self, mp_, R_, T_, K_, dist):
+            pts_ = (R_ @ np.asarray(mp_, float).T).T + T_
+            self.proj.append((len(self.proj), self.sample_solves, pts_))
+            return pts_[:, None, :], None
+
+        def Rodrigues(self, R_):
+            return R_, None
+
+    cases = []
+    for ci, (npt, out_frac, noise) in enumerate([(200, 0.1, 5e-4), (200, 0.45, 1e-3), (150, 0.7, 1e-3), (300, 0.3, 2e-3)]):
+        shim = Cv2Shim()
+        ransac = ref_functions("lib/pysixd/misc.py", ["pnp_ransac_custom"], env={"cv2": shim})["pnp_ransac_custom"]
+        Rg = tf.random_rotation_matrix(rng.random(3))[:3, :3]
+        tg = rng.uniform(-0.3, 0.3, 3) + np.array([0, 0, 0.9])
+        mpts = rng.uniform(-0.1, 0.1, (npt, 3))
+        cpts = (Rg @ mpts.T).T + tg + rng.normal(0, noise, (npt, 3))
+        bad = rng.random(npt) < out_frac
+        cpts[bad] += rng.uniform(-0.1, 0.1, (int(bad.sum()), 3))
+        thr_r = 0.005
+        np.random.seed(1000 + ci)
+        pose_r = ransac(cpts, mpts, None, ransac_iter=100, ransac_min_iter=10, ransac_reprojErr=thr_r)
+        # inlier count of iteration i = first projection recorded after the i-th sample solve
+        counts_r, seen = [], 0
+        for _, ns, pts_ in shim.proj:
+            if ns > seen:
+                counts_r.append(int((np.linalg.norm(pts_ - cpts, axis=1) < thr_r).sum()))
+                seen = ns
+        cases.append((mpts, cpts, np.array(counts_r), shim.sample_solves, pose_r))
+        out["ransac%d_model" % ci], out["ransac%d_cam" % ci] = mpts, cpts
+        out["ransac%d_counts" % ci], out["ransac%d_iters" % ci] = np.array(counts_r), np.array(shim.sample_solves)
+        out["ransac%d_pose" % ci], out["ransac%d_seed" % ci] = pose_r, np.array(1000 + ci)
+    out["ransac_thr"], out["ransac_cases"] = np.array(0.005), np.array(len(cases))
     np.savez_compressed(os.path.join(GOLD, "path_golden.npz"), **out)
-    print("path_golden.npz", len(out), "gate n:", npts)
+    print("path_golden.npz", len(out), "gate n:", npts, "ransac iters:", [c[3] for c in cases])
 
 
 def gen_fps():

@@ -84,3 +84,31 @@ def test_loader_backprojection_matches_reference_lines(g):
         ref = g["loader_depth_xyz"][i]
         assert np.array_equal(q[2].view(np.uint32), ref[2].view(np.uint32))
         assert (np.abs(q[:2] - ref[:2]) <= 1.2e-7 * ref[2][None]).all()
+
+
+def test_ransac_loop_rules_match_reference_loop(g):
+    """misc.pnp_ransac_custom (misc.py:58-142) executed from source behind a cv2 shim that makes its solver calls
+    3D-3D (see oracle/gen_golden.py): the oracle reproduces (a) the inlier count of every iteration -- same sampling
+    call, all points scored, strict '<' -- and (b) the iteration at which the adaptive rule (:134-138) stops the loop,
+    including the reference's quirk that a sample with w^10 below 1 ulp gives k = -inf and ends the loop at
+    min_iter + 1."""
+    thr = float(g["ransac_thr"])
+    for ci in range(int(g["ransac_cases"])):
+        mpts, cpts = g["ransac%d_model" % ci], g["ransac%d_cam" % ci]
+        counts_ref, iters = g["ransac%d_counts" % ci], int(g["ransac%d_iters" % ci])
+        assert len(counts_ref) == iters
+        n = len(mpts)
+        np.random.seed(int(g["ransac%d_seed" % ci]))
+        counts = []
+        for _ in range(iters):
+            idx = np.random.choice(n, 10, replace=False)  # misc.py:91
+            M = po.kabsch(mpts[idx].T, cpts[idx].T)
+            errs = np.linalg.norm(po.transform_pts_Rt(mpts, M[:3, :3], M[:3, 3]) - cpts, axis=1)  # :108-109
+            counts.append(int((errs < thr).sum()))  # :111
+        assert counts == counts_ref.tolist()
+        # the stop rule on a longer sequence: the oracle must stop by itself where the reference loop did
+        longer = np.concatenate([counts_ref, np.full(40, counts_ref.max())])
+        best, examined = po.select_best(longer, np.ones(len(longer), np.uint8), n, min_inliers=4, adaptive=True,
+                                        confidence=0.995, min_iter=10)
+        assert examined == iters
+        assert best == int(np.argmax(counts_ref[:iters])) or counts_ref[:iters].max() < 4
