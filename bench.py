@@ -303,6 +303,11 @@ def gpu_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    numa_node = None
+    if world > 1:  # one process per GPU: keep each rank's pinned host buffers on its GPU's NUMA node
+        from rdpn6d_b200.distributed import bind_to_gpu_numa_node
+
+        numa_node = bind_to_gpu_numa_node(local_rank)
     batch = make_workload()
 
     cpu_base = None
@@ -622,6 +627,7 @@ def gpu_arm(args):
                                        "host tensors.  Same rdpn_pose_solve_host call via rdpn6d_b200.pose_solver.HostPoseSolver."},
         "host_path_matches_device_path": host_matches_device,
         "gather_ok": gather_ok,
+        "numa_node_rank0": numa_node,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,

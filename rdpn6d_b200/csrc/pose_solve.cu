@@ -73,16 +73,20 @@ struct SolveArgs {
 // chains, barriers), so the SM is kept busy by thread-level parallelism across ROIs rather than by
 // staging whole ROIs in shared memory (the first version did: 112 KB and 126 registers per CTA capped
 // the SM at 16 warps and 57 % issue utilisation).
-//   1  L2 prefetch of this ROI's planes; mask min/max straight from global (coalesced float4)
-//   2  GATE only (no divisions): 16 pixels per thread from coalesced float4 loads -> selection bits
-//   3  deterministic counting sort of the gated pixels by region id (warp match_any ranks + per-warp
-//      bucket cursors) -> pix[slot], srid[slot]; run table of the non-empty buckets
+//   1  L2 prefetch of this ROI's planes; the thread's mask quads into registers; mask min/max (one barrier,
+//      every thread folds the eight partials); the thread's first hypothesis triplet is requested now
+//   2  GATE, mask first (no divisions): the mask test runs on all 16 pixels of the thread, depth / coor / region
+//      ids are loaded only for quads with a passing pixel; sort pass A (per-warp bucket histogram, shared-memory
+//      atomics) rides along
+//   3  deterministic counting sort of the gated pixels by region id: bucket cursors by one thread per bucket +
+//      block scan, slots from warp match_any ranks -> pix[slot], srid[slot]; run table of the non-empty buckets
 //   4  hypothesis generation: 3 gathered pixels each, FP64 closed form, rounded once to FP32
 //   5  per chunk of <= 1024 gated slots: STAGING (one thread per slot gathers the raw pixel and computes
 //      (cam xyz, w) with the exact S1 arithmetic into a float4 list in shared memory), then
-//   6  SCORING: one thread per hypothesis; per run the transformed anchor R a + t is computed once
-//      (9 FMA) and every point costs 1 LDS.128 + 3 FADD + FMUL + 2 FFMA + FSETP + predicated IADD
-//   7  best hypothesis, FP64 refit sums, closed-form rotation, outputs
+//   6  SCORING: two hypotheses per thread, warp-aligned groups of warps split the runs; per run the transformed
+//      anchor R a + t is computed once (9 FMA per hypothesis) and every point costs 1/2 LDS.128 + 3 FADD + FMUL +
+//      2 FFMA + FSETP + predicated IADD per hypothesis
+//   7  best hypothesis, FP64 refit moments (two sweeps of nine), closed-form rotation, outputs
 #ifndef RDPN_CHUNK_SLOTS
 #define RDPN_CHUNK_SLOTS 1024
 #endif
@@ -105,7 +109,6 @@ struct __align__(128) FusedSmem {
     uint8_t srid[RDPN_P];           // slot -> region id (non-decreasing)
     uint32_t selmap[RDPN_P / 32];   // gate bitmap by pixel
     RoiConst rc;
-    RoiGate gate;
     float red_f[2][SW];
     int n_sel;
     int n_runs;

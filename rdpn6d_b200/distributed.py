@@ -72,3 +72,44 @@ def solve_sharded(solver, batch_local, total, group=None):
     else:
         rows = torch.zeros(0, 16, dtype=torch.float32, device=batch_local["depth"].device)
     return gather_rows(rows, total, group)
+
+
+def _parse_cpulist(txt):
+    cpus = set()
+    for part in txt.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process (one per GPU) to the CPUs of the NUMA node its GPU hangs off, BEFORE it allocates pinned host
+    buffers: first-touch then places them on that node and the host-buffer plugin call (copies and the gated pull
+    alike) does not cross the socket interconnect.  Returns the node, or None when the topology cannot be read
+    (the process is then left alone).  The reference launches one process per GPU the same way
+    (core/gdrn_modeling/main_gdrn.py via launch) but leaves placement to the OS."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(visible.split(",")[device_index]) if visible else device_index
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.lower().split(":", 1)
+        path = "/sys/bus/pci/devices/%s:%s/numa_node" % (dom[-4:], rest)
+        node = int(open(path).read())
+        if node < 0:
+            return None
+        cpus = _parse_cpulist(open("/sys/devices/system/node/node%d/cpulist" % node).read())
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
