@@ -86,6 +86,74 @@ __device__ __forceinline__ void kabsch3(const double (*a)[3], const double (*c)[
     for (int r = 0; r < 3; ++r) Rt[4 * r + 3] = mc[r] - (Rt[4 * r] * ma[0] + Rt[4 * r + 1] * ma[1] + Rt[4 * r + 2] * ma[2]);
 }
 
+// ---- register-lean form of kabsch3 for the fused solver ----------------------------------------------------
+// One side (object or camera) of a 3-pair hypothesis: triangle test with the exact arithmetic of triangle_ok, the
+// orthonormal in-plane basis (e1, n; e2 = n x e1 is recomputed where needed), the in-plane coordinates of the three
+// points relative to p0 -- (0,0), (u1,0), (u2,v2) -- and the centroid.  Everything derives from the two edge vectors,
+// so the 3 x 3 inputs never live as doubles.
+struct TriSide {
+    double e1[3], n[3];  // unit first edge, unit normal
+    double u1, u2, v2;   // in-plane coordinates of p1 and p2
+    double m[3];         // centroid
+    bool ok;
+};
+__device__ __forceinline__ void tri_side(const float (*p)[3], TriSide& o) {
+    const double p0x = (double)p[0][0], p0y = (double)p[0][1], p0z = (double)p[0][2];
+    const double e1x = __dsub_rn((double)p[1][0], p0x), e1y = __dsub_rn((double)p[1][1], p0y), e1z = __dsub_rn((double)p[1][2], p0z);
+    const double e2x = __dsub_rn((double)p[2][0], p0x), e2y = __dsub_rn((double)p[2][1], p0y), e2z = __dsub_rn((double)p[2][2], p0z);
+    const double nx = __dsub_rn(__dmul_rn(e1y, e2z), __dmul_rn(e1z, e2y));
+    const double ny = __dsub_rn(__dmul_rn(e1z, e2x), __dmul_rn(e1x, e2z));
+    const double nz = __dsub_rn(__dmul_rn(e1x, e2y), __dmul_rn(e1y, e2x));
+    const double a2 = __dadd_rn(__dadd_rn(__dmul_rn(nx, nx), __dmul_rn(ny, ny)), __dmul_rn(nz, nz));
+    const double l1 = __dadd_rn(__dadd_rn(__dmul_rn(e1x, e1x), __dmul_rn(e1y, e1y)), __dmul_rn(e1z, e1z));
+    const double l2 = __dadd_rn(__dadd_rn(__dmul_rn(e2x, e2x), __dmul_rn(e2y, e2y)), __dmul_rn(e2z, e2z));
+    o.ok = a2 > __dmul_rn(RDPN_DEGENERATE_SIN2, __dmul_rn(l1, l2));  // == triangle_ok, bit for bit
+    const double il = rsqrt(l1), in = rsqrt(a2);
+    o.e1[0] = e1x * il; o.e1[1] = e1y * il; o.e1[2] = e1z * il;
+    o.n[0] = nx * in; o.n[1] = ny * in; o.n[2] = nz * in;
+    o.u1 = l1 * il;                                   // |e1|
+    o.u2 = (e1x * e2x + e1y * e2y + e1z * e2z) * il;  // e2 . e1^
+    o.v2 = a2 * in * il;                              // e2 . (n^ x e1^) = |n| / |e1|
+    o.m[0] = p0x + (e1x + e2x) * (1.0 / 3.0);
+    o.m[1] = p0y + (e1y + e2y) * (1.0 / 3.0);
+    o.m[2] = p0z + (e1z + e2z) * (1.0 / 3.0);
+}
+// Pose from the two sides (same closed form as kabsch3: map normal to normal, rotate in-plane by atan2(sum cross,
+// sum dot) of the centred in-plane coordinates).  The object side arrives partly parked in `scr` (stride `ss`
+// doubles: e1a[3], na[3], ma[0], ma[1]) so that both bases never sit in registers together.  P: 3x4 row-major FP32.
+__device__ __forceinline__ void kabsch3_sides(const double* scr, int ss, double ma2, double u1a, double u2a, double v2a,
+                                              const TriSide& c, float* P) {
+    // centred in-plane coordinates: x = (0, u1, u2) - (u1 + u2) / 3, y = (0, 0, v2) - v2 / 3
+    const double mua = (u1a + u2a) * (1.0 / 3.0), mva = v2a * (1.0 / 3.0);
+    const double muc = (c.u1 + c.u2) * (1.0 / 3.0), mvc = c.v2 * (1.0 / 3.0);
+    const double xa0 = -mua, xa1 = u1a - mua, xa2 = u2a - mua, ya01 = -mva, ya2 = v2a - mva;
+    const double xc0 = -muc, xc1 = c.u1 - muc, xc2 = c.u2 - muc, yc01 = -mvc, yc2 = c.v2 - mvc;
+    const double sdot = (xc0 * xa0 + yc01 * ya01) + (xc1 * xa1 + yc01 * ya01) + (xc2 * xa2 + yc2 * ya2);
+    const double scross = (yc01 * xa0 - xc0 * ya01) + (yc01 * xa1 - xc1 * ya01) + (yc2 * xa2 - xc2 * ya2);
+    const double ih = rsqrt(sdot * sdot + scross * scross);
+    const double cs = sdot * ih, sn = scross * ih;
+    // images of e1a, e2a: f1 = cs e1c + sn e2c, f2 = cs e2c - sn e1c with e2c = nc x e1c
+    const double e2c0 = c.n[1] * c.e1[2] - c.n[2] * c.e1[1];
+    const double e2c1 = c.n[2] * c.e1[0] - c.n[0] * c.e1[2];
+    const double e2c2 = c.n[0] * c.e1[1] - c.n[1] * c.e1[0];
+    const double f1[3] = {cs * c.e1[0] + sn * e2c0, cs * c.e1[1] + sn * e2c1, cs * c.e1[2] + sn * e2c2};
+    const double f2[3] = {cs * e2c0 - sn * c.e1[0], cs * e2c1 - sn * c.e1[1], cs * e2c2 - sn * c.e1[2]};
+    const double e1a0 = scr[0 * ss], e1a1 = scr[1 * ss], e1a2 = scr[2 * ss];
+    const double na0 = scr[3 * ss], na1 = scr[4 * ss], na2 = scr[5 * ss];
+    const double ma0 = scr[6 * ss], ma1 = scr[7 * ss];
+    const double e2a0 = na1 * e1a2 - na2 * e1a1, e2a1 = na2 * e1a0 - na0 * e1a2, e2a2 = na0 * e1a1 - na1 * e1a0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const double r0 = f1[r] * e1a0 + f2[r] * e2a0 + c.n[r] * na0;
+        const double r1 = f1[r] * e1a1 + f2[r] * e2a1 + c.n[r] * na1;
+        const double r2 = f1[r] * e1a2 + f2[r] * e2a2 + c.n[r] * na2;
+        P[4 * r + 0] = (float)r0;
+        P[4 * r + 1] = (float)r1;
+        P[4 * r + 2] = (float)r2;
+        P[4 * r + 3] = (float)(c.m[r] - (r0 * ma0 + r1 * ma1 + r2 * ma2));
+    }
+}
+
 // S[i*3+j] = sum_w c_i a_j (camera row, object column), i.e. v1 . v0^T of transform.py:942.
 // R (row-major) maximises sum c^T R a over SO(3).
 __device__ __forceinline__ void quat_to_rot(double q0, double q1, double q2, double q3, double* R) {

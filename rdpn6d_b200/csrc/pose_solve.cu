@@ -91,6 +91,7 @@ struct SolveArgs {
 #define RDPN_CHUNK_SLOTS 1024
 #endif
 constexpr int CHUNK = RDPN_CHUNK_SLOTS;  // gated slots staged in shared memory at a time (dense mode: CHUNK / 2)
+static_assert(CHUNK >= 4 * ST, "hypothesis generation parks 8 doubles per thread in the staging buffer");
 
 struct FinishSmem {  // scratch of the select + refit tail
     double red_d[SW][18];
@@ -535,26 +536,46 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
             for (int v = 0; v < 3; ++v) ok = ok && ((s.selmap[ii[v] >> 5] >> (ii[v] & 31)) & 1u);
         }
         if (ok) {
-            double A[3][3], C[3][3];
+            // register-lean closed form (kabsch_math.cuh): the object side is solved first and parked -- eight
+            // doubles per thread in the staging buffer, which is idle until the barrier that ends this phase --
+            // then the camera side, so the two bases never sit in registers together (the straightforward form
+            // spilled ~60 values per thread to local memory that misses the 32 KB L1 half of the time)
+            double* scr = reinterpret_cast<double*>(s.chunk) + t;  // scr[k * ST], k < 8: conflict-free columns
+            float pf[3][3];
+            int rr[3];
+            float4 cw[3], ob[3];
 #pragma unroll
             for (int v = 0; v < 3; ++v) {
-                const int p = ii[v];
-                float4 cw, ob;
-                gather_s1<DENSE>(pl, rc, p, false, in.mask_mode, cw, ob);
-                C[v][0] = (double)cw.x; C[v][1] = (double)cw.y; C[v][2] = (double)cw.z;
+                gather_s1<DENSE>(pl, rc, ii[v], false, in.mask_mode, cw[v], ob[v]);
+                if (!DENSE) rr[v] = __ldg(pl.rid + ii[v]);
+            }
+#pragma unroll
+            for (int v = 0; v < 3; ++v) {
                 if (DENSE) {
-                    A[v][0] = (double)ob.x; A[v][1] = (double)ob.y; A[v][2] = (double)ob.z;
+                    pf[v][0] = ob[v].x; pf[v][1] = ob[v].y; pf[v][2] = ob[v].z;
                 } else {
-                    const float4 an = anchors[__ldg(pl.rid + p)];
-                    A[v][0] = (double)an.x; A[v][1] = (double)an.y; A[v][2] = (double)an.z;
+                    const float4 an = anchors[rr[v]];
+                    pf[v][0] = an.x; pf[v][1] = an.y; pf[v][2] = an.z;
                 }
             }
-            ok = triangle_ok(A[0], A[1], A[2]) && triangle_ok(C[0], C[1], C[2]);
-            if (ok) {
-                double Rt[12];
-                kabsch3(A, C, Rt);
+            double ma2, u1a, u2a, v2a;
+            {
+                TriSide sa;
+                tri_side(pf, sa);
+                ok = sa.ok;
+                scr[0 * ST] = sa.e1[0]; scr[1 * ST] = sa.e1[1]; scr[2 * ST] = sa.e1[2];
+                scr[3 * ST] = sa.n[0];  scr[4 * ST] = sa.n[1];  scr[5 * ST] = sa.n[2];
+                scr[6 * ST] = sa.m[0];  scr[7 * ST] = sa.m[1];
+                ma2 = sa.m[2]; u1a = sa.u1; u2a = sa.u2; v2a = sa.v2;
+            }
 #pragma unroll
-                for (int i = 0; i < 12; ++i) P[i] = (float)Rt[i];
+            for (int v = 0; v < 3; ++v) { pf[v][0] = cw[v].x; pf[v][1] = cw[v].y; pf[v][2] = cw[v].z; }
+            TriSide sc;
+            tri_side(pf, sc);
+            ok = ok && sc.ok;
+            if (ok) {
+                // ma[2] rides in a register: patch it into the last scratch use by passing ma2 separately
+                kabsch3_sides(scr, ST, ma2, u1a, u2a, v2a, sc, P);
             }
         }
         if (!ok) {
