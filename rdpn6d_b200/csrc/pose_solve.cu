@@ -921,42 +921,44 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
                 for (int w = 0; w < SW; ++w) acc += f.red_d[w][lane];
                 f.bc_d[lane] = acc;
             }
-            __syncwarp();
             if (lane == 0) {
-                int tot_inl = 0;
+                int ti = 0;
 #pragma unroll
-                for (int w = 0; w < SW; ++w) tot_inl += f.red_i[w];
-                f.h_eff = tot_inl;  // h_eff is free after the best selection: reuse as the broadcast slot
-                if (tot_inl >= 3) {
-                    double m[18];
-#pragma unroll
-                    for (int i = 0; i < 18; ++i) m[i] = f.bc_d[i];
-                    const double isw = 1.0 / m[0];
-                    const double mcp[3] = {m[1] * isw, m[2] * isw, m[3] * isw};  // centroids relative to the pivot
-                    const double map[3] = {m[4] * isw, m[5] * isw, m[6] * isw};
-                    const double mc[3] = {mcp[0] + (double)cp0.x, mcp[1] + (double)cp0.y, mcp[2] + (double)cp0.z};
-                    const double ma[3] = {map[0] + (double)ap0.x, map[1] + (double)ap0.y, map[2] + (double)ap0.z};
-                    double cov[9];
-#pragma unroll
-                    for (int r = 0; r < 3; ++r)
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) cov[3 * r + c] = m[7 + 3 * r + c] - m[1 + r] * map[c];  // sum w c a^T - (sum w c)(mean a)^T
-                    const double gb = m[16] - (m[1] * mcp[0] + m[2] * mcp[1] + m[3] * mcp[2]);
-                    const double ga = m[17] - (m[4] * map[0] + m[5] * map[1] + m[6] * map[2]);
-                    double Rm[9];
-                    rotation_from_cov(cov, ga, gb, Rm);
-                    double sc = 1.0;
-                    if (a.prm.with_scale) sc = sqrt(gb / ga);  // transform.py:971-975
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) {
-                        const double tr = mc[r] - sc * (Rm[3 * r] * ma[0] + Rm[3 * r + 1] * ma[1] + Rm[3 * r + 2] * ma[2]);
-                        f.pose[4 * r + 0] = (float)(sc * Rm[3 * r + 0]);
-                        f.pose[4 * r + 1] = (float)(sc * Rm[3 * r + 1]);
-                        f.pose[4 * r + 2] = (float)(sc * Rm[3 * r + 2]);
-                        f.pose[4 * r + 3] = (float)tr;
-                    }
-                    f.bc_d[19] = sc;
+                for (int w = 0; w < SW; ++w) ti += f.red_i[w];
+                f.h_eff = ti;  // h_eff is free after the best selection: reuse as the broadcast slot
+            }
+            __syncwarp();
+            if (f.h_eff >= 3) {
+                // The moments stay in shared memory (the per-warp partials are consumed: red_d is scratch now):
+                // lanes 0-8 form the cross-covariance, lanes 9 / 10 the spreads, lane 0 solves for the rotation
+                // reading S from shared memory, lanes 0-2 assemble one pose row each.  Nothing here holds the 18
+                // moments, S and R in registers at once (that version spilled ~140 values of the solving lane).
+                double* S = &f.red_d[0][0];  // S[0..8] | ga S[9] | gb S[10] | R S[16..24]
+                const double isw = 1.0 / f.bc_d[0];
+                if (lane < 9) {
+                    const int r = lane / 3, c = lane - 3 * r;
+                    S[lane] = f.bc_d[7 + lane] - f.bc_d[1 + r] * (f.bc_d[4 + c] * isw);  // sum w c a^T - (sum w c)(mean a)^T
+                } else if (lane == 9) {
+                    S[9] = f.bc_d[17] - (f.bc_d[4] * (f.bc_d[4] * isw) + f.bc_d[5] * (f.bc_d[5] * isw) + f.bc_d[6] * (f.bc_d[6] * isw));
+                } else if (lane == 10) {
+                    S[10] = f.bc_d[16] - (f.bc_d[1] * (f.bc_d[1] * isw) + f.bc_d[2] * (f.bc_d[2] * isw) + f.bc_d[3] * (f.bc_d[3] * isw));
                 }
+                __syncwarp();
+                if (lane == 0) rotation_from_cov(S, S[9], S[10], S + 16);
+                __syncwarp();
+                const double sc = a.prm.with_scale ? sqrt(S[10] / S[9]) : 1.0;  // transform.py:971-975
+                if (lane < 3) {
+                    const int r = lane;
+                    const double ma0 = f.bc_d[4] * isw + (double)ap0.x, ma1 = f.bc_d[5] * isw + (double)ap0.y,
+                                 ma2 = f.bc_d[6] * isw + (double)ap0.z;
+                    const double mcr = f.bc_d[1 + r] * isw + (double)(r == 0 ? cp0.x : (r == 1 ? cp0.y : cp0.z));
+                    const double r0 = S[16 + 3 * r], r1 = S[17 + 3 * r], r2 = S[18 + 3 * r];
+                    f.pose[4 * r + 0] = (float)(sc * r0);
+                    f.pose[4 * r + 1] = (float)(sc * r1);
+                    f.pose[4 * r + 2] = (float)(sc * r2);
+                    f.pose[4 * r + 3] = (float)(mcr - sc * (r0 * ma0 + r1 * ma1 + r2 * ma2));
+                }
+                if (lane == 0) f.bc_d[19] = sc;
             }
         }
         __syncthreads();
