@@ -510,8 +510,10 @@ def gpu_arm(args):
     _lib.check(L.rdpn_ctx_create(local_rank, ctypes.byref(ctx)), "ctx_create")
     e2e_steps = max(3, min(args.steps, 30))
 
+    hyp_arg = [pin["hyp_idx"].data_ptr()]  # [None]: the kernel draws the triplets itself
+
     def host_call():
-        _lib.check(L.rdpn_pose_solve_host(ctx, ctypes.byref(inp), pin["hyp_idx"].data_ptr(), None, ctypes.byref(prm),
+        _lib.check(L.rdpn_pose_solve_host(ctx, ctypes.byref(inp), hyp_arg[0], None, ctypes.byref(prm),
                                           ctypes.byref(outs)), "pose_solve_host")
 
     def time_host_calls(transfer):
@@ -540,6 +542,12 @@ def gpu_arm(args):
     copy_pose = h_pose.clone()
     e2e_s, h2d, e2e_used = time_host_calls(_lib.TRANSFER_AUTO)  # pinned buffers -> gated pull
     transfers_identical = bool(torch.equal(copy_pose, h_pose))
+    e2e_pose = h_pose.clone()
+    hyp_arg[0] = None  # supplementary: no hypothesis triplets from the host, the solver samples them (seed 0)
+    auto_s, auto_bytes, _ = time_host_calls(_lib.TRANSFER_AUTO)
+    auto_ok = float((h_stat == 0).float().mean())
+    hyp_arg[0] = pin["hyp_idx"].data_ptr()
+    h_pose.copy_(e2e_pose)
     L.rdpn_ctx_destroy(ctx)
     host_input_bytes = B * (BYTES_MAPS + H * 12 + R * 12 + 16 + 12)
     d2h = B * (48 + 4 + 4)
@@ -574,10 +582,26 @@ def gpu_arm(args):
         mixed_call()
     mixed_s = time.perf_counter() - t0
     mixed.close()
+    # ... and with the triplets drawn by the kernel (what the evaluator hook rdpn6d_b200.evaluator does)
+    mixed2 = pose_solver.HostPoseSolver(device=local_rank, inlier_thr=INLIER_THR, num_hyp=H, seed=0, count_bytes=True)
+    mixed2_call = mixed2.plan(pin["depth"], pin["Kp"], d_cx, d_cy, d_cz, s0["mask"], pin["extent"], None, s0["region_idx"],
+                              pin["anchors"])
+    mixed2_call()
+    mixed2_bytes = mixed2.last_h2d_bytes
+    mixed2.set_option(_lib.OPT_COUNT_BYTES, 0)
+    for _ in range(3):
+        mixed2_call()
     if world > 1:
-        t = torch.tensor([mixed_s], device=dev)
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(mixed_steps):
+        mixed2_call()
+    mixed2_s = time.perf_counter() - t0
+    mixed2.close()
+    if world > 1:
+        t = torch.tensor([mixed_s, mixed2_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        mixed_s = float(t)
+        mixed_s, mixed2_s = float(t[0]), float(t[1])
 
     # ---- FP32 work actually issued by the scoring stage (valid hypotheses x gated points) ----
     diag = pose_solver.PoseSolver(inlier_thr=INLIER_THR, want_hyp=True)
@@ -618,6 +642,11 @@ def gpu_arm(args):
                 "timer": "perf_counter around synchronous calls"},
         "e2e_full_copy": {"value": total * e2e_steps / copy_s, "unit": UNIT, "h2d_bytes_per_step": copy_bytes,
                           "d2h_bytes_per_step": d2h, "note": "same call with RDPN_TRANSFER_COPY: every input tensor copied"},
+        "e2e_internal_sampling": {"value": total * e2e_steps / auto_s, "unit": UNIT, "h2d_bytes_per_step": auto_bytes,
+                                  "d2h_bytes_per_step": d2h, "solved_fraction": auto_ok,
+                                  "note": "supplementary: same call with hyp_idx = NULL -- the kernel draws the 256 triplets per ROI "
+                                          "itself from a seeded counter-based stream (the reference's loop samples internally too, "
+                                          "misc.py:91), so no triplets cross the bus"},
         "transfers_identical": transfers_identical,
         "e2e_head_on_device": {"value": total * mixed_steps / mixed_s, "unit": UNIT,
                                "h2d_bytes_per_step": mixed_bytes, "d2h_bytes_per_step": d2h, "matches_e2e": mixed_ok,
@@ -625,6 +654,8 @@ def gpu_arm(args):
                                        "already device-resident and used in place; depth maps, per-ROI scalars, anchors and hypothesis "
                                        "triplets in pinned host memory (depth fetched only where the mask passes); results to pinned "
                                        "host tensors.  Same rdpn_pose_solve_host call via rdpn6d_b200.pose_solver.HostPoseSolver."},
+        "e2e_head_on_device_internal_sampling": {"value": total * mixed_steps / mixed2_s, "unit": UNIT,
+                                                 "h2d_bytes_per_step": mixed2_bytes, "d2h_bytes_per_step": d2h},
         "host_path_matches_device_path": host_matches_device,
         "gather_ok": gather_ok,
         "numa_node_rank0": numa_node,

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RDPN_VERSION 100 /* 0.1.0 */
+#define RDPN_VERSION 101 /* 0.1.1: rdpn_solve_params gained seed / roi_base */
 
 /* negative error codes (positive values are cudaError_t) */
 #define RDPN_E_BADARG (-1)    /* NULL / non-positive size / unsupported option */
@@ -145,6 +145,9 @@ typedef struct rdpn_solve_params {
     int32_t adaptive;    /* misc.py:134-138 early stop emulated on the hypothesis order             */
     float confidence;    /* 0.995 (misc.py:73)                                                      */
     int32_t min_iter;    /* 10 (misc.py:63)                                                         */
+    uint32_t seed;       /* internal sampling (hyp_idx == NULL): stream seed                        */
+    int32_t roi_base;    /* internal sampling: global index of ROI 0 of this call (shards / chunks  */
+                         /* of one job pass their offset so that results do not depend on batching) */
 } rdpn_solve_params;
 
 typedef struct rdpn_solve_outputs {
@@ -161,7 +164,16 @@ typedef struct rdpn_solve_outputs {
                               block that is all-gathered across GPUs          (may be NULL)            */
 } rdpn_solve_outputs;
 
-/* hyp_idx [B,H,3] int32 absolute pixel indices (0..4095); t_net [B,3] or NULL (translation sanity). */
+/* hyp_idx [B,H,3] int32 absolute pixel indices (0..4095); t_net [B,3] or NULL (translation sanity).
+ *
+ * hyp_idx == NULL: the solver draws the triplets itself, as the reference's loop does with np.random.choice
+ * (misc.py:91), from a counter-based stream so that runs are reproducible and independent of batching:
+ *     g[0..n)  = the ROI's gated pixels in raster order
+ *     fmix32(x): x ^= x >> 16; x *= 0x85ebca6b; x ^= x >> 13; x *= 0xc2b2ae35; x ^= x >> 16      (uint32)
+ *     key      = fmix32(fmix32(fmix32(seed ^ 0x9e3779b9) ^ (roi_base + b)) ^ (3 * h + v))
+ *     pixel of vertex v of hypothesis h = g[(uint64(key) * n) >> 32]
+ * (oracle/pose_oracle.py:sample_triplets is the same arithmetic; tests feed its output back as explicit hyp_idx
+ * and demand bit-identical results). */
 int rdpn_pose_solve(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, const float* d_t_net,
                     const rdpn_solve_params* prm, const rdpn_solve_outputs* out, void* stream);
 

@@ -309,6 +309,31 @@ _u8p = ctypes.POINTER(ctypes.c_uint8)
 _i32p = ctypes.POINTER(ctypes.c_int32)
 
 
+def _fmix32(x):
+    x = np.asarray(x, dtype=np.uint32)
+    x = x ^ (x >> np.uint32(16))
+    x = x * np.uint32(0x85EBCA6B)
+    x = x ^ (x >> np.uint32(13))
+    x = x * np.uint32(0xC2B2AE35)
+    return x ^ (x >> np.uint32(16))
+
+
+def sample_triplets(sel, H, seed, roi_index):
+    """The solver's internal hypothesis sampling (include/rdpn6d_b200.h, rdpn_pose_solve with hyp_idx == NULL):
+    the stand-in for np.random.choice at misc.py:91, counter-based so that it is reproducible.  sel: [P] bool gate of
+    one ROI; returns [H,3] int32 absolute pixel indices (all -1 when nothing is gated)."""
+    g = np.nonzero(np.asarray(sel).reshape(-1))[0]
+    n = len(g)
+    if n == 0:
+        return np.full((H, 3), -1, np.int32)
+    with np.errstate(over="ignore"):
+        kroi = _fmix32(_fmix32(np.uint32(seed) ^ np.uint32(0x9E3779B9)) ^ np.uint32(roi_index & 0xFFFFFFFF))
+        hv = np.arange(3 * H, dtype=np.uint32)
+        key = _fmix32(kroi ^ hv)
+    k = (key.astype(np.uint64) * np.uint64(n)) >> np.uint64(32)
+    return g[k.astype(np.int64)].astype(np.int32).reshape(H, 3)
+
+
 def sq_cut(thr):
     """Smallest float32 x with sqrtf(x) >= thr: (sqrt(d2) < thr) <=> (d2 < sq_cut(thr))."""
     f = liboracle().oracle_sq_cut

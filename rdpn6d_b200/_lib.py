@@ -32,7 +32,7 @@ class SolveParams(ctypes.Structure):
         ("inlier_thr", ctypes.c_float), ("num_hyp", ctypes.c_int32), ("min_pts", ctypes.c_int32),
         ("min_inliers", ctypes.c_int32), ("weighted", ctypes.c_int32), ("refit_iters", ctypes.c_int32),
         ("with_scale", ctypes.c_int32), ("adaptive", ctypes.c_int32), ("confidence", ctypes.c_float),
-        ("min_iter", ctypes.c_int32),
+        ("min_iter", ctypes.c_int32), ("seed", ctypes.c_uint32), ("roi_base", ctypes.c_int32),
     ]
 
 

@@ -348,7 +348,7 @@ static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 int rdpn_pose_solve_host(rdpn_ctx* c, const rdpn_roi_inputs* h, const int32_t* h_hyp, const float* h_tnet,
                          const rdpn_solve_params* prm, const rdpn_solve_outputs* ho) {
     using namespace rdpn;
-    if (!c || !h || !h_hyp || !prm || !ho || h->B <= 0 || prm->num_hyp <= 0) return RDPN_E_BADARG;
+    if (!c || !h || !prm || !ho || h->B <= 0 || prm->num_hyp <= 0) return RDPN_E_BADARG;  // h_hyp NULL: internal sampling
     if (!ho->pose || !ho->n_inliers || !ho->status) return RDPN_E_BADARG;
     if (!h->depth || !h->coor_x || !h->coor_y || !h->coor_z || !h->mask || !h->Kp || !h->extent) return RDPN_E_BADARG;
     if ((h->region_idx == nullptr) != (h->anchors == nullptr)) return RDPN_E_BADARG;
@@ -517,7 +517,9 @@ int rdpn_pose_solve_host(rdpn_ctx* c, const rdpn_roi_inputs* h, const int32_t* h
         dout.inlier_mask = (uint8_t*)dst[O_IMASK];
         dout.hyp_counts = (int32_t*)dst[O_HCNT];
         dout.hyp_poses = (float*)dst[O_HPOSE];
-        rc = rdpn_pose_solve(&di, (const int32_t*)src[I_HYP], (const float*)src[I_TNET], prm, &dout, st);
+        rdpn_solve_params pc = *prm;
+        pc.roi_base = prm->roi_base + b0;  // internal sampling must not depend on the chunking
+        rc = rdpn_pose_solve(&di, (const int32_t*)src[I_HYP], (const float*)src[I_TNET], &pc, &dout, st);
         if (rc) break;
         for (int i = 0; i < NOUT; ++i)
             if (out[i].move == MOVE_COPY)

@@ -102,6 +102,7 @@ struct FinishSmem {  // scratch of the select + refit tail
     float pose[12];
     unsigned long long red_k[SW];
     int red_i[SW];
+    int red_j[SW];
 };
 
 struct __align__(128) FusedSmem {
@@ -109,6 +110,7 @@ struct __align__(128) FusedSmem {
     uint16_t pix[RDPN_P];           // slot -> pixel
     uint8_t srid[RDPN_P];           // slot -> region id (non-decreasing)
     uint32_t selmap[RDPN_P / 32];   // gate bitmap by pixel
+    uint16_t selpfx[RDPN_P / 32 + 2];  // internal sampling: gated pixels before word w (raster order), [128] = all
     RoiConst rc;
     float red_f[2][SW];
     int n_sel;
@@ -169,6 +171,15 @@ __device__ __forceinline__ float resid2_pt(float tx, float ty, float tz, float c
 // c += (d2 < cut): one FSETP + one predicated IADD (the C++ form compiles to three instructions)
 __device__ __forceinline__ void count_if_lt(int& c, float d2, float cut) {
     asm("{\n.reg .pred p;\nsetp.lt.f32 p, %1, %2;\n@p add.s32 %0, %0, 1;\n}" : "+r"(c) : "f"(d2), "f"(cut));
+}
+// counter-based stream of the internal hypothesis sampling (include/rdpn6d_b200.h, oracle sample_triplets)
+__device__ __forceinline__ uint32_t fmix32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x85ebca6bu;
+    x ^= x >> 13;
+    x *= 0xc2b2ae35u;
+    x ^= x >> 16;
+    return x;
 }
 // R a + t with the contract's FMA order (oracle/pose_oracle.c:resid2)
 __device__ __forceinline__ void xform(const float* P, float ax, float ay, float az, float& x, float& y, float& z) {
@@ -278,7 +289,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
     }
     // the thread's first hypothesis triplet is requested now (DRAM) and consumed in phase 4
     int pre0 = -1, pre1 = -1, pre2 = -1;
-    if (t < H) {
+    if (a.hyp_idx && t < H) {
         const int32_t* ip = a.hyp_idx + ((size_t)b * H + t) * 3;
         pre0 = __ldg(ip);
         pre1 = __ldg(ip + 1);
@@ -424,18 +435,26 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
             tot += c[w];
         }
         const int packed = tot | ((tot > 0 ? 1 : 0) << 16);
-        int x = packed;
+        // internal sampling: the same scan also ranks the gate bitmap (gated pixels before each 32-pixel word)
+        const bool sampling = a.hyp_idx == nullptr;
+        const int pc = (sampling && t < RDPN_P / 32) ? __popc(s.selmap[t]) : 0;
+        int x = packed, xs = pc;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
+            const int ys = __shfl_up_sync(0xffffffffu, xs, o);
+            if (lane >= o) { x += y; xs += ys; }
         }
-        if (lane == 31) f.red_i[warp] = x;
+        if (lane == 31) { f.red_i[warp] = x; f.red_j[warp] = xs; }
         __syncthreads();
-        int base = 0;
+        int base = 0, bases = 0;
 #pragma unroll
         for (int w = 0; w < SW; ++w)
-            if (w < warp) base += f.red_i[w];
+            if (w < warp) { base += f.red_i[w]; bases += f.red_j[w]; }
+        if (sampling && t < RDPN_P / 32) {
+            s.selpfx[t] = (uint16_t)(bases + xs - pc);
+            if (t == RDPN_P / 32 - 1) s.selpfx[RDPN_P / 32] = (uint16_t)(bases + xs);
+        }
         const int excl = base + x - packed;
         int run = excl & 0xFFFF;
         const int kk = excl >> 16;
@@ -526,9 +545,30 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
     PHASE_MARK(5);
     // ---- 4: hypothesis generation (FP64 closed form), one hypothesis per thread, pixels gathered ----
     for (int h = t; h < H; h += ST) {
-        const int32_t* ip = a.hyp_idx + ((size_t)b * H + h) * 3;
-        const bool first = h == t;
-        const int ii[3] = {first ? pre0 : ip[0], first ? pre1 : ip[1], first ? pre2 : ip[2]};
+        int ii[3];
+        if (a.hyp_idx) {
+            const int32_t* ip = a.hyp_idx + ((size_t)b * H + h) * 3;
+            const bool first = h == t;
+            ii[0] = first ? pre0 : ip[0];
+            ii[1] = first ? pre1 : ip[1];
+            ii[2] = first ? pre2 : ip[2];
+        } else {
+            // draw the triplet: k-th gated pixel in raster order, k from the counter-based stream (rank-select on
+            // the gate bitmap: binary search over the per-word prefix, then the j-th set bit of the word)
+            const uint32_t nsel = s.selpfx[RDPN_P / 32];
+            const uint32_t kroi = fmix32(fmix32(a.prm.seed ^ 0x9e3779b9u) ^ (uint32_t)(a.prm.roi_base + b));
+#pragma unroll
+            for (int v = 0; v < 3; ++v) {
+                const uint32_t key = fmix32(kroi ^ (uint32_t)(3 * h + v));
+                const uint32_t k = (uint32_t)(((unsigned long long)key * nsel) >> 32);
+                int lo = 0;
+#pragma unroll
+                for (int step = RDPN_P / 64; step; step >>= 1)
+                    if (s.selpfx[lo + step] <= k) lo += step;
+                const unsigned j = k - s.selpfx[lo];
+                ii[v] = nsel ? lo * 32 + (int)__fns(s.selmap[lo], 0, (int)j + 1) : -1;
+            }
+        }
         bool ok = ((unsigned)ii[0] < RDPN_P) && ((unsigned)ii[1] < RDPN_P) && ((unsigned)ii[2] < RDPN_P);
         float* P = hyp + (size_t)h * 12;
         if (ok) {
@@ -1134,7 +1174,7 @@ int rdpn_pose_solve(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, const f
     bool dense = false;
     int rc = rdpn::check_roi_inputs(in, &dense);
     if (rc) return rc;
-    if (!d_hyp_idx || !prm || !out || !out->pose || !out->n_inliers || !out->status) return RDPN_E_BADARG;
+    if (!prm || !out || !out->pose || !out->n_inliers || !out->status) return RDPN_E_BADARG;  // d_hyp_idx NULL: internal sampling
     if (prm->num_hyp <= 0 || !(prm->inlier_thr > 0.f)) return RDPN_E_BADARG;
     if (out->inlier_mask && ((uintptr_t)out->inlier_mask & 15)) return RDPN_E_ALIGN;
     rdpn::SolveArgs a;

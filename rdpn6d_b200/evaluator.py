@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import geometry
-from .pose_solver import MASK_L1, PoseSolver, sample_hypotheses, correspond, STATUS_OK, STATUS_T_SANITY
+from .pose_solver import MASK_L1, PoseSolver, STATUS_OK, STATUS_T_SANITY
 
 logger = logging.getLogger(__name__)
 PNP_TYPE = "gpu_ransac_kabsch"
@@ -41,17 +41,19 @@ class GpuRansacKabsch:
         """depth_is_scale_normalised: roi_coord_2d[:, 2] holds depth / resize_ratio (data_loader.py:563); the
         solver multiplies it back (depth_div = 1 / resize_ratio) so that the 3D-3D solve is metric."""
         self.num_hyp = num_hyp
+        # the kernel draws the RANSAC triplets itself (seeded counter-based stream): no separate S1 pass, no
+        # multinomial -- the step is one launch
         self.solver = PoseSolver(inlier_thr=inlier_thr, mask_thr=mask_thr, mask_mode=mask_mode, weighted=weighted,
-                                 refit_iters=refit_iters)
+                                 refit_iters=refit_iters, num_hyp=num_hyp, seed=seed)
         self.mask_thr, self.mask_mode = mask_thr, mask_mode
         self.label_to_obj_id = label_to_obj_id or (lambda label: int(label) + 1)
         self.depth_is_scale_normalised = depth_is_scale_normalised
-        self.gen_seed = seed
-        self._gen = None
+        self._roi_base = 0  # ROIs seen so far: keeps the sampling stream independent of how the job is batched
         self._predictions = []
 
     def reset(self):
         self._predictions = []
+        self._roi_base = 0
 
     def process(self, inputs, outputs, out_dict):
         """Fills self._predictions like process_pnp_ransac; returns the rows appended by this call."""
@@ -75,14 +77,10 @@ class GpuRansacKabsch:
         if fps.dim() == 2:
             fps = fps[None].expand(n, -1, -1)
         args = (depth, Kp, out_dict["coor_x"], out_dict["coor_y"], out_dict["coor_z"], out_dict["mask"], extent)
-        s1 = correspond(*args, region_idx=region_idx, anchors=fps, depth_div=depth_div, mask_mode=self.mask_mode,
-                        mask_thr=self.mask_thr, want_obj=False)
-        if self._gen is None:
-            self._gen = torch.Generator(device=dev)
-            self._gen.manual_seed(self.gen_seed)
-        hyp = sample_hypotheses(s1["sel"], self.num_hyp, generator=self._gen)
         t_net = out_dict["trans"].detach().float() if "trans" in out_dict else None
-        res = self.solver(*args, hyp, region_idx=region_idx, anchors=fps, depth_div=depth_div, t_net=t_net)
+        res = self.solver(*args, None, region_idx=region_idx, anchors=fps, depth_div=depth_div, t_net=t_net,
+                          roi_base=self._roi_base)
+        self._roi_base += n
         rows = res.rows16().cpu().numpy()  # the single device->host copy of the step
         net_rot = out_dict["rot"].detach().cpu().numpy() if "rot" in out_dict else None
         net_t = t_net.cpu().numpy() if t_net is not None else None

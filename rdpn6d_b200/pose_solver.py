@@ -139,10 +139,14 @@ class PoseSolver:
 
     def __init__(self, inlier_thr=0.005, min_pts=4, min_inliers=4, weighted=False, refit_iters=1, with_scale=False,
                  adaptive=False, confidence=0.995, min_iter=10, mask_mode=MASK_L1, mask_thr=0.5,
-                 want_inlier_mask=False, want_hyp=False):
+                 want_inlier_mask=False, want_hyp=False, num_hyp=256, seed=0):
+        """num_hyp / seed: used when a call passes hyp_idx=None -- the kernel then draws the triplets itself from a
+        counter-based stream (include/rdpn6d_b200.h), the stand-in for np.random.choice at misc.py:91."""
         self.prm = dict(inlier_thr=float(inlier_thr), min_pts=int(min_pts), min_inliers=int(min_inliers),
                         weighted=int(bool(weighted)), refit_iters=int(refit_iters), with_scale=int(bool(with_scale)),
-                        adaptive=int(bool(adaptive)), confidence=float(confidence), min_iter=int(min_iter))
+                        adaptive=int(bool(adaptive)), confidence=float(confidence), min_iter=int(min_iter),
+                        seed=int(seed) & 0xFFFFFFFF)
+        self.num_hyp = int(num_hyp)
         self.mask_mode = mask_mode
         self.mask_thr = mask_thr
         self.want_inlier_mask = want_inlier_mask
@@ -167,25 +171,30 @@ class PoseSolver:
             self._out[key] = o
         return self._out[key]
 
-    def __call__(self, depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx, region_idx=None, anchors=None,
-                 depth_div=None, t_net=None, stream=None):
+    def __call__(self, depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx=None, region_idx=None, anchors=None,
+                 depth_div=None, t_net=None, stream=None, roi_base=0):
+        """hyp_idx=None: the kernel draws self.num_hyp triplets per ROI itself (seeded; roi_base = global index of
+        ROI 0 of this call, so that shards of one job reproduce the single-GPU result)."""
         L = _lib.lib()
         inp = _Inputs(depth, Kp, coor_x, coor_y, coor_z, mask, extent, region_idx, anchors, depth_div,
                       self.mask_mode, self.mask_thr)
         B, dev = inp.B, inp.dev
-        assert hyp_idx.dim() == 3 and hyp_idx.shape[0] == B and hyp_idx.shape[2] == 3, tuple(hyp_idx.shape)
-        H = hyp_idx.shape[1]
-        hyp = _vec(hyp_idx, (B, H, 3), "hyp_idx", torch.int32)
+        if hyp_idx is None:
+            H, hyp = self.num_hyp, None
+        else:
+            assert hyp_idx.dim() == 3 and hyp_idx.shape[0] == B and hyp_idx.shape[2] == 3, tuple(hyp_idx.shape)
+            H = hyp_idx.shape[1]
+            hyp = _vec(hyp_idx, (B, H, 3), "hyp_idx", torch.int32)
         tn = _vec(t_net, (B, 3), "t_net") if t_net is not None else None
-        prm = _lib.SolveParams(num_hyp=H, **self.prm)
+        prm = _lib.SolveParams(num_hyp=H, roi_base=int(roi_base), **self.prm)
         o = self._buffers(B, H, dev)
         outs = _lib.SolveOutputs()
         for k in ("pose", "n_inliers", "status", "best_h", "n_sel", "inlier_mask", "hyp_counts", "hyp_poses", "scale", "rows16"):
             setattr(outs, k, o[k].data_ptr() if k in o else None)
         st = (stream or torch.cuda.current_stream(dev)).cuda_stream
         with torch.cuda.device(dev):
-            rc = L.rdpn_pose_solve(ctypes.byref(inp.struct), hyp.data_ptr(), tn.data_ptr() if tn is not None else None,
-                                   ctypes.byref(prm), ctypes.byref(outs), st)
+            rc = L.rdpn_pose_solve(ctypes.byref(inp.struct), hyp.data_ptr() if hyp is not None else None,
+                                   tn.data_ptr() if tn is not None else None, ctypes.byref(prm), ctypes.byref(outs), st)
         _lib.check(rc, "pose_solve")
         self._keep = (inp, hyp, tn)  # keep inputs alive until the next call (stream-ordered use)
         return PoseSolveResult(pose=o["pose"].view(B, 3, 4), n_inliers=o["n_inliers"], status=o["status"],
@@ -201,8 +210,8 @@ class SolvePlan:
         self._solver, self._inp, self._hyp, self._tn, self._prm, self._outs = solver, inp, hyp, tn, prm, outs
         self.result = result
         self._fn = _lib.lib().rdpn_pose_solve
-        self._args = (ctypes.byref(inp.struct), hyp.data_ptr(), tn.data_ptr() if tn is not None else None,
-                      ctypes.byref(prm), ctypes.byref(outs))
+        self._args = (ctypes.byref(inp.struct), hyp.data_ptr() if hyp is not None else None,
+                      tn.data_ptr() if tn is not None else None, ctypes.byref(prm), ctypes.byref(outs))
         self._dev = inp.dev
 
     def launch(self, stream=None):
@@ -213,16 +222,19 @@ class SolvePlan:
         return self.result
 
 
-def make_plan(solver, depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx, region_idx=None, anchors=None,
-              depth_div=None, t_net=None):
+def make_plan(solver, depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx=None, region_idx=None, anchors=None,
+              depth_div=None, t_net=None, roi_base=0):
     """Prepare a reusable launch of `solver` on fixed device buffers (private output buffers)."""
     inp = _Inputs(depth, Kp, coor_x, coor_y, coor_z, mask, extent, region_idx, anchors, depth_div,
                   solver.mask_mode, solver.mask_thr)
     B, dev = inp.B, inp.dev
-    H = hyp_idx.shape[1]
-    hyp = _vec(hyp_idx, (B, H, 3), "hyp_idx", torch.int32)
+    if hyp_idx is None:
+        H, hyp = solver.num_hyp, None
+    else:
+        H = hyp_idx.shape[1]
+        hyp = _vec(hyp_idx, (B, H, 3), "hyp_idx", torch.int32)
     tn = _vec(t_net, (B, 3), "t_net") if t_net is not None else None
-    prm = _lib.SolveParams(num_hyp=H, **solver.prm)
+    prm = _lib.SolveParams(num_hyp=H, roi_base=int(roi_base), **solver.prm)
     solver._out.pop((B, H, str(dev)), None)
     o = solver._buffers(B, H, dev)
     solver._out.pop((B, H, str(dev)), None)  # the plan owns these buffers
@@ -237,11 +249,11 @@ def make_plan(solver, depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx, 
     return SolvePlan(solver, inp, hyp, tn, prm, outs, res)
 
 
-def pose_solve(depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx, region_idx=None, anchors=None,
-               depth_div=None, t_net=None, stream=None, **kw):
+def pose_solve(depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx=None, region_idx=None, anchors=None,
+               depth_div=None, t_net=None, stream=None, roi_base=0, **kw):
     """One-shot functional form of PoseSolver (see its constructor for the keyword arguments)."""
     return PoseSolver(**kw)(depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx, region_idx, anchors,
-                            depth_div, t_net, stream)
+                            depth_div, t_net, stream, roi_base)
 
 
 def sample_hypotheses(sel, H, generator=None):
@@ -287,7 +299,7 @@ class HostPoseSolver:
         self.set_option(_lib.OPT_COUNT_BYTES, int(bool(count_bytes)))
         self.pin_outputs = pin_outputs
         s = PoseSolver(**solver_kw)
-        self.prm, self.mask_mode, self.mask_thr = s.prm, s.mask_mode, s.mask_thr
+        self.prm, self.mask_mode, self.mask_thr, self.num_hyp = s.prm, s.mask_mode, s.mask_thr, s.num_hyp
         self.want_inlier_mask, self.want_hyp = s.want_inlier_mask, s.want_hyp
         self._out = {}
 
@@ -338,12 +350,12 @@ class HostPoseSolver:
             self._out[key] = o
         return self._out[key]
 
-    def plan(self, depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx, region_idx=None, anchors=None,
-             depth_div=None, t_net=None):
+    def plan(self, depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx=None, region_idx=None, anchors=None,
+             depth_div=None, t_net=None, roi_base=0):
         """Prepare a call on fixed buffers: returns a zero-argument callable that is one ctypes call (a serving loop
         that refills the same pinned buffers pays no per-step Python bookkeeping) and yields the PoseSolveResult."""
         B = depth.shape[0]
-        H = hyp_idx.shape[1]
+        H = self.num_hyp if hyp_idx is None else hyp_idx.shape[1]
         f32, t = torch.float32, {}
         for name, x in (("depth", depth), ("coor_x", coor_x), ("coor_y", coor_y), ("coor_z", coor_z), ("mask", mask)):
             t[name] = self._cpu(x, (B, P), f32, name)
@@ -358,13 +370,13 @@ class HostPoseSolver:
             t["anchors"] = self._cpu(anchors, (B, R, 3), f32, "anchors")
         if depth_div is not None:
             t["depth_div"] = self._cpu(depth_div, (B,), f32, "depth_div")
-        hyp = self._cpu(hyp_idx, (B, H, 3), torch.int32, "hyp_idx")
+        hyp = self._cpu(hyp_idx, (B, H, 3), torch.int32, "hyp_idx") if hyp_idx is not None else None
         tn = self._cpu(t_net, (B, 3), f32, "t_net") if t_net is not None else None
         s = _lib.RoiInputs()
         for k in ("depth", "Kp", "depth_div", "coor_x", "coor_y", "coor_z", "mask", "extent", "region_idx", "anchors"):
             setattr(s, k, t[k].data_ptr() if k in t else None)
         s.num_regions, s.mask_mode, s.mask_thr, s.B = R, _mask_mode(self.mask_mode), float(self.mask_thr), B
-        prm = _lib.SolveParams(num_hyp=H, **self.prm)
+        prm = _lib.SolveParams(num_hyp=H, roi_base=int(roi_base), **self.prm)
         o = self._buffers(B, H)
         outs = _lib.SolveOutputs()
         for k in ("pose", "n_inliers", "status", "best_h", "n_sel", "inlier_mask", "hyp_counts", "hyp_poses", "scale"):
@@ -373,8 +385,8 @@ class HostPoseSolver:
                               n_sel=o["n_sel"], inlier_mask=o.get("inlier_mask"), hyp_counts=o.get("hyp_counts"),
                               hyp_poses=o.get("hyp_poses"), scale=o["scale"], rows=None)
         fn, ctx = self._L.rdpn_pose_solve_host, self._ctx
-        cargs = (ctx, ctypes.byref(s), hyp.data_ptr(), tn.data_ptr() if tn is not None else None, ctypes.byref(prm),
-                 ctypes.byref(outs))
+        cargs = (ctx, ctypes.byref(s), hyp.data_ptr() if hyp is not None else None,
+                 tn.data_ptr() if tn is not None else None, ctypes.byref(prm), ctypes.byref(outs))
         keep = (t, hyp, tn, s, prm, outs)  # the C structs point into these
 
         def run(_keep=keep):
@@ -385,6 +397,7 @@ class HostPoseSolver:
 
         return run
 
-    def __call__(self, depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx, region_idx=None, anchors=None,
-                 depth_div=None, t_net=None):
-        return self.plan(depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx, region_idx, anchors, depth_div, t_net)()
+    def __call__(self, depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx=None, region_idx=None, anchors=None,
+                 depth_div=None, t_net=None, roi_base=0):
+        return self.plan(depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx, region_idx, anchors, depth_div, t_net,
+                         roi_base)()

@@ -169,3 +169,27 @@ def test_roi_crop_restatement_matches_cv2():
         if t == 0:
             c, s = np.array([3, 3], np.float32), np.float32(80)
         assert np.array_equal(po.roi_crop_depth(depth, c, s), po.roi_crop_depth_cv2(depth, c, s))
+
+
+def test_sample_triplets_stream_properties():
+    """The internal hypothesis sampling (hyp_idx == NULL): deterministic, drawn from the gated pixels only,
+    different per ROI / seed, roughly uniform; empty gate -> all -1."""
+    rng = np.random.default_rng(0)
+    sel = rng.random(4096) < 0.1
+    a = po.sample_triplets(sel, 256, 7, 3)
+    assert a.shape == (256, 3) and a.dtype == np.int32
+    assert np.array_equal(a, po.sample_triplets(sel, 256, 7, 3))
+    assert sel[a.reshape(-1)].all()
+    assert not np.array_equal(a, po.sample_triplets(sel, 256, 8, 3))
+    assert not np.array_equal(a, po.sample_triplets(sel, 256, 7, 4))
+    # the first H' hypotheses of a longer draw are the shorter draw (counter = 3 h + v)
+    assert np.array_equal(a[:64], po.sample_triplets(sel, 64, 7, 3))
+    big = po.sample_triplets(sel, 20000, 1, 0).reshape(-1)
+    g = np.nonzero(sel)[0]
+    counts = np.bincount(np.searchsorted(g, big), minlength=len(g))
+    assert counts.min() > 0.5 * counts.mean() and counts.max() < 1.6 * counts.mean()
+    assert (po.sample_triplets(np.zeros(4096, bool), 8, 1, 0) == -1).all()
+    # known answer: pins the hash itself (fmix32 chain documented in include/rdpn6d_b200.h)
+    one = np.zeros(4096, bool)
+    one[[5, 77, 1000, 4095]] = True
+    assert po.sample_triplets(one, 2, 42, 9).tolist() == [[77, 1000, 77], [5, 77, 77]]

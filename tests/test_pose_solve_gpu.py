@@ -429,3 +429,46 @@ def test_sample_hypotheses_draws_gated_pixels(cuda):
     assert hyp.shape == (5, 64, 3) and hyp.dtype == torch.int32
     picked = torch.gather(s1["sel"].long(), 1, hyp.reshape(5, -1).long())
     assert bool(picked.all())
+
+
+def test_internal_sampling_equals_explicit_triplets_from_the_oracle(cuda):
+    """hyp_idx=None: the kernel draws the triplets itself (counter-based stream documented in the header).  The
+    oracle's sample_triplets is the same arithmetic on the oracle's own gate: feeding its triplets back explicitly
+    must give bit-identical results -- for the device call, for the chunked host call and for a sharded call with
+    roi_base."""
+    B, H, seed = 300, 96, 1234
+    b = synth.tile_batch(synth.make_batch(30, H=8, seed=31, occlusion_max=0.5), B)
+    g = _to_cuda(b)
+    args = (g["depth"], g["Kp"], g["coor"][:, 0], g["coor"][:, 1], g["coor"][:, 2], g["mask"], g["extent"])
+    kw = dict(region_idx=g["region_idx"], anchors=g["anchors"])
+    solver = pose_solver.PoseSolver(inlier_thr=THR, num_hyp=H, seed=seed, want_inlier_mask=True, want_hyp=True)
+    auto = solver(*args, None, **kw)
+    auto = {k: getattr(auto, k).clone() for k in ("pose", "n_inliers", "status", "best_h", "n_sel", "inlier_mask", "hyp_counts")}
+    # the oracle's gate and sampling
+    hyp = np.zeros((B, H, 3), np.int32)
+    for i in range(B):
+        c = po.correspondences(b["depth"][i], b["Kp"][i], b["coor"][i], b["mask"][i], b["extent"][i], b["region_idx"][i],
+                               b["anchors"][i])
+        hyp[i] = po.sample_triplets(c["sel"], H, seed, i)
+    expl = solver(*args, torch.from_numpy(hyp).cuda(), **kw)
+    for k, v in auto.items():
+        assert torch.equal(v, getattr(expl, k)), k
+    assert float((auto["status"] == 0).float().mean()) > 0.8
+    # a different seed draws different triplets
+    other = pose_solver.PoseSolver(inlier_thr=THR, num_hyp=H, seed=seed + 1, want_hyp=True)(*args, None, **kw)
+    assert not torch.equal(other.hyp_counts, auto["hyp_counts"])
+    # shard [100, 300) with roi_base = 100 reproduces the tail of the full call
+    sl = slice(100, 300)
+    part = pose_solver.PoseSolver(inlier_thr=THR, num_hyp=H, seed=seed)(*[a[sl] for a in args], None,
+                                                                       region_idx=g["region_idx"][sl], anchors=g["anchors"][sl],
+                                                                       roi_base=100)
+    assert torch.equal(part.pose.view(torch.int32), auto["pose"][sl].view(torch.int32))
+    assert torch.equal(part.best_h, auto["best_h"][sl])
+    # host call, chunks of 64 ROIs: chunking must not change the stream
+    t = {k: (None if v is None else torch.from_numpy(np.ascontiguousarray(v)).pin_memory()) for k, v in b.items()}
+    hs = pose_solver.HostPoseSolver(inlier_thr=THR, num_hyp=H, seed=seed, chunk_rois=64)
+    res = hs(t["depth"], t["Kp"], t["coor"][:, 0].contiguous().pin_memory(), t["coor"][:, 1].contiguous().pin_memory(),
+             t["coor"][:, 2].contiguous().pin_memory(), t["mask"], t["extent"], None, t["region_idx"], t["anchors"])
+    assert torch.equal(res.pose.view(torch.int32), auto["pose"].cpu().view(torch.int32))
+    assert torch.equal(res.best_h, auto["best_h"].cpu())
+    hs.close()
