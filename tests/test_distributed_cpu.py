@@ -67,3 +67,11 @@ def test_gather_rows_gloo(world, total):
 def test_gather_rows_single_process_is_identity():
     x = torch.randn(5, 16)
     assert D.gather_rows(x, 5) is x
+
+
+def test_numa_helper_parses_cpulists_and_never_raises():
+    from rdpn6d_b200.distributed import _parse_cpulist, bind_to_gpu_numa_node
+
+    assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert _parse_cpulist("") == set()
+    assert bind_to_gpu_numa_node(0) in (None, 0, 1, 2, 3, 4, 5, 6, 7)  # no GPU / no NUMA info here: leaves the process alone
