@@ -230,6 +230,36 @@ def test_full_size_ycbv_8192_incl_symmetric(cuda):
             assert po.te(pose[i][:, 3], ores[i]["pose"][:, 3]) <= TRANS_TOL_M, i
 
 
+def test_mp6d_scale_65536_rois_shard_invariance(cuda):
+    """BASELINE configs[4]: 65 536 ROIs (5.6 GB of maps).  Size-independent properties on ONE GPU: every tile copy of
+    the 64 base ROIs gives the same bits, and solving the job in the contiguous shards of an 8-rank run
+    (my_distributed_sampler.py:189-192) reproduces the single-call rows -- with explicit triplets and with the
+    kernel-drawn ones (roi_base keeps the stream independent of the sharding)."""
+    from rdpn6d_b200 import distributed
+
+    B, U, H = 65536, 64, 64
+    models = synth.make_models(20, 32, seed=9, n_symmetric=4)
+    base = synth.make_batch(U, models=models, H=H, seed=4242, K=synth.K_YCBV, occlusion_max=0.5)
+    g = {k: (None if v is None else torch.from_numpy(v).cuda().repeat(B // U, *([1] * (v.ndim - 1)))) for k, v in base.items()}
+    args = [g["depth"], g["Kp"], g["coor"][:, 0].contiguous(), g["coor"][:, 1].contiguous(), g["coor"][:, 2].contiguous(),
+            g["mask"], g["extent"]]
+    solver = pose_solver.PoseSolver(inlier_thr=THR, num_hyp=H, seed=5)
+    full = solver(*args, g["hyp_idx"], region_idx=g["region_idx"], anchors=g["anchors"])
+    rows = full.rows16().clone()
+    assert rows.shape == (B, 16)
+    assert torch.equal(rows.view(B // U, U, 16)[0].expand(B // U, U, 16), rows.view(B // U, U, 16))
+    assert float((full.status == 0).float().mean()) > 0.9
+    auto_rows = solver(*args, None, region_idx=g["region_idx"], anchors=g["anchors"]).rows16().clone()
+    assert not torch.equal(auto_rows[:U], auto_rows[U:2 * U])  # every ROI draws its own triplets
+    for rank in (0, 3, 7):
+        b0, b1 = distributed.shard_range(B, rank, 8)
+        sl = slice(b0, b1)
+        part = solver(*[a[sl] for a in args], g["hyp_idx"][sl], region_idx=g["region_idx"][sl], anchors=g["anchors"][sl])
+        assert torch.equal(part.rows16(), rows[sl])
+        part = solver(*[a[sl] for a in args], None, region_idx=g["region_idx"][sl], anchors=g["anchors"][sl], roi_base=b0)
+        assert torch.equal(part.rows16(), auto_rows[sl])
+
+
 def test_many_gated_points_multi_chunk(cuda):
     """More than 1024 gated pixels per ROI: the staging/scoring loop runs several chunks and the refit
     re-gathers its slots.  Big objects filling the crop, no dropout, no outliers."""
