@@ -664,7 +664,7 @@ def gpu_arm(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": ncu_traffic_bytes(), "traffic_source": "profiles/r1/ncu_pose_solve_summary.csv (ncu --set full, "
                      "dram__bytes_read.sum + dram__bytes_write.sum of one launch of this workload)",
-                     "kernel": "rdpn::pose_solve_kernel<false>", "kernel_ms": kernel_ms,
+                     "kernel": "rdpn::pose_solve_kernel<false, false>", "kernel_ms": kernel_ms,
                      "kernel_ms_note": "average duration of back-to-back launches on ONE stream (no overlap)",
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                      "note": "the fused solver is FP32-pipe bound (3x4 transforms x hypotheses x points), see fp32"},

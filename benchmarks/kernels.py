@@ -110,6 +110,16 @@ def bench_solve():
         ms = ev_time(lambda i: plans[i % len(plans)].launch(), 50)
         ns = float(plans[0].result.n_sel.double().mean())
         print(json.dumps({"bench": "pose_solve", "B": B, "H": H, "R": R, "ms": ms, "rois_per_s": B / (ms * 1e-3), "mean_n_sel": ns}), flush=True)
+    # S pairs per hypothesis, drawn by the kernel (misc.py:72 samples 10): same workload as the first row
+    sets = _sets(1024, 256, 64, 4)
+    for S in (3, 10):
+        solver = pose_solver.PoseSolver(inlier_thr=0.005, num_hyp=256, seed=1, sample_size=S)
+        plans = [pose_solver.make_plan(solver, s["depth"], s["Kp"], s["coor"][:, 0].contiguous(), s["coor"][:, 1].contiguous(),
+                                       s["coor"][:, 2].contiguous(), s["mask"], s["extent"], None, s["region_idx"], s["anchors"]) for s in sets]
+        ms = ev_time(lambda i: plans[i % len(plans)].launch(), 50)
+        ok = float((plans[0].result.status == 0).float().mean())
+        print(json.dumps({"bench": "pose_solve_internal_sampling", "B": 1024, "H": 256, "R": 64, "sample_size": S, "ms": ms,
+                          "rois_per_s": 1024 / (ms * 1e-3), "solved_fraction": ok}), flush=True)
     sets = _sets(1024, 256, 32, 1, dense=True)
     s = sets[0]
     solver = pose_solver.PoseSolver(inlier_thr=0.005)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RDPN_VERSION 101 /* 0.1.1: rdpn_solve_params gained seed / roi_base */
+#define RDPN_VERSION 102 /* 0.1.2: rdpn_solve_params gained sample_size (S-pair hypotheses) */
 
 /* negative error codes (positive values are cudaError_t) */
 #define RDPN_E_BADARG (-1)    /* NULL / non-positive size / unsupported option */
@@ -41,6 +41,8 @@ extern "C" {
 #define RDPN_STATUS_NO_CONSENSUS 3 /* no valid hypothesis reached min_inliers: pose = -100 fill   */
 
 /* mask post-processing modes (engine_utils.py:118-136 get_out_mask) */
+#define RDPN_MAX_SAMPLE 16 /* largest sample_size (pairs per hypothesis) */
+
 #define RDPN_MASK_RAW 0 /* mask already is a probability                     */
 #define RDPN_MASK_L1 1  /* per-ROI (m - min) / (max - min), no epsilon       */
 #define RDPN_MASK_BCE 2 /* sigmoid                                           */
@@ -148,6 +150,8 @@ typedef struct rdpn_solve_params {
     uint32_t seed;       /* internal sampling (hyp_idx == NULL): stream seed                        */
     int32_t roi_base;    /* internal sampling: global index of ROI 0 of this call (shards / chunks  */
                          /* of one job pass their offset so that results do not depend on batching) */
+    int32_t sample_size; /* S: correspondences per hypothesis, 3 .. RDPN_MAX_SAMPLE; 0 means 3.     */
+                         /* misc.py:72,91 samples random_sample_num = 10 pairs per iteration        */
 } rdpn_solve_params;
 
 typedef struct rdpn_solve_outputs {
@@ -164,15 +168,23 @@ typedef struct rdpn_solve_outputs {
                               block that is all-gathered across GPUs          (may be NULL)            */
 } rdpn_solve_outputs;
 
-/* hyp_idx [B,H,3] int32 absolute pixel indices (0..4095); t_net [B,3] or NULL (translation sanity).
+/* hyp_idx [B,H,S] int32 absolute pixel indices (0..4095), S = prm->sample_size (3 by default); t_net [B,3] or
+ * NULL (translation sanity).
+ *
+ * A hypothesis is valid iff its S pixels passed the gate, are pairwise distinct (the reference samples without
+ * replacement, misc.py:91) and, on the object side and on the camera side, some triangle (p0, pi, pj) of the sample
+ * is non-degenerate (sin^2 of the angle at p0 > 1e-6; for S = 3 that is the one triangle there is).  S = 3: the
+ * closed-form 3-pair Kabsch; S > 3: Kabsch of the S pairs (FP64 moments, closed-form rotation), both rounded once
+ * to FP32 (transform.py:913-980 semantics).
  *
  * hyp_idx == NULL: the solver draws the triplets itself, as the reference's loop does with np.random.choice
  * (misc.py:91), from a counter-based stream so that runs are reproducible and independent of batching:
  *     g[0..n)  = the ROI's gated pixels in raster order
  *     fmix32(x): x ^= x >> 16; x *= 0x85ebca6b; x ^= x >> 13; x *= 0xc2b2ae35; x ^= x >> 16      (uint32)
- *     key      = fmix32(fmix32(fmix32(seed ^ 0x9e3779b9) ^ (roi_base + b)) ^ (3 * h + v))
+ *     key      = fmix32(fmix32(fmix32(seed ^ 0x9e3779b9) ^ (roi_base + b)) ^ (S * h + v))
  *     pixel of vertex v of hypothesis h = g[(uint64(key) * n) >> 32]
- * (oracle/pose_oracle.py:sample_triplets is the same arithmetic; tests feed its output back as explicit hyp_idx
+ * (draws are independent, so a sample may repeat a pixel: such a hypothesis is invalid like any other and does not
+ * consume an iteration.  oracle/pose_oracle.py:sample_triplets is the same arithmetic; tests feed its output back as explicit hyp_idx
  * and demand bit-identical results). */
 int rdpn_pose_solve(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, const float* d_t_net,
                     const rdpn_solve_params* prm, const rdpn_solve_outputs* out, void* stream);

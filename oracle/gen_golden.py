@@ -27,6 +27,8 @@ Files written (small, committed):
                         allo -> ego, pose assembly  utils.py:39-94, pose_from_pred_centroid_z.py:52-141, with the one
                                                   missing third-party call (transforms3d.axangles.axangle2mat =
                                                   Rodrigues' formula) supplied by the oracle
+  ransac_roi_golden.npz  misc.pnp_ransac_custom (misc.py:58-142) run from source on the correspondences of 4 synthetic
+                      ROIs (10 pairs per sample, reference Kabsch, float64 scoring): sampled pixel sets + inlier counts
 """
 import importlib.util
 import os
@@ -69,6 +71,30 @@ def ref_functions(rel, names, env=None):
 
         exec(compile(textwrap.dedent(seg), os.path.join(REF, rel), "exec"), ns)
     return {n: ns[n] for n in names}
+
+
+class _Cv2Shim:
+    """cv2 stand-in that makes misc.pnp_ransac_custom's 2D-3D solver calls 3D-3D: solvePnP -> the reference's own
+    Kabsch (transform.affine_matrix_from_points), projectPoints -> rigid apply, Rodrigues -> identity."""
+    SOLVEPNP_ITERATIVE = 0
+
+    def __init__(self, tf):
+        self.tf, self.sample_solves, self.proj = tf, 0, []
+
+    def solvePnP(self, mp_, ip_, K_, dist, flags=0):
+        if len(mp_) == 10:
+            self.sample_solves += 1
+        M = self.tf.affine_matrix_from_points(np.asarray(mp_, float).T, np.asarray(ip_, float).T, shear=False, scale=False,
+                                         usesvd=True)
+        return True, M[:3, :3].copy(), M[:3, 3].copy()
+
+    def projectPoints(self, mp_, R_, T_, K_, dist):
+        pts_ = (R_ @ np.asarray(mp_, float).T).T + T_
+        self.proj.append((len(self.proj), self.sample_solves, pts_))
+        return pts_[:, None, :], None
+
+    def Rodrigues(self, R_):
+        return R_, None
 
 
 def gen_path():
@@ -184,26 +210,7 @@ def gen_path():
     # Rodrigues -> identity): the loop, its sampling, its strict '<' inlier rule and its adaptive stop run as written.
     # Recorded: inlier count of every iteration and the number of iterations executed.  (The loop's SELECTION rule --
     # lowest mean error over all points -- is deliberately not the composite's)
-    class Cv2Shim:
-        SOLVEPNP_ITERATIVE = 0
-
-        def __init__(self):
-            self.sample_solves, self.proj = 0, []
-
-        def solvePnP(self, mp_, ip_, K_, dist, flags=0):
-            if len(mp_) == 10:
-                self.sample_solves += 1
-            M = tf.affine_matrix_from_points(np.asarray(mp_, float).T, np.asarray(ip_, float).T, shear=False, scale=False,
-                                             usesvd=True)
-            return True, M[:3, :3].copy(), M[:3, 3].copy()
-
-        def projectPoints(self, mp_, R_, T_, K_, dist):
-            pts_ = (R_ @ np.asarray(mp_, float).T).T + T_
-            self.proj.append((len(self.proj), self.sample_solves, pts_))
-            return pts_[:, None, :], None
-
-        def Rodrigues(self, R_):
-            return R_, None
+    Cv2Shim = lambda: _Cv2Shim(tf)  # noqa: E731
 
     cases = []
     for ci, (npt, out_frac, noise) in enumerate([(200, 0.1, 5e-4), (200, 0.45, 1e-3), (150, 0.7, 1e-3), (300, 0.3, 2e-3)]):
@@ -370,18 +377,71 @@ def gen_pose(tf):
     print("pose_golden.npz", out["out_status"], out["out_ninl"])
 
 
+def gen_ransac_roi(tf):
+    """The reference's RANSAC loop on the correspondences of whole synthetic ROIs: misc.pnp_ransac_custom (misc.py:58-142)
+    executed from source behind the 3D-3D cv2 shim on the gated (object, camera) pairs of each ROI -- 10 pairs per
+    sample (misc.py:72,91), the reference's Kabsch on every solve, every point scored in float64, adaptive stop.
+    Stored: the ROI planes, the sampled pixel sets of every iteration as hyp_idx [B,H,10] (-1 beyond the iteration at
+    which the loop stopped) and the loop's inlier count per iteration.  The solver is run on the same planes with the
+    same index sets (sample_size = 10) and must reproduce those counts (tests/test_oracle_pose.py,
+    tests/test_pose_solve_gpu.py)."""
+    from oracle import pose_oracle as po
+    from rdpn6d_b200 import synth
+
+    B, HMAX, S, thr = 4, 128, 10, 0.005
+    models = synth.make_models(4, 32, seed=9, n_symmetric=1)
+    # two ROIs with 1 mm noise and 15 % outlier pixels (the adaptive rule stops the loop right after min_iter: either w
+    # is high, or a contaminated sample scores w^10 < 1 ulp and k = -inf) and two with 4 mm noise and no outliers
+    # (every sample scores a middling w, k stays huge: the loop runs all 100 iterations)
+    b0 = synth.make_batch(2, models=models, H=8, seed=20260301, occlusion_max=0.3)
+    b1 = synth.make_batch(2, models=models, H=8, seed=20260302, occlusion_max=0.3, outlier_frac=0.0, noise_sigma=0.004)
+    b = {k: np.concatenate([b0[k], b1[k]]) for k in ("depth", "Kp", "coor", "mask", "extent", "region_idx", "anchors")}
+    hyp = np.full((B, HMAX, S), -1, np.int32)
+    counts = np.full((B, HMAX), -1, np.int32)
+    iters = np.zeros(B, np.int32)
+    for r in range(B):
+        c = po.correspondences(b["depth"][r], b["Kp"][r], b["coor"][r], b["mask"][r], b["extent"][r], b["region_idx"][r],
+                               b["anchors"][r])
+        pix = np.nonzero(c["sel"])[0]
+        mpts = c["obj"][:, pix].T.astype(np.float64)
+        cpts = c["cam"][:, pix].T.astype(np.float64)
+        shim = _Cv2Shim(tf)
+        ransac = ref_functions("lib/pysixd/misc.py", ["pnp_ransac_custom"], env={"cv2": shim})["pnp_ransac_custom"]
+        np.random.seed(2000 + r)
+        ransac(cpts, mpts, None, ransac_iter=100, ransac_min_iter=10, ransac_reprojErr=thr)
+        cr, seen = [], 0
+        for _, ns, pts_ in shim.proj:  # inlier count of iteration i = first projection after the i-th sample solve
+            if ns > seen:
+                cr.append(int((np.linalg.norm(pts_ - cpts, axis=1) < thr).sum()))
+                seen = ns
+        n_it = shim.sample_solves
+        assert len(cr) == n_it <= HMAX
+        # replay the loop's sampling calls (misc.py:91 is its only use of the generator) and check the replay
+        np.random.seed(2000 + r)
+        for i in range(n_it):
+            idx = np.random.choice(len(pix), S, replace=False)
+            M = tf.affine_matrix_from_points(mpts[idx].T, cpts[idx].T, shear=False, scale=False, usesvd=True)
+            e = np.linalg.norm((M[:3, :3] @ mpts.T).T + M[:3, 3] - cpts, axis=1)
+            assert int((e < thr).sum()) == cr[i], (r, i)
+            hyp[r, i] = pix[idx]
+        counts[r, :n_it] = cr
+        iters[r] = n_it
+    out = {k: b[k] for k in ("depth", "Kp", "coor", "mask", "extent", "region_idx", "anchors")}
+    out.update(hyp_idx=hyp, counts=counts, iters=iters, thr=np.float32(thr))
+    np.savez_compressed(os.path.join(GOLD, "ransac_roi_golden.npz"), **out)
+    print("ransac_roi_golden.npz iters", iters, "max counts", counts.max(axis=1))
+
+
 def main():
     if not os.path.isdir(REF):
         sys.exit("reference not mounted at %s" % REF)
     os.makedirs(GOLD, exist_ok=True)
     tf = _load("ref_transform", "lib/pysixd/transform.py")
     du = _load("ref_data_utils", "core/utils/data_utils.py")
-    gen_fps()
-    gen_kabsch(tf)
-    gen_affine(du)
-    gen_region(du)
-    gen_pose(tf)
-    gen_path()
+    gens = dict(fps=gen_fps, kabsch=lambda: gen_kabsch(tf), affine=lambda: gen_affine(du), region=lambda: gen_region(du),
+                pose=lambda: gen_pose(tf), path=gen_path, ransac_roi=lambda: gen_ransac_roi(tf))
+    for name in (sys.argv[1:] or list(gens)):  # python -m oracle.gen_golden [name ...]
+        gens[name]()
 
 
 if __name__ == "__main__":

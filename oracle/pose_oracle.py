@@ -265,22 +265,35 @@ def _triangle_ok(p0, p1, p2):
 
 
 def hypothesis_poses(obj, cam, sel, hyp_idx):
-    """obj, cam: [3,P] float32; sel: [P] bool; hyp_idx: [H,3] absolute pixel indices.
+    """obj, cam: [3,P] float32; sel: [P] bool; hyp_idx: [H,S] absolute pixel indices, S >= 3 pairs per hypothesis
+    (3 = the minimal 3D-3D sample; the reference's loop draws random_sample_num = 10, misc.py:72,91).
 
-    A hypothesis is valid iff its three pixels passed the gate and both triangles are
-    non-degenerate (misc.py:95-101 carries the same intent as a commented-out determinant check).
-    Pose = Kabsch of the three pairs in float64 (numpy SVD, as transform.py), rounded to float32.
+    A hypothesis is valid iff its S pixels passed the gate, are pairwise distinct (misc.py:91 samples without
+    replacement; for S = 3 a repeated pixel is a degenerate triangle anyway) and each side has a non-degenerate
+    triangle through its first point (misc.py:95-101 carries the same intent as a commented-out determinant check).  Pose = Kabsch of the S pairs in float64 (numpy SVD, as transform.py), rounded to float32.
     Returns Rt[H,12] float32 (R row-major | t interleaved as 3x4) and valid[H] uint8.
     """
     hyp_idx = np.asarray(hyp_idx, dtype=np.int64)
-    H = hyp_idx.shape[0]
+    H, S = hyp_idx.shape
     P = obj.shape[1]
     inb = ((hyp_idx >= 0) & (hyp_idx < P)).all(axis=1)
     idx = np.clip(hyp_idx, 0, P - 1)
-    a = obj.T.astype(F64)[idx]  # [H,3,3] (hyp, vertex, xyz)
+    a = obj.T.astype(F64)[idx]  # [H,S,3] (hyp, vertex, xyz)
     c = cam.T.astype(F64)[idx]
     valid = inb & sel[idx].all(axis=1)
-    valid &= _triangle_ok(a[:, 0], a[:, 1], a[:, 2]) & _triangle_ok(c[:, 0], c[:, 1], c[:, 2])
+    if S > 3:
+        srt = np.sort(hyp_idx, axis=1)
+        valid &= (srt[:, 1:] != srt[:, :-1]).all(axis=1)
+    # non-degeneracy: some triangle (p0, pi, pj), 0 < i < j, passes the test -- on the object side and on the camera side
+    # (S = 3: the one triangle there is).  In anchor mode several sampled pixels may share an anchor, so a fixed
+    # triangle would reject samples the reference's loop solves without trouble.
+    ok_a = np.zeros(H, bool)
+    ok_c = np.zeros(H, bool)
+    for i in range(1, S):
+        for j in range(i + 1, S):
+            ok_a |= _triangle_ok(a[:, 0], a[:, i], a[:, j])
+            ok_c |= _triangle_ok(c[:, 0], c[:, i], c[:, j])
+    valid &= ok_a & ok_c
     Rt = np.zeros((H, 3, 4), dtype=F32)
     if valid.any():
         av = a[valid]
@@ -318,20 +331,22 @@ def _fmix32(x):
     return x ^ (x >> np.uint32(16))
 
 
-def sample_triplets(sel, H, seed, roi_index):
+def sample_triplets(sel, H, seed, roi_index, sample_size=3):
     """The solver's internal hypothesis sampling (include/rdpn6d_b200.h, rdpn_pose_solve with hyp_idx == NULL):
     the stand-in for np.random.choice at misc.py:91, counter-based so that it is reproducible.  sel: [P] bool gate of
-    one ROI; returns [H,3] int32 absolute pixel indices (all -1 when nothing is gated)."""
+    one ROI; returns [H,S] int32 absolute pixel indices (all -1 when nothing is gated).  Draws are independent: a
+    sample that repeats a pixel is an invalid hypothesis (hypothesis_poses)."""
+    S = int(sample_size)
     g = np.nonzero(np.asarray(sel).reshape(-1))[0]
     n = len(g)
     if n == 0:
-        return np.full((H, 3), -1, np.int32)
+        return np.full((H, S), -1, np.int32)
     with np.errstate(over="ignore"):
         kroi = _fmix32(_fmix32(np.uint32(seed) ^ np.uint32(0x9E3779B9)) ^ np.uint32(roi_index & 0xFFFFFFFF))
-        hv = np.arange(3 * H, dtype=np.uint32)
+        hv = np.arange(S * H, dtype=np.uint32)
         key = _fmix32(kroi ^ hv)
     k = (key.astype(np.uint64) * np.uint64(n)) >> np.uint64(32)
-    return g[k.astype(np.int64)].astype(np.int32).reshape(H, 3)
+    return g[k.astype(np.int64)].astype(np.int32).reshape(H, S)
 
 
 def sq_cut(thr):

@@ -33,6 +33,7 @@ class SolveParams(ctypes.Structure):
         ("min_inliers", ctypes.c_int32), ("weighted", ctypes.c_int32), ("refit_iters", ctypes.c_int32),
         ("with_scale", ctypes.c_int32), ("adaptive", ctypes.c_int32), ("confidence", ctypes.c_float),
         ("min_iter", ctypes.c_int32), ("seed", ctypes.c_uint32), ("roi_base", ctypes.c_int32),
+        ("sample_size", ctypes.c_int32),
     ]
 
 
@@ -78,6 +79,8 @@ SIGNATURES = {
     "rdpn_launch_count": (ctypes.c_ulonglong, []),
     "rdpn_fp32_peak_probe": (ctypes.c_int, [ctypes.c_int, c_f64p]),
 }
+
+MAX_SAMPLE = 16  # RDPN_MAX_SAMPLE
 
 # rdpn_ctx_set_option keys / transfer strategies (include/rdpn6d_b200.h)
 TRANSFER_AUTO, TRANSFER_COPY, TRANSFER_PULL = 0, 1, 2

@@ -36,7 +36,7 @@ struct PullArgs {
     uint8_t* d_rid;
     unsigned long long* pulled_quads;  // device counter (quads fetched per plane)
     // small per-ROI arrays fetched by the same kernel (all nullptr: they were copied instead)
-    const int32_t* h_hyp;      // [nb,H,3]
+    const int32_t* h_hyp;      // [nb,H,S]
     const float* h_anchors;    // [nb,R,3] or nullptr
     const float* h_kp;         // [nb,4]
     const float* h_ext;        // [nb,3]
@@ -48,7 +48,7 @@ struct PullArgs {
     float* d_ext;
     float* d_div;
     float* d_tnet;
-    int H3;                    // H * 3
+    int H3;                    // H * S
     int R3;                    // R * 3
     int mask_mode;
     float mask_thr;
@@ -355,6 +355,8 @@ int rdpn_pose_solve_host(rdpn_ctx* c, const rdpn_roi_inputs* h, const int32_t* h
     RDPN_CUDA_TRY(cudaSetDevice(c->device));
     const bool dense = h->region_idx == nullptr;
     const int H = prm->num_hyp, R = dense ? 0 : h->num_regions;
+    if (prm->sample_size != 0 && (prm->sample_size < 3 || prm->sample_size > RDPN_MAX_SAMPLE)) return RDPN_E_BADARG;
+    const int SS = prm->sample_size ? prm->sample_size : 3;  // pairs per hypothesis
     const size_t P = RDPN_P, CH = (size_t)c->chunk;
     const bool may_pull = c->transfer != RDPN_TRANSFER_COPY;
 
@@ -394,7 +396,7 @@ int rdpn_pose_solve_host(rdpn_ctx* c, const rdpn_roi_inputs* h, const int32_t* h
     const size_t o_kp = off; off += al256(CH * 16);
     const size_t o_ext = off; off += al256(CH * 12);
     const size_t o_div = off; off += al256(CH * 4);
-    const size_t o_hyp = off; off += al256(CH * (size_t)H * 12);
+    const size_t o_hyp = off; off += al256(CH * (size_t)H * SS * 4);
     const size_t o_tnet = off; off += al256(CH * 12);
     const size_t o_pose = off; off += al256(CH * 48);
     const size_t o_ninl = off; off += al256(CH * 4);
@@ -415,7 +417,7 @@ int rdpn_pose_solve_host(rdpn_ctx* c, const rdpn_roi_inputs* h, const int32_t* h
         c->buf_bytes = off;
     }
     const size_t in_off[NIN] = {o_depth, o_cx, o_cy, o_cz, o_rid, o_mask, o_anc, o_kp, o_ext, o_div, o_hyp, o_tnet};
-    const size_t in_roi_bytes[NIN] = {P * 4, P * 4, P * 4, P * 4, P, P * 4, (size_t)R * 12, 16, 12, 4, (size_t)H * 12, 12};
+    const size_t in_roi_bytes[NIN] = {P * 4, P * 4, P * 4, P * 4, P, P * 4, (size_t)R * 12, 16, 12, 4, (size_t)H * SS * 4, 12};
     const size_t out_off[NOUT] = {o_pose, o_ninl, o_stat, o_best, o_nsel, o_scale, o_imask, o_hcnt, o_hpose};
     const size_t out_roi_bytes[NOUT] = {48, 4, 4, 4, 4, 4, P, (size_t)H * 4, (size_t)H * 48};
 
@@ -478,7 +480,7 @@ int rdpn_pose_solve_host(rdpn_ctx* c, const rdpn_roi_inputs* h, const int32_t* h
             pa.d_ext = (float*)(d + o_ext);
             pa.d_div = (float*)(d + o_div);
             pa.d_tnet = (float*)(d + o_tnet);
-            pa.H3 = H * 3;
+            pa.H3 = H * SS;
             pa.R3 = R * 3;
             pa.mask_mode = h->mask_mode;
             pa.mask_thr = h->mask_thr;

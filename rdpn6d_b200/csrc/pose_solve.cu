@@ -80,7 +80,8 @@ struct SolveArgs {
 //      atomics) rides along
 //   3  deterministic counting sort of the gated pixels by region id: bucket cursors by one thread per bucket +
 //      block scan, slots from warp match_any ranks -> pix[slot], srid[slot]; run table of the non-empty buckets
-//   4  hypothesis generation: 3 gathered pixels each, FP64 closed form, rounded once to FP32
+//   4  hypothesis generation: 3 gathered pixels each, FP64 closed form, rounded once to FP32 (S > 3 pairs per
+//      hypothesis: hyp_from_sample, FP64 moments + closed-form rotation)
 //   5  per chunk of <= 1024 gated slots: STAGING (one thread per slot gathers the raw pixel and computes
 //      (cam xyz, w) with the exact S1 arithmetic into a float4 list in shared memory), then
 //   6  SCORING: two hypotheses per thread, warp-aligned groups of warps split the runs; per run the transformed
@@ -103,6 +104,16 @@ struct FinishSmem {  // scratch of the select + refit tail
     unsigned long long red_k[SW];
     int red_i[SW];
     int red_j[SW];
+};
+
+// the raw planes of one ROI in global memory
+struct RoiPlanes {
+    const float* depth;
+    const float* cx;
+    const float* cy;
+    const float* cz;
+    const float* mask;
+    const uint8_t* rid;
 };
 
 struct __align__(128) FusedSmem {
@@ -139,16 +150,6 @@ __device__ __forceinline__ void pixel_s1(const RoiConst& rc, int pix, float d_ra
         obj[0] = obj[1] = obj[2] = 0.f;
     }
 }
-
-// the raw planes of one ROI in global memory
-struct RoiPlanes {
-    const float* depth;
-    const float* cx;
-    const float* cy;
-    const float* cz;
-    const float* mask;
-    const uint8_t* rid;
-};
 
 // gather one gated pixel and run S1 on it (cam xyz, w | obj xyz)
 template <bool DENSE>
@@ -236,8 +237,109 @@ struct FusedLayout {  // byte offsets of the dynamic tail behind FusedSmem
     int hyp;          // float[H][12]
     int hcnt;         // int[H]
     int vlist;        // uint16[H] indices of the valid hypotheses
+    int planes;       // RoiPlanes copy for the out-of-line S > 3 hypothesis path (MULTI instantiations only)
     int total;
 };
+
+// rank-select on the gate bitmap: pixel index of the k-th gated pixel in raster order (internal sampling)
+__device__ __forceinline__ int kth_gated_pixel(const uint32_t* selmap, const uint16_t* selpfx, uint32_t k) {
+    int lo = 0;
+#pragma unroll
+    for (int step = RDPN_P / 64; step; step >>= 1)
+        if (selpfx[lo + step] <= k) lo += step;
+    const unsigned j = k - selpfx[lo];
+    return lo * 32 + (int)__fns(selmap[lo], 0, (int)j + 1);
+}
+
+// Hypothesis from S > 3 pairs (misc.py:72,91 samples random_sample_num = 10): Kabsch of the S pairs,
+// transform.py:913-980 semantics.  FP64 raw moments about the first pair (exact FP32 differences), closed-form
+// rotation, rounded once to FP32.  Valid iff the S pixels are gated and pairwise distinct (sampling without
+// replacement) and each side has a non-degenerate triangle (p0, pi, pj) (the S = 3 test, over the sample).
+// Out of line: the default S = 3 path must not pay registers for it.
+template <bool DENSE>
+__device__ __noinline__ bool hyp_from_sample(const FusedSmem& s, const RoiPlanes& pl, const float4* anchors,
+                                             const int32_t* idx_in, uint32_t kroi, int h, int S, float* P) {
+    const RoiConst& rc = s.rc;  // pl and rc are the shared-memory copies (no stack traffic for by-reference arguments)
+    const uint32_t* selmap = s.selmap;
+    const uint16_t* selpfx = s.selpfx;
+    int ii[RDPN_MAX_SAMPLE];
+    const uint32_t nsel = selpfx[RDPN_P / 32];
+    for (int v = 0; v < S; ++v) {
+        if (idx_in) {
+            ii[v] = idx_in[v];
+        } else {
+            const uint32_t key = fmix32(kroi ^ (uint32_t)(S * h + v));
+            ii[v] = nsel ? kth_gated_pixel(selmap, selpfx, (uint32_t)(((unsigned long long)key * nsel) >> 32)) : -1;
+        }
+    }
+    for (int v = 0; v < S; ++v) {
+        if ((unsigned)ii[v] >= RDPN_P) return false;
+        if (!((selmap[ii[v] >> 5] >> (ii[v] & 31)) & 1u)) return false;
+        for (int u = 0; u < v; ++u)
+            if (ii[u] == ii[v]) return false;
+    }
+    float pc[RDPN_MAX_SAMPLE][3], pa[RDPN_MAX_SAMPLE][3];  // local memory: this path is not the default one
+    for (int v = 0; v < S; ++v) {
+        float4 cw, ob;
+        gather_s1<DENSE>(pl, rc, ii[v], false, RDPN_MASK_RAW, cw, ob);  // unweighted: the mask is not read
+        if (!DENSE) ob = anchors[__ldg(pl.rid + ii[v])];
+        pc[v][0] = cw.x; pc[v][1] = cw.y; pc[v][2] = cw.z;
+        pa[v][0] = ob.x; pa[v][1] = ob.y; pa[v][2] = ob.z;
+    }
+    // each side needs one non-degenerate triangle (p0, pi, pj) (oracle hypothesis_poses; bit-identical test)
+    bool ok_a = false, ok_c = false;
+    {
+        const double a0[3] = {(double)pa[0][0], (double)pa[0][1], (double)pa[0][2]};
+        const double c0[3] = {(double)pc[0][0], (double)pc[0][1], (double)pc[0][2]};
+        for (int i = 1; i < S && !(ok_a && ok_c); ++i) {
+            const double ai[3] = {(double)pa[i][0], (double)pa[i][1], (double)pa[i][2]};
+            const double ci[3] = {(double)pc[i][0], (double)pc[i][1], (double)pc[i][2]};
+            for (int j = i + 1; j < S && !(ok_a && ok_c); ++j) {
+                const double aj[3] = {(double)pa[j][0], (double)pa[j][1], (double)pa[j][2]};
+                const double cj[3] = {(double)pc[j][0], (double)pc[j][1], (double)pc[j][2]};
+                if (!ok_a) ok_a = triangle_ok(a0, ai, aj);
+                if (!ok_c) ok_c = triangle_ok(c0, ci, cj);
+            }
+        }
+    }
+    if (!ok_a || !ok_c) return false;
+    double m[17];  // sum c (3) | sum a (3) | sum c a^T (9) | sum |c|^2 | sum |a|^2, all about pair 0
+#pragma unroll
+    for (int i = 0; i < 17; ++i) m[i] = 0.0;
+    const float c0f[3] = {pc[0][0], pc[0][1], pc[0][2]}, a0f[3] = {pa[0][0], pa[0][1], pa[0][2]};
+    for (int v = 1; v < S; ++v) {
+        const double c[3] = {(double)pc[v][0] - (double)c0f[0], (double)pc[v][1] - (double)c0f[1], (double)pc[v][2] - (double)c0f[2]};
+        const double a[3] = {(double)pa[v][0] - (double)a0f[0], (double)pa[v][1] - (double)a0f[1], (double)pa[v][2] - (double)a0f[2]};
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            m[i] += c[i];
+            m[3 + i] += a[i];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) m[6 + 3 * i + j] += c[i] * a[j];
+        }
+        m[15] += c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+        m[16] += a[0] * a[0] + a[1] * a[1] + a[2] * a[2];
+    }
+    const double inv = 1.0 / (double)S;
+    double Sc[9], R[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Sc[3 * i + j] = m[6 + 3 * i + j] - m[i] * (m[3 + j] * inv);
+    const double ga = m[16] - (m[3] * m[3] + m[4] * m[4] + m[5] * m[5]) * inv;
+    const double gb = m[15] - (m[0] * m[0] + m[1] * m[1] + m[2] * m[2]) * inv;
+    rotation_from_cov(Sc, ga, gb, R);
+    const double ma[3] = {m[3] * inv + (double)a0f[0], m[4] * inv + (double)a0f[1], m[5] * inv + (double)a0f[2]};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const double mc = m[r] * inv + (double)c0f[r];
+        P[4 * r + 0] = (float)R[3 * r + 0];
+        P[4 * r + 1] = (float)R[3 * r + 1];
+        P[4 * r + 2] = (float)R[3 * r + 2];
+        P[4 * r + 3] = (float)(mc - (R[3 * r] * ma[0] + R[3 * r + 1] * ma[1] + R[3 * r + 2] * ma[2]));
+    }
+    return true;
+}
 
 #ifndef RDPN_SOLVE_CTAS
 #define RDPN_SOLVE_CTAS 4
@@ -249,7 +351,9 @@ struct FusedLayout {  // byte offsets of the dynamic tail behind FusedSmem
 #ifndef RDPN_SERIAL_WARP
 #define RDPN_SERIAL_WARP (SW - 1)
 #endif
-template <bool DENSE>
+// MULTI: S > 3 pairs per hypothesis (a separate instantiation, so that the default S = 3 kernel carries neither the
+// call nor its register pressure)
+template <bool DENSE, bool MULTI = false>
 __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveArgs a, FusedLayout lay) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FusedSmem& s = *reinterpret_cast<FusedSmem*>(smem_raw);
@@ -288,8 +392,9 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
         if (!DENSE && t < 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(pl.rid + t * 64));
     }
     // the thread's first hypothesis triplet is requested now (DRAM) and consumed in phase 4
+    const int SS = MULTI ? a.prm.sample_size : 3;  // pairs per hypothesis (3 .. RDPN_MAX_SAMPLE)
     int pre0 = -1, pre1 = -1, pre2 = -1;
-    if (a.hyp_idx && t < H) {
+    if (a.hyp_idx && t < H && !MULTI) {
         const int32_t* ip = a.hyp_idx + ((size_t)b * H + t) * 3;
         pre0 = __ldg(ip);
         pre1 = __ldg(ip + 1);
@@ -308,6 +413,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
         }
         rc.div = in.depth_div ? in.depth_div[b] : 0.f;
         rc.mn = rc.mx = 0.f;
+        if (MULTI) *reinterpret_cast<RoiPlanes*>(smem_raw + lay.planes) = pl;
         f.best_h = -1;
         f.n_best = 0;
         f.h_eff = H;
@@ -545,6 +651,18 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
     PHASE_MARK(5);
     // ---- 4: hypothesis generation (FP64 closed form), one hypothesis per thread, pixels gathered ----
     for (int h = t; h < H; h += ST) {
+        if (MULTI) {  // S-pair hypotheses (misc.py:72,91): out-of-line Kabsch of the sample
+            float* P = hyp + (size_t)h * 12;
+            const uint32_t kroi = fmix32(fmix32(a.prm.seed ^ 0x9e3779b9u) ^ (uint32_t)(a.prm.roi_base + b));
+            const bool ok = hyp_from_sample<DENSE>(s, *reinterpret_cast<const RoiPlanes*>(smem_raw + lay.planes), anchors,
+                                                   a.hyp_idx ? a.hyp_idx + ((size_t)b * H + h) * SS : nullptr, kroi, h, SS, P);
+            if (!ok) {
+#pragma unroll
+                for (int i = 0; i < 12; ++i) P[i] = 0.f;
+            }
+            hcnt[h] = ok ? 0 : -1;
+            continue;
+        }
         int ii[3];
         if (a.hyp_idx) {
             const int32_t* ip = a.hyp_idx + ((size_t)b * H + h) * 3;
@@ -561,12 +679,7 @@ __global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveAr
             for (int v = 0; v < 3; ++v) {
                 const uint32_t key = fmix32(kroi ^ (uint32_t)(3 * h + v));
                 const uint32_t k = (uint32_t)(((unsigned long long)key * nsel) >> 32);
-                int lo = 0;
-#pragma unroll
-                for (int step = RDPN_P / 64; step; step >>= 1)
-                    if (s.selpfx[lo + step] <= k) lo += step;
-                const unsigned j = k - s.selpfx[lo];
-                ii[v] = nsel ? lo * 32 + (int)__fns(s.selmap[lo], 0, (int)j + 1) : -1;
+                ii[v] = nsel ? kth_gated_pixel(s.selmap, s.selpfx, k) : -1;
             }
         }
         bool ok = ((unsigned)ii[0] < RDPN_P) && ((unsigned)ii[1] < RDPN_P) && ((unsigned)ii[2] < RDPN_P);
@@ -1131,7 +1244,7 @@ int check_roi_inputs(const rdpn_roi_inputs* in, bool* dense) {
     return 0;
 }
 
-template <bool DENSE>
+template <bool DENSE, bool MULTI>
 static int launch_solve(const SolveArgs& a, cudaStream_t st) {
     const int H = a.prm.num_hyp;
     const int R = DENSE ? 1 : a.in.num_regions;
@@ -1145,15 +1258,16 @@ static int launch_solve(const SolveArgs& a, cudaStream_t st) {
     lay.hyp = (int)off;     off = al(off + (size_t)H * 12 * sizeof(float));
     lay.hcnt = (int)off;    off = al(off + (size_t)H * sizeof(int));
     lay.vlist = (int)off;   off = al(off + (size_t)H * sizeof(uint16_t));
+    lay.planes = (int)off;  if (MULTI) off = al(off + sizeof(RoiPlanes));
     lay.total = (int)off;
     const size_t smem = off;
     if (smem > 227 * 1024) return RDPN_E_TOOLARGE;
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
-        RDPN_CUDA_TRY(cudaFuncSetAttribute(pose_solve_kernel<DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RDPN_CUDA_TRY(cudaFuncSetAttribute(pose_solve_kernel<DENSE, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem = smem;
     }
-    pose_solve_kernel<DENSE><<<a.in.B, ST, smem, st>>>(a, lay);
+    pose_solve_kernel<DENSE, MULTI><<<a.in.B, ST, smem, st>>>(a, lay);
     ++g_launch_count;
     RDPN_LAUNCH_CHECK();
     return 0;
@@ -1176,16 +1290,20 @@ int rdpn_pose_solve(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, const f
     if (rc) return rc;
     if (!prm || !out || !out->pose || !out->n_inliers || !out->status) return RDPN_E_BADARG;  // d_hyp_idx NULL: internal sampling
     if (prm->num_hyp <= 0 || !(prm->inlier_thr > 0.f)) return RDPN_E_BADARG;
+    if (prm->sample_size != 0 && (prm->sample_size < 3 || prm->sample_size > RDPN_MAX_SAMPLE)) return RDPN_E_BADARG;
     if (out->inlier_mask && ((uintptr_t)out->inlier_mask & 15)) return RDPN_E_ALIGN;
     rdpn::SolveArgs a;
     a.in = *in;
     a.hyp_idx = d_hyp_idx;
     a.t_net = d_t_net;
     a.prm = *prm;
+    if (a.prm.sample_size == 0) a.prm.sample_size = 3;
     a.out = *out;
     a.sq_cut = rdpn::host_sq_cut(prm->inlier_thr);
     rdpn::host_mask_cut(in->mask_thr, &a.mask_cut, &a.mask_cut_incl);
-    return dense ? rdpn::launch_solve<true>(a, (cudaStream_t)stream) : rdpn::launch_solve<false>(a, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a.prm.sample_size > 3) return dense ? rdpn::launch_solve<true, true>(a, st) : rdpn::launch_solve<false, true>(a, st);
+    return dense ? rdpn::launch_solve<true, false>(a, st) : rdpn::launch_solve<false, false>(a, st);
 }
 
 int rdpn_kabsch(const float* d_src, const float* d_dst, const float* d_w, int N, int with_scale, float* d_out_M,

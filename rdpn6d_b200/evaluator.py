@@ -37,14 +37,17 @@ class GpuRansacKabsch:
     """Stateful processor holding the solver configuration and the accumulated predictions."""
 
     def __init__(self, num_hyp=256, inlier_thr=0.005, mask_thr=0.5, mask_mode=MASK_L1, weighted=False, refit_iters=1,
-                 label_to_obj_id=None, depth_is_scale_normalised=True, seed=0):
+                 label_to_obj_id=None, depth_is_scale_normalised=True, seed=0, sample_size=3, adaptive=False):
         """depth_is_scale_normalised: roi_coord_2d[:, 2] holds depth / resize_ratio (data_loader.py:563); the
-        solver multiplies it back (depth_div = 1 / resize_ratio) so that the 3D-3D solve is metric."""
+        solver multiplies it back (depth_div = 1 / resize_ratio) so that the 3D-3D solve is metric.
+        sample_size: pairs per RANSAC sample (3 = minimal; misc.py:72 uses random_sample_num = 10); adaptive: the
+        reference loop's early stop (misc.py:134-138)."""
         self.num_hyp = num_hyp
         # the kernel draws the RANSAC triplets itself (seeded counter-based stream): no separate S1 pass, no
         # multinomial -- the step is one launch
         self.solver = PoseSolver(inlier_thr=inlier_thr, mask_thr=mask_thr, mask_mode=mask_mode, weighted=weighted,
-                                 refit_iters=refit_iters, num_hyp=num_hyp, seed=seed)
+                                 refit_iters=refit_iters, num_hyp=num_hyp, seed=seed, sample_size=sample_size,
+                                 adaptive=adaptive)
         self.mask_thr, self.mask_mode = mask_thr, mask_mode
         self.label_to_obj_id = label_to_obj_id or (lambda label: int(label) + 1)
         self.depth_is_scale_normalised = depth_is_scale_normalised

@@ -13,7 +13,8 @@ Inputs follow the reference's tensors at the evaluator boundary
   mask         [B,1,64,64] or [B,64,64] raw head mask
   extent       [B,3]       roi_extent
   region_idx   [B,64,64] uint8 (geometry.region_argmax of out_dict["region"]) + anchors [B,R,3] (fps)
-  hyp_idx      [B,H,3] int32 absolute pixel indices of each hypothesis' three correspondences
+  hyp_idx      [B,H,S] int32 absolute pixel indices of each hypothesis' S correspondences (S = 3 by default;
+               the reference's loop samples random_sample_num = 10, misc.py:72,91)
 PoseSolver / correspond take CUDA tensors; HostPoseSolver takes CPU tensors and moves them itself (host-buffer
 plugin call).  Either way the arithmetic runs in the CUDA kernels: there is no CPU compute path.
 """
@@ -134,14 +135,28 @@ class PoseSolveResult:
                           self.n_sel.float()[:, None], self.best_h.float()[:, None]], dim=1)
 
 
+def _hyp_arg(hyp_idx, B, num_hyp, sample_size, conv):
+    """(H, S, tensor | None) of a call: explicit hyp_idx [B,H,S] or the solver's internal sampling."""
+    if hyp_idx is None:
+        return num_hyp, sample_size, None
+    if hyp_idx.dim() != 3 or hyp_idx.shape[0] != B or not 3 <= hyp_idx.shape[2] <= _lib.MAX_SAMPLE:
+        raise ValueError("hyp_idx must be [B,H,S] with 3 <= S <= %d, got %s" % (_lib.MAX_SAMPLE, tuple(hyp_idx.shape)))
+    H, S = hyp_idx.shape[1], hyp_idx.shape[2]
+    return H, S, conv(hyp_idx, (B, H, S))
+
+
 class PoseSolver:
     """Reusable launcher: output buffers are allocated once per (B, H) and reused (graph friendly)."""
 
     def __init__(self, inlier_thr=0.005, min_pts=4, min_inliers=4, weighted=False, refit_iters=1, with_scale=False,
                  adaptive=False, confidence=0.995, min_iter=10, mask_mode=MASK_L1, mask_thr=0.5,
-                 want_inlier_mask=False, want_hyp=False, num_hyp=256, seed=0):
-        """num_hyp / seed: used when a call passes hyp_idx=None -- the kernel then draws the triplets itself from a
-        counter-based stream (include/rdpn6d_b200.h), the stand-in for np.random.choice at misc.py:91."""
+                 want_inlier_mask=False, want_hyp=False, num_hyp=256, seed=0, sample_size=3):
+        """num_hyp / seed / sample_size: used when a call passes hyp_idx=None -- the kernel then draws num_hyp samples of
+        sample_size pixels itself from a counter-based stream (include/rdpn6d_b200.h), the stand-in for np.random.choice
+        at misc.py:91.  With explicit hyp_idx [B,H,S] both H and S come from the tensor."""
+        if not 3 <= int(sample_size) <= _lib.MAX_SAMPLE:
+            raise ValueError("sample_size must be in 3..%d" % _lib.MAX_SAMPLE)
+        self.sample_size = int(sample_size)
         self.prm = dict(inlier_thr=float(inlier_thr), min_pts=int(min_pts), min_inliers=int(min_inliers),
                         weighted=int(bool(weighted)), refit_iters=int(refit_iters), with_scale=int(bool(with_scale)),
                         adaptive=int(bool(adaptive)), confidence=float(confidence), min_iter=int(min_iter),
@@ -179,14 +194,9 @@ class PoseSolver:
         inp = _Inputs(depth, Kp, coor_x, coor_y, coor_z, mask, extent, region_idx, anchors, depth_div,
                       self.mask_mode, self.mask_thr)
         B, dev = inp.B, inp.dev
-        if hyp_idx is None:
-            H, hyp = self.num_hyp, None
-        else:
-            assert hyp_idx.dim() == 3 and hyp_idx.shape[0] == B and hyp_idx.shape[2] == 3, tuple(hyp_idx.shape)
-            H = hyp_idx.shape[1]
-            hyp = _vec(hyp_idx, (B, H, 3), "hyp_idx", torch.int32)
+        H, S, hyp = _hyp_arg(hyp_idx, B, self.num_hyp, self.sample_size, lambda x, shp: _vec(x, shp, "hyp_idx", torch.int32))
         tn = _vec(t_net, (B, 3), "t_net") if t_net is not None else None
-        prm = _lib.SolveParams(num_hyp=H, roi_base=int(roi_base), **self.prm)
+        prm = _lib.SolveParams(num_hyp=H, roi_base=int(roi_base), sample_size=S, **self.prm)
         o = self._buffers(B, H, dev)
         outs = _lib.SolveOutputs()
         for k in ("pose", "n_inliers", "status", "best_h", "n_sel", "inlier_mask", "hyp_counts", "hyp_poses", "scale", "rows16"):
@@ -228,13 +238,9 @@ def make_plan(solver, depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx=N
     inp = _Inputs(depth, Kp, coor_x, coor_y, coor_z, mask, extent, region_idx, anchors, depth_div,
                   solver.mask_mode, solver.mask_thr)
     B, dev = inp.B, inp.dev
-    if hyp_idx is None:
-        H, hyp = solver.num_hyp, None
-    else:
-        H = hyp_idx.shape[1]
-        hyp = _vec(hyp_idx, (B, H, 3), "hyp_idx", torch.int32)
+    H, S, hyp = _hyp_arg(hyp_idx, B, solver.num_hyp, solver.sample_size, lambda x, shp: _vec(x, shp, "hyp_idx", torch.int32))
     tn = _vec(t_net, (B, 3), "t_net") if t_net is not None else None
-    prm = _lib.SolveParams(num_hyp=H, roi_base=int(roi_base), **solver.prm)
+    prm = _lib.SolveParams(num_hyp=H, roi_base=int(roi_base), sample_size=S, **solver.prm)
     solver._out.pop((B, H, str(dev)), None)
     o = solver._buffers(B, H, dev)
     solver._out.pop((B, H, str(dev)), None)  # the plan owns these buffers
@@ -256,8 +262,8 @@ def pose_solve(depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx=None, re
                             depth_div, t_net, stream, roi_base)
 
 
-def sample_hypotheses(sel, H, generator=None):
-    """Draw hyp_idx [B,H,3] int32 uniformly (with replacement) from each ROI's gated pixels.
+def sample_hypotheses(sel, H, generator=None, sample_size=3):
+    """Draw hyp_idx [B,H,S] int32 uniformly (with replacement) from each ROI's gated pixels.
 
     The reference draws its RANSAC samples with np.random.choice inside the loop
     (lib/pysixd/misc.py:91); here randomness is lifted out into an explicit tensor so that runs are
@@ -268,8 +274,8 @@ def sample_hypotheses(sel, H, generator=None):
     w = sel.reshape(B, -1).float()
     empty = w.sum(dim=1) == 0
     w[empty, 0] = 1.0
-    idx = torch.multinomial(w, H * 3, replacement=True, generator=generator)
-    return idx.view(B, H, 3).to(torch.int32)
+    idx = torch.multinomial(w, H * sample_size, replacement=True, generator=generator)
+    return idx.view(B, H, sample_size).to(torch.int32)
 
 
 class HostPoseSolver:
@@ -300,6 +306,7 @@ class HostPoseSolver:
         self.pin_outputs = pin_outputs
         s = PoseSolver(**solver_kw)
         self.prm, self.mask_mode, self.mask_thr, self.num_hyp = s.prm, s.mask_mode, s.mask_thr, s.num_hyp
+        self.sample_size = s.sample_size
         self.want_inlier_mask, self.want_hyp = s.want_inlier_mask, s.want_hyp
         self._out = {}
 
@@ -355,7 +362,7 @@ class HostPoseSolver:
         """Prepare a call on fixed buffers: returns a zero-argument callable that is one ctypes call (a serving loop
         that refills the same pinned buffers pays no per-step Python bookkeeping) and yields the PoseSolveResult."""
         B = depth.shape[0]
-        H = self.num_hyp if hyp_idx is None else hyp_idx.shape[1]
+        H, S, hyp = _hyp_arg(hyp_idx, B, self.num_hyp, self.sample_size, lambda x, shp: self._cpu(x, shp, torch.int32, "hyp_idx"))
         f32, t = torch.float32, {}
         for name, x in (("depth", depth), ("coor_x", coor_x), ("coor_y", coor_y), ("coor_z", coor_z), ("mask", mask)):
             t[name] = self._cpu(x, (B, P), f32, name)
@@ -370,13 +377,12 @@ class HostPoseSolver:
             t["anchors"] = self._cpu(anchors, (B, R, 3), f32, "anchors")
         if depth_div is not None:
             t["depth_div"] = self._cpu(depth_div, (B,), f32, "depth_div")
-        hyp = self._cpu(hyp_idx, (B, H, 3), torch.int32, "hyp_idx") if hyp_idx is not None else None
         tn = self._cpu(t_net, (B, 3), f32, "t_net") if t_net is not None else None
         s = _lib.RoiInputs()
         for k in ("depth", "Kp", "depth_div", "coor_x", "coor_y", "coor_z", "mask", "extent", "region_idx", "anchors"):
             setattr(s, k, t[k].data_ptr() if k in t else None)
         s.num_regions, s.mask_mode, s.mask_thr, s.B = R, _mask_mode(self.mask_mode), float(self.mask_thr), B
-        prm = _lib.SolveParams(num_hyp=H, roi_base=int(roi_base), **self.prm)
+        prm = _lib.SolveParams(num_hyp=H, roi_base=int(roi_base), sample_size=S, **self.prm)
         o = self._buffers(B, H)
         outs = _lib.SolveOutputs()
         for k in ("pose", "n_inliers", "status", "best_h", "n_sel", "inlier_mask", "hyp_counts", "hyp_poses", "scale"):

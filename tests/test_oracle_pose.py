@@ -193,3 +193,48 @@ def test_sample_triplets_stream_properties():
     one = np.zeros(4096, bool)
     one[[5, 77, 1000, 4095]] = True
     assert po.sample_triplets(one, 2, 42, 9).tolist() == [[77, 1000, 77], [5, 77, 77]]
+
+
+def test_s10_hypotheses_reproduce_reference_ransac_loop(gold):
+    """oracle/gen_golden.py:gen_ransac_roi ran misc.pnp_ransac_custom (misc.py:58-142) from source on the gated pairs of
+    four synthetic ROIs (10 pairs per sample, misc.py:72,91).  The oracle on the same planes and pixel sets
+    (hypothesis_poses with S = 10, float32 scoring) reproduces the loop's inlier count of every iteration up to
+    boundary ties of the float32 scoring, and its adaptive rule stops where the loop stopped."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ransac_roi_golden.npz"))
+    thr = float(g["thr"])
+    exact = total = 0
+    for r in range(4):
+        c = po.correspondences(g["depth"][r], g["Kp"][r], g["coor"][r], g["mask"][r], g["extent"][r], g["region_idx"][r],
+                               g["anchors"][r])
+        n_it = int(g["iters"][r])
+        hyp = g["hyp_idx"][r].copy()
+        Rt, valid = po.hypothesis_poses(c["obj"], c["cam"], c["sel"], hyp)
+        assert valid[:n_it].all() and not valid[n_it:].any()
+        pix = np.nonzero(c["sel"])[0]
+        counts = po.score_hypotheses(c["obj"][:, pix].T, c["cam"][:, pix].T, Rt, valid, thr)
+        d = counts[:n_it].astype(int) - g["counts"][r, :n_it]
+        assert np.abs(d).max() <= 2, (r, d)
+        exact += int((d == 0).sum())
+        total += n_it
+        if n_it < 20:  # the loop stopped by its adaptive rule: with valid samples appended the oracle stops there too
+            hyp[n_it:] = hyp[0]
+            Rt, valid = po.hypothesis_poses(c["obj"], c["cam"], c["sel"], hyp)
+            counts = po.score_hypotheses(c["obj"][:, pix].T, c["cam"][:, pix].T, Rt, valid, thr)
+            _, examined = po.select_best(counts, valid, len(pix), 4, True, 0.995, 10)
+            assert examined == n_it
+    assert exact >= 0.97 * total
+
+
+def test_s_pair_validity_rules():
+    b = synth.make_batch(1, H=8, seed=5)
+    c = po.correspondences(b["depth"][0], b["Kp"][0], b["coor"][0], b["mask"][0], b["extent"][0], b["region_idx"][0],
+                           b["anchors"][0])
+    pix = np.nonzero(c["sel"])[0]
+    off = np.nonzero(~c["sel"])[0]
+    good = pix[np.linspace(0, len(pix) - 1, 6).astype(int)]
+    hyp = np.stack([good, np.r_[good[:5], good[0]], np.r_[good[:5], off[0]], np.r_[good[:5], -1]]).astype(np.int32)
+    Rt, valid = po.hypothesis_poses(c["obj"], c["cam"], c["sel"], hyp)
+    assert valid.tolist() == [1, 0, 0, 0]  # ok | repeated pixel | ungated pixel | out of range
+    M = po.kabsch(c["obj"][:, good].astype(np.float64), c["cam"][:, good].astype(np.float64))
+    assert np.allclose(Rt[0].reshape(3, 4), M[:3, :4], atol=1e-6)
+    assert po.sample_triplets(c["sel"], 5, 1, 0, sample_size=7).shape == (5, 7)

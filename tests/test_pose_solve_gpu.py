@@ -502,3 +502,131 @@ def test_internal_sampling_equals_explicit_triplets_from_the_oracle(cuda):
     assert torch.equal(res.pose.view(torch.int32), auto["pose"].cpu().view(torch.int32))
     assert torch.equal(res.best_h, auto["best_h"].cpu())
     hs.close()
+
+
+def _ransac_roi_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ransac_roi_golden.npz"))
+    b = {k: g[k] for k in ("depth", "Kp", "coor", "mask", "extent", "region_idx", "anchors")}
+    return g, b
+
+
+def test_s10_samples_reproduce_the_reference_ransac_loop(cuda, golden_dir):
+    """misc.pnp_ransac_custom (misc.py:58-142) was run from source on the correspondences of four synthetic ROIs
+    (oracle/gen_golden.py:gen_ransac_roi): 10 pairs per sample (misc.py:72,91), the reference's Kabsch on every solve,
+    every point scored in float64, strict '<'.  The solver, fed the same planes and the same pixel sets
+    (sample_size = 10), must reproduce the loop's inlier count of every iteration -- against the oracle under the
+    usual bit-exactness rules, against the float64 reference loop up to boundary ties of the FP32 scoring."""
+    g, b = _ransac_roi_golden(golden_dir)
+    hyp, ref, iters, thr = g["hyp_idx"], g["counts"], g["iters"], float(g["thr"])
+    assert hyp.shape[2] == 10
+    ores = po.pose_solve_batch(b, hyp, thr)
+    res = _solve(_to_cuda({**b, "hyp_idx": hyp}), inlier_thr=thr)
+    cnt = res.hyp_counts.cpu().numpy()
+    hp = res.hyp_poses.reshape(4, -1, 12).cpu().numpy()
+    exact = total = 0
+    for r in range(4):
+        o, n_it = ores[r], int(iters[r])
+        assert int(res.status[r]) == o["status"] and int(res.n_sel[r]) == o["n_sel"]
+        assert int(res.best_h[r]) == o["best_h"] and int(res.n_inliers[r]) == o["n_inl"]
+        assert np.array_equal(res.inlier_mask[r].reshape(-1).cpu().numpy(), o["inlier_mask"])
+        assert po.re_rad_small(res.pose[r].cpu().numpy()[:, :3], o["pose"][:, :3]) <= ROT_TOL_RAD
+        assert po.te(res.pose[r].cpu().numpy()[:, 3], o["pose"][:, 3]) <= TRANS_TOL_M
+        assert o["valid"][:n_it].all() and not o["valid"][n_it:].any()
+        np.testing.assert_allclose(hp[r], o["Rt_hyp"], atol=2e-6)
+        same = (hp[r].view(np.uint32) == o["Rt_hyp"].view(np.uint32)).all(axis=1)
+        assert np.array_equal(cnt[r][same], o["counts"][same])
+        assert np.abs(cnt[r][~same].astype(int) - o["counts"][~same]).max(initial=0) <= 2
+        assert same.mean() > 0.9
+        # the reference loop itself
+        d = cnt[r, :n_it].astype(int) - ref[r, :n_it]
+        assert np.abs(d).max() <= 2, (r, d)
+        assert (cnt[r, n_it:] == 0).all()
+        exact += int((d == 0).sum())
+        total += n_it
+    assert exact >= 0.97 * total, (exact, total)
+
+
+def test_s10_adaptive_stop_matches_the_reference_loop(cuda, golden_dir):
+    """The reference loop stopped by itself after iters[r] iterations on the two clean ROIs (misc.py:134-138).  With
+    further valid samples appended, the solver in adaptive mode must stop at the same iteration: its winner is the best
+    of the first iters[r] hypotheses although a later one scores more."""
+    g, b = _ransac_roi_golden(golden_dir)
+    hyp, ref, iters, thr = g["hyp_idx"].copy(), g["counts"], g["iters"], float(g["thr"])
+    for r in range(2):
+        n_it = int(iters[r])
+        assert n_it < 20
+        top = int(np.argmax(ref[r, :n_it]))
+        hyp[r, n_it:] = hyp[r, top]  # valid samples behind the stop
+        # make a later hypothesis the global best by a margin: refine it to the ROI's consensus (oracle refit pose is
+        # not expressible as a sample, so reuse the top sample: ties never displace the earlier winner, misc.py:121)
+    sel = slice(0, 2)
+    bb = {k: v[sel] for k, v in b.items()}
+    ores = po.pose_solve_batch(bb, hyp[sel], thr, adaptive=True, confidence=0.995, min_iter=10)
+    res = _solve(_to_cuda({**bb, "hyp_idx": hyp[sel]}), inlier_thr=thr, adaptive=True, confidence=0.995, min_iter=10)
+    for r in range(2):
+        n_it = int(iters[r])
+        counts = ores[r]["counts"]
+        _, examined = po.select_best(counts, ores[r]["valid"], ores[r]["n_sel"], 4, True, 0.995, 10)
+        assert examined == n_it, (examined, n_it)  # the oracle stops where the reference loop stopped
+        assert int(res.best_h[r]) == ores[r]["best_h"] < n_it
+        assert int(res.n_inliers[r]) == ores[r]["n_inl"]
+
+
+@pytest.mark.parametrize("S", [4, 10, 16])
+def test_internal_sampling_with_larger_samples(cuda, S):
+    """hyp_idx=None with sample_size S: kernel-drawn samples == oracle.sample_triplets(sample_size=S) fed back explicitly,
+    on the device call and on the chunked host call; samples that repeat a pixel are invalid hypotheses."""
+    B, H, seed = 64, 64, 77
+    b = synth.tile_batch(synth.make_batch(16, H=8, seed=41, occlusion_max=0.4), B)
+    g = _to_cuda(b)
+    args = (g["depth"], g["Kp"], g["coor"][:, 0], g["coor"][:, 1], g["coor"][:, 2], g["mask"], g["extent"])
+    kw = dict(region_idx=g["region_idx"], anchors=g["anchors"])
+    solver = pose_solver.PoseSolver(inlier_thr=THR, num_hyp=H, seed=seed, sample_size=S, want_inlier_mask=True, want_hyp=True)
+    auto = solver(*args, None, **kw)
+    auto = {k: getattr(auto, k).clone() for k in ("pose", "n_inliers", "status", "best_h", "n_sel", "inlier_mask", "hyp_counts")}
+    hyp = np.zeros((B, H, S), np.int32)
+    ndup = 0
+    for i in range(B):
+        c = po.correspondences(b["depth"][i], b["Kp"][i], b["coor"][i], b["mask"][i], b["extent"][i], b["region_idx"][i],
+                               b["anchors"][i])
+        hyp[i] = po.sample_triplets(c["sel"], H, seed, i, sample_size=S)
+        srt = np.sort(hyp[i], axis=1)
+        dup = (srt[:, 1:] == srt[:, :-1]).any(axis=1)
+        ndup += int(dup.sum())
+        assert (auto["hyp_counts"][i].cpu().numpy()[dup] == 0).all()  # repeated pixel: invalid, scores nothing
+    assert S == 4 or ndup > 0
+    expl = solver(*args, torch.from_numpy(hyp).cuda(), **kw)
+    for k, v in auto.items():
+        assert torch.equal(v, getattr(expl, k)), k
+    assert float((auto["status"] == 0).float().mean()) > 0.8
+    # oracle parity on the explicit samples
+    ores = po.pose_solve_batch({k: v[:16] for k, v in b.items() if v is not None}, hyp[:16], THR)
+    for i in range(16):
+        assert int(expl.best_h[i]) == ores[i]["best_h"] and int(expl.n_inliers[i]) == ores[i]["n_inl"]
+        assert np.array_equal(expl.inlier_mask[i].reshape(-1).cpu().numpy(), ores[i]["inlier_mask"])
+    # host call (pinned buffers, gated pull, chunks of 32 ROIs): explicit [B,H,S] samples and kernel-drawn ones
+    t = {k: (None if v is None else torch.from_numpy(np.ascontiguousarray(v)).pin_memory()) for k, v in b.items()}
+    hs = pose_solver.HostPoseSolver(inlier_thr=THR, num_hyp=H, seed=seed, sample_size=S, chunk_rois=32)
+    hargs = (t["depth"], t["Kp"], t["coor"][:, 0].contiguous().pin_memory(), t["coor"][:, 1].contiguous().pin_memory(),
+             t["coor"][:, 2].contiguous().pin_memory(), t["mask"], t["extent"])
+    for h_in in (None, torch.from_numpy(hyp).pin_memory()):
+        res = hs(*hargs, h_in, t["region_idx"], t["anchors"])
+        assert torch.equal(res.pose.view(torch.int32), auto["pose"].cpu().view(torch.int32))
+        assert torch.equal(res.best_h, auto["best_h"].cpu())
+    hs.close()
+
+
+def test_sample_size_out_of_range_is_rejected(cuda):
+    b = synth.make_batch(2, H=8, seed=3)
+    g = _to_cuda(b)
+    with pytest.raises(ValueError):
+        pose_solver.PoseSolver(sample_size=2)
+    with pytest.raises(ValueError):
+        pose_solver.PoseSolver()(g["depth"], g["Kp"], g["coor"][:, 0], g["coor"][:, 1], g["coor"][:, 2], g["mask"], g["extent"],
+                                 torch.zeros(2, 8, 17, dtype=torch.int32, device="cuda"), region_idx=g["region_idx"],
+                                 anchors=g["anchors"])
+    L = _lib.lib()
+    prm = _lib.SolveParams(inlier_thr=THR, num_hyp=8, min_pts=4, min_inliers=4, refit_iters=1, sample_size=17)
+    inp = _lib.RoiInputs(depth=16, Kp=16, coor_x=16, coor_y=16, coor_z=16, mask=16, extent=16, B=1, mask_mode=1)
+    out = _lib.SolveOutputs(pose=16, n_inliers=16, status=16)
+    assert L.rdpn_pose_solve(ctypes.byref(inp), None, None, ctypes.byref(prm), ctypes.byref(out), None) == -1
