@@ -172,8 +172,8 @@ typedef struct rdpn_solve_outputs {
  * NULL (translation sanity).
  *
  * A hypothesis is valid iff its S pixels passed the gate, are pairwise distinct (the reference samples without
- * replacement, misc.py:91) and, on the object side and on the camera side, some triangle (p0, pi, pj) of the sample
- * is non-degenerate (sin^2 of the angle at p0 > 1e-6; for S = 3 that is the one triangle there is).  S = 3: the
+ * replacement, misc.py:91) and, on the object side and on the camera side, some triangle (p0, p_{v-1}, p_v),
+ * 2 <= v < S, of the sample is non-degenerate (sin^2 of the angle at p0 > 1e-6; for S = 3 that is the one triangle there is).  S = 3: the
  * closed-form 3-pair Kabsch; S > 3: Kabsch of the S pairs (FP64 moments, closed-form rotation), both rounded once
  * to FP32 (transform.py:913-980 semantics).
  *

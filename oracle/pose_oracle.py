@@ -270,7 +270,7 @@ def hypothesis_poses(obj, cam, sel, hyp_idx):
 
     A hypothesis is valid iff its S pixels passed the gate, are pairwise distinct (misc.py:91 samples without
     replacement; for S = 3 a repeated pixel is a degenerate triangle anyway) and each side has a non-degenerate
-    triangle through its first point (misc.py:95-101 carries the same intent as a commented-out determinant check).  Pose = Kabsch of the S pairs in float64 (numpy SVD, as transform.py), rounded to float32.
+    triangle (p0, p_{v-1}, p_v) (misc.py:95-101 carries the same intent as a commented-out determinant check).  Pose = Kabsch of the S pairs in float64 (numpy SVD, as transform.py), rounded to float32.
     Returns Rt[H,12] float32 (R row-major | t interleaved as 3x4) and valid[H] uint8.
     """
     hyp_idx = np.asarray(hyp_idx, dtype=np.int64)
@@ -284,15 +284,14 @@ def hypothesis_poses(obj, cam, sel, hyp_idx):
     if S > 3:
         srt = np.sort(hyp_idx, axis=1)
         valid &= (srt[:, 1:] != srt[:, :-1]).all(axis=1)
-    # non-degeneracy: some triangle (p0, pi, pj), 0 < i < j, passes the test -- on the object side and on the camera side
-    # (S = 3: the one triangle there is).  In anchor mode several sampled pixels may share an anchor, so a fixed
-    # triangle would reject samples the reference's loop solves without trouble.
+    # non-degeneracy: some triangle (p0, p_{v-1}, p_v), 2 <= v < S, passes the test -- on the object side and on the
+    # camera side (S = 3: the one triangle there is).  In anchor mode several sampled pixels may share an anchor, so
+    # a single fixed triangle would reject samples the reference's loop solves without trouble.
     ok_a = np.zeros(H, bool)
     ok_c = np.zeros(H, bool)
-    for i in range(1, S):
-        for j in range(i + 1, S):
-            ok_a |= _triangle_ok(a[:, 0], a[:, i], a[:, j])
-            ok_c |= _triangle_ok(c[:, 0], c[:, i], c[:, j])
+    for v in range(2, S):
+        ok_a |= _triangle_ok(a[:, 0], a[:, v - 1], a[:, v])
+        ok_c |= _triangle_ok(c[:, 0], c[:, v - 1], c[:, v])
     valid &= ok_a & ok_c
     Rt = np.zeros((H, 3, 4), dtype=F32)
     if valid.any():

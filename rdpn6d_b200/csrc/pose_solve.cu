@@ -254,7 +254,7 @@ __device__ __forceinline__ int kth_gated_pixel(const uint32_t* selmap, const uin
 // Hypothesis from S > 3 pairs (misc.py:72,91 samples random_sample_num = 10): Kabsch of the S pairs,
 // transform.py:913-980 semantics.  FP64 raw moments about the first pair (exact FP32 differences), closed-form
 // rotation, rounded once to FP32.  Valid iff the S pixels are gated and pairwise distinct (sampling without
-// replacement) and each side has a non-degenerate triangle (p0, pi, pj) (the S = 3 test, over the sample).
+// replacement) and each side has a non-degenerate triangle (p0, p_{v-1}, p_v) (the S = 3 test, along the sample).
 // Out of line: the default S = 3 path must not pay registers for it.
 template <bool DENSE>
 __device__ __noinline__ bool hyp_from_sample(const FusedSmem& s, const RoiPlanes& pl, const float4* anchors,
@@ -278,48 +278,49 @@ __device__ __noinline__ bool hyp_from_sample(const FusedSmem& s, const RoiPlanes
         for (int u = 0; u < v; ++u)
             if (ii[u] == ii[v]) return false;
     }
-    float pc[RDPN_MAX_SAMPLE][3], pa[RDPN_MAX_SAMPLE][3];  // local memory: this path is not the default one
+    // One pass over the sample, nothing parked in local memory: pair 0 is the pivot of the FP64 moments (exact FP32
+    // differences) and the apex of the degeneracy test -- each side needs one non-degenerate triangle
+    // (p0, p_{v-1}, p_v), 2 <= v < S (oracle hypothesis_poses; bit-identical test).
+    double m[17];  // sum c (3) | sum a (3) | sum c a^T (9) | sum |c|^2 | sum |a|^2, all about pair 0
+#pragma unroll
+    for (int i = 0; i < 17; ++i) m[i] = 0.0;
+    float c0f[3] = {0.f, 0.f, 0.f}, a0f[3] = {0.f, 0.f, 0.f}, cpf[3] = {0.f, 0.f, 0.f}, apf[3] = {0.f, 0.f, 0.f};
+    bool ok_a = false, ok_c = false;
+#pragma unroll 1
     for (int v = 0; v < S; ++v) {
         float4 cw, ob;
         gather_s1<DENSE>(pl, rc, ii[v], false, RDPN_MASK_RAW, cw, ob);  // unweighted: the mask is not read
         if (!DENSE) ob = anchors[__ldg(pl.rid + ii[v])];
-        pc[v][0] = cw.x; pc[v][1] = cw.y; pc[v][2] = cw.z;
-        pa[v][0] = ob.x; pa[v][1] = ob.y; pa[v][2] = ob.z;
-    }
-    // each side needs one non-degenerate triangle (p0, pi, pj) (oracle hypothesis_poses; bit-identical test)
-    bool ok_a = false, ok_c = false;
-    {
-        const double a0[3] = {(double)pa[0][0], (double)pa[0][1], (double)pa[0][2]};
-        const double c0[3] = {(double)pc[0][0], (double)pc[0][1], (double)pc[0][2]};
-        for (int i = 1; i < S && !(ok_a && ok_c); ++i) {
-            const double ai[3] = {(double)pa[i][0], (double)pa[i][1], (double)pa[i][2]};
-            const double ci[3] = {(double)pc[i][0], (double)pc[i][1], (double)pc[i][2]};
-            for (int j = i + 1; j < S && !(ok_a && ok_c); ++j) {
-                const double aj[3] = {(double)pa[j][0], (double)pa[j][1], (double)pa[j][2]};
-                const double cj[3] = {(double)pc[j][0], (double)pc[j][1], (double)pc[j][2]};
-                if (!ok_a) ok_a = triangle_ok(a0, ai, aj);
-                if (!ok_c) ok_c = triangle_ok(c0, ci, cj);
+        if (v == 0) {
+            c0f[0] = cw.x; c0f[1] = cw.y; c0f[2] = cw.z;
+            a0f[0] = ob.x; a0f[1] = ob.y; a0f[2] = ob.z;
+        } else {
+            if (v >= 2 && !(ok_a && ok_c)) {
+                const double p0a[3] = {(double)a0f[0], (double)a0f[1], (double)a0f[2]};
+                const double p1a[3] = {(double)apf[0], (double)apf[1], (double)apf[2]};
+                const double p2a[3] = {(double)ob.x, (double)ob.y, (double)ob.z};
+                const double p0c[3] = {(double)c0f[0], (double)c0f[1], (double)c0f[2]};
+                const double p1c[3] = {(double)cpf[0], (double)cpf[1], (double)cpf[2]};
+                const double p2c[3] = {(double)cw.x, (double)cw.y, (double)cw.z};
+                if (!ok_a) ok_a = triangle_ok(p0a, p1a, p2a);
+                if (!ok_c) ok_c = triangle_ok(p0c, p1c, p2c);
             }
+            const double c[3] = {(double)cw.x - (double)c0f[0], (double)cw.y - (double)c0f[1], (double)cw.z - (double)c0f[2]};
+            const double a[3] = {(double)ob.x - (double)a0f[0], (double)ob.y - (double)a0f[1], (double)ob.z - (double)a0f[2]};
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                m[i] += c[i];
+                m[3 + i] += a[i];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) m[6 + 3 * i + j] += c[i] * a[j];
+            }
+            m[15] += c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+            m[16] += a[0] * a[0] + a[1] * a[1] + a[2] * a[2];
         }
+        cpf[0] = cw.x; cpf[1] = cw.y; cpf[2] = cw.z;
+        apf[0] = ob.x; apf[1] = ob.y; apf[2] = ob.z;
     }
     if (!ok_a || !ok_c) return false;
-    double m[17];  // sum c (3) | sum a (3) | sum c a^T (9) | sum |c|^2 | sum |a|^2, all about pair 0
-#pragma unroll
-    for (int i = 0; i < 17; ++i) m[i] = 0.0;
-    const float c0f[3] = {pc[0][0], pc[0][1], pc[0][2]}, a0f[3] = {pa[0][0], pa[0][1], pa[0][2]};
-    for (int v = 1; v < S; ++v) {
-        const double c[3] = {(double)pc[v][0] - (double)c0f[0], (double)pc[v][1] - (double)c0f[1], (double)pc[v][2] - (double)c0f[2]};
-        const double a[3] = {(double)pa[v][0] - (double)a0f[0], (double)pa[v][1] - (double)a0f[1], (double)pa[v][2] - (double)a0f[2]};
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            m[i] += c[i];
-            m[3 + i] += a[i];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) m[6 + 3 * i + j] += c[i] * a[j];
-        }
-        m[15] += c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
-        m[16] += a[0] * a[0] + a[1] * a[1] + a[2] * a[2];
-    }
     const double inv = 1.0 / (double)S;
     double Sc[9], R[9];
 #pragma unroll
