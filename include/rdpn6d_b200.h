@@ -277,6 +277,17 @@ void rdpn_ctx_destroy(rdpn_ctx* ctx);
 int rdpn_ctx_set_option(rdpn_ctx* ctx, int key, int value);
 int rdpn_pose_solve_host(rdpn_ctx* ctx, const rdpn_roi_inputs* h_in, const int32_t* h_hyp_idx, const float* h_t_net,
                          const rdpn_solve_params* prm, const rdpn_solve_outputs* h_out);
+/* Asynchronous form of rdpn_pose_solve_host for a serving loop that keeps the bus busy across steps: _submit queues
+ * the whole call (transfers, gated pull, solver, result copies) on the context's streams and returns a ticket; the
+ * outputs are complete once rdpn_ctx_wait(ctx, ticket) returns.  Calls complete in submission order per pipeline
+ * stage; up to 8 may be outstanding (a ninth submit first waits for the oldest).  Inputs and outputs of an outstanding
+ * call must not be touched, and concurrent calls need distinct output buffers.  Pinned or device buffers keep the
+ * call asynchronous; pageable ones are copied synchronously by the CUDA runtime.  rdpn_ctx_last_h2d_bytes describes
+ * synchronous calls only. */
+int rdpn_pose_solve_host_submit(rdpn_ctx* ctx, const rdpn_roi_inputs* h_in, const int32_t* h_hyp_idx,
+                                const float* h_t_net, const rdpn_solve_params* prm, const rdpn_solve_outputs* h_out,
+                                int* out_ticket);
+int rdpn_ctx_wait(rdpn_ctx* ctx, int ticket);
 /* Host -> device bytes of the last rdpn_pose_solve_host call: copied tensors, plus the fetched sectors of
  * the gated pull when RDPN_OPT_COUNT_BYTES is on.  rdpn_ctx_last_transfer: the strategy that call used. */
 unsigned long long rdpn_ctx_last_h2d_bytes(const rdpn_ctx* ctx);

@@ -76,6 +76,9 @@ SIGNATURES = {
     "rdpn_ctx_last_transfer": (ctypes.c_int, [c_vp]),
     "rdpn_pose_solve_host": (ctypes.c_int, [c_vp, ctypes.POINTER(RoiInputs), c_vp, c_vp, ctypes.POINTER(SolveParams),
                                             ctypes.POINTER(SolveOutputs)]),
+    "rdpn_pose_solve_host_submit": (ctypes.c_int, [c_vp, ctypes.POINTER(RoiInputs), c_vp, c_vp, ctypes.POINTER(SolveParams),
+                                                   ctypes.POINTER(SolveOutputs), ctypes.POINTER(ctypes.c_int)]),
+    "rdpn_ctx_wait": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "rdpn_launch_count": (ctypes.c_ulonglong, []),
     "rdpn_fp32_peak_probe": (ctypes.c_int, [ctypes.c_int, c_f64p]),
 }

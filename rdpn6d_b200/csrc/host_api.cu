@@ -270,6 +270,7 @@ void farthest_point_sampling(float* pts, int* idxs, int pn, int sn) {
 // ------------------------------------------------------------------------------------------------
 #define RDPN_CHUNK_MAX 1024
 #define RDPN_STAGES 4  // pipeline depth: stage buffers / streams in flight
+#define RDPN_MAX_INFLIGHT 8  // submitted calls that may be outstanding (ring of completion events)
 
 struct rdpn_ctx {
     int device;
@@ -284,6 +285,9 @@ struct rdpn_ctx {
     unsigned long long pulled_seen;
     unsigned long long last_h2d_bytes;
     int last_transfer;
+    cudaEvent_t ev[RDPN_MAX_INFLIGHT][RDPN_STAGES];  // completion of submitted calls (created on first use)
+    unsigned next_ticket;
+    unsigned counted_ticket;  // submitted calls whose pulled quads are already in pulled_seen
 };
 
 static int env_int(const char* name, int dflt) {
@@ -314,6 +318,9 @@ void rdpn_ctx_destroy(rdpn_ctx* c) {
         if (c->st[i]) cudaStreamDestroy(c->st[i]);
     }
     if (c->d_pulled) cudaFree(c->d_pulled);
+    for (int t = 0; t < RDPN_MAX_INFLIGHT; ++t)
+        for (int i = 0; i < RDPN_STAGES; ++i)
+            if (c->ev[t][i]) cudaEventDestroy(c->ev[t][i]);
     free(c);
 }
 
@@ -345,8 +352,15 @@ int rdpn_ctx_last_transfer(const rdpn_ctx* c) { return c ? c->last_transfer : 0;
 
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-int rdpn_pose_solve_host(rdpn_ctx* c, const rdpn_roi_inputs* h, const int32_t* h_hyp, const float* h_tnet,
-                         const rdpn_solve_params* prm, const rdpn_solve_outputs* ho) {
+struct HostCallInfo {  // what the synchronous form reports after the call
+    unsigned long long moved;     // bytes of copied tensors and whole small arrays
+    unsigned long long per_quad;  // bytes per fetched 16-byte quad group of the gated pull
+    bool any_pull, pull_planes;
+};
+
+// Queues the whole call (transfers, gated pull, solver, result copies) on the context's streams; does not wait.
+static int host_queue(rdpn_ctx* c, const rdpn_roi_inputs* h, const int32_t* h_hyp, const float* h_tnet,
+                      const rdpn_solve_params* prm, const rdpn_solve_outputs* ho, HostCallInfo* info) {
     using namespace rdpn;
     if (!c || !h || !prm || !ho || h->B <= 0 || prm->num_hyp <= 0) return RDPN_E_BADARG;  // h_hyp NULL: internal sampling
     if (!ho->pose || !ho->n_inliers || !ho->status) return RDPN_E_BADARG;
@@ -408,6 +422,7 @@ int rdpn_pose_solve_host(rdpn_ctx* c, const rdpn_roi_inputs* h, const int32_t* h
     const size_t o_hcnt = off; off += al256(CH * (size_t)H * 4);
     const size_t o_hpose = off; off += al256(ho->hyp_poses ? CH * (size_t)H * 48 : 16);
     if (off > c->buf_bytes) {
+        for (int i = 0; i < RDPN_STAGES; ++i) RDPN_CUDA_TRY(cudaStreamSynchronize(c->st[i]));  // submitted calls may use them
         for (int i = 0; i < RDPN_STAGES; ++i) {
             if (c->buf[i]) cudaFree(c->buf[i]);
             c->buf[i] = nullptr;
@@ -528,25 +543,77 @@ int rdpn_pose_solve_host(rdpn_ctx* c, const rdpn_roi_inputs* h, const int32_t* h
                 RDPN_CUDA_TRY(cudaMemcpyAsync((unsigned char*)out[i].host + (size_t)b0 * out_roi_bytes[i], d + out_off[i],
                                               nb * out_roi_bytes[i], cudaMemcpyDeviceToHost, st));
     }
+    info->moved = moved;
+    info->any_pull = any_pull;
+    info->pull_planes = pull_planes;
+    info->per_quad = 0;
+    for (int i = I_DEPTH; i <= I_CZ; ++i) info->per_quad += in[i].move == MOVE_PULL ? 16 : 0;
+    info->per_quad += in[I_RID].move == MOVE_PULL ? 4 : 0;
+    return rc;
+}
+
+static int host_drain(rdpn_ctx* c) {
     cudaError_t es = cudaSuccess;
     for (int i = 0; i < RDPN_STAGES; ++i) {
         const cudaError_t e = cudaStreamSynchronize(c->st[i]);
         if (es == cudaSuccess) es = e;
     }
+    return (int)es;
+}
+
+int rdpn_pose_solve_host(rdpn_ctx* c, const rdpn_roi_inputs* h, const int32_t* h_hyp, const float* h_tnet,
+                         const rdpn_solve_params* prm, const rdpn_solve_outputs* ho) {
+    HostCallInfo info;
+    memset(&info, 0, sizeof(info));
+    if (c && c->count && c->counted_ticket != c->next_ticket) {  // submitted calls moved the counter: step over them
+        const int e0 = host_drain(c);
+        if (e0) return e0;
+        RDPN_CUDA_TRY(cudaMemcpy(&c->pulled_seen, c->d_pulled, sizeof(c->pulled_seen), cudaMemcpyDeviceToHost));
+        c->counted_ticket = c->next_ticket;
+    }
+    const int rc = host_queue(c, h, h_hyp, h_tnet, prm, ho, &info);
+    if (rc == RDPN_E_BADARG || rc == RDPN_E_ALIGN) return rc;  // rejected before anything was queued
+    const int es = host_drain(c);
     if (rc) return rc;
-    if (es != cudaSuccess) return (int)es;
-    c->last_transfer = any_pull ? RDPN_TRANSFER_PULL : RDPN_TRANSFER_COPY;
-    c->last_h2d_bytes = moved;
-    if (pull_planes && c->count) {
+    if (es) return es;
+    c->last_transfer = info.any_pull ? RDPN_TRANSFER_PULL : RDPN_TRANSFER_COPY;
+    c->last_h2d_bytes = info.moved;
+    if (info.pull_planes && c->count) {
         unsigned long long tot = 0;
         RDPN_CUDA_TRY(cudaMemcpy(&tot, c->d_pulled, sizeof(tot), cudaMemcpyDeviceToHost));
         const unsigned long long quads = tot - c->pulled_seen;
         c->pulled_seen = tot;
-        unsigned long long per_quad = 0;
-        for (int i = I_DEPTH; i <= I_CZ; ++i) per_quad += in[i].move == MOVE_PULL ? 16 : 0;
-        per_quad += in[I_RID].move == MOVE_PULL ? 4 : 0;
-        c->last_h2d_bytes += quads * per_quad;
+        c->last_h2d_bytes += quads * info.per_quad;
     }
+    return 0;
+}
+
+int rdpn_pose_solve_host_submit(rdpn_ctx* c, const rdpn_roi_inputs* h, const int32_t* h_hyp, const float* h_tnet,
+                                const rdpn_solve_params* prm, const rdpn_solve_outputs* ho, int* out_ticket) {
+    if (!c || !out_ticket) return RDPN_E_BADARG;
+    const int t = (int)(c->next_ticket % RDPN_MAX_INFLIGHT);
+    RDPN_CUDA_TRY(cudaSetDevice(c->device));
+    for (int i = 0; i < RDPN_STAGES; ++i) {
+        if (!c->ev[t][i]) RDPN_CUDA_TRY(cudaEventCreateWithFlags(&c->ev[t][i], cudaEventDisableTiming));
+        else RDPN_CUDA_TRY(cudaEventSynchronize(c->ev[t][i]));  // the ring is full: wait for its oldest call
+    }
+    HostCallInfo info;
+    memset(&info, 0, sizeof(info));
+    const int rc = host_queue(c, h, h_hyp, h_tnet, prm, ho, &info);
+    if (rc) {
+        if (rc != RDPN_E_BADARG && rc != RDPN_E_ALIGN) host_drain(c);
+        return rc;
+    }
+    for (int i = 0; i < RDPN_STAGES; ++i) RDPN_CUDA_TRY(cudaEventRecord(c->ev[t][i], c->st[i]));
+    c->last_transfer = info.any_pull ? RDPN_TRANSFER_PULL : RDPN_TRANSFER_COPY;
+    c->next_ticket++;
+    *out_ticket = t;
+    return 0;
+}
+
+int rdpn_ctx_wait(rdpn_ctx* c, int ticket) {
+    if (!c || ticket < 0 || ticket >= RDPN_MAX_INFLIGHT || !c->ev[ticket][0]) return RDPN_E_BADARG;
+    for (int i = 0; i < RDPN_STAGES; ++i) RDPN_CUDA_TRY(cudaEventSynchronize(c->ev[ticket][i]));
     return 0;
 }
 

@@ -358,9 +358,13 @@ class HostPoseSolver:
         return self._out[key]
 
     def plan(self, depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx=None, region_idx=None, anchors=None,
-             depth_div=None, t_net=None, roi_base=0):
+             depth_div=None, t_net=None, roi_base=0, private_outputs=False):
         """Prepare a call on fixed buffers: returns a zero-argument callable that is one ctypes call (a serving loop
-        that refills the same pinned buffers pays no per-step Python bookkeeping) and yields the PoseSolveResult."""
+        that refills the same pinned buffers pays no per-step Python bookkeeping) and yields the PoseSolveResult.
+
+        The callable also has the asynchronous pair `ticket = run.submit()` / `result = run.wait(ticket)`
+        (rdpn_pose_solve_host_submit / rdpn_ctx_wait): a loop that submits step i + 1 before it waits for step i keeps
+        the bus busy across steps.  Plans that are in flight together need private_outputs=True (own result buffers)."""
         B = depth.shape[0]
         H, S, hyp = _hyp_arg(hyp_idx, B, self.num_hyp, self.sample_size, lambda x, shp: self._cpu(x, shp, torch.int32, "hyp_idx"))
         f32, t = torch.float32, {}
@@ -383,7 +387,11 @@ class HostPoseSolver:
             setattr(s, k, t[k].data_ptr() if k in t else None)
         s.num_regions, s.mask_mode, s.mask_thr, s.B = R, _mask_mode(self.mask_mode), float(self.mask_thr), B
         prm = _lib.SolveParams(num_hyp=H, roi_base=int(roi_base), sample_size=S, **self.prm)
+        if private_outputs:
+            self._out.pop((B, H), None)
         o = self._buffers(B, H)
+        if private_outputs:
+            self._out.pop((B, H), None)  # the plan owns these buffers
         outs = _lib.SolveOutputs()
         for k in ("pose", "n_inliers", "status", "best_h", "n_sel", "inlier_mask", "hyp_counts", "hyp_poses", "scale"):
             setattr(outs, k, o[k].data_ptr() if k in o else None)
@@ -401,6 +409,21 @@ class HostPoseSolver:
                 _lib.check(rc, "pose_solve_host")
             return res
 
+        fn_submit, fn_wait, ticket = self._L.rdpn_pose_solve_host_submit, self._L.rdpn_ctx_wait, ctypes.c_int(-1)
+
+        def submit():
+            rc = fn_submit(*cargs, ctypes.byref(ticket))
+            if rc:
+                _lib.check(rc, "pose_solve_host_submit")
+            return ticket.value
+
+        def wait(tk):
+            rc = fn_wait(ctx, tk)
+            if rc:
+                _lib.check(rc, "ctx_wait")
+            return res
+
+        run.submit, run.wait = submit, wait
         return run
 
     def __call__(self, depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx=None, region_idx=None, anchors=None,

@@ -630,3 +630,60 @@ def test_sample_size_out_of_range_is_rejected(cuda):
     inp = _lib.RoiInputs(depth=16, Kp=16, coor_x=16, coor_y=16, coor_z=16, mask=16, extent=16, B=1, mask_mode=1)
     out = _lib.SolveOutputs(pose=16, n_inliers=16, status=16)
     assert L.rdpn_pose_solve(ctypes.byref(inp), None, None, ctypes.byref(prm), ctypes.byref(out), None) == -1
+
+
+def test_host_call_submit_wait_pipeline(cuda):
+    """rdpn_pose_solve_host_submit / rdpn_ctx_wait: calls in flight together (own inputs, own outputs) give the results
+    of the synchronous call, in any wait order, also when the ticket ring wraps (more than 8 submissions)."""
+    B, H = 300, 32
+    batches = [synth.tile_batch(synth.make_batch(20, H=H, seed=50 + i, occlusion_max=0.4), B) for i in range(3)]
+    hs = pose_solver.HostPoseSolver(inlier_thr=THR, chunk_rois=64)
+
+    def pinned(b):
+        t = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in b.items() if v is not None}
+        cs = [t["coor"][:, c].contiguous().pin_memory() for c in range(3)]
+        return (t["depth"], t["Kp"], cs[0], cs[1], cs[2], t["mask"], t["extent"], t["hyp_idx"], t["region_idx"], t["anchors"])
+
+    args = [pinned(b) for b in batches]
+    want = []
+    for a in args:
+        r = hs(*a)
+        want.append((r.pose.clone(), r.best_h.clone(), r.n_inliers.clone(), r.status.clone()))
+    plans = [hs.plan(*a, private_outputs=True) for a in args]
+    outs = [p() for p in plans]  # the plans' own result objects
+    assert len({o.pose.data_ptr() for o in outs}) == 3
+    for order in ((0, 1, 2), (2, 0, 1)):
+        for o in outs:  # results of a previous round must not leak into this one
+            o.pose.zero_()
+            o.best_h.zero_()
+        tickets = [p.submit() for p in plans]
+        for i in order:
+            r = plans[i].wait(tickets[i])
+            assert torch.equal(r.pose.view(torch.int32), want[i][0].view(torch.int32)), (order, i)
+            assert torch.equal(r.best_h, want[i][1]) and torch.equal(r.n_inliers, want[i][2])
+            assert torch.equal(r.status, want[i][3])
+    # depth-2 loop over 20 steps (ring of 8 tickets wraps): every step's result is checked after its wait
+    prev = None
+    for step in range(20):
+        i = step % 3
+        if prev is not None and prev[0] == i:  # a plan must not be resubmitted while it is in flight
+            plans[prev[0]].wait(prev[1])
+            prev = None
+        tk = plans[i].submit()
+        if prev is not None:
+            r = plans[prev[0]].wait(prev[1])
+            assert torch.equal(r.pose.view(torch.int32), want[prev[0]][0].view(torch.int32)), step
+        prev = (i, tk)
+    r = plans[prev[0]].wait(prev[1])
+    assert torch.equal(r.pose.view(torch.int32), want[prev[0]][0].view(torch.int32))
+    # the synchronous call still reports its own bytes after submitted calls (counter stepped over)
+    hs.set_option(_lib.OPT_COUNT_BYTES, 1)
+    hs(*args[0])
+    n0 = hs.last_h2d_bytes
+    tk = plans[1].submit()
+    plans[1].wait(tk)
+    hs(*args[0])
+    assert hs.last_h2d_bytes == n0 > 0
+    L = _lib.lib()
+    assert L.rdpn_ctx_wait(hs._ctx, 99) == -1
+    hs.close()
