@@ -237,7 +237,7 @@ def reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -758,13 +758,33 @@ def gpu_arm(args):
     }
     if cpu_base is not None:
         line["cpu_baseline"] = cpu_base
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout: keep a private handle to the real stdout and point fd 1 at stderr, so
+    that anything a library prints there (NCCL's version banner under NCCL_DEBUG=VERSION, for one) cannot get in."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
