@@ -424,6 +424,10 @@ def gpu_arm(args):
         torch.cuda.synchronize()
 
     if world > 1:
+        # rehearse the collective of the timed region once more, at its full size, after the pre-heat
+        gather_group(0)
+        state["pending"].wait()
+        state["pending"] = None
         dist.barrier()
     torch.cuda.synchronize()
     launches0 = _lib.launch_count()
