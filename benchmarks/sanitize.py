@@ -28,6 +28,13 @@ def main():
         for opts in (dict(), dict(weighted=True, refit_iters=2, adaptive=True)):
             pose_solver.pose_solve(g["depth"], g["Kp"], g["coor"][:, 0], g["coor"][:, 1], g["coor"][:, 2], g["mask"], g["extent"],
                                    g["hyp_idx"], g["region_idx"], g["anchors"], want_inlier_mask=True, want_hyp=True, **opts)
+        # S = 10 pairs per hypothesis (the out-of-line Kabsch of the sample), explicit and kernel-drawn samples
+        sel = pose_solver.correspond(g["depth"], g["Kp"], g["coor"][:, 0], g["coor"][:, 1], g["coor"][:, 2], g["mask"],
+                                     g["extent"], g["region_idx"], g["anchors"])["sel"]
+        hyp10 = pose_solver.sample_hypotheses(sel, 32, sample_size=10)
+        for h_in in (hyp10, None):
+            pose_solver.pose_solve(g["depth"], g["Kp"], g["coor"][:, 0], g["coor"][:, 1], g["coor"][:, 2], g["mask"], g["extent"],
+                                   h_in, g["region_idx"], g["anchors"], want_hyp=True, num_hyp=32, sample_size=10)
     # host-buffer plugin call: gated pull (pinned) and full copy (pageable)
     b = synth.make_batch(6, H=32, seed=12)
     for pinned in (True, False):
@@ -37,7 +44,12 @@ def main():
         if pinned:
             cx, cy, cz = cx.pin_memory(), cy.pin_memory(), cz.pin_memory()
         hs = pose_solver.HostPoseSolver(inlier_thr=0.005, chunk_rois=4, count_bytes=True)
-        hs(t["depth"], t["Kp"], cx, cy, cz, t["mask"], t["extent"], t["hyp_idx"], t["region_idx"], t["anchors"])
+        hargs = (t["depth"], t["Kp"], cx, cy, cz, t["mask"], t["extent"], t["hyp_idx"], t["region_idx"], t["anchors"])
+        hs(*hargs)
+        plans = [hs.plan(*hargs, private_outputs=True) for _ in range(2)]  # two submitted calls in flight
+        tickets = [p.submit() for p in plans]
+        for p, tk in zip(plans, tickets):
+            p.wait(tk)
         hs.close()
     # correspondence features / region targets
     geometry.coor_feat(torch.rand(2, 1, 64, 64, device="cuda"), torch.rand(2, 1, 64, 64, device="cuda"), torch.rand(2, 1, 64, 64, device="cuda"),
