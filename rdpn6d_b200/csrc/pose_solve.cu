@@ -257,26 +257,30 @@ __device__ __forceinline__ int kth_gated_pixel(const uint32_t* selmap, const uin
 // replacement) and each side has a non-degenerate triangle (p0, p_{v-1}, p_v) (the S = 3 test, along the sample).
 // Out of line: the default S = 3 path must not pay registers for it.
 template <bool DENSE>
-__device__ __noinline__ bool hyp_from_sample(const FusedSmem& s, const RoiPlanes& pl, const float4* anchors,
+__device__ __noinline__ bool hyp_from_sample(FusedSmem& s, const RoiPlanes& pl, const float4* anchors,
                                              const int32_t* idx_in, uint32_t kroi, int h, int S, float* P) {
     const RoiConst& rc = s.rc;  // pl and rc are the shared-memory copies (no stack traffic for by-reference arguments)
     const uint32_t* selmap = s.selmap;
     const uint16_t* selpfx = s.selpfx;
-    int ii[RDPN_MAX_SAMPLE];
+    // the sample's pixel indices live in the staging buffer (idle until the barrier that ends hypothesis generation):
+    // column threadIdx.x of a [RDPN_MAX_SAMPLE][ST] int array, conflict-free.  A per-thread array would sit in local
+    // memory, and with four CTAs per SM local memory misses L1 nine times out of ten.
+    static_assert(sizeof(float4) * CHUNK >= sizeof(int) * RDPN_MAX_SAMPLE * ST, "staging buffer holds the sample indices");
+    int* ii = reinterpret_cast<int*>(s.chunk) + threadIdx.x;
     const uint32_t nsel = selpfx[RDPN_P / 32];
     for (int v = 0; v < S; ++v) {
+        int px;
         if (idx_in) {
-            ii[v] = idx_in[v];
+            px = idx_in[v];
         } else {
             const uint32_t key = fmix32(kroi ^ (uint32_t)(S * h + v));
-            ii[v] = nsel ? kth_gated_pixel(selmap, selpfx, (uint32_t)(((unsigned long long)key * nsel) >> 32)) : -1;
+            px = nsel ? kth_gated_pixel(selmap, selpfx, (uint32_t)(((unsigned long long)key * nsel) >> 32)) : -1;
         }
-    }
-    for (int v = 0; v < S; ++v) {
-        if ((unsigned)ii[v] >= RDPN_P) return false;
-        if (!((selmap[ii[v] >> 5] >> (ii[v] & 31)) & 1u)) return false;
+        if ((unsigned)px >= RDPN_P) return false;
+        if (!((selmap[px >> 5] >> (px & 31)) & 1u)) return false;
         for (int u = 0; u < v; ++u)
-            if (ii[u] == ii[v]) return false;
+            if (ii[u * ST] == px) return false;
+        ii[v * ST] = px;
     }
     // One pass over the sample, nothing parked in local memory: pair 0 is the pivot of the FP64 moments (exact FP32
     // differences) and the apex of the degeneracy test -- each side needs one non-degenerate triangle
@@ -289,8 +293,9 @@ __device__ __noinline__ bool hyp_from_sample(const FusedSmem& s, const RoiPlanes
 #pragma unroll 1
     for (int v = 0; v < S; ++v) {
         float4 cw, ob;
-        gather_s1<DENSE>(pl, rc, ii[v], false, RDPN_MASK_RAW, cw, ob);  // unweighted: the mask is not read
-        if (!DENSE) ob = anchors[__ldg(pl.rid + ii[v])];
+        const int px = ii[v * ST];
+        gather_s1<DENSE>(pl, rc, px, false, RDPN_MASK_RAW, cw, ob);  // unweighted: the mask is not read
+        if (!DENSE) ob = anchors[__ldg(pl.rid + px)];
         if (v == 0) {
             c0f[0] = cw.x; c0f[1] = cw.y; c0f[2] = cw.z;
             a0f[0] = ob.x; a0f[1] = ob.y; a0f[2] = ob.z;
@@ -354,8 +359,11 @@ __device__ __noinline__ bool hyp_from_sample(const FusedSmem& s, const RoiPlanes
 #endif
 // MULTI: S > 3 pairs per hypothesis (a separate instantiation, so that the default S = 3 kernel carries neither the
 // call nor its register pressure)
+#ifndef RDPN_MULTI_CTAS
+#define RDPN_MULTI_CTAS 3
+#endif
 template <bool DENSE, bool MULTI = false>
-__global__ void __launch_bounds__(ST, RDPN_SOLVE_CTAS) pose_solve_kernel(SolveArgs a, FusedLayout lay) {
+__global__ void __launch_bounds__(ST, MULTI ? RDPN_MULTI_CTAS : RDPN_SOLVE_CTAS) pose_solve_kernel(SolveArgs a, FusedLayout lay) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FusedSmem& s = *reinterpret_cast<FusedSmem*>(smem_raw);
     FinishSmem& f = s.fin;
