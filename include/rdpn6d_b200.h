@@ -277,7 +277,9 @@ void rdpn_ctx_destroy(rdpn_ctx* ctx);
 int rdpn_ctx_set_option(rdpn_ctx* ctx, int key, int value);
 int rdpn_pose_solve_host(rdpn_ctx* ctx, const rdpn_roi_inputs* h_in, const int32_t* h_hyp_idx, const float* h_t_net,
                          const rdpn_solve_params* prm, const rdpn_solve_outputs* h_out);
-/* Asynchronous form of rdpn_pose_solve_host for a serving loop that keeps the bus busy across steps: _submit queues
+/* Asynchronous form of rdpn_pose_solve_host for a loop that processes batch after batch, as the reference's
+ * gdrn_inference_on_dataset does (core/gdrn_modeling/gdrn_evaluator.py:649: model forward, then evaluator.process,
+ * per batch), and must keep the bus busy across steps: _submit queues
  * the whole call (transfers, gated pull, solver, result copies) on the context's streams and returns a ticket; the
  * outputs are complete once rdpn_ctx_wait(ctx, ticket) returns.  Calls complete in submission order per pipeline
  * stage; up to 8 may be outstanding (a ninth submit first waits for the oldest).  Inputs and outputs of an outstanding
