@@ -687,3 +687,36 @@ def test_host_call_submit_wait_pipeline(cuda):
     L = _lib.lib()
     assert L.rdpn_ctx_wait(hs._ctx, 99) == -1
     hs.close()
+
+
+@pytest.mark.parametrize("S", [5, 10])
+def test_dense_mode_with_larger_samples(cuda, S):
+    """Dense mode (no anchors: the object point is the de-normalised coordinate itself) with S pairs per hypothesis:
+    the DENSE instantiation of the S > 3 path against the oracle, on samples drawn by the oracle's stream."""
+    b = synth.make_batch(6, H=8, seed=58, dense=True)
+    H = 96
+    hyp = np.zeros((6, H, S), np.int32)
+    for i in range(6):
+        c = po.correspondences(b["depth"][i], b["Kp"][i], b["coor"][i], b["mask"][i], b["extent"][i])
+        hyp[i] = po.sample_triplets(c["sel"], H, 9, i, sample_size=S)
+    ores = po.pose_solve_batch(b, hyp, THR)
+    g = _to_cuda({**b, "hyp_idx": hyp})
+    res = _solve(g)
+    cnt = res.hyp_counts.cpu().numpy()
+    hp = res.hyp_poses.reshape(6, H, 12).cpu().numpy()
+    for i, o in enumerate(ores):
+        assert int(res.status[i]) == o["status"] and int(res.n_sel[i]) == o["n_sel"]
+        assert int(res.best_h[i]) == o["best_h"] and int(res.n_inliers[i]) == o["n_inl"]
+        assert np.array_equal(res.inlier_mask[i].reshape(-1).cpu().numpy(), o["inlier_mask"])
+        np.testing.assert_allclose(hp[i], o["Rt_hyp"], atol=2e-6)
+        same = (hp[i].view(np.uint32) == o["Rt_hyp"].view(np.uint32)).all(axis=1)
+        assert np.array_equal(cnt[i][same], o["counts"][same])
+        assert np.abs(cnt[i][~same].astype(int) - o["counts"][~same]).max(initial=0) <= 2
+        assert same.mean() > 0.9
+        assert po.re_rad_small(res.pose[i].cpu().numpy()[:, :3], o["pose"][:, :3]) <= ROT_TOL_RAD
+        assert po.te(res.pose[i].cpu().numpy()[:, 3], o["pose"][:, 3]) <= TRANS_TOL_M
+    # kernel-drawn samples are the same samples
+    auto = pose_solver.PoseSolver(inlier_thr=THR, num_hyp=H, seed=9, sample_size=S, want_hyp=True)(
+        g["depth"], g["Kp"], g["coor"][:, 0], g["coor"][:, 1], g["coor"][:, 2], g["mask"], g["extent"], None)
+    assert torch.equal(auto.hyp_counts, res.hyp_counts) and torch.equal(auto.best_h, res.best_h)
+    assert torch.equal(auto.pose.view(torch.int32), res.pose.view(torch.int32))
