@@ -111,6 +111,13 @@ def test_evaluator_hook_end_to_end(cuda):
         assert po.re_rad_small(R, b["gt_pose"][i][:, :3]) < 0.03
         assert po.te(t, b["gt_pose"][i][:, 3]) < 0.003
         assert r["time"] > 0
+    # the reference loop's sampling (10 pairs per sample, misc.py:72) and early stop (misc.py:134-138) through the hook
+    ev10 = evaluator.GpuRansacKabsch(num_hyp=128, inlier_thr=0.005, sample_size=10, adaptive=True)
+    rows10 = ev10.process(inputs, [{"time": 0.0}, {"time": 0.0}], out_dict)
+    assert len(rows10) == 6
+    for i, r in enumerate(rows10):
+        assert po.re_rad_small(np.array(r["R"]).reshape(3, 3), b["gt_pose"][i][:, :3]) < 0.03
+        assert po.te(np.array(r["t"]) / 1000.0, b["gt_pose"][i][:, 3]) < 0.003
 
 
 def test_gather_rows_single_gpu_identity(cuda):
