@@ -27,6 +27,7 @@ Files written (small, committed):
                         allo -> ego, pose assembly  utils.py:39-94, pose_from_pred_centroid_z.py:52-141, with the one
                                                   missing third-party call (transforms3d.axangles.axangle2mat =
                                                   Rodrigues' formula) supplied by the oracle
+  rows_golden.json    BOP result rows from GDRN_Evaluator.pose_prediction_to_json (gdrn_evaluator.py:483-513) run from source
   ransac_roi_golden.npz  misc.pnp_ransac_custom (misc.py:58-142) run from source on the correspondences of 4 synthetic
                       ROIs (10 pairs per sample, reference Kabsch, float64 scoring): sampled pixel sets + inlier counts
 """
@@ -432,6 +433,33 @@ def gen_ransac_roi(tf):
     print("ransac_roi_golden.npz iters", iters, "max counts", counts.max(axis=1))
 
 
+def gen_rows():
+    """BOP result rows: GDRN_Evaluator.pose_prediction_to_json (gdrn_evaluator.py:483-513) executed from source with its
+    helper to_list (test_utils.py:29-30); the evaluator hook must emit the same dicts."""
+    import json
+    import types
+
+    fns = ref_functions("core/gdrn_modeling/test_utils.py", ["to_list"])
+    to_json = ref_functions("core/gdrn_modeling/gdrn_evaluator.py", ["pose_prediction_to_json"], env=fns)["pose_prediction_to_json"]
+    rng = np.random.default_rng(29)
+    me = types.SimpleNamespace(cfg=None)
+    tf = _load("ref_transform", "lib/pysixd/transform.py")
+    cases = []
+    for i in range(6):
+        pose = np.concatenate([tf.random_rotation_matrix(rng.random(3))[:3, :3],
+                               rng.uniform(-0.5, 1.5, (3, 1))], axis=1).astype(np.float32 if i % 2 else np.float64)
+        kw = dict(scene_id=str(i + 1), im_id=100 + i, obj_id=i % 3 + 1)
+        if i % 3:
+            kw["score"] = float(rng.random())
+        if i >= 3:
+            kw["pose_time"] = float(rng.random())
+        out = to_json(me, pose, **kw)
+        cases.append(dict(pose=pose.astype(np.float64).tolist(), pose_dtype=str(pose.dtype), kwargs=kw, rows=out))
+    with open(os.path.join(GOLD, "rows_golden.json"), "w") as f:
+        json.dump(cases, f, indent=0)
+    print("rows_golden.json", len(cases))
+
+
 def main():
     if not os.path.isdir(REF):
         sys.exit("reference not mounted at %s" % REF)
@@ -439,7 +467,7 @@ def main():
     tf = _load("ref_transform", "lib/pysixd/transform.py")
     du = _load("ref_data_utils", "core/utils/data_utils.py")
     gens = dict(fps=gen_fps, kabsch=lambda: gen_kabsch(tf), affine=lambda: gen_affine(du), region=lambda: gen_region(du),
-                pose=lambda: gen_pose(tf), path=gen_path, ransac_roi=lambda: gen_ransac_roi(tf))
+                pose=lambda: gen_pose(tf), path=gen_path, ransac_roi=lambda: gen_ransac_roi(tf), rows=gen_rows)
     for name in (sys.argv[1:] or list(gens)):  # python -m oracle.gen_golden [name ...]
         gens[name]()
 

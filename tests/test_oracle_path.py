@@ -112,3 +112,17 @@ def test_ransac_loop_rules_match_reference_loop(g):
                                         confidence=0.995, min_iter=10)
         assert examined == iters
         assert best == int(np.argmax(counts_ref[:iters])) or counts_ref[:iters].max() < 4
+
+
+def test_bop_rows_match_reference_pose_prediction_to_json(golden_dir):
+    """The evaluator hook's result rows against GDRN_Evaluator.pose_prediction_to_json (gdrn_evaluator.py:483-513)
+    executed from source (oracle/gen_golden.py:gen_rows): same keys, R row-major, t in millimetres, same float values."""
+    import json
+
+    from rdpn6d_b200 import evaluator
+
+    cases = json.load(open(os.path.join(golden_dir, "rows_golden.json")))
+    assert len(cases) >= 6
+    for c in cases:
+        pose = np.array(c["pose"], np.float64).astype(c["pose_dtype"])
+        assert evaluator.pose_prediction_to_json(pose, **c["kwargs"]) == c["rows"]
