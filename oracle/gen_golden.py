@@ -27,6 +27,8 @@ Files written (small, committed):
                         allo -> ego, pose assembly  utils.py:39-94, pose_from_pred_centroid_z.py:52-141, with the one
                                                   missing third-party call (transforms3d.axangles.axangle2mat =
                                                   Rodrigues' formula) supplied by the oracle
+  fps_center_golden.npz  the reference's Python FPS surface (fps_utils.py:6-21 + data_utils.get_fps_and_center :217-226) run
+                      from source on top of the reference's own C++ build
   rows_golden.json    BOP result rows from GDRN_Evaluator.pose_prediction_to_json (gdrn_evaluator.py:483-513) run from source
   ransac_roi_golden.npz  misc.pnp_ransac_custom (misc.py:58-142) run from source on the correspondences of 4 synthetic
                       ROIs (10 pairs per sample, reference Kabsch, float64 scoring): sampled pixel sets + inlier counts
@@ -460,6 +462,47 @@ def gen_rows():
     print("rows_golden.json", len(cases))
 
 
+def gen_fps_center():
+    """a12: the reference's Python FPS surface executed from source -- fps_utils.farthest_point_sampling
+    (core/csrc/fps/fps_utils.py:6-21, its cffi handles replaced by ctypes handles on the reference's own C++ build in
+    oracle/_ref) and data_utils.get_fps_and_center (core/utils/data_utils.py:217-226) on top of it."""
+    import ctypes
+    import types
+
+    from oracle import build as _obuild
+    from rdpn6d_b200.synth import fps_cloud
+
+    _obuild()
+    cdll = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libfps_ref.so"))
+    for fn in (cdll.farthest_point_sampling_init_center, cdll.farthest_point_sampling):
+        fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        fn.restype = None
+    ffi = types.SimpleNamespace(cast=lambda ctype, addr: ctypes.c_void_p(addr))
+    wrap = ref_functions("core/csrc/fps/fps_utils.py", ["farthest_point_sampling"], env={"ffi": ffi, "lib": cdll})
+    mod = types.ModuleType("core.csrc.fps.fps_utils")
+    mod.farthest_point_sampling = wrap["farthest_point_sampling"]
+    saved = {k: sys.modules.get(k) for k in ("core", "core.csrc", "core.csrc.fps", "core.csrc.fps.fps_utils")}
+    for k in ("core", "core.csrc", "core.csrc.fps"):
+        sys.modules[k] = types.ModuleType(k)
+    sys.modules["core.csrc.fps.fps_utils"] = mod
+    try:
+        get = ref_functions("core/utils/data_utils.py", ["get_fps_and_center"])["get_fps_and_center"]
+        out = {}
+        for name, cloud in (("f64", fps_cloud(3000, seed=6).astype(np.float64) * 1.000000123),
+                            ("f32", fps_cloud(2000, seed=7))):
+            out[name + "_pts"] = cloud
+            for n in (8, 32):
+                out["%s_fps%d_and_center" % (name, n)] = get(cloud, num_fps=n, init_center=True)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    np.savez_compressed(os.path.join(GOLD, "fps_center_golden.npz"), **out)
+    print("fps_center_golden.npz", {k: (v.shape, str(v.dtype)) for k, v in out.items() if "and_center" in k})
+
+
 def main():
     if not os.path.isdir(REF):
         sys.exit("reference not mounted at %s" % REF)
@@ -467,7 +510,7 @@ def main():
     tf = _load("ref_transform", "lib/pysixd/transform.py")
     du = _load("ref_data_utils", "core/utils/data_utils.py")
     gens = dict(fps=gen_fps, kabsch=lambda: gen_kabsch(tf), affine=lambda: gen_affine(du), region=lambda: gen_region(du),
-                pose=lambda: gen_pose(tf), path=gen_path, ransac_roi=lambda: gen_ransac_roi(tf), rows=gen_rows)
+                pose=lambda: gen_pose(tf), path=gen_path, ransac_roi=lambda: gen_ransac_roi(tf), rows=gen_rows, fps_center=gen_fps_center)
     for name in (sys.argv[1:] or list(gens)):  # python -m oracle.gen_golden [name ...]
         gens[name]()
 

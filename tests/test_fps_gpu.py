@@ -96,3 +96,15 @@ def test_bad_arguments_fail_loudly(cuda):
     assert L.rdpn_fps_init_center(t.data_ptr(), idx.data_ptr(), 10, 4, None, 0, None) == -3  # workspace
     with pytest.raises(AssertionError):
         fps_utils.fps_indices(torch.zeros(10, 2, device="cuda"), 2)
+
+
+def test_get_fps_and_center_matches_reference_python_surface(cuda, golden_dir):
+    """The numpy face of fps_utils.get_fps_and_center against the reference's own Python surface run from source
+    (tests/golden/fps_center_golden.npz): same rows, same dtype."""
+    g = np.load(os.path.join(golden_dir, "fps_center_golden.npz"))
+    for name in ("f64", "f32"):
+        for n in (8, 32):
+            want = g["%s_fps%d_and_center" % (name, n)]
+            got = fps_utils.get_fps_and_center(g[name + "_pts"], n)
+            assert got.dtype == want.dtype and got.shape == want.shape
+            assert np.array_equal(got, want)

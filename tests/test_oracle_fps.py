@@ -76,3 +76,17 @@ def test_get_fps_and_center_shape():
     out = get_fps_and_center(p, 8)
     assert out.shape == (9, 3)
     np.testing.assert_allclose(out[-1], p.mean(0))
+
+
+def test_get_fps_and_center_matches_reference_python_surface(golden_dir):
+    """a12: fps_utils.farthest_point_sampling (core/csrc/fps/fps_utils.py:6-21) + data_utils.get_fps_and_center
+    (core/utils/data_utils.py:217-226) executed from source on the reference's own C++ build
+    (oracle/gen_golden.py:gen_fps_center): same rows, same dtype (float64 input -> float32-rounded samples in a float64
+    array with a float64 centre; float32 input -> float32)."""
+    g = np.load(os.path.join(golden_dir, "fps_center_golden.npz"))
+    for name in ("f64", "f32"):
+        for n in (8, 32):
+            want = g["%s_fps%d_and_center" % (name, n)]
+            got = get_fps_and_center(g[name + "_pts"], n)
+            assert got.dtype == want.dtype and got.shape == want.shape
+            assert np.array_equal(got, want)
