@@ -29,6 +29,7 @@ Files written (small, committed):
                                                   Rodrigues' formula) supplied by the oracle
   fps_center_golden.npz  the reference's Python FPS surface (fps_utils.py:6-21 + data_utils.get_fps_and_center :217-226) run
                       from source on top of the reference's own C++ build
+  sampler_golden.json per-rank index ranges of InferenceSampler (my_distributed_sampler.py:170-199) run from source
   rows_golden.json    BOP result rows from GDRN_Evaluator.pose_prediction_to_json (gdrn_evaluator.py:483-513) run from source
   ransac_roi_golden.npz  misc.pnp_ransac_custom (misc.py:58-142) run from source on the correspondences of 4 synthetic
                       ROIs (10 pairs per sample, reference Kabsch, float64 scoring): sampled pixel sets + inlier counts
@@ -503,6 +504,35 @@ def gen_fps_center():
     print("fps_center_golden.npz", {k: (v.shape, str(v.dtype)) for k, v in out.items() if "and_center" in k})
 
 
+def gen_sampler():
+    """(e): the reference's shard rule -- class InferenceSampler (core/utils/my_distributed_sampler.py:170-199) executed
+    from source with a stand-in for detectron2's comm (rank / world size): the index range of every rank."""
+    import ast
+    import json
+    import textwrap
+    import types
+
+    rel = "core/utils/my_distributed_sampler.py"
+    src = open(os.path.join(REF, rel)).read()
+    node = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.ClassDef) and n.name == "InferenceSampler")
+    state = {"rank": 0, "world": 1}
+    comm = types.SimpleNamespace(get_rank=lambda: state["rank"], get_world_size=lambda: state["world"])
+    ns = {"Sampler": object, "comm": comm}
+    exec(compile(textwrap.dedent(ast.get_source_segment(src, node)), os.path.join(REF, rel), "exec"), ns)
+    cases = []
+    for size in (1, 2, 7, 8, 10, 1000, 1024, 8192, 65536, 65537):
+        for world in (1, 2, 3, 4, 8):
+            ranges = []
+            for rank in range(world):
+                state.update(rank=rank, world=world)
+                idx = list(ns["InferenceSampler"](size))
+                ranges.append([idx[0], idx[-1] + 1] if idx else None)
+            cases.append([size, world, ranges])
+    with open(os.path.join(GOLD, "sampler_golden.json"), "w") as f:
+        json.dump(cases, f)
+    print("sampler_golden.json", len(cases))
+
+
 def main():
     if not os.path.isdir(REF):
         sys.exit("reference not mounted at %s" % REF)
@@ -510,7 +540,7 @@ def main():
     tf = _load("ref_transform", "lib/pysixd/transform.py")
     du = _load("ref_data_utils", "core/utils/data_utils.py")
     gens = dict(fps=gen_fps, kabsch=lambda: gen_kabsch(tf), affine=lambda: gen_affine(du), region=lambda: gen_region(du),
-                pose=lambda: gen_pose(tf), path=gen_path, ransac_roi=lambda: gen_ransac_roi(tf), rows=gen_rows, fps_center=gen_fps_center)
+                pose=lambda: gen_pose(tf), path=gen_path, ransac_roi=lambda: gen_ransac_roi(tf), rows=gen_rows, fps_center=gen_fps_center, sampler=gen_sampler)
     for name in (sys.argv[1:] or list(gens)):  # python -m oracle.gen_golden [name ...]
         gens[name]()
 

@@ -25,6 +25,22 @@ def test_shard_rule_matches_inference_sampler():
     assert D.shard_range(0, 0, 2) == (0, 0)
 
 
+def test_shard_rule_matches_reference_sampler_run_from_source(golden_dir):
+    """class InferenceSampler (my_distributed_sampler.py:170-199) executed from source (oracle/gen_golden.py:gen_sampler):
+    shard_range gives every rank the index range the reference's sampler gives it (None = an empty shard)."""
+    import json
+
+    cases = json.load(open(os.path.join(golden_dir, "sampler_golden.json")))
+    assert len(cases) >= 40
+    for size, world, ranges in cases:
+        for rank, want in enumerate(ranges):
+            b, e = D.shard_range(size, rank, world)
+            if want is None:
+                assert b == e
+            else:
+                assert [b, e] == want, (size, world, rank)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
