@@ -29,6 +29,7 @@ Files written (small, committed):
                                                   Rodrigues' formula) supplied by the oracle
   fps_center_golden.npz  the reference's Python FPS surface (fps_utils.py:6-21 + data_utils.get_fps_and_center :217-226) run
                       from source on top of the reference's own C++ build
+  roi_scalars_golden.json  bbox -> (centre, scale, resize ratio, wh): data_loader.py:477-482, :488 run from their source lines
   sampler_golden.json per-rank index ranges of InferenceSampler (my_distributed_sampler.py:170-199) run from source
   rows_golden.json    BOP result rows from GDRN_Evaluator.pose_prediction_to_json (gdrn_evaluator.py:483-513) run from source
   ransac_roi_golden.npz  misc.pnp_ransac_custom (misc.py:58-142) run from source on the correspondences of 4 synthetic
@@ -533,6 +534,33 @@ def gen_sampler():
     print("sampler_golden.json", len(cases))
 
 
+def gen_roi_scalars():
+    """a1: the loader's ROI scalars -- data_loader.py:477-482 (bbox centre, bw / bh, padded scale clipped to the image)
+    executed from their source lines, plus the resize ratio of :488 (out_res / scale)."""
+    import json
+    import textwrap
+    import types
+
+    lines = open(os.path.join(REF, "core/gdrn_modeling/data_loader.py")).read().splitlines()
+    block = textwrap.dedent("\n".join(lines[476:482]))  # 1-based lines 477..482
+    assert block.startswith("x1, y1, x2, y2 = bbox") and "DZI_PAD_SCALE" in block, block
+    assert 'roi_infos["resize_ratio"].append(out_res / scale)' in lines[487]
+    rng = np.random.default_rng(31)
+    cases = []
+    boxes = [rng.uniform(0, 400, 2).tolist() + (rng.uniform(0, 400, 2) + rng.uniform(5, 230, 2)).tolist() for _ in range(12)]
+    boxes += [[10.0, 20.0, 10.4, 20.2], [0.0, 0.0, 640.0, 480.0], [100.0, 50.0, 100.0, 300.0], [5.5, 7.25, 600.0, 470.0]]
+    for bb in boxes:
+        for pad, (im_H, im_W) in ((1.5, (480, 640)), (1.0, (480, 640)), (1.5, (1080, 1920))):
+            env = dict(np=np, bbox=np.array(bb), im_H=im_H, im_W=im_W,
+                       cfg=types.SimpleNamespace(INPUT=types.SimpleNamespace(DZI_PAD_SCALE=pad)))
+            exec(compile(block, "data_loader.py:477-482", "exec"), env)
+            cases.append(dict(bbox=bb, pad=pad, im_H=im_H, im_W=im_W, center=[float(v) for v in env["bbox_center"]],
+                              scale=float(env["scale"]), resize_ratio=float(64 / env["scale"]), wh=[float(env["bw"]), float(env["bh"])]))
+    with open(os.path.join(GOLD, "roi_scalars_golden.json"), "w") as f:
+        json.dump(cases, f)
+    print("roi_scalars_golden.json", len(cases))
+
+
 def main():
     if not os.path.isdir(REF):
         sys.exit("reference not mounted at %s" % REF)
@@ -540,7 +568,7 @@ def main():
     tf = _load("ref_transform", "lib/pysixd/transform.py")
     du = _load("ref_data_utils", "core/utils/data_utils.py")
     gens = dict(fps=gen_fps, kabsch=lambda: gen_kabsch(tf), affine=lambda: gen_affine(du), region=lambda: gen_region(du),
-                pose=lambda: gen_pose(tf), path=gen_path, ransac_roi=lambda: gen_ransac_roi(tf), rows=gen_rows, fps_center=gen_fps_center, sampler=gen_sampler)
+                pose=lambda: gen_pose(tf), path=gen_path, ransac_roi=lambda: gen_ransac_roi(tf), rows=gen_rows, fps_center=gen_fps_center, sampler=gen_sampler, roi_scalars=gen_roi_scalars)
     for name in (sys.argv[1:] or list(gens)):  # python -m oracle.gen_golden [name ...]
         gens[name]()
 

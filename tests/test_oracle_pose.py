@@ -238,3 +238,15 @@ def test_s_pair_validity_rules():
     M = po.kabsch(c["obj"][:, good].astype(np.float64), c["cam"][:, good].astype(np.float64))
     assert np.allclose(Rt[0].reshape(3, 4), M[:3, :4], atol=1e-6)
     assert po.sample_triplets(c["sel"], 5, 1, 0, sample_size=7).shape == (5, 7)
+
+
+def test_roi_scalars_match_loader_lines(golden_dir):
+    """a1: data_loader.py:477-482 + :488 executed from their source lines (oracle/gen_golden.py:gen_roi_scalars), incl.
+    boxes thinner than a pixel (bw = bh = 1) and boxes whose padded scale is clipped to the image."""
+    import json
+
+    cases = json.load(open(os.path.join(golden_dir, "roi_scalars_golden.json")))
+    assert len(cases) >= 40
+    for c in cases:
+        center, scale, rr, wh = po.roi_scalars(c["bbox"], c["im_H"], c["im_W"], dzi_pad_scale=c["pad"])
+        assert center.tolist() == c["center"] and scale == c["scale"] and rr == c["resize_ratio"] and wh.tolist() == c["wh"]
