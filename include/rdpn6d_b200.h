@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RDPN_VERSION 102 /* 0.1.2: rdpn_solve_params gained sample_size (S-pair hypotheses) */
+#define RDPN_VERSION 200 /* 0.2.0: three-kernel pipeline (rdpn_pose_solve_ws), rdpn_solve_params gained pipeline / chunk_rois */
 
 /* negative error codes (positive values are cudaError_t) */
 #define RDPN_E_BADARG (-1)    /* NULL / non-positive size / unsupported option */
@@ -152,7 +152,28 @@ typedef struct rdpn_solve_params {
                          /* of one job pass their offset so that results do not depend on batching) */
     int32_t sample_size; /* S: correspondences per hypothesis, 3 .. RDPN_MAX_SAMPLE; 0 means 3.     */
                          /* misc.py:72,91 samples random_sample_num = 10 pairs per iteration        */
+    int32_t pipeline;    /* RDPN_PIPELINE_*: which implementation runs (results are the same)       */
+    int32_t chunk_rois;  /* pipeline: ROIs per pass through the three kernels (0 = default, 4096)   */
+    int32_t select_rule; /* RDPN_SELECT_*: which pose the RANSAC stage returns                      */
 } rdpn_solve_params;
+
+/* Which pose wins (lib/pysixd/misc.py:113-132):
+ *   MOST_INLIERS   the earliest hypothesis with the largest inlier count, refit on its inliers (misc.py:121-126
+ *                  without the mean-error bookkeeping; SURVEY section 7's parity definition)
+ *   MIN_MEAN_ERR   the reference loop's return value: every hypothesis that raises the best inlier count is refit on
+ *                  its inliers, and of all sample fits and refits seen on the way the pose with the lowest mean
+ *                  residual over ALL gated points is returned (misc.py:113-120, 127-132) */
+#define RDPN_SELECT_MOST_INLIERS 0
+#define RDPN_SELECT_MIN_MEAN_ERR 1
+
+/* Implementations of the solve (identical counts / masks / winner; refit pose equal to FP32 rounding):
+ *   AUTO   the three-kernel pipeline where it applies (anchor mode, R <= 128), else the fused kernel
+ *   FUSED  one kernel, one CTA per ROI (pose_solve.cu)
+ *   SPLIT  gate_pack (HBM-bound, bulk-TMA ring) -> score (FP32 cores) -> refit (warp per ROI);
+ *          RDPN_E_TOOLARGE where it does not apply */
+#define RDPN_PIPELINE_AUTO 0
+#define RDPN_PIPELINE_FUSED 1
+#define RDPN_PIPELINE_SPLIT 2
 
 typedef struct rdpn_solve_outputs {
     float* pose;           /* [B,12] row-major 3x4 (R|t), FP32                                       */
@@ -188,6 +209,16 @@ typedef struct rdpn_solve_outputs {
  * and demand bit-identical results). */
 int rdpn_pose_solve(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, const float* d_t_net,
                     const rdpn_solve_params* prm, const rdpn_solve_outputs* out, void* stream);
+/* Same call with a caller-owned scratch buffer for the pipeline's per-ROI packages (sorted correspondences, region
+ * runs, hypothesis poses: ~20 KB touched per ROI): allocates nothing and never synchronises, so it can be captured
+ * in a CUDA graph.  d_ws must be 128-byte aligned and hold at least one package (rdpn_pose_solve_workspace_bytes(1, ..));
+ * rdpn_pose_solve_workspace_bytes(B, H, R, chunk_rois) is the size at which a chunk of min(B, chunk_rois) ROIs goes
+ * through each kernel in one launch (R = 0: dense mode).  rdpn_pose_solve itself keeps one such buffer per (device,
+ * stream) and grows it on demand (growing synchronises that stream once). */
+size_t rdpn_pose_solve_workspace_bytes(int B, int num_hyp, int num_regions, int chunk_rois);
+int rdpn_pose_solve_ws(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, const float* d_t_net,
+                       const rdpn_solve_params* prm, const rdpn_solve_outputs* out, void* d_ws, size_t ws_bytes,
+                       void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * B4  Batched weighted Kabsch / Umeyama -- lib/pysixd/transform.py:913-1029

@@ -33,7 +33,8 @@ class SolveParams(ctypes.Structure):
         ("min_inliers", ctypes.c_int32), ("weighted", ctypes.c_int32), ("refit_iters", ctypes.c_int32),
         ("with_scale", ctypes.c_int32), ("adaptive", ctypes.c_int32), ("confidence", ctypes.c_float),
         ("min_iter", ctypes.c_int32), ("seed", ctypes.c_uint32), ("roi_base", ctypes.c_int32),
-        ("sample_size", ctypes.c_int32),
+        ("sample_size", ctypes.c_int32), ("pipeline", ctypes.c_int32), ("chunk_rois", ctypes.c_int32),
+        ("select_rule", ctypes.c_int32),
     ]
 
 
@@ -60,6 +61,9 @@ SIGNATURES = {
     "rdpn_correspond": (ctypes.c_int, [ctypes.POINTER(RoiInputs), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "rdpn_pose_solve": (ctypes.c_int, [ctypes.POINTER(RoiInputs), c_vp, c_vp, ctypes.POINTER(SolveParams),
                                        ctypes.POINTER(SolveOutputs), c_vp]),
+    "rdpn_pose_solve_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "rdpn_pose_solve_ws": (ctypes.c_int, [ctypes.POINTER(RoiInputs), c_vp, c_vp, ctypes.POINTER(SolveParams),
+                                          ctypes.POINTER(SolveOutputs), c_vp, ctypes.c_size_t, c_vp]),
     "rdpn_kabsch": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_vp, ctypes.c_int, c_vp]),
     "rdpn_centroid_z_to_pose": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int,
                                                ctypes.c_int, c_vp, c_vp, ctypes.c_int, c_vp]),
@@ -84,6 +88,8 @@ SIGNATURES = {
 }
 
 MAX_SAMPLE = 16  # RDPN_MAX_SAMPLE
+PIPELINE_AUTO, PIPELINE_FUSED, PIPELINE_SPLIT = 0, 1, 2  # RDPN_PIPELINE_*
+SELECT_MOST_INLIERS, SELECT_MIN_MEAN_ERR = 0, 1  # RDPN_SELECT_*
 
 # rdpn_ctx_set_option keys / transfer strategies (include/rdpn6d_b200.h)
 TRANSFER_AUTO, TRANSFER_COPY, TRANSFER_PULL = 0, 1, 2

@@ -11,8 +11,16 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librdpn6d_b200.so")
-SOURCES = ["fps.cu", "correspond.cu", "pose_solve.cu", "geometry.cu", "roi_crop.cu", "coor_feat.cu", "host_api.cu"]
-HEADERS = ["common.cuh", "kabsch_math.cuh", os.path.join("..", "..", "include", "rdpn6d_b200.h")]
+SOURCES = ["fps.cu", "correspond.cu", "pose_solve.cu", "solve_split.cu", "geometry.cu", "roi_crop.cu", "coor_feat.cu",
+           "host_api.cu"]
+
+
+def _headers():
+    """every csrc/*.cuh + the public header: editing any of them makes the library stale"""
+    import glob
+
+    return sorted(os.path.basename(h) for h in glob.glob(os.path.join(CSRC, "*.cuh"))) + [
+        os.path.join("..", "..", "include", "rdpn6d_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
@@ -30,7 +38,7 @@ def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    deps = [os.path.join(CSRC, s) for s in SOURCES + _headers()] + [os.path.abspath(__file__)]
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 

@@ -17,6 +17,7 @@
 #include <stdlib.h>
 
 namespace rdpn {
+int ensure_func_smem(const void* func, int slot, size_t bytes);
 extern unsigned long long g_launch_count;
 
 
@@ -156,13 +157,10 @@ extern "C" int rdpn_coor_feat(const float* d_coor_x, const float* d_coor_y, cons
     cudaStream_t st = (cudaStream_t)stream;
     const int tp = R <= 32 ? 512 : 256;
     const int smem = R * tp * 4;
-    static int attr_smem[2] = {0, 0};
-    if (smem > attr_smem[tp == 512]) {
-        if (tp == 512)
-            RDPN_CUDA_TRY(cudaFuncSetAttribute(rdpn::coor_feat_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        else
-            RDPN_CUDA_TRY(cudaFuncSetAttribute(rdpn::coor_feat_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_smem[tp == 512] = smem;
+    {
+        const int rc = tp == 512 ? rdpn::ensure_func_smem((const void*)rdpn::coor_feat_kernel<512>, 6, (size_t)smem)
+                                 : rdpn::ensure_func_smem((const void*)rdpn::coor_feat_kernel<256>, 7, (size_t)smem);
+        if (rc) return rc;
     }
     if (tp == 512)
         rdpn::coor_feat_kernel<512><<<B * (RDPN_P / 512), 512, smem, st>>>(d_coor_x, d_coor_y, d_coor_z, d_roi_coord_2d, d_region, d_fps,

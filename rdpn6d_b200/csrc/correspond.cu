@@ -19,6 +19,8 @@
 
 namespace rdpn {
 extern unsigned long long g_launch_count;
+int device_sm_count(int* sms);
+int ensure_func_smem(const void* func, int slot, size_t bytes);
 
 constexpr int C_CT = 512;           // compute threads (16 warps: the per-pixel IEEE divisions are latency-bound, TLP hides them)
 constexpr int C_CW = C_CT / 32;     // compute warps
@@ -217,15 +219,11 @@ template <bool DENSE>
 static int launch_correspond(const rdpn_roi_inputs* in, float* cam, float* obj, float* w, uint8_t* sel, int32_t* nsel,
                              cudaStream_t st) {
     const size_t smem = sizeof(S1Smem);
-    static bool attr_set = false;
-    static int sms = 0;
-    if (!attr_set) {
-        int dev = 0;
-        RDPN_CUDA_TRY(cudaGetDevice(&dev));
-        RDPN_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        RDPN_CUDA_TRY(cudaFuncSetAttribute(correspond_kernel<DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    int sms = 0;
+    int rc = device_sm_count(&sms);
+    if (rc) return rc;
+    rc = ensure_func_smem((const void*)correspond_kernel<DENSE>, 4 + (DENSE ? 1 : 0), smem);
+    if (rc) return rc;
     const int grid = in->B < sms ? in->B : sms;
     correspond_kernel<DENSE><<<grid, C_NT, smem, st>>>(*in, cam, obj, w, sel, nsel);
     ++g_launch_count;

@@ -10,8 +10,84 @@
 #include <string.h>
 #include <time.h>
 
+#include <mutex>
+#include <vector>
+
 namespace rdpn {
 unsigned long long g_launch_count = 0;
+
+// ------------------------------------------------------------------------------------------------
+// Per-device launch state.  Function attributes (opt-in dynamic shared memory) and the SM count belong to a device,
+// not to the process: every launcher asks here, keyed by the CURRENT device, under a mutex.
+// ------------------------------------------------------------------------------------------------
+#define RDPN_MAX_DEVICES 64
+#define RDPN_ATTR_SLOTS 32
+struct DevState {
+    int sms;
+    size_t attr[RDPN_ATTR_SLOTS];
+};
+static std::mutex g_dev_mu;
+static DevState g_dev[RDPN_MAX_DEVICES];
+
+int device_sm_count(int* sms) {
+    int dev = 0;
+    RDPN_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= RDPN_MAX_DEVICES) return RDPN_E_BADARG;
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    if (!g_dev[dev].sms) RDPN_CUDA_TRY(cudaDeviceGetAttribute(&g_dev[dev].sms, cudaDevAttrMultiProcessorCount, dev));
+    *sms = g_dev[dev].sms;
+    return 0;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize >= bytes for `func` on the current device (slot: one per kernel instantiation)
+int ensure_func_smem(const void* func, int slot, size_t bytes) {
+    int dev = 0;
+    RDPN_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= RDPN_MAX_DEVICES || slot < 0 || slot >= RDPN_ATTR_SLOTS) return RDPN_E_BADARG;
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    if (bytes > g_dev[dev].attr[slot]) {
+        RDPN_CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        g_dev[dev].attr[slot] = bytes;
+    }
+    return 0;
+}
+
+// Workspace of the plain rdpn_pose_solve entry (no workspace argument): one buffer per (device, stream), grown on
+// demand.  Growing synchronises that stream once (the old buffer may be in use); steady state allocates nothing.
+struct WsEntry {
+    int dev;
+    cudaStream_t st;
+    void* p;
+    size_t bytes;
+};
+static std::mutex g_ws_mu;
+static std::vector<WsEntry> g_ws;
+
+int cached_workspace(cudaStream_t st, size_t need, void** out, size_t* out_bytes) {
+    int dev = 0;
+    RDPN_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    WsEntry* e = nullptr;
+    for (auto& w : g_ws)
+        if (w.dev == dev && w.st == st) e = &w;
+    if (!e) {
+        g_ws.push_back(WsEntry{dev, st, nullptr, 0});
+        e = &g_ws.back();
+    }
+    if (e->bytes < need) {
+        if (e->p) {
+            RDPN_CUDA_TRY(cudaStreamSynchronize(st));
+            cudaFree(e->p);
+            e->p = nullptr;
+            e->bytes = 0;
+        }
+        RDPN_CUDA_TRY(cudaMalloc(&e->p, need));
+        e->bytes = need;
+    }
+    *out = e->p;
+    *out_bytes = e->bytes;
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Gated pull: the solver only ever reads depth / coor / region-id values of pixels whose MASK test

@@ -169,7 +169,7 @@ __device__ __forceinline__ double det3(double a, double b, double c, double d, d
     return a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
 }
 
-__device__ __noinline__ void rotation_from_cov_jacobi(const double* S, double* R);
+static __device__ __noinline__ void rotation_from_cov_jacobi(const double* S, double* R);
 
 // Ga = sum_w |a - a_mean|^2, Gb = sum_w |c - c_mean|^2 (only used as the Newton start: any upper bound of
 // the largest eigenvalue works).
@@ -243,7 +243,7 @@ __device__ __forceinline__ void rotation_from_cov(const double* S, double Ga, do
     quat_to_rot(q0, q1, q2, q3, R);
 }
 
-__device__ __noinline__ void rotation_from_cov_jacobi(const double* S, double* R) {
+static __device__ __noinline__ void rotation_from_cov_jacobi(const double* S, double* R) {
     // Horn's N with Sh_ij = sum a_i c_j = S[j*3+i]
     const double Sxx = S[0], Sxy = S[3], Sxz = S[6];
     const double Syx = S[1], Syy = S[4], Syz = S[7];

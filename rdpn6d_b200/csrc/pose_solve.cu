@@ -21,13 +21,20 @@
 #include "common.cuh"
 #include "gate.cuh"
 #include "kabsch_math.cuh"
+#include "solve_common.cuh"
 
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace rdpn {
 extern unsigned long long g_launch_count;
+int ensure_func_smem(const void* func, int slot, size_t bytes);                                  // host_api.cu
+int cached_workspace(cudaStream_t st, size_t need, void** out, size_t* out_bytes);               // host_api.cu
+bool split_supported(const SolveArgs& a, bool dense);                                            // solve_split.cu
+size_t split_pkg_stride(int H, int R, bool dense);                                               // solve_split.cu
+int launch_split(const SolveArgs& a, bool dense, void* ws, size_t ws_bytes, int chunk_rois, cudaStream_t st);
 
 // Optional per-phase cycle stamps (tuning builds only: RDPN_NVCC_EXTRA=-DRDPN_PHASE_CLOCKS, benchmarks/phase_clocks.py)
 #ifdef RDPN_PHASE_CLOCKS
@@ -53,17 +60,6 @@ __device__ long long* g_phase_clk = nullptr;  // [B][16]
 constexpr int ST = RDPN_SOLVE_THREADS;  // threads per CTA (256; 128 works too: benchmarks show no gain)
 constexpr int SW = ST / 32;          // warps
 constexpr int QPT = RDPN_P / 4 / ST;  // pixel quads per thread (4)
-
-struct SolveArgs {
-    rdpn_roi_inputs in;
-    const int32_t* hyp_idx;
-    const float* t_net;
-    rdpn_solve_params prm;
-    rdpn_solve_outputs out;
-    float sq_cut;  // smallest FP32 x with sqrtf(x) >= thr
-    double mask_cut;    // midpoint between mask_thr and its FP32 successor
-    int mask_cut_incl;  // ties-to-even: 1 when the quotient may equal the midpoint
-};
 
 // ---------------------------------------------------------------------------------------------
 // fused solver
@@ -106,16 +102,6 @@ struct FinishSmem {  // scratch of the select + refit tail
     int red_j[SW];
 };
 
-// the raw planes of one ROI in global memory
-struct RoiPlanes {
-    const float* depth;
-    const float* cx;
-    const float* cy;
-    const float* cz;
-    const float* mask;
-    const uint8_t* rid;
-};
-
 struct __align__(128) FusedSmem {
     float4 chunk[CHUNK];            // (cam xyz, w) by slot of the current chunk; dense: second half = obj xyz
     uint16_t pix[RDPN_P];           // slot -> pixel
@@ -128,85 +114,6 @@ struct __align__(128) FusedSmem {
     int n_runs;
     FinishSmem fin;
 };
-
-// one pixel of S1 with the exact oracle arithmetic; cam (and obj in dense mode)
-template <bool DENSE>
-__device__ __forceinline__ void pixel_s1(const RoiConst& rc, int pix, float d_raw, float cxn, float cyn, float czn,
-                                         float (&cam)[3], float (&obj)[3]) {
-    const float u = (float)(4 * (pix & 63));
-    const float v = (float)(4 * (pix >> 6));
-    float d = d_raw;
-    if (rc.div != 0.f) d = __fdiv_rn(d, rc.div);                          // data_loader.py:563
-    const float X = __fdiv_rn(__fmul_rn(__fsub_rn(u, rc.cx), d), rc.fx);  // :573
-    const float Y = __fdiv_rn(__fmul_rn(__fsub_rn(v, rc.cy), d), rc.fy);  // :574
-    const float dx = __fmul_rn(__fsub_rn(cxn, 0.5f), rc.ext[0]);          // gdrn_evaluator.py:103-105
-    const float dy = __fmul_rn(__fsub_rn(cyn, 0.5f), rc.ext[1]);
-    const float dz = __fmul_rn(__fsub_rn(czn, 0.5f), rc.ext[2]);
-    if (DENSE) {
-        cam[0] = X; cam[1] = Y; cam[2] = d;
-        obj[0] = dx; obj[1] = dy; obj[2] = dz;
-    } else {
-        cam[0] = __fsub_rn(X, dx); cam[1] = __fsub_rn(Y, dy); cam[2] = __fsub_rn(d, dz);
-        obj[0] = obj[1] = obj[2] = 0.f;
-    }
-}
-
-// gather one gated pixel and run S1 on it (cam xyz, w | obj xyz)
-template <bool DENSE>
-__device__ __forceinline__ void gather_s1(const RoiPlanes& pl, const RoiConst& rc, int p, bool weighted, int mask_mode,
-                                          float4& camw, float4& objv) {
-    float cam[3], obj[3];
-    pixel_s1<DENSE>(rc, p, __ldg(pl.depth + p), __ldg(pl.cx + p), __ldg(pl.cy + p), __ldg(pl.cz + p), cam, obj);
-    const float w = weighted ? mask_prob(__ldg(pl.mask + p), mask_mode, rc.mn, rc.mx) : 1.f;
-    camw = make_float4(cam[0], cam[1], cam[2], w);
-    objv = make_float4(obj[0], obj[1], obj[2], 0.f);
-}
-
-__device__ __forceinline__ float resid2_pt(float tx, float ty, float tz, float cx, float cy, float cz) {
-    const float dx = __fsub_rn(tx, cx), dy = __fsub_rn(ty, cy), dz = __fsub_rn(tz, cz);
-    float d2 = __fmul_rn(dx, dx);
-    d2 = __fmaf_rn(dy, dy, d2);
-    d2 = __fmaf_rn(dz, dz, d2);
-    return d2;
-}
-// c += (d2 < cut): one FSETP + one predicated IADD (the C++ form compiles to three instructions)
-__device__ __forceinline__ void count_if_lt(int& c, float d2, float cut) {
-    asm("{\n.reg .pred p;\nsetp.lt.f32 p, %1, %2;\n@p add.s32 %0, %0, 1;\n}" : "+r"(c) : "f"(d2), "f"(cut));
-}
-// counter-based stream of the internal hypothesis sampling (include/rdpn6d_b200.h, oracle sample_triplets)
-__device__ __forceinline__ uint32_t fmix32(uint32_t x) {
-    x ^= x >> 16;
-    x *= 0x85ebca6bu;
-    x ^= x >> 13;
-    x *= 0xc2b2ae35u;
-    x ^= x >> 16;
-    return x;
-}
-// R a + t with the contract's FMA order (oracle/pose_oracle.c:resid2)
-__device__ __forceinline__ void xform(const float* P, float ax, float ay, float az, float& x, float& y, float& z) {
-    x = __fmaf_rn(P[0], ax, P[3]);
-    x = __fmaf_rn(P[1], ay, x);
-    x = __fmaf_rn(P[2], az, x);
-    y = __fmaf_rn(P[4], ax, P[7]);
-    y = __fmaf_rn(P[5], ay, y);
-    y = __fmaf_rn(P[6], az, y);
-    z = __fmaf_rn(P[8], ax, P[11]);
-    z = __fmaf_rn(P[9], ay, z);
-    z = __fmaf_rn(P[10], az, z);
-}
-__device__ __forceinline__ float resid2(const float* P, float ax, float ay, float az, float cx, float cy, float cz) {
-    float x, y, z;
-    xform(P, ax, ay, az, x, y, z);
-    return resid2_pt(x, y, z, cx, cy, cz);
-}
-
-// misc.py:134-138: k = log10(1-conf) / log10(1 - w^10), stop once i_ransac > max(k, min_iter).  Kept out of line:
-// double pow/log10 are ~1500 instructions that only the (non-default) adaptive mode needs.
-__device__ __noinline__ bool adaptive_stop(int count, int n, int i_ransac, double log_1m_conf, int min_iter) {
-    const double wr = (double)count / (double)n;
-    const double k = log_1m_conf / log10(1.0 - pow(wr, 10.0));
-    return (double)i_ransac > fmax(k, (double)min_iter);
-}
 
 // block-wide sum of NV doubles; result valid in every thread (via f.bc_d[0..NV)).
 template <int NV>
@@ -240,16 +147,6 @@ struct FusedLayout {  // byte offsets of the dynamic tail behind FusedSmem
     int planes;       // RoiPlanes copy for the out-of-line S > 3 hypothesis path (MULTI instantiations only)
     int total;
 };
-
-// rank-select on the gate bitmap: pixel index of the k-th gated pixel in raster order (internal sampling)
-__device__ __forceinline__ int kth_gated_pixel(const uint32_t* selmap, const uint16_t* selpfx, uint32_t k) {
-    int lo = 0;
-#pragma unroll
-    for (int step = RDPN_P / 64; step; step >>= 1)
-        if (selpfx[lo + step] <= k) lo += step;
-    const unsigned j = k - selpfx[lo];
-    return lo * 32 + (int)__fns(selmap[lo], 0, (int)j + 1);
-}
 
 // Hypothesis from S > 3 pairs (misc.py:72,91 samples random_sample_num = 10): Kabsch of the S pairs,
 // transform.py:913-980 semantics.  FP64 raw moments about the first pair (exact FP32 differences), closed-form
@@ -1271,10 +1168,9 @@ static int launch_solve(const SolveArgs& a, cudaStream_t st) {
     lay.total = (int)off;
     const size_t smem = off;
     if (smem > 227 * 1024) return RDPN_E_TOOLARGE;
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        RDPN_CUDA_TRY(cudaFuncSetAttribute(pose_solve_kernel<DENSE, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
+    {
+        const int rc = ensure_func_smem((const void*)pose_solve_kernel<DENSE, MULTI>, (DENSE ? 1 : 0) + (MULTI ? 2 : 0), smem);
+        if (rc) return rc;
     }
     pose_solve_kernel<DENSE, MULTI><<<a.in.B, ST, smem, st>>>(a, lay);
     ++g_launch_count;
@@ -1292,27 +1188,91 @@ int rdpn_debug_set_phase_clocks(long long* d_buf) {
 }
 #endif
 
-int rdpn_pose_solve(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, const float* d_t_net,
-                    const rdpn_solve_params* prm, const rdpn_solve_outputs* out, void* stream) {
-    bool dense = false;
-    int rc = rdpn::check_roi_inputs(in, &dense);
+static int env_int_(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+#define RDPN_DEFAULT_CHUNK_ROIS 4096
+
+static int solve_prepare(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, const float* d_t_net, const rdpn_solve_params* prm,
+                         const rdpn_solve_outputs* out, rdpn::SolveArgs* a, bool* dense) {
+    int rc = rdpn::check_roi_inputs(in, dense);
     if (rc) return rc;
     if (!prm || !out || !out->pose || !out->n_inliers || !out->status) return RDPN_E_BADARG;  // d_hyp_idx NULL: internal sampling
     if (prm->num_hyp <= 0 || !(prm->inlier_thr > 0.f)) return RDPN_E_BADARG;
     if (prm->sample_size != 0 && (prm->sample_size < 3 || prm->sample_size > RDPN_MAX_SAMPLE)) return RDPN_E_BADARG;
+    if (prm->pipeline < RDPN_PIPELINE_AUTO || prm->pipeline > RDPN_PIPELINE_SPLIT || prm->chunk_rois < 0) return RDPN_E_BADARG;
+    if (prm->select_rule != RDPN_SELECT_MOST_INLIERS) return RDPN_E_BADARG;  // MIN_MEAN_ERR: not yet
     if (out->inlier_mask && ((uintptr_t)out->inlier_mask & 15)) return RDPN_E_ALIGN;
-    rdpn::SolveArgs a;
-    a.in = *in;
-    a.hyp_idx = d_hyp_idx;
-    a.t_net = d_t_net;
-    a.prm = *prm;
-    if (a.prm.sample_size == 0) a.prm.sample_size = 3;
-    a.out = *out;
-    a.sq_cut = rdpn::host_sq_cut(prm->inlier_thr);
-    rdpn::host_mask_cut(in->mask_thr, &a.mask_cut, &a.mask_cut_incl);
-    cudaStream_t st = (cudaStream_t)stream;
+    if (out->hyp_poses && ((uintptr_t)out->hyp_poses & 15)) return RDPN_E_ALIGN;
+    a->in = *in;
+    a->hyp_idx = d_hyp_idx;
+    a->t_net = d_t_net;
+    a->prm = *prm;
+    if (a->prm.sample_size == 0) a->prm.sample_size = 3;
+    a->out = *out;
+    a->sq_cut = rdpn::host_sq_cut(prm->inlier_thr);
+    rdpn::host_mask_cut(in->mask_thr, &a->mask_cut, &a->mask_cut_incl);
+    return 0;
+}
+
+// which implementation runs: the three-kernel pipeline (solve_split.cu) unless the caller or RDPN_SOLVE_PIPELINE
+// (tuning: "fused" / "split") asks for the fused kernel, or the problem is outside what the pipeline supports
+static bool use_split(const rdpn::SolveArgs& a, bool dense, int* err) {
+    int mode = a.prm.pipeline;
+    if (mode == RDPN_PIPELINE_AUTO) {
+        const char* e = getenv("RDPN_SOLVE_PIPELINE");
+        if (e && !strcmp(e, "fused")) mode = RDPN_PIPELINE_FUSED;
+        if (e && !strcmp(e, "split")) mode = RDPN_PIPELINE_SPLIT;
+    }
+    const bool ok = rdpn::split_supported(a, dense);
+    *err = (mode == RDPN_PIPELINE_SPLIT && !ok) ? RDPN_E_TOOLARGE : 0;
+    return mode != RDPN_PIPELINE_FUSED && ok;
+}
+
+static int solve_fused(const rdpn::SolveArgs& a, bool dense, cudaStream_t st) {
     if (a.prm.sample_size > 3) return dense ? rdpn::launch_solve<true, true>(a, st) : rdpn::launch_solve<false, true>(a, st);
     return dense ? rdpn::launch_solve<true, false>(a, st) : rdpn::launch_solve<false, false>(a, st);
+}
+
+size_t rdpn_pose_solve_workspace_bytes(int B, int num_hyp, int num_regions, int chunk_rois) {
+    if (B <= 0 || num_hyp <= 0) return 0;
+    const bool dense = num_regions <= 0;
+    const size_t stride = rdpn::split_pkg_stride(num_hyp, dense ? 1 : num_regions, dense);
+    int chunk = chunk_rois > 0 ? chunk_rois : env_int_("RDPN_SOLVE_CHUNK", RDPN_DEFAULT_CHUNK_ROIS);
+    if (chunk > B) chunk = B;
+    return stride * (size_t)chunk;
+}
+
+int rdpn_pose_solve_ws(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, const float* d_t_net, const rdpn_solve_params* prm,
+                       const rdpn_solve_outputs* out, void* d_ws, size_t ws_bytes, void* stream) {
+    rdpn::SolveArgs a;
+    bool dense = false;
+    int rc = solve_prepare(in, d_hyp_idx, d_t_net, prm, out, &a, &dense);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    int err = 0;
+    if (!use_split(a, dense, &err)) return err ? err : solve_fused(a, dense, st);
+    const int chunk = a.prm.chunk_rois > 0 ? a.prm.chunk_rois : env_int_("RDPN_SOLVE_CHUNK", RDPN_DEFAULT_CHUNK_ROIS);
+    return rdpn::launch_split(a, dense, d_ws, ws_bytes, chunk, st);
+}
+
+int rdpn_pose_solve(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, const float* d_t_net,
+                    const rdpn_solve_params* prm, const rdpn_solve_outputs* out, void* stream) {
+    rdpn::SolveArgs a;
+    bool dense = false;
+    int rc = solve_prepare(in, d_hyp_idx, d_t_net, prm, out, &a, &dense);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    int err = 0;
+    if (!use_split(a, dense, &err)) return err ? err : solve_fused(a, dense, st);
+    const int chunk = a.prm.chunk_rois > 0 ? a.prm.chunk_rois : env_int_("RDPN_SOLVE_CHUNK", RDPN_DEFAULT_CHUNK_ROIS);
+    const size_t need = rdpn_pose_solve_workspace_bytes(in->B, a.prm.num_hyp, dense ? 0 : in->num_regions, chunk);
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    rc = rdpn::cached_workspace(st, need, &ws, &ws_bytes);
+    if (rc) return rc;
+    return rdpn::launch_split(a, dense, ws, ws_bytes, chunk, st);
 }
 
 int rdpn_kabsch(const float* d_src, const float* d_dst, const float* d_w, int N, int with_scale, float* d_out_M,

@@ -29,6 +29,13 @@ from . import _lib
 MASK_RAW, MASK_L1, MASK_BCE = 0, 1, 2
 _MASK_MODES = {"raw": MASK_RAW, "none": MASK_RAW, "l1": MASK_L1, "bce": MASK_BCE}
 STATUS_OK, STATUS_FEW_POINTS, STATUS_T_SANITY, STATUS_NO_CONSENSUS = 0, 1, 2, 3
+_PIPELINES = {"auto": _lib.PIPELINE_AUTO, "fused": _lib.PIPELINE_FUSED, "split": _lib.PIPELINE_SPLIT}
+
+
+def _workspace(B, H, R, chunk_rois, dev):
+    """Scratch for the pipeline's per-ROI packages (rdpn_pose_solve_workspace_bytes), a uint8 CUDA tensor."""
+    n = int(_lib.lib().rdpn_pose_solve_workspace_bytes(int(B), int(H), int(R), int(chunk_rois)))
+    return torch.empty(max(n, 128), dtype=torch.uint8, device=dev)
 P = 64 * 64
 
 
@@ -150,8 +157,10 @@ class PoseSolver:
 
     def __init__(self, inlier_thr=0.005, min_pts=4, min_inliers=4, weighted=False, refit_iters=1, with_scale=False,
                  adaptive=False, confidence=0.995, min_iter=10, mask_mode=MASK_L1, mask_thr=0.5,
-                 want_inlier_mask=False, want_hyp=False, num_hyp=256, seed=0, sample_size=3):
-        """num_hyp / seed / sample_size: used when a call passes hyp_idx=None -- the kernel then draws num_hyp samples of
+                 want_inlier_mask=False, want_hyp=False, num_hyp=256, seed=0, sample_size=3, pipeline="auto", chunk_rois=0):
+        """pipeline: "auto" (three-kernel pipeline gate_pack -> score -> refit where it applies, else the fused kernel),
+        "fused", "split"; chunk_rois: ROIs per pass through the three kernels (0 = library default).
+        num_hyp / seed / sample_size: used when a call passes hyp_idx=None -- the kernel then draws num_hyp samples of
         sample_size pixels itself from a counter-based stream (include/rdpn6d_b200.h), the stand-in for np.random.choice
         at misc.py:91.  With explicit hyp_idx [B,H,S] both H and S come from the tensor."""
         if not 3 <= int(sample_size) <= _lib.MAX_SAMPLE:
@@ -160,8 +169,10 @@ class PoseSolver:
         self.prm = dict(inlier_thr=float(inlier_thr), min_pts=int(min_pts), min_inliers=int(min_inliers),
                         weighted=int(bool(weighted)), refit_iters=int(refit_iters), with_scale=int(bool(with_scale)),
                         adaptive=int(bool(adaptive)), confidence=float(confidence), min_iter=int(min_iter),
-                        seed=int(seed) & 0xFFFFFFFF)
+                        seed=int(seed) & 0xFFFFFFFF, pipeline=_PIPELINES[pipeline] if isinstance(pipeline, str) else int(pipeline),
+                        chunk_rois=int(chunk_rois))
         self.num_hyp = int(num_hyp)
+        self._ws = {}
         self.mask_mode = mask_mode
         self.mask_thr = mask_thr
         self.want_inlier_mask = want_inlier_mask
@@ -202,9 +213,14 @@ class PoseSolver:
         for k in ("pose", "n_inliers", "status", "best_h", "n_sel", "inlier_mask", "hyp_counts", "hyp_poses", "scale", "rows16"):
             setattr(outs, k, o[k].data_ptr() if k in o else None)
         st = (stream or torch.cuda.current_stream(dev)).cuda_stream
+        wkey = (B, H, inp.struct.num_regions, str(dev), st)
+        if wkey not in self._ws:
+            self._ws[wkey] = _workspace(B, H, inp.struct.num_regions, self.prm["chunk_rois"], dev)
+        ws = self._ws[wkey]
         with torch.cuda.device(dev):
-            rc = L.rdpn_pose_solve(ctypes.byref(inp.struct), hyp.data_ptr() if hyp is not None else None,
-                                   tn.data_ptr() if tn is not None else None, ctypes.byref(prm), ctypes.byref(outs), st)
+            rc = L.rdpn_pose_solve_ws(ctypes.byref(inp.struct), hyp.data_ptr() if hyp is not None else None,
+                                      tn.data_ptr() if tn is not None else None, ctypes.byref(prm), ctypes.byref(outs),
+                                      ws.data_ptr(), ws.numel(), st)
         _lib.check(rc, "pose_solve")
         self._keep = (inp, hyp, tn)  # keep inputs alive until the next call (stream-ordered use)
         return PoseSolveResult(pose=o["pose"].view(B, 3, 4), n_inliers=o["n_inliers"], status=o["status"],
@@ -216,12 +232,14 @@ class SolvePlan:
     """A fully prepared launch (C structs built once): `launch()` is a single ctypes call, so a
     benchmark or serving loop pays no per-step Python tensor bookkeeping."""
 
-    def __init__(self, solver, inp, hyp, tn, prm, outs, result):
+    def __init__(self, solver, inp, hyp, tn, prm, outs, result, ws):
         self._solver, self._inp, self._hyp, self._tn, self._prm, self._outs = solver, inp, hyp, tn, prm, outs
         self.result = result
-        self._fn = _lib.lib().rdpn_pose_solve
+        self._ws = ws  # the plan's own package scratch: plans may run concurrently on different streams
+        self._fn = _lib.lib().rdpn_pose_solve_ws
         self._args = (ctypes.byref(inp.struct), hyp.data_ptr() if hyp is not None else None,
-                      tn.data_ptr() if tn is not None else None, ctypes.byref(prm), ctypes.byref(outs))
+                      tn.data_ptr() if tn is not None else None, ctypes.byref(prm), ctypes.byref(outs),
+                      ws.data_ptr(), ws.numel())
         self._dev = inp.dev
 
     def launch(self, stream=None):
@@ -250,9 +268,8 @@ def make_plan(solver, depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx=N
     res = PoseSolveResult(pose=o["pose"].view(B, 3, 4), n_inliers=o["n_inliers"], status=o["status"],
                           best_h=o["best_h"], n_sel=o["n_sel"], inlier_mask=o.get("inlier_mask"),
                           hyp_counts=o.get("hyp_counts"), hyp_poses=o.get("hyp_poses"), scale=o["scale"], rows=o["rows16"])
-    with torch.cuda.device(dev):
-        pass
-    return SolvePlan(solver, inp, hyp, tn, prm, outs, res)
+    ws = _workspace(B, H, inp.struct.num_regions, solver.prm["chunk_rois"], dev)
+    return SolvePlan(solver, inp, hyp, tn, prm, outs, res, ws)
 
 
 def pose_solve(depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx=None, region_idx=None, anchors=None,

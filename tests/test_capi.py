@@ -39,13 +39,13 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header_sizes():
     # x86-64 SysV: 10 pointers + 4 x 4-byte scalars; 10 x 4-byte; 9 pointers
     assert ctypes.sizeof(_lib.RoiInputs) == 10 * 8 + 16
-    assert ctypes.sizeof(_lib.SolveParams) == 52
+    assert ctypes.sizeof(_lib.SolveParams) == 64
     assert ctypes.sizeof(_lib.SolveOutputs) == 10 * 8
 
 
 def test_version_and_error_strings():
     L = _lib.lib()
-    assert L.rdpn_version() == 102
+    assert L.rdpn_version() == 200
     assert L.rdpn_error_string(0) == b"success"
     assert b"aligned" in L.rdpn_error_string(-2)
     assert L.rdpn_fps_workspace_bytes(512) >= 514 * 12 + 24

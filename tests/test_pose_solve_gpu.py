@@ -41,6 +41,19 @@ def _solve(g, **kw):
     assert torch.equal(fast.best_h, res.best_h) and torch.equal(fast.n_inliers, res.n_inliers)
     assert torch.equal(fast.status, res.status) and torch.equal(fast.n_sel, res.n_sel)
     assert torch.equal(fast.inlier_mask, res.inlier_mask)
+    # ... and the two implementations (three-kernel pipeline / fused kernel) agree: integers and hypothesis poses bit for
+    # bit, the refit pose to FP32 rounding (its FP64 sums run in a different order)
+    if g.get("region_idx") is not None:
+        assert _lib.lib().rdpn_pose_solve_workspace_bytes(1, 8, 32, 0) > 0
+        fused = pose_solver.PoseSolver(want_inlier_mask=True, want_hyp=True, pipeline="fused", **kw)(*args, **kwargs)
+        split = pose_solver.PoseSolver(want_inlier_mask=True, want_hyp=True, pipeline="split", chunk_rois=5, **kw)(*args, **kwargs)
+        for other in (fused, split):
+            for name in ("best_h", "n_inliers", "status", "n_sel", "inlier_mask", "hyp_counts"):
+                assert torch.equal(getattr(other, name), getattr(res, name)), name
+            assert torch.equal(other.hyp_poses.view(torch.int32), res.hyp_poses.view(torch.int32))
+            ok = res.status == 0
+            assert torch.allclose(other.pose[ok], res.pose[ok], rtol=0, atol=2e-6)
+            assert torch.equal(other.pose[~ok], res.pose[~ok])
     return res
 
 
