@@ -22,14 +22,23 @@ CONFIGS = {
 }
 
 
-def ev_time(fn, iters, warm=3):
+def ev_time(fn, iters, warm=3, streams=None):
+    """CUDA-event time per call; with `streams`, call i goes to streams[i % len] (steady state of a serving loop that
+    keeps two calls in flight) and the timed region is bracketed on the current stream by fork / join events."""
     for i in range(warm):
         fn(i)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cur = torch.cuda.current_stream()
     e0.record()
+    if streams:
+        for s in streams:
+            s.wait_stream(cur)
     for i in range(iters):
         fn(i)
+    if streams:
+        for s in streams:
+            cur.wait_stream(s)
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters
@@ -52,6 +61,7 @@ def main():
     ap.add_argument("--chunks", default="0")
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--weighted", type=int, default=1)
+    ap.add_argument("--streams", type=int, default=1, help="calls in flight (round-robin over this many streams)")
     a = ap.parse_args()
     torch.cuda.set_device(0)
     for name in a.configs.split(","):
@@ -64,10 +74,11 @@ def main():
             plans = [pose_solver.make_plan(solver, s["depth"], s["Kp"], s["coor"][:, 0].contiguous(), s["coor"][:, 1].contiguous(),
                                            s["coor"][:, 2].contiguous(), s["mask"], s["extent"], s["hyp_idx"], s["region_idx"],
                                            s["anchors"]) for s in sets]
-            ms = ev_time(lambda i: plans[i % nsets].launch(), a.iters)
+            strs = [torch.cuda.Stream() for _ in range(a.streams)] if a.streams > 1 else None
+            ms = ev_time(lambda i: plans[i % nsets].launch(strs[i % a.streams] if strs else None), a.iters, streams=strs)
             r = plans[0].launch()
             torch.cuda.synchronize()
-            rec = {"bench": "pipeline", "config": name, "B": B, "H": H, "R": R, "pipeline": pipe, "chunk_rois": chunk, "ms": ms,
+            rec = {"bench": "pipeline", "config": name, "B": B, "H": H, "R": R, "pipeline": pipe, "chunk_rois": chunk, "streams": a.streams, "ms": ms,
                    "rois_per_s": B / (ms * 1e-3), "solved": float((r.status == 0).float().mean())}
             if ref is None:
                 ref = (r.best_h.clone(), r.n_inliers.clone(), r.pose.clone())

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librdpn6d_b200.so")
-SOURCES = ["fps.cu", "correspond.cu", "pose_solve.cu", "solve_split.cu", "geometry.cu", "roi_crop.cu", "coor_feat.cu",
+SOURCES = ["fps.cu", "correspond.cu", "pose_solve.cu", "solve_pipe.cu", "geometry.cu", "roi_crop.cu", "coor_feat.cu",
            "host_api.cu"]
 
 

@@ -59,6 +59,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (clock64() - t0 > (1ll << 32)) __trap();
     }
 }
+// Same, for waits that are expected to last microseconds (a CTA waiting for its own first copy): the polling warps
+// back off with nanosleep so that their spinning does not take issue slots from the SM's other CTAs.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    unsigned ns = 64;
+    while (!mbar_try(bar, parity)) {
+        __nanosleep(ns);
+        if (ns < 512) ns <<= 1;
+        if (clock64() - t0 > (1ll << 32)) __trap();
+    }
+}
 // global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned.
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

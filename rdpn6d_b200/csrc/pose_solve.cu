@@ -1192,7 +1192,7 @@ static int env_int_(const char* name, int dflt) {
     const char* v = getenv(name);
     return v && *v ? atoi(v) : dflt;
 }
-#define RDPN_DEFAULT_CHUNK_ROIS 4096
+#define RDPN_DEFAULT_CHUNK_ROIS 2048
 
 static int solve_prepare(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, const float* d_t_net, const rdpn_solve_params* prm,
                          const rdpn_solve_outputs* out, rdpn::SolveArgs* a, bool* dense) {
@@ -1240,8 +1240,8 @@ size_t rdpn_pose_solve_workspace_bytes(int B, int num_hyp, int num_regions, int 
     const bool dense = num_regions <= 0;
     const size_t stride = rdpn::split_pkg_stride(num_hyp, dense ? 1 : num_regions, dense);
     int chunk = chunk_rois > 0 ? chunk_rois : env_int_("RDPN_SOLVE_CHUNK", RDPN_DEFAULT_CHUNK_ROIS);
-    if (chunk > B) chunk = B;
-    return stride * (size_t)chunk;
+    if (chunk >= B) return stride * (size_t)B;
+    return stride * (size_t)chunk * 2;  // two package buffers: K1 of chunk c + 1 overlaps K2 / K3 of chunk c
 }
 
 int rdpn_pose_solve_ws(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, const float* d_t_net, const rdpn_solve_params* prm,
