@@ -33,7 +33,8 @@ extern unsigned long long g_launch_count;
 int ensure_func_smem(const void* func, int slot, size_t bytes);                                  // host_api.cu
 int cached_workspace(cudaStream_t st, size_t need, void** out, size_t* out_bytes);               // host_api.cu
 bool split_supported(const SolveArgs& a, bool dense);                                            // solve_split.cu
-size_t split_pkg_stride(int H, int R, bool dense);                                               // solve_split.cu
+size_t split_pkg_stride(int H, int R, bool dense);                                               // solve_pipe.cu
+size_t split_workspace_bytes(int B, int H, int R, int chunk_rois);                               // solve_pipe.cu
 int launch_split(const SolveArgs& a, bool dense, void* ws, size_t ws_bytes, int chunk_rois, cudaStream_t st);
 
 // Optional per-phase cycle stamps (tuning builds only: RDPN_NVCC_EXTRA=-DRDPN_PHASE_CLOCKS, benchmarks/phase_clocks.py)
@@ -1192,7 +1193,7 @@ static int env_int_(const char* name, int dflt) {
     const char* v = getenv(name);
     return v && *v ? atoi(v) : dflt;
 }
-#define RDPN_DEFAULT_CHUNK_ROIS 2048
+#define RDPN_DEFAULT_CHUNK_ROIS 8192
 
 static int solve_prepare(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, const float* d_t_net, const rdpn_solve_params* prm,
                          const rdpn_solve_outputs* out, rdpn::SolveArgs* a, bool* dense) {
@@ -1238,10 +1239,9 @@ static int solve_fused(const rdpn::SolveArgs& a, bool dense, cudaStream_t st) {
 size_t rdpn_pose_solve_workspace_bytes(int B, int num_hyp, int num_regions, int chunk_rois) {
     if (B <= 0 || num_hyp <= 0) return 0;
     const bool dense = num_regions <= 0;
-    const size_t stride = rdpn::split_pkg_stride(num_hyp, dense ? 1 : num_regions, dense);
-    int chunk = chunk_rois > 0 ? chunk_rois : env_int_("RDPN_SOLVE_CHUNK", RDPN_DEFAULT_CHUNK_ROIS);
-    if (chunk >= B) return stride * (size_t)B;
-    return stride * (size_t)chunk * 2;  // two package buffers: K1 of chunk c + 1 overlaps K2 / K3 of chunk c
+    if (dense) return 128;  // dense mode runs the fused kernel: no workspace
+    const int chunk = chunk_rois > 0 ? chunk_rois : env_int_("RDPN_SOLVE_CHUNK", RDPN_DEFAULT_CHUNK_ROIS);
+    return rdpn::split_workspace_bytes(B, num_hyp, num_regions, chunk);
 }
 
 int rdpn_pose_solve_ws(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, const float* d_t_net, const rdpn_solve_params* prm,

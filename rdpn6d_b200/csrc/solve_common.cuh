@@ -103,6 +103,122 @@ __device__ __forceinline__ float resid2(const float* P, float ax, float ay, floa
     return resid2_pt(x, y, z, cx, cy, cz);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Inlier scoring of region-sorted correspondences, shared by the fused kernel and the pipeline's K2
+// ---------------------------------------------------------------------------------------------
+// Where a pass finds the FP32 pose of compacted hypothesis j and where its count goes:
+//   PosePlanar  K2: rows of pose j at hyp[r * H + j] (conflict-free LDS.128), counts indexed by j
+//   PoseListed  fused kernel: pose of hypothesis h = vlist[j] at hyp[3 h .. 3 h + 2], counts indexed by h
+struct PosePlanar {
+    const float4* hyp;
+    int H;
+    __device__ __forceinline__ int slot(int j) const { return j; }
+    __device__ __forceinline__ void rows(int j, float4& r0, float4& r1, float4& r2) const {
+        r0 = hyp[j]; r1 = hyp[H + j]; r2 = hyp[2 * H + j];
+    }
+};
+struct PoseListed {
+    const float4* hyp;
+    const uint16_t* vlist;
+    __device__ __forceinline__ int slot(int j) const { return (int)vlist[j]; }
+    __device__ __forceinline__ void rows(int h, float4& r0, float4& r1, float4& r2) const {
+        r0 = hyp[3 * h]; r1 = hyp[3 * h + 1]; r2 = hyp[3 * h + 2];
+    }
+};
+
+// One pass: K hypotheses per lane (compacted indices j0 + 32 u + lane, u < K) against the staged slots [i0, i1)
+// (c0 = slot index of pts[0]).  Every staged point (one LDS.128 broadcast) and every run header is shared by the lane's K
+// hypotheses: 4 LDS + 32 K arithmetic instructions per four points, so the more hypotheses a lane carries the fewer
+// instructions a pair costs.  Per run the transformed anchor R a + t once per hypothesis (misc.py:108-111 semantics,
+// FP32 contract of oracle/pose_oracle.c).
+template <int K, class POSE>
+__device__ __forceinline__ void score_pass(const float4* __restrict__ pts, const float4* __restrict__ runtab, int nruns,
+                                           const POSE pose, int j0, int nvalid, int i0, int i1, int c0, float cut, int* hcnt) {
+    const int lane = threadIdx.x & 31;
+    int sl[K], cnt[K];
+#pragma unroll
+    for (int u = 0; u < K; ++u) {
+        const int j = j0 + 32 * u + lane;
+        sl[u] = pose.slot(j < nvalid ? j : nvalid - 1);  // idle lanes recompute a valid hypothesis
+        cnt[u] = 0;
+    }
+#pragma unroll 1
+    for (int k = 0; k < nruns; ++k) {
+        const float4 rh = runtab[k];
+        const unsigned se = __float_as_uint(rh.w);
+        int p = max((int)(se & 0xFFFFu), i0) - c0;  // slot -> index into the staged chunk
+        const int e = min((int)(se >> 16), i1) - c0;
+        if (p >= e) continue;
+        float tx[K], ty[K], tz[K];
+#pragma unroll
+        for (int u = 0; u < K; ++u) {
+            float4 r0, r1, r2;
+            pose.rows(sl[u], r0, r1, r2);
+            const float P[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+            xform(P, rh.x, rh.y, rh.z, tx[u], ty[u], tz[u]);
+        }
+#pragma unroll 1
+        for (; p + 4 <= e; p += 4) {
+            const float4 q0 = pts[p], q1 = pts[p + 1], q2 = pts[p + 2], q3 = pts[p + 3];
+#pragma unroll
+            for (int u = 0; u < K; ++u) {
+                count_if_lt(cnt[u], resid2_pt(tx[u], ty[u], tz[u], q0.x, q0.y, q0.z), cut);
+                count_if_lt(cnt[u], resid2_pt(tx[u], ty[u], tz[u], q1.x, q1.y, q1.z), cut);
+                count_if_lt(cnt[u], resid2_pt(tx[u], ty[u], tz[u], q2.x, q2.y, q2.z), cut);
+                count_if_lt(cnt[u], resid2_pt(tx[u], ty[u], tz[u], q3.x, q3.y, q3.z), cut);
+            }
+        }
+#pragma unroll 1
+        for (; p < e; ++p) {
+            const float4 q0 = pts[p];
+#pragma unroll
+            for (int u = 0; u < K; ++u) count_if_lt(cnt[u], resid2_pt(tx[u], ty[u], tz[u], q0.x, q0.y, q0.z), cut);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < K; ++u) {
+        const int j = j0 + 32 * u + lane;
+        if (j < nvalid && cnt[u]) atomicAdd(&hcnt[sl[u]], cnt[u]);
+    }
+}
+
+// cost of one pass per four points, in issue slots (4 LDS + loop + 32 per hypothesis of a lane)
+__device__ __forceinline__ int pass_cost(int k) { return 9 + 32 * k; }
+
+// Warp `wi` of `nw` scores its share of nvalid hypotheses x staged slots [c0, c1): the hypotheses form passes of 4 per
+// lane (128 per pass) plus one last pass of 1..4 per lane, the (pass, point) plane is cut into nw slices of equal
+// cost, one per warp, whatever the number of valid hypotheses (the cut points are rounded to whole points the same way
+// on both sides: nothing is lost or counted twice).  Counts are ADDED to hcnt (shared-memory atomics).
+template <class POSE>
+__device__ __forceinline__ void score_slices(const float4* __restrict__ pts, const float4* __restrict__ runtab, int nruns,
+                                             const POSE pose, int nvalid, int c0, int c1, float cut, int* hcnt, int wi, int nw) {
+    const int nfull = nvalid >> 7;               // passes with 4 hypotheses per lane
+    const int rem = nvalid - (nfull << 7);
+    const int klast = (rem + 31) >> 5;           // 0 .. 4 hypotheses per lane in the last pass
+    const int ctot = nfull * pass_cost(4) + (klast ? pass_cost(klast) : 0);
+    const int m = c1 - c0;
+    const long long tot = (long long)ctot * m;
+    const int lo = (int)(tot * wi / nw), hi = (int)(tot * (wi + 1) / nw);  // tot < 2^31 for H <= 8192 at 1024 staged slots
+    int off = 0;
+    for (int ps = 0; ps < nfull + (klast ? 1 : 0); ++ps) {
+        const int k = ps < nfull ? 4 : klast;
+        const int len = pass_cost(k) * m;
+        const int a0 = lo > off ? lo : off, a1 = hi < off + len ? hi : off + len;
+        if (a0 < a1) {
+            const int i0 = c0 + (a0 - off + pass_cost(k) - 1) / pass_cost(k);
+            const int i1 = c0 + (a1 - off + pass_cost(k) - 1) / pass_cost(k);
+            const int j0 = ps << 7;
+            if (i0 < i1) {
+                if (k == 4) score_pass<4, POSE>(pts, runtab, nruns, pose, j0, nvalid, i0, i1, c0, cut, hcnt);
+                else if (k == 3) score_pass<3, POSE>(pts, runtab, nruns, pose, j0, nvalid, i0, i1, c0, cut, hcnt);
+                else if (k == 2) score_pass<2, POSE>(pts, runtab, nruns, pose, j0, nvalid, i0, i1, c0, cut, hcnt);
+                else score_pass<1, POSE>(pts, runtab, nruns, pose, j0, nvalid, i0, i1, c0, cut, hcnt);
+            }
+        }
+        off += len;
+    }
+}
+
 // misc.py:134-138: k = log10(1-conf) / log10(1 - w^10), stop once i_ransac > max(k, min_iter).  Kept out of line:
 // double pow/log10 are ~1500 instructions that only the (non-default) adaptive mode needs.
 static __device__ __noinline__ bool adaptive_stop(int count, int n, int i_ransac, double log_1m_conf, int min_iter) {

@@ -23,7 +23,7 @@
 // chunk's packages stay in the 126 MB L2 between the kernels.
 #include "solve_common.cuh"
 
-#include <mutex>
+#include <stdlib.h>
 
 namespace rdpn {
 extern unsigned long long g_launch_count;
@@ -77,13 +77,31 @@ __device__ __forceinline__ int warp_min_i(int v) {
     return v;
 }
 
+// ---- per-ROI hand-over flags between the kernels (programmatic dependent launch, see launch_split) ----
+__device__ __forceinline__ void st_release_i32(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// A wait that lasts longer than ~2 s of SM clocks is a protocol bug: trap instead of hanging the device.
+__device__ __forceinline__ void wait_flag(const int* p) {
+    if (ld_acquire_u32(reinterpret_cast<const unsigned*>(p)) != 0u) return;
+    const long long t0 = clock64();
+    unsigned ns = 32;
+    while (ld_acquire_u32(reinterpret_cast<const unsigned*>(p)) == 0u) {
+        __nanosleep(ns);
+        if (ns < 1024) ns <<= 1;
+        if (clock64() - t0 > (1ll << 32)) __trap();
+    }
+}
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // =============================================================================================
 // K1: gate + S1 + sort + hypotheses, one warp per ROI
 // =============================================================================================
 constexpr int FR_W = 4;             // warps (ROIs) per CTA
 constexpr int FR_T = FR_W * 32;
 #ifndef RDPN_FRONT_CTAS
-#define RDPN_FRONT_CTAS 8           // CTAs per SM the register budget is sized for (64 registers per thread)
+#define RDPN_FRONT_CTAS 5           // CTAs per SM the register budget is sized for: 96 registers per thread, no spills
+                                    // (8 CTAs at 64 registers spill the FP64 hypothesis solve: measured 4 % slower overall)
 #endif
 
 struct FrontLayout {  // per-warp shared memory (byte offsets)
@@ -195,10 +213,44 @@ static __device__ __noinline__ bool hyp_from_sample_list(const uint32_t* selmap,
     return true;
 }
 
+// Mask test of one quad -> 4 bits.  L1 mode: the two-sided FP32 filter of gate.cuh decides almost every pixel; the
+// exact FP64 comparison runs only when some lane of the warp has a pixel inside the filter's band (warp vote), so the
+// common path is 4 FADD + 8 FSETP.  Decisions are those of mask_pass(), bit for bit.
+__device__ __forceinline__ unsigned mask_nibble(const float4& m, int mode, float thr, float mn, const RoiGate& g) {
+    const float mm[4] = {m.x, m.y, m.z, m.w};
+    unsigned nib = 0u;
+    if (mode == RDPN_MASK_L1) {
+        if (!(g.b > 0.f)) return 0u;  // flat mask: 0/0 = NaN never passes (engine_utils.py:128 has no eps)
+        unsigned amb = 0u;
+        float av[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            av[j] = __fsub_rn(mm[j], mn);
+            const bool in = av[j] > g.hi, out = av[j] < g.lo;
+            nib |= (in ? 1u : 0u) << j;
+            amb |= ((!in && !out) ? 1u : 0u) << j;
+        }
+        if (__any_sync(0xffffffffu, amb != 0u)) {
+            const double r = __dmul_rn((double)g.b, g.cut);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if ((amb >> j) & 1u) {
+                    const double l = (double)av[j];
+                    if (g.incl ? (l >= r) : (l > r)) nib |= 1u << j;  // NaN -> false
+                }
+        }
+        return nib;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) nib |= (mask_pass(mm[j], mode, thr, mn, g) ? 1u : 0u) << j;
+    return nib;
+}
+
 template <bool MULTI>
 __global__ void __launch_bounds__(FR_T, RDPN_FRONT_CTAS) front_kernel(SolveArgs a, unsigned char* __restrict__ ws, PkgLayout lay,
-                                                                        FrontLayout fl) {
+                                                                        FrontLayout fl, int* __restrict__ fdone) {
     extern __shared__ __align__(128) unsigned char fsm[];
+    pdl_launch_dependents();  // K2's CTAs may take the slots this grid's last wave leaves free; they wait per ROI on fdone
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const rdpn_roi_inputs& in = a.in;
     const int b = blockIdx.x * FR_W + warp;
@@ -220,6 +272,15 @@ __global__ void __launch_bounds__(FR_T, RDPN_FRONT_CTAS) front_kernel(SolveArgs 
     const float4* cz4 = reinterpret_cast<const float4*>(in.coor_z + po);
     const uchar4* rid4 = reinterpret_cast<const uchar4*>(in.region_idx + po);
 
+    // everything this warp will certainly read is requested from DRAM now: the mask plane (128 lines) and the ROI's
+    // hypothesis samples; the other planes are requested per quad in pass 2
+#pragma unroll
+    for (int u = 0; u < 4; ++u) asm volatile("prefetch.global.L2 [%0];" ::"l"(in.mask + po + 32 * (32 * u + lane)));
+    if (a.hyp_idx) {
+        const int hb = a.prm.num_hyp * (MULTI ? a.prm.sample_size : 3) * 4;  // bytes of this ROI's samples
+        const char* hp = reinterpret_cast<const char*>(a.hyp_idx) + (size_t)b * hb;
+        for (int o = 128 * lane; o < hb; o += 128 * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(hp + o));
+    }
     // ---- 0: per-ROI constants (every lane: warp-uniform loads), anchors, zeroed histogram ----
     RoiConst rc;
     rc.fx = __ldg(in.Kp + 4 * b + 0);
@@ -273,10 +334,7 @@ __global__ void __launch_bounds__(FR_T, RDPN_FRONT_CTAS) front_kernel(SolveArgs 
 #pragma unroll
         for (int k8 = 0; k8 < 8; ++k8) {
             const int q = 32 * (8 * kk + k8) + lane;
-            const float mm[4] = {mq[k8].x, mq[k8].y, mq[k8].z, mq[k8].w};
-            unsigned nib = 0u;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) nib |= (mask_pass(mm[j], in.mask_mode, in.mask_thr, rc.mn, gate) ? 1u : 0u) << j;
+            const unsigned nib = mask_nibble(mq[k8], in.mask_mode, in.mask_thr, rc.mn, gate);
             const unsigned bal = __ballot_sync(0xffffffffu, nib != 0u);
             if (nib) {
                 qlist[nq + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)((unsigned)q | (nib << 10));
@@ -406,31 +464,39 @@ __global__ void __launch_bounds__(FR_T, RDPN_FRONT_CTAS) front_kernel(SolveArgs 
         uint8_t* srid_g = pkg + lay.srid;
         uint16_t* pix_g = reinterpret_cast<uint16_t*>(pkg + lay.pix);
 #pragma unroll 1
-        for (int i0 = 0; i0 < n; i0 += 32) {
-            const int i = i0 + lane;
-            const bool valid = i < n;
-            uint32_t kv = 0u;
-            float4 cw = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) {
-                kv = key_g[i];
-                cw = rast_g[i];
+        for (int i0 = 0; i0 < n; i0 += 64) {  // two rounds per trip: both rounds' loads are in flight before the first match
+            uint32_t kv[2] = {0u, 0u};
+            float4 cw[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int i = i0 + 32 * u + lane;
+                cw[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < n) {
+                    kv[u] = key_g[i];
+                    cw[u] = rast_g[i];
+                }
             }
-            const unsigned rid = valid ? (kv >> 16) : (unsigned)R;
-            const unsigned m = __match_any_sync(0xffffffffu, rid);
-            const int leader = __ffs(m) - 1;
-            int c0 = 0;
-            if (valid && lane == leader) {
-                c0 = (int)cur[rid];
-                cur[rid] = (uint32_t)(c0 + __popc(m));
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (i0 + 32 * u >= n) break;  // warp-uniform
+                const bool valid = i0 + 32 * u + lane < n;
+                const unsigned rid = valid ? (kv[u] >> 16) : (unsigned)R;
+                const unsigned m = __match_any_sync(0xffffffffu, rid);
+                const int leader = __ffs(m) - 1;
+                int c0 = 0;
+                if (valid && lane == leader) {
+                    c0 = (int)cur[rid];
+                    cur[rid] = (uint32_t)(c0 + __popc(m));
+                }
+                c0 = __shfl_sync(0xffffffffu, c0, leader);
+                if (valid) {
+                    const int sl = c0 + __popc(m & ((1u << lane) - 1u));
+                    slots_g[sl] = cw[u];
+                    srid_g[sl] = (uint8_t)rid;
+                    pix_g[sl] = (uint16_t)(kv[u] & 0xFFFFu);
+                }
+                __syncwarp();
             }
-            c0 = __shfl_sync(0xffffffffu, c0, leader);
-            if (valid) {
-                const int sl = c0 + __popc(m & ((1u << lane) - 1u));
-                slots_g[sl] = cw;
-                srid_g[sl] = (uint8_t)rid;
-                pix_g[sl] = (uint16_t)(kv & 0xFFFFu);
-            }
-            __syncwarp();
         }
     }
 
@@ -447,11 +513,22 @@ __global__ void __launch_bounds__(FR_T, RDPN_FRONT_CTAS) front_kernel(SolveArgs 
         const int SS = MULTI ? a.prm.sample_size : 3;
         const uint32_t kroi = fmix32(fmix32(a.prm.seed ^ 0x9e3779b9u) ^ (uint32_t)(a.prm.roi_base + b));
         const uint32_t nsel = (uint32_t)n;
+        // explicit samples: the next round's indices are loaded while this round computes
+        int nx0 = -1, nx1 = -1, nx2 = -1;
+        if (!MULTI && !sampling && lane < H) {
+            const int32_t* ip = a.hyp_idx + ((size_t)b * H + lane) * 3;
+            nx0 = __ldg(ip); nx1 = __ldg(ip + 1); nx2 = __ldg(ip + 2);
+        }
 #pragma unroll 1
         for (int h0 = 0; h0 < H; h0 += 32) {
             const int h = h0 + lane;
             float P[12];
             bool ok = false;
+            const int cu0 = nx0, cu1 = nx1, cu2 = nx2;
+            if (!MULTI && !sampling && h + 32 < H) {
+                const int32_t* ip = a.hyp_idx + ((size_t)b * H + h + 32) * 3;
+                nx0 = __ldg(ip); nx1 = __ldg(ip + 1); nx2 = __ldg(ip + 2);
+            }
             if (h < H) {
                 if (MULTI) {
                     ok = hyp_from_sample_list(selmap, selpfx, anchors, rast_g, key_g, reinterpret_cast<int*>(wsm + fl.scr) + lane,
@@ -459,10 +536,9 @@ __global__ void __launch_bounds__(FR_T, RDPN_FRONT_CTAS) front_kernel(SolveArgs 
                 } else {
                     int ii[3];
                     if (!sampling) {
-                        const int32_t* ip = a.hyp_idx + ((size_t)b * H + h) * 3;
-                        ii[0] = __ldg(ip);
-                        ii[1] = __ldg(ip + 1);
-                        ii[2] = __ldg(ip + 2);
+                        ii[0] = cu0;
+                        ii[1] = cu1;
+                        ii[2] = cu2;
                     } else {
 #pragma unroll
                         for (int v = 0; v < 3; ++v) {
@@ -529,6 +605,9 @@ __global__ void __launch_bounds__(FR_T, RDPN_FRONT_CTAS) front_kernel(SolveArgs 
         *reinterpret_cast<int4*>(pkg) = make_int4(n, nruns, nvalid, 0);
         if (a.out.n_sel) a.out.n_sel[b] = n;
     }
+    __threadfence();  // every lane's package writes before the flag
+    __syncwarp();
+    if (lane == 0) st_release_i32(fdone + b, 1);
 }
 
 // =============================================================================================
@@ -564,70 +643,13 @@ static ScoreLayout make_score_layout(int H, int R) {
     return l;
 }
 
-// One pass: K hypotheses per lane (j0 + 32 u + lane, u < K) against the staged slots [i0, i1).  Every staged point (one
-// LDS.128 broadcast) and every run header is shared by the lane's K hypotheses: 4 LDS + 32 K arithmetic instructions per
-// four points, so the more hypotheses a lane carries the fewer instructions a pair costs.  Per run the transformed
-// anchor R a + t once per hypothesis (pose rows from shared memory: conflict-free planar layout).
-template <int K>
-__device__ __forceinline__ void score_pass(const float4* __restrict__ pts, const float4* __restrict__ runtab, int nruns,
-                                           const float4* __restrict__ hyp, int H, int j0, int nvalid, int i0, int i1, int c0,
-                                           float cut, int* hcnt_s) {
-    const int lane = threadIdx.x & 31;
-    int jl[K], cnt[K];
-#pragma unroll
-    for (int u = 0; u < K; ++u) {
-        const int j = j0 + 32 * u + lane;
-        jl[u] = j < nvalid ? j : nvalid - 1;  // idle lanes recompute a valid hypothesis
-        cnt[u] = 0;
-    }
-#pragma unroll 1
-    for (int k = 0; k < nruns; ++k) {
-        const float4 rh = runtab[k];
-        const unsigned se = __float_as_uint(rh.w);
-        int p = max((int)(se & 0xFFFFu), i0) - c0;  // slot -> index into the staged chunk
-        const int e = min((int)(se >> 16), i1) - c0;
-        if (p >= e) continue;
-        float tx[K], ty[K], tz[K];
-#pragma unroll
-        for (int u = 0; u < K; ++u) {
-            const float4 r0 = hyp[jl[u]], r1 = hyp[H + jl[u]], r2 = hyp[2 * H + jl[u]];
-            const float P[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
-            xform(P, rh.x, rh.y, rh.z, tx[u], ty[u], tz[u]);
-        }
-#pragma unroll 1
-        for (; p + 4 <= e; p += 4) {
-            const float4 q0 = pts[p], q1 = pts[p + 1], q2 = pts[p + 2], q3 = pts[p + 3];
-#pragma unroll
-            for (int u = 0; u < K; ++u) {
-                count_if_lt(cnt[u], resid2_pt(tx[u], ty[u], tz[u], q0.x, q0.y, q0.z), cut);
-                count_if_lt(cnt[u], resid2_pt(tx[u], ty[u], tz[u], q1.x, q1.y, q1.z), cut);
-                count_if_lt(cnt[u], resid2_pt(tx[u], ty[u], tz[u], q2.x, q2.y, q2.z), cut);
-                count_if_lt(cnt[u], resid2_pt(tx[u], ty[u], tz[u], q3.x, q3.y, q3.z), cut);
-            }
-        }
-#pragma unroll 1
-        for (; p < e; ++p) {
-            const float4 q0 = pts[p];
-#pragma unroll
-            for (int u = 0; u < K; ++u) count_if_lt(cnt[u], resid2_pt(tx[u], ty[u], tz[u], q0.x, q0.y, q0.z), cut);
-        }
-    }
-#pragma unroll
-    for (int u = 0; u < K; ++u) {
-        const int j = j0 + 32 * u + lane;
-        if (j < nvalid && cnt[u]) atomicAdd(&hcnt_s[j], cnt[u]);
-    }
-}
-
-// cost of one pass per four points, in issue slots (4 LDS + loop + 32 per hypothesis of a lane)
-__device__ __forceinline__ int pass_cost(int k) { return 9 + 32 * k; }
-
 // Non-persistent on purpose: a CTA's synchronisation is one mbarrier wait on its bulk-TMA copy (points, run table and
 // hypothesis poses into shared memory) and one barrier before the counts are written back; the SM's other resident
 // CTAs cover both.  The (pass, point) plane is cut into SC_W slices of equal cost, one per warp, whatever the number
 // of valid hypotheses.
 __global__ void __launch_bounds__(SC_T, RDPN_SCORE_REGS_CTAS) score_kernel(int H, int min_pts, float cut, unsigned char* __restrict__ ws,
-                                                                            PkgLayout lay, ScoreLayout sl) {
+                                                                            PkgLayout lay, ScoreLayout sl, const int* __restrict__ fdone,
+                                                                            int* __restrict__ sdone) {
     extern __shared__ __align__(128) unsigned char sc_raw[];
     const float4* pts = reinterpret_cast<const float4*>(sc_raw + sl.pts);
     const float4* hyp = reinterpret_cast<const float4*>(sc_raw + sl.hyp);
@@ -637,20 +659,22 @@ __global__ void __launch_bounds__(SC_T, RDPN_SCORE_REGS_CTAS) score_kernel(int H
     const int warp = threadIdx.x >> 5;
     const int b = blockIdx.x;
     unsigned char* pkg = ws + (size_t)b * lay.stride;
-    const int4 hd = __ldg(reinterpret_cast<const int4*>(pkg));
-    const int n = hd.x, nruns = hd.y, nvalid = hd.z;
-    if (nvalid <= 0 || n <= 0 || n < min_pts) return;  // uniform across the CTA
+    pdl_launch_dependents();  // K3's warps wait per ROI on sdone
     if (threadIdx.x == 0) {
+        wait_flag(fdone + b);  // this ROI's package is complete (K1 may still be running elsewhere)
+        asm volatile("fence.proxy.async;" ::: "memory");  // written through the generic proxy, read by bulk TMA
         mbar_init(bar, 1);
         mbar_fence_init();
     }
+    __syncthreads();  // package visible, barrier initialised
+    const int4 hd = __ldcg(reinterpret_cast<const int4*>(pkg));
+    const int n = hd.x, nruns = hd.y, nvalid = hd.z;
+    if (nvalid <= 0 || n <= 0 || n < min_pts) {  // uniform across the CTA: nothing to score
+        if (threadIdx.x == 0) st_release_i32(sdone + b, 1);
+        return;
+    }
     for (int j = threadIdx.x; j < nvalid; j += SC_T) hcnt_s[j] = 0;
-    __syncthreads();  // barrier initialised, counts zeroed
-    // passes: as many hypotheses per lane as possible (4), the rest in one last pass
-    const int nfull = nvalid >> 7;               // passes with 4 hypotheses per lane
-    const int rem = nvalid - (nfull << 7);
-    const int klast = (rem + 31) >> 5;           // 0 .. 4 hypotheses per lane in the last pass
-    const int ctot = nfull * pass_cost(4) + (klast ? pass_cost(klast) : 0);
+    __syncthreads();  // counts zeroed
     unsigned phase = 0;
     for (int c0 = 0; c0 < n; c0 += SC_CHUNK) {
         const int c1 = min(n, c0 + SC_CHUNK);
@@ -668,35 +692,16 @@ __global__ void __launch_bounds__(SC_T, RDPN_SCORE_REGS_CTAS) score_kernel(int H
                     bulk_g2s(sc_raw + sl.hyp + (size_t)r * H * 16, pkg + lay.hyp + (size_t)r * H * 16, b_hyp, bar);
             }
         }
-        // this warp's slice of the (pass, point) plane: [lo, hi) in units of cost x point
-        const int m = c1 - c0;
-        const int tot = ctot * m;  // <= (H / 128 + 1) * 137 * SC_CHUNK: far below 2^31 / SC_W for H <= 2048
-        const int lo = tot * warp / SC_W, hi = tot * (warp + 1) / SC_W;
         mbar_wait_backoff(bar, phase & 1);
-        int off = 0;
-        for (int ps = 0; ps < nfull + (klast ? 1 : 0); ++ps) {
-            const int k = ps < nfull ? 4 : klast;
-            const int len = pass_cost(k) * m;
-            const int a0 = lo > off ? lo : off, a1 = hi < off + len ? hi : off + len;
-            if (a0 < a1) {
-                // round the cut points to whole points: both neighbours use the same rounding, nothing is lost or doubled
-                const int i0 = c0 + (a0 - off + pass_cost(k) - 1) / pass_cost(k);
-                const int i1 = c0 + (a1 - off + pass_cost(k) - 1) / pass_cost(k);
-                const int j0 = ps << 7;
-                if (i0 < i1) {
-                    if (k == 4) score_pass<4>(pts, runtab, nruns, hyp, H, j0, nvalid, i0, i1, c0, cut, hcnt_s);
-                    else if (k == 3) score_pass<3>(pts, runtab, nruns, hyp, H, j0, nvalid, i0, i1, c0, cut, hcnt_s);
-                    else if (k == 2) score_pass<2>(pts, runtab, nruns, hyp, H, j0, nvalid, i0, i1, c0, cut, hcnt_s);
-                    else score_pass<1>(pts, runtab, nruns, hyp, H, j0, nvalid, i0, i1, c0, cut, hcnt_s);
-                }
-            }
-            off += len;
-        }
+        score_slices(pts, runtab, nruns, PosePlanar{hyp, H}, nvalid, c0, c1, cut, hcnt_s, warp, SC_W);
         ++phase;
     }
     __syncthreads();  // every warp's partial counts are in
     int* hcnt = reinterpret_cast<int*>(pkg + lay.hcnt);
     for (int j = threadIdx.x; j < nvalid; j += SC_T) hcnt[j] = hcnt_s[j];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_i32(sdone + b, 1);
 }
 
 // =============================================================================================
@@ -711,14 +716,18 @@ constexpr int RF_W = RDPN_REFIT_WARPS;  // warps (ROIs) per CTA
 #endif
 constexpr int RF_U = 4;                 // slots per lane in flight
 
-__global__ void __launch_bounds__(RF_W * 32, RDPN_REFIT_CTAS) refit_kernel(SolveArgs a, const unsigned char* __restrict__ ws, PkgLayout lay) {
+__global__ void __launch_bounds__(RF_W * 32, RDPN_REFIT_CTAS) refit_kernel(SolveArgs a, const unsigned char* __restrict__ ws, PkgLayout lay,
+                                                                           const int* __restrict__ sdone) {
     extern __shared__ __align__(16) unsigned char rf_smem[];  // float[RF_W][3 R]: the ROI's anchors, one row per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.x * RF_W + warp;
     if (b >= a.in.B) return;
     const int H = a.prm.num_hyp;
     const unsigned char* pkg = ws + (size_t)b * lay.stride;
-    const int4 h0 = *reinterpret_cast<const int4*>(pkg);
+    if (lane == 0) wait_flag(sdone + b);  // this ROI's counts are final (K2 may still be running elsewhere)
+    __syncwarp();
+    // package reads below go to L2 (ld.global.cg): the kernels overlap, so this SM's L1 is not known to be clean
+    const int4 h0 = __ldcg(reinterpret_cast<const int4*>(pkg));
     const int n = h0.x, nvalid = h0.z;
     const bool enough = n >= a.prm.min_pts;
     if (a.out.inlier_mask) {  // zero-fill; inliers are scattered in after the last refit
@@ -736,14 +745,14 @@ __global__ void __launch_bounds__(RF_W * 32, RDPN_REFIT_CTAS) refit_kernel(Solve
             const double lc = log10(1.0 - (double)a.prm.confidence);
             int js = 0x7FFFFFFF;
             for (int j = lane; j < nvalid; j += 32)
-                if (adaptive_stop(hcnt[j], n, j + 1, lc, a.prm.min_iter)) js = min(js, j);
+                if (adaptive_stop(__ldcg(hcnt + j), n, j + 1, lc, a.prm.min_iter)) js = min(js, j);
             js = warp_min_i(js);
             if (js != 0x7FFFFFFF) jlim = js + 1;
         }
         unsigned long long kbest = 0ull;
         for (int j = lane; j < nvalid; j += 32) {
-            const int c = hcnt[j];
-            if (a.out.hyp_counts) a.out.hyp_counts[(size_t)b * H + vh[j]] = c;
+            const int c = __ldcg(hcnt + j);
+            if (a.out.hyp_counts) a.out.hyp_counts[(size_t)b * H + __ldcg(vh + j)] = c;
             if (j < jlim && c >= a.prm.min_inliers && c > 0) {
                 const unsigned long long k = ((unsigned long long)(unsigned)c << 32) | (unsigned)(0x7FFFFFFF - j);
                 kbest = k > kbest ? k : kbest;
@@ -776,13 +785,13 @@ __global__ void __launch_bounds__(RF_W * 32, RDPN_REFIT_CTAS) refit_kernel(Solve
         for (int i = lane; i < R3; i += 32) anc[i] = __ldg(ag + i);
         __syncwarp();
     }
-    const int best = (int)vh[best_j];
+    const int best = (int)__ldcg(vh + best_j);
     float P[12];
     {
         const float4* hp = reinterpret_cast<const float4*>(pkg + lay.hyp) + best_j;
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            const float4 v = hp[(size_t)r * H];
+            const float4 v = __ldcg(hp + (size_t)r * H);
             P[4 * r] = v.x; P[4 * r + 1] = v.y; P[4 * r + 2] = v.z; P[4 * r + 3] = v.w;
         }
     }
@@ -793,10 +802,10 @@ __global__ void __launch_bounds__(RF_W * 32, RDPN_REFIT_CTAS) refit_kernel(Solve
     float out_scale = 1.f;
     const int iters = a.prm.refit_iters < 1 ? 1 : a.prm.refit_iters;
     // pivot of the raw moments (exact FP32 differences): slot 0
-    const float4 cp0 = slots[0];
+    const float4 cp0 = __ldcg(slots);
     float4 ap0;
     {
-        const int r0 = 3 * (int)srid[0];
+        const int r0 = 3 * (int)__ldcg(srid);
         ap0 = make_float4(anc[r0], anc[r0 + 1], anc[r0 + 2], 0.f);
     }
     for (int it = 0; it < iters; ++it) {
@@ -814,8 +823,8 @@ __global__ void __launch_bounds__(RF_W * 32, RDPN_REFIT_CTAS) refit_kernel(Solve
             for (int u = 0; u < RF_U; ++u) {  // every load of the batch in flight before the first use
                 const int i = i0 + 32 * u;
                 if (i < n) {
-                    cpv[u] = slots[i];
-                    ridv[u] = (int)srid[i];
+                    cpv[u] = __ldcg(slots + i);
+                    ridv[u] = (int)__ldcg(srid + i);
                 }
             }
 #pragma unroll
@@ -853,11 +862,11 @@ __global__ void __launch_bounds__(RF_W * 32, RDPN_REFIT_CTAS) refit_kernel(Solve
                 if (k < 32) {
                     inl = (marks >> k) & 1u;
                 } else {
-                    const float4 cp = slots[i];
-                    const int r3 = 3 * (int)srid[i];
+                    const float4 cp = __ldcg(slots + i);
+                    const int r3 = 3 * (int)__ldcg(srid + i);
                     inl = resid2(P, anc[r3], anc[r3 + 1], anc[r3 + 2], cp.x, cp.y, cp.z) < cut;
                 }
-                if (inl) a.out.inlier_mask[(size_t)b * RDPN_P + pixs[i]] = 1;
+                if (inl) a.out.inlier_mask[(size_t)b * RDPN_P + __ldcg(pixs + i)] = 1;
             }
         }
         // every lane solves the same 3 x 3 problem (no divergence, no broadcast)
@@ -917,6 +926,10 @@ __global__ void __launch_bounds__(RF_W * 32, RDPN_REFIT_CTAS) refit_kernel(Solve
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
 static SolveArgs shifted(const SolveArgs& a, int b0, int nb) {
     SolveArgs c = a;
     const int H = a.prm.num_hyp, S = a.prm.sample_size, R = a.in.num_regions;
@@ -957,110 +970,88 @@ size_t split_pkg_stride(int H, int R, bool dense) {
     return (size_t)make_layout(H, R).stride;
 }
 
-// Side stream + events of the two-stream schedule, one set per device (created on first use, never destroyed).
-struct PipeStreams {
-    cudaStream_t aux;
-    cudaEvent_t fork, join, front[2], done[2];
-    bool ok;
-};
-static std::mutex g_pipe_mu;
-static PipeStreams g_pipe[64];
-static int pipe_streams(PipeStreams** out) {
-    int dev = 0;
-    RDPN_CUDA_TRY(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) return RDPN_E_BADARG;
-    std::lock_guard<std::mutex> lk(g_pipe_mu);
-    PipeStreams& p = g_pipe[dev];
-    if (!p.ok) {
-        RDPN_CUDA_TRY(cudaStreamCreateWithFlags(&p.aux, cudaStreamNonBlocking));
-        cudaEvent_t* ev[6] = {&p.fork, &p.join, &p.front[0], &p.front[1], &p.done[0], &p.done[1]};
-        for (auto e : ev) RDPN_CUDA_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-        p.ok = true;
-    }
-    *out = &p;
-    return 0;
+// Workspace: [fdone[chunk], sdone[chunk] : int, 128-byte aligned] [chunk packages]
+static size_t flags_bytes(int chunk) { return (2 * (size_t)chunk * sizeof(int) + 127) & ~(size_t)127; }
+
+size_t split_workspace_bytes(int B, int H, int R, int chunk_rois) {
+    int chunk = chunk_rois > 0 && chunk_rois < B ? chunk_rois : B;
+    return flags_bytes(chunk) + (size_t)chunk * make_layout(H, R).stride;
+}
+
+// K2 and K3 are launched with programmatic stream serialisation (PDL): their CTAs may be scheduled as soon as every CTA
+// of the kernel before has STARTED (griddepcontrol.launch_dependents is the first instruction of K1 / K2), i.e. into the
+// SM slots the last, partially filled wave of that kernel leaves free, and each of them waits for exactly the ROI it
+// works on (acquire-load on the ROI's flag) instead of for the whole grid.  No deadlock: a waiting CTA is only ever
+// resident when every CTA it can wait for is resident or done.
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 template <bool MULTI>
-static int launch_front(const SolveArgs& a, unsigned char* ws, const PkgLayout& lay, cudaStream_t st) {
-    const FrontLayout fl = make_front_layout(a.in.num_regions);
-    const size_t smem = (size_t)FR_W * fl.per_warp;
-    if (smem > 227 * 1024) return RDPN_E_TOOLARGE;
-    const int rc = ensure_func_smem((const void*)front_kernel<MULTI>, SLOT_FRONT + (MULTI ? 1 : 0), smem);
-    if (rc) return rc;
-    front_kernel<MULTI><<<(a.in.B + FR_W - 1) / FR_W, FR_T, smem, st>>>(a, ws, lay, fl);
-    ++g_launch_count;
-    RDPN_LAUNCH_CHECK();
-    return 0;
-}
-static int launch_score_refit(const SolveArgs& a, unsigned char* ws, const PkgLayout& lay, cudaStream_t st) {
+static int launch_chunk(const SolveArgs& a, unsigned char* ws, const PkgLayout& lay, cudaStream_t st) {
     const int B = a.in.B, H = a.prm.num_hyp, R = a.in.num_regions;
-    {
+    static const bool pdl = env_int("RDPN_PIPE_PDL", 1) != 0;
+    const size_t fb = flags_bytes(B);
+    int* fdone = reinterpret_cast<int*>(ws);
+    int* sdone = fdone + B;
+    unsigned char* pk = ws + fb;
+    RDPN_CUDA_TRY(cudaMemsetAsync(ws, 0, fb, st));
+    {  // K1
+        const FrontLayout fl = make_front_layout(R);
+        const size_t smem = (size_t)FR_W * fl.per_warp;
+        if (smem > 227 * 1024) return RDPN_E_TOOLARGE;
+        const int rc = ensure_func_smem((const void*)front_kernel<MULTI>, SLOT_FRONT + (MULTI ? 1 : 0), smem);
+        if (rc) return rc;
+        front_kernel<MULTI><<<(B + FR_W - 1) / FR_W, FR_T, smem, st>>>(a, pk, lay, fl, fdone);
+        ++g_launch_count;
+        RDPN_LAUNCH_CHECK();
+    }
+    {  // K2
         const ScoreLayout sl = make_score_layout(H, R);
         if (sl.total > 227 * 1024) return RDPN_E_TOOLARGE;
         const int rc = ensure_func_smem((const void*)score_kernel, SLOT_SCORE, sl.total);
         if (rc) return rc;
-        score_kernel<<<B, SC_T, sl.total, st>>>(H, a.prm.min_pts, a.sq_cut, ws, lay, sl);
+        RDPN_CUDA_TRY(launch_pdl(score_kernel, dim3(B), dim3(SC_T), sl.total, st, pdl, H, a.prm.min_pts, a.sq_cut, pk, lay, sl,
+                                 (const int*)fdone, sdone));
         ++g_launch_count;
-        RDPN_LAUNCH_CHECK();
     }
-    {
+    {  // K3
         const size_t smem = (size_t)RF_W * 3 * R * sizeof(float);
         const int rc = ensure_func_smem((const void*)refit_kernel, SLOT_REFIT, smem);
         if (rc) return rc;
-        refit_kernel<<<(B + RF_W - 1) / RF_W, RF_W * 32, smem, st>>>(a, ws, lay);
+        RDPN_CUDA_TRY(launch_pdl(refit_kernel, dim3((B + RF_W - 1) / RF_W), dim3(RF_W * 32), smem, st, pdl, a, (const unsigned char*)pk,
+                                 lay, (const int*)sdone));
         ++g_launch_count;
-        RDPN_LAUNCH_CHECK();
     }
     return 0;
 }
 
-// Schedule.  One chunk: K1 -> K2 -> K3 on the caller's stream.  Several chunks and room for two package buffers: K1
-// of chunk c + 1 (latency-bound, a third of the issue slots) runs on the caller's stream WHILE K2 / K3 of chunk c
-// (issue-bound) run on a side stream; a chunk is sized so that K1's grid takes about half of the SMs' warp slots and
-// the block scheduler co-locates the two kernels.  Fork / join by events: the call stays asynchronous and capturable.
+// K1 -> K2 -> K3 on the caller's stream, in chunks of as many ROIs as the workspace holds (chunk_rois caps it).
 int launch_split(const SolveArgs& a, bool dense, void* ws, size_t ws_bytes, int chunk_rois, cudaStream_t st) {
     if (dense) return RDPN_E_TOOLARGE;
     const int H = a.prm.num_hyp, R = a.in.num_regions, B = a.in.B;
     const PkgLayout lay = make_layout(H, R);
     if (!ws || ((uintptr_t)ws & 127)) return RDPN_E_WORKSPACE;
-    size_t cap = ws_bytes / lay.stride;
-    if (cap < 1) return RDPN_E_WORKSPACE;
+    int chunk = chunk_rois > 0 && chunk_rois < B ? chunk_rois : B;
+    while (chunk > 1 && flags_bytes(chunk) + (size_t)chunk * lay.stride > ws_bytes) chunk = (chunk + 1) / 2;
+    if (flags_bytes(chunk) + (size_t)chunk * lay.stride > ws_bytes) return RDPN_E_WORKSPACE;
     const bool multi = a.prm.sample_size > 3;
-    int chunk = chunk_rois > 0 ? chunk_rois : B;
-    if (chunk > B) chunk = B;
-    const bool two = B > chunk && cap >= 2 * (size_t)chunk;  // two buffers of one chunk each
-    if (!two) {
-        if ((size_t)chunk > cap) chunk = (int)cap;
-        for (int b0 = 0; b0 < B; b0 += chunk) {
-            const SolveArgs c = shifted(a, b0, B - b0 < chunk ? B - b0 : chunk);
-            int rc = multi ? launch_front<true>(c, (unsigned char*)ws, lay, st) : launch_front<false>(c, (unsigned char*)ws, lay, st);
-            if (!rc) rc = launch_score_refit(c, (unsigned char*)ws, lay, st);
-            if (rc) return rc;
-        }
-        return 0;
-    }
-    PipeStreams* ps = nullptr;
-    int rc = pipe_streams(&ps);
-    if (rc) return rc;
-    RDPN_CUDA_TRY(cudaEventRecord(ps->fork, st));
-    RDPN_CUDA_TRY(cudaStreamWaitEvent(ps->aux, ps->fork, 0));
-    int ci = 0;
-    for (int b0 = 0; b0 < B; b0 += chunk, ++ci) {
-        const int buf = ci & 1;
-        unsigned char* w = (unsigned char*)ws + (size_t)buf * chunk * lay.stride;
+    for (int b0 = 0; b0 < B; b0 += chunk) {
         const SolveArgs c = shifted(a, b0, B - b0 < chunk ? B - b0 : chunk);
-        if (ci >= 2) RDPN_CUDA_TRY(cudaStreamWaitEvent(st, ps->done[buf], 0));  // K3 of chunk ci - 2 is done with the buffer
-        rc = multi ? launch_front<true>(c, w, lay, st) : launch_front<false>(c, w, lay, st);
+        const int rc = multi ? launch_chunk<true>(c, (unsigned char*)ws, lay, st) : launch_chunk<false>(c, (unsigned char*)ws, lay, st);
         if (rc) return rc;
-        RDPN_CUDA_TRY(cudaEventRecord(ps->front[buf], st));
-        RDPN_CUDA_TRY(cudaStreamWaitEvent(ps->aux, ps->front[buf], 0));
-        rc = launch_score_refit(c, w, lay, ps->aux);
-        if (rc) return rc;
-        RDPN_CUDA_TRY(cudaEventRecord(ps->done[buf], ps->aux));
     }
-    RDPN_CUDA_TRY(cudaEventRecord(ps->join, ps->aux));
-    RDPN_CUDA_TRY(cudaStreamWaitEvent(st, ps->join, 0));
     return 0;
 }
 
