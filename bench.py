@@ -1,28 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- ROI poses/sec of the dense-correspondence -> pose path (backproject + residual + mask
-gate + RANSAC scoring + Kabsch refit) on N B200s of one node.
+gate + RANSAC scoring + weighted Kabsch refit) on N B200s of one node.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one pass of the fused solver (one kernel launch) over one batch of synthetic ROIs.  The
-workload at N=1 is BASELINE.json configs[1]: LM-O, 8 objects, 1024 ROIs, 256 hypotheses/ROI; at N>1
-every rank processes its own 1024-ROI shard per step (weak scaling); the [shard,16] result rows of the timed
-steps are collected on the device and all-gathered over NCCL once, inside the timed region, as the reference
-gathers its predictions once per evaluation (gdrn_evaluator.py:439-442); --gather-every G gathers after every
-G steps instead (G = 1: every step, pipelined behind the next step's kernel).
+Workloads (BASELINE.json `configs`):
+  N = 1   configs[2]: YCB-V, 21 object models of which 5 symmetric, ONE batch of 8192 ROIs (64x64 maps: depth +
+          residual xyz + mask + region id), 256 RANSAC hypotheses/ROI, 32 anchors/object, camera of ref/ycbv.py:89,
+          weighted Kabsch refit.  A step = one rdpn_pose_solve call over the batch.  The 705 MB of maps of one batch
+          exceed the 126 MB L2, and two input sets alternate.  configs[1] (LM-O, 1024 ROIs, 64 anchors) rides along as
+          the `lmo` key and configs[3] (FPS, 1 M points -> 8 / 64 / 512) as the `fps` key.
+  N > 1   configs[4]: ONE job of 65 536 ROIs (the YCB-V maps tiled), STRONG scaling: rank r solves the contiguous shard
+          the reference's InferenceSampler would give it (core/utils/my_distributed_sampler.py:189-192) with roi_base =
+          its first ROI, and the [shard,16] result rows of every step are all-gathered over NCCL inside the timed region
+          (gdrn_evaluator.py:439-442 gathers the predictions), the gather of step i overlapping the solve of step i + 1.
+          A step = one pass over the whole job.  After the timed region rank 0 solves the WHOLE job alone and demands
+          that the gathered block equals it bit for bit (`parity.gather_vs_single_gpu`).
 
-One JSON line is printed by rank 0 (see the keys at the bottom).  `value` is device-resident
-throughput (inputs already in HBM), `e2e` is the same metric through the host-buffer C-ABI plugin entry with every
-input and output in pinned host memory (transfers + kernels + results inside the timed region): the asynchronous
-pair rdpn_pose_solve_host_submit / rdpn_ctx_wait in a loop of depth 2 (step i + 1 is submitted before step i is
-waited for, so the bus stays busy across steps); `e2e_synchronous` is one synchronous rdpn_pose_solve_host call per
-step.  With pinned buffers the library uses its gated-pull transfer: the mask planes are copied, depth /
-coor / region ids are fetched over PCIe only where the mask test passes; `e2e_full_copy` is the synchronous call with
-every tensor copied, `h2d_bytes_per_step` is measured by the library.
+One JSON line is printed by rank 0 (keys at the bottom).  `value` is device-resident throughput (inputs already in
+HBM); `e2e` is the same metric through the host-buffer C-ABI plugin entry with every input and output in pinned host
+memory (transfers + kernels + results inside the timed region): the asynchronous pair rdpn_pose_solve_host_submit /
+rdpn_ctx_wait in a loop of depth 2.  `parity` compares the timed workload with the CPU oracle (every unique ROI) outside
+the timed region.  `roofline` / `fp32` / `kernels` give the per-kernel durations measured with CUDA events in this run.
 
---impl reference times the CPU implementation of the same path (the oracle port of the reference's
-functions, oracle/pose_oracle.py + oracle/pose_oracle.c) on all host cores.
+--impl reference times the CPU implementation of the same path (the oracle port of the reference's functions,
+oracle/pose_oracle.py + oracle/pose_oracle.c) on all host cores, on the same workload.
 """
 import argparse
 import ctypes
@@ -40,62 +43,69 @@ if ROOT not in sys.path:
 
 METRIC = "ROI poses/sec (backproject+residual+RANSAC-Kabsch)"
 UNIT = "ROI poses/s"
-ROIS_PER_GPU = 1024
-NUM_HYP = 256
-NUM_OBJECTS = 8
-NUM_REGIONS = 64  # LM-O config: NUM_REGIONS=64 (configs/gdrn/lmo/...40e.py:63)
 INLIER_THR = 0.005
-N_INPUT_SETS = 4  # rotating input sets so every step reads its ROI maps from HBM, not L2
-# algorithmic bytes per ROI (DESIGN.md "Kernels"): maps 5 x 16384 + 4096 region ids, hypothesis triplets
-# H x 12, anchors R x 12, Kp 16, extent 12, outputs 12 x 4 + 5 x 4
-BYTES_MAPS = 5 * 16384 + 4096
+JOB_ROIS = 65536  # configs[4]
+# name: rois per batch, hypotheses, anchors per object, object models, symmetric ones, camera, unique ROIs generated
+# (numpy ray casting; they are tiled to the batch size), occlusion U(0, max), seeds
+WORKLOADS = {
+    "ycbv": dict(rois=8192, H=256, R=32, objects=21, symmetric=5, K="ycbv", unique=84, occlusion=0.5, seed=777, model_seed=7,
+                 title="YCB-V 21-object batch of 8192 ROIs incl. 5 symmetric objects (BASELINE configs[2])"),
+    "lmo": dict(rois=1024, H=256, R=64, objects=8, symmetric=0, K="lm", unique=128, occlusion=0.6, seed=20260101, model_seed=1,
+                title="LM-O 8-object batch of 1024 ROIs, 256 RANSAC hypotheses/ROI (BASELINE configs[1])"),
+}
+BYTES_MAPS = 5 * 16384 + 4096  # five FP32 planes + region ids per ROI
 
 
 def bytes_per_roi(H, R):
+    """algorithmic bytes per ROI: maps, hypothesis triplets H x 12, anchors R x 12, Kp 16,
+    extent 12, outputs 12 x 4 + 5 x 4"""
     return BYTES_MAPS + H * 12 + R * 12 + 16 + 12 + 48 + 20
 
 
-def ncu_traffic_bytes(path=None):
-    """DRAM bytes (read + write) of ONE launch of the fused solver on this workload, from the committed
-    `ncu --set full` capture (profiles/r1/ncu_pose_solve_summary.csv); None when the summary is absent."""
-    import csv
+def make_base(name):
+    """The unique ROIs of a workload (numpy)."""
+    from rdpn6d_b200 import synth
 
-    path = path or os.path.join(ROOT, "profiles", "r1", "ncu_pose_solve_summary.csv")
-    try:
-        rows = list(csv.reader(open(path)))
-        hdr, units, vals = rows[0], rows[1], rows[2]
-        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        tot = 0.0
-        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            i = hdr.index(name)
-            tot += float(vals[i]) * scale[units[i]]
-        return tot
-    except Exception:
-        return None
+    w = WORKLOADS[name]
+    models = synth.make_models(w["objects"], w["R"], seed=w["model_seed"], n_symmetric=w["symmetric"])
+    return synth.make_batch(w["unique"], models=models, H=w["H"], seed=w["seed"], K=synth.K_YCBV if w["K"] == "ycbv" else synth.K_LM,
+                            occlusion_max=w["occlusion"])
+
+
+def tile(base, n, start=0):
+    """ROIs [start, start + n) of the endless tiling of `base` (numpy dict)."""
+    out = {}
+    u = next(v for v in base.values() if v is not None).shape[0]
+    idx = (np.arange(start, start + n) % u)
+    for k, v in base.items():
+        out[k] = None if v is None else np.ascontiguousarray(v[idx])
+    return out
 
 
 def workload_config(n_gpus):
+    w = WORKLOADS["ycbv"]
+    if n_gpus == 1:
+        return {
+            "workload": w["title"] + ": 64x64 maps (depth + residual xyz + mask + region id), %d hypotheses/ROI, %d anchors/object, "
+                        "camera ref/ycbv.py:89" % (w["H"], w["R"]),
+            "rois_per_step": w["rois"], "hypotheses": w["H"], "num_regions": w["R"], "inlier_thr_m": INLIER_THR,
+            "refit": "weighted Kabsch on the winner's inliers (mask probability weights), 1 iteration",
+            "l2": "one batch of maps = %.0f MB > 126 MB L2; two input sets alternate" % (w["rois"] * BYTES_MAPS / 1e6),
+            "streams": "one CUDA stream, one rdpn_pose_solve call per step (pipeline of three kernels chained by programmatic "
+                       "dependent launch); timed with CUDA events on that stream",
+            "parallelism": "single GPU",
+        }
     return {
-        "workload": "LM-O 8-object batch of %d ROIs/GPU (64x64 maps: depth + residual xyz + mask + region id), "
-                    "%d RANSAC hypotheses/ROI, %d anchors/object" % (ROIS_PER_GPU, NUM_HYP, NUM_REGIONS),
-        "rois_per_gpu": ROIS_PER_GPU, "global_rois_per_step": ROIS_PER_GPU * n_gpus, "hypotheses": NUM_HYP,
-        "num_regions": NUM_REGIONS, "inlier_thr_m": INLIER_THR, "refit": "unweighted Kabsch on inliers, 1 iteration",
-        "l2": "%d rotating input sets (%.0f MB) > 126 MB L2" % (N_INPUT_SETS, N_INPUT_SETS * ROIS_PER_GPU * BYTES_MAPS / 1e6),
-        "streams": "steps alternate over 2 CUDA streams (launch tails overlap); timed with events on the parent stream",
-        "parallelism": "roi-shard x%d, one NCCL all-gather of the [steps*shard,16] result rows inside the timed region "
-                       "(the reference gathers once per evaluation, gdrn_evaluator.py:439-442)" % n_gpus if n_gpus > 1
-                       else "single GPU",
+        "workload": "MP6D-scale job of %d ROIs (BASELINE configs[4]; the YCB-V maps of configs[2] tiled), sharded over %d GPUs by the "
+                    "InferenceSampler rule, NCCL all-gather of the [shard,16] pose rows every step" % (JOB_ROIS, n_gpus),
+        "rois_per_step": JOB_ROIS, "rois_per_gpu": -(-JOB_ROIS // n_gpus), "hypotheses": w["H"], "num_regions": w["R"],
+        "inlier_thr_m": INLIER_THR, "refit": "weighted Kabsch on the winner's inliers, 1 iteration",
+        "l2": "a shard's maps (%.0f MB) exceed the 126 MB L2" % (-(-JOB_ROIS // n_gpus) * BYTES_MAPS / 1e6),
+        "streams": "solve on one stream, the all-gather of step i on a second stream overlapping the solve of step i + 1; "
+                   "timed with CUDA events, max over ranks",
+        "parallelism": "roi-shard x%d (strong scaling of one %d-ROI job), one all_gather_into_tensor per step inside the timed "
+                       "region" % (n_gpus, JOB_ROIS),
     }
-
-
-def make_workload(seed=20260101, n_unique=128):
-    """configs[1]: 8 object models cycled, occlusion cut-outs U(0,60)%.  128 unique ROIs are
-    generated and tiled to 1024 (generation is numpy ray casting; uniqueness does not change the work)."""
-    from rdpn6d_b200 import synth
-
-    models = synth.make_models(NUM_OBJECTS, NUM_REGIONS, seed=1)
-    base = synth.make_batch(n_unique, models=models, H=NUM_HYP, seed=seed, occlusion_max=0.6)
-    return synth.tile_batch(base, ROIS_PER_GPU)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -115,7 +125,7 @@ def _cpu_solve_range(rng):
 
     b0, b1 = rng
     sub = {k: (None if v is None else v[b0:b1]) for k, v in _CPU_BATCH.items()}
-    res = po.pose_solve_batch(sub, sub["hyp_idx"], INLIER_THR)
+    res = po.pose_solve_batch(sub, sub["hyp_idx"], INLIER_THR, weighted=True)
     return [r["status"] for r in res]
 
 
@@ -153,6 +163,30 @@ def _cpu_as_run_range(rng):
     return n_ok
 
 
+def _cpu_loader_as_written_range(rng):
+    """The loader's back-projection AS WRITTEN (core/gdrn_modeling/data_loader.py:537-576): per ROI two 256 x 256 pixel
+    maps built by nested Python list comprehensions, float32 arithmetic on the full crop, then the [:, ::4, ::4] of :625.
+    Timing only (its arithmetic is what oracle.backproject_roi restates on the 64 x 64 grid)."""
+    b0, b1 = rng
+    c = _CPU_BATCH
+    acc = 0.0
+    for b in range(b0, b1):
+        rows, cols = 256, 256
+        ymap = np.array([[j for i in range(cols)] for j in range(rows)]).astype(np.float32)
+        xmap = np.array([[i for i in range(cols)] for j in range(rows)]).astype(np.float32)
+        depth = np.repeat(np.repeat(c["depth"][b], 4, axis=0), 4, axis=1)[:, :, np.newaxis]  # stand-in for the 256 x 256 crop
+        fx, fy, cx, cy = [float(v) for v in c["Kp"][b]]
+        pt2 = depth.astype(np.float32)
+        pt0 = (xmap[:, :, np.newaxis] - cx) * pt2 / fx
+        pt1 = (ymap[:, :, np.newaxis] - cy) * pt2 / fy
+        xyz = np.concatenate((pt0, pt1, pt2), axis=2).transpose(2, 0, 1)[:, ::4, ::4]
+        acc += float(xyz[2, 0, 0])
+    return acc
+
+
+_CPU_FNS = {"port": _cpu_solve_range, "as_run": _cpu_as_run_range, "loader_as_written": _cpu_loader_as_written_range}
+
+
 def run_cpu(batch, n_rois, fn, cores, min_seconds=0.0, max_rounds=64):
     """Throughput (ROIs/s) of `fn` over the first n_rois ROIs on `cores` processes; repeats the sample until
     min_seconds of wall time has been measured."""
@@ -163,11 +197,11 @@ def run_cpu(batch, n_rois, fn, cores, min_seconds=0.0, max_rounds=64):
     ranges = [(i, min(i + chunk, n_rois)) for i in range(0, n_rois, chunk)]
     ctx = mp.get_context("fork")
     with ctx.Pool(cores, initializer=_cpu_init, initargs=(batch,)) as pool:
-        pool.map(_cpu_solve_range if fn == "port" else _cpu_as_run_range, ranges[:cores])  # warm-up (imports, page-in)
+        pool.map(_CPU_FNS[fn], ranges[:cores])  # warm-up (imports, page-in)
         t0 = time.perf_counter()
         rounds = 0
         while True:
-            pool.map(_cpu_solve_range if fn == "port" else _cpu_as_run_range, ranges)
+            pool.map(_CPU_FNS[fn], ranges)
             rounds += 1
             dt = time.perf_counter() - t0
             if dt >= min_seconds or rounds >= max_rounds:
@@ -190,7 +224,7 @@ def cpu_baseline_leg(batch):
     v1, dt1, r1 = run_cpu(batch, 32, "port", 1, min_seconds=1.0)
     out = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
            "sample": "first %d ROIs of the workload x %d passes, multiprocessing Pool(%d) over ROIs, "
-                     "oracle/pose_oracle.py (numpy float32 S1 + C float32 scoring + numpy SVD Kabsch)" % (n, rounds, cores),
+                     "oracle/pose_oracle.py (numpy float32 S1 + C float32 scoring + numpy SVD weighted Kabsch)" % (n, rounds, cores),
            "single_core_value": v1}
     try:
         va, _, _ = run_cpu(batch, 64, "as_run", cores, min_seconds=2.0)
@@ -200,6 +234,11 @@ def cpu_baseline_leg(batch):
     except Exception as e:  # cv2 missing on the box: the port number stands alone
         out["as_run_cv2_value"] = None
         out["as_run_cv2_note"] = "unavailable: %r" % (e,)
+    vl, _, _ = run_cpu(batch, 2 * cores, "loader_as_written", cores, min_seconds=2.0, max_rounds=8)
+    out["loader_as_written_value"] = vl
+    out["loader_as_written_note"] = ("back-projection only, as the loader writes it (data_loader.py:537-576: per-ROI pixel maps by "
+                                     "nested list comprehensions on the 256 x 256 crop); the port above evaluates the same formula "
+                                     "vectorised on the 64 x 64 grid the network consumes")
     return out
 
 
@@ -211,7 +250,7 @@ def reference_arm(args):
     import oracle
 
     oracle.liboracle()
-    batch = make_workload()
+    batch = tile(make_base("ycbv"), 256)
     cores = host_cores()
     n = 256  # bounded sample per step
     import multiprocessing as mp
@@ -229,10 +268,11 @@ def reference_arm(args):
     value = n * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak" if args.gpus == 1 else "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": min(cores, n), "kind": "port",
-                         "sample": "each step = first %d ROIs of the workload through oracle/pose_oracle.py on a "
+                         "sample": "each step = the first %d ROIs of the workload through oracle/pose_oracle.py (weighted refit) on a "
                                    "multiprocessing Pool(%d)" % (n, min(cores, n))},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -293,12 +333,89 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def step_noacc(plans, streams, i):
-    """Pre-heat step: the kernel only (no row collection, no collective)."""
+def _to_dev(b, dev, shift=0):
+    """distinct device copies; rolling the ROI order makes each set a different address stream"""
     import torch
 
-    with torch.cuda.stream(streams[i % 2]):
-        plans[i % N_INPUT_SETS].launch()
+    out = {}
+    for k, v in b.items():
+        out[k] = None if v is None else torch.from_numpy(np.roll(v, shift, axis=0).copy() if shift else v).to(dev)
+    return out
+
+
+def _plan(solver, s, roi_base=0):
+    from rdpn6d_b200 import pose_solver
+
+    return pose_solver.make_plan(solver, s["depth"], s["Kp"], s["coor"][:, 0].contiguous(), s["coor"][:, 1].contiguous(),
+                                 s["coor"][:, 2].contiguous(), s["mask"], s["extent"], s["hyp_idx"], s["region_idx"], s["anchors"],
+                                 roi_base=roi_base)
+
+
+def _ev_ms(fn, iters, warm=3):
+    import torch
+
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def parity_vs_oracle(base, res, weighted=True):
+    """The first len(base) ROIs of a device result against the CPU oracle on the same inputs and hypothesis index sets:
+    winner / inlier count / status must be identical (bit-exact integer work), poses within the north_star tolerance."""
+    from oracle import pose_oracle as po
+
+    U = base["depth"].shape[0]
+    outs = po.pose_solve_batch(base, base["hyp_idx"], INLIER_THR, weighted=weighted)
+    pose = res.pose[:U].cpu().numpy().astype(np.float64)
+    ninl, status, best = res.n_inliers[:U].cpu().numpy(), res.status[:U].cpu().numpy(), res.best_h[:U].cpu().numpy()
+    nsel = res.n_sel[:U].cpu().numpy()
+    bad_count = bad_status = bad_winner = bad_nsel = 0
+    max_re = max_te = 0.0
+    for b, o in enumerate(outs):
+        bad_status += int(o["status"] != status[b])
+        bad_nsel += int(o["n_sel"] != nsel[b])
+        if o["status"] != 0 or status[b] != 0:
+            continue
+        bad_count += int(o["n_inl"] != ninl[b])
+        bad_winner += int(o["best_h"] != best[b])
+        max_re = max(max_re, po.re_rad_small(pose[b, :, :3], o["pose"][:, :3]))
+        max_te = max(max_te, po.te(pose[b, :, 3], o["pose"][:, 3]))
+    return {"rois_checked": U, "count_mismatch": bad_count, "winner_mismatch": bad_winner, "status_mismatch": bad_status,
+            "gated_count_mismatch": bad_nsel, "max_re_rad": max_re, "max_te_m": max_te,
+            "tolerance": "counts / winner / status bit-exact; rotation 1e-5 rad, translation 1e-6 m (1e-3 mm) in FP32 (north_star)",
+            "ok": bool(bad_count == 0 and bad_winner == 0 and bad_status == 0 and bad_nsel == 0 and max_re <= 1e-5 and max_te <= 1e-6)}
+
+
+def fps_block(dev):
+    """BASELINE configs[3]: 1 M-point cloud -> 8 / 64 / 512 keypoints, the reference's own C++ build beside it."""
+    import torch
+
+    from oracle import libfps_ref
+    from oracle.fps import fps_indices_port, fps_indices_reference
+    from rdpn6d_b200 import fps_utils, synth
+
+    cloud = synth.fps_cloud(1_000_000, seed=0)
+    t = torch.from_numpy(cloud).to(dev)
+    have_ref = libfps_ref() is not None
+    out = {"n_points": 1_000_000, "cpu_kind": "reference" if have_ref else "port",
+           "cpu_note": "core/csrc/fps/src/farthest_point_sampling.cpp compiled by oracle/Makefile (oracle/_ref/libfps_ref.so), one host core"
+                       if have_ref else "oracle/fps_oracle.c (the reference build is absent), one host core", "runs": []}
+    for k in (8, 64, 512):
+        ms = _ev_ms(lambda i: fps_utils.fps_indices(t, k), 10)
+        idx = fps_utils.fps_indices(t, k).cpu().numpy()
+        t0 = time.perf_counter()
+        ref = (fps_indices_reference if have_ref else fps_indices_port)(cloud, k)
+        cpu_ms = 1e3 * (time.perf_counter() - t0)
+        out["runs"].append({"k": k, "ms": ms, "us_per_pick": 1e3 * ms / k, "cpu_ms": cpu_ms, "speedup": cpu_ms / ms,
+                            "bit_exact": bool(np.array_equal(idx, ref))})
+    return out
 
 
 def gpu_arm(args):
@@ -310,19 +427,23 @@ def gpu_arm(args):
         from rdpn6d_b200.distributed import bind_to_gpu_numa_node
 
         numa_node = bind_to_gpu_numa_node(local_rank)
-    batch = make_workload()
+    W = WORKLOADS["ycbv"]
+    H, R = W["H"], W["R"]
+    base = make_base("ycbv")
+    base_lmo = make_base("lmo") if world == 1 else None
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle
 
         oracle.liboracle()
-        cpu_base = cpu_baseline_leg(batch)  # before CUDA is initialised in this process (fork safety)
+        cpu_base = cpu_baseline_leg(tile(base, 256))  # before CUDA is initialised in this process (fork safety)
 
     import torch
     import torch.distributed as dist
 
     from rdpn6d_b200 import _lib, pose_solver
+    from rdpn6d_b200.distributed import shard_range, shard_size
 
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
@@ -332,112 +453,82 @@ def gpu_arm(args):
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
 
-    def to_dev(b, shift):
-        # distinct device copies; rolling the ROI order makes each set a different address stream
-        out = {}
-        for k, v in b.items():
-            if v is None:
-                out[k] = None
-            else:
-                out[k] = torch.from_numpy(np.roll(v, shift, axis=0).copy()).to(dev)
-        return out
+    total = W["rois"] if world == 1 else JOB_ROIS
+    begin, end = shard_range(total, rank, world)
+    B = end - begin                       # this rank's ROIs per step
+    shard = shard_size(total, world)      # padded shard of the fixed-size all-gather
+    host_batch = tile(base, B, start=begin)
+    nsets = 2 if world == 1 else 1
+    sets = [_to_dev(host_batch, dev, 37 * i) for i in range(nsets)]
+    solver = pose_solver.PoseSolver(inlier_thr=INLIER_THR, weighted=True)
+    if world == 1:
+        plans = [_plan(solver, s) for s in sets]
+    else:  # two plans on the same inputs: double-buffered result rows for the overlapped gather
+        plans = [_plan(solver, sets[0], roi_base=begin) for _ in range(2)]
+    nplans = len(plans)
 
-    sets = [to_dev(batch, 37 * i) for i in range(N_INPUT_SETS)]
-    solver = pose_solver.PoseSolver(inlier_thr=INLIER_THR)
-    plans = [pose_solver.make_plan(solver, s["depth"], s["Kp"], s["coor"][:, 0].contiguous(), s["coor"][:, 1].contiguous(),
-                                   s["coor"][:, 2].contiguous(), s["mask"], s["extent"], s["hyp_idx"], s["region_idx"],
-                                   s["anchors"]) for s in sets]
-    B, H, R = ROIS_PER_GPU, NUM_HYP, NUM_REGIONS
-    total = B * world
-    G = args.gather_every if args.gather_every > 0 else max(args.steps, 1)  # steps per gather
-    acc = gathered = None
-    if world > 1:
-        acc = [torch.empty(G, B, 16, dtype=torch.float32, device=dev) for _ in range(2)]  # rows of the current / previous group
-        gathered = [torch.empty(world * G, B, 16, dtype=torch.float32, device=dev) for _ in range(2)]
-
-    # consecutive steps alternate over two streams so that the tail of one launch (the last CTAs of a
-    # 1024-ROI grid leave most SMs idle) overlaps the head of the next -- a continuous ROI stream does the same
-    streams = [torch.cuda.Stream(dev) for _ in range(2)]
-    state = {"pending": None}
+    comp = torch.cuda.Stream(dev)
+    gath = torch.cuda.Stream(dev) if world > 1 else None
+    gathered = [torch.zeros(world * shard, 16, dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
+    send = [torch.zeros(shard, 16, dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
+    ev_solve = [torch.cuda.Event() for _ in range(2)]
+    ev_gath = [torch.cuda.Event() for _ in range(2)]
 
     def step(i):
-        with torch.cuda.stream(streams[i % 2]):
-            p = plans[i % N_INPUT_SETS]
-            res = p.launch()
+        k = i % nplans
+        with torch.cuda.stream(comp):
+            if world > 1 and i >= 2:
+                comp.wait_event(ev_gath[k])  # the rows of plan k (step i - 2) have been sent
+            res = plans[k].launch(comp)
             if world > 1:
-                acc[(i // G) % 2][i % G].copy_(res.rows16(), non_blocking=True)
-        if world > 1 and (i % G) == G - 1:
-            gather_group((i // G) % 2)
-        return res
+                send[k][:B].copy_(res.rows, non_blocking=True)
+                ev_solve[k].record(comp)
+        if world > 1:
+            with torch.cuda.stream(gath):
+                gath.wait_event(ev_solve[k])
+                dist.all_gather_into_tensor(gathered[k].view(-1), send[k].view(-1))
+                ev_gath[k].record(gath)
 
-    def gather_group(g):
-        """All-gather the rows of group g (both compute streams must have finished writing them)."""
-        gs = torch.cuda.current_stream(dev)
-        for st in streams:
-            ev = torch.cuda.Event()
-            ev.record(st)
-            gs.wait_event(ev)
-        if state["pending"] is not None:
-            state["pending"].wait()
-        state["pending"] = dist.all_gather_into_tensor(gathered[g].view(-1),
-                                                       acc[g].reshape(-1), async_op=True)
-
-    def fork():  # both streams start after everything already queued on the current stream
+    def fork():
         ev = torch.cuda.Event()
         ev.record()
-        for st in streams:
-            st.wait_event(ev)
+        comp.wait_event(ev)
+        if gath is not None:
+            gath.wait_event(ev)
 
-    def join():  # the current stream continues after both streams
-        for st in streams:
-            ev = torch.cuda.Event()
-            ev.record(st)
-            torch.cuda.current_stream().wait_event(ev)
+    def join():
+        cur = torch.cuda.current_stream()
+        for st in (comp, gath):
+            if st is not None:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                cur.wait_event(ev)
 
-    def drain(n_steps):
-        """Gather a trailing partial group and wait for the last collective."""
-        if world > 1:
-            if n_steps % G:
-                gather_group(((n_steps - 1) // G) % 2)
-            if state["pending"] is not None:
-                state["pending"].wait()
-                state["pending"] = None
+    def run(n):
+        fork()
+        for i in range(n):
+            step(i)
+        join()
 
-    fork()
     nw = max(args.warmup, 3)
-    for i in range(nw):
-        step(i)
-    join()
-    drain(nw)
+    run(nw)
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank if os.environ.get("CUDA_VISIBLE_DEVICES") is None else
                            int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
     sampler.start()
-    # pre-heat ~0.7 s under the same load so that the sampled clocks are the steady-state ones
+    # pre-heat under the same load so that the sampled clocks are the steady-state ones
     t_heat = time.perf_counter()
     while time.perf_counter() - t_heat < args.preheat:
-        fork()
-        for i in range(50):
-            step_noacc(plans, streams, i)
-        join()
+        run(8)
         torch.cuda.synchronize()
-
     if world > 1:
-        # rehearse the collective of the timed region once more, at its full size, after the pre-heat
-        gather_group(0)
-        state["pending"].wait()
-        state["pending"] = None
         dist.barrier()
     torch.cuda.synchronize()
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    fork()
-    for i in range(args.steps):
-        step(i)
-    join()
-    drain(args.steps)
+    run(args.steps)
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -446,81 +537,108 @@ def gpu_arm(args):
     launches = _lib.launch_count() - launches0
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
+    parity = {}
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t)
-        # the gathered block of this rank holds every rank's rows of the last group, in rank order
-        last = gathered[((args.steps - 1) // G) % 2].view(world, G, B, 16)
-        gather_ok = bool(torch.equal(last[rank], acc[((args.steps - 1) // G) % 2]))
-    else:
-        gather_ok = None
+        # cross-rank correctness: the gathered block of the last step against ONE GPU solving the whole job
+        last = gathered[(args.steps - 1) % 2]
+        if rank == 0:
+            whole = _to_dev(tile(base, total), dev)
+            single = _plan(solver, whole).launch()
+            torch.cuda.synchronize()
+            got = torch.cat([last[r * shard: r * shard + (shard_range(total, r, world)[1] - shard_range(total, r, world)[0])]
+                             for r in range(world)], 0)
+            diff = (got.view(torch.int32) != single.rows.view(torch.int32)).any(dim=1)
+            parity["gather_vs_single_gpu"] = {"rows_compared": int(total), "mismatched_rows": int(diff.sum()),
+                                              "note": "all_gather_into_tensor block of the last timed step (rank order = ROI order, "
+                                                      "my_distributed_sampler.py:189-192) against one rdpn_pose_solve over the whole "
+                                                      "job on rank 0; bit-wise comparison of the [total,16] rows"}
+            del whole, single
+            torch.cuda.empty_cache()
 
-    # ---- kernel-only duration of the dominant kernel (no gather), for the roofline ----
+    # ---- per-kernel durations of the pipeline (CUDA events between the kernels, no overlap), fused kernel beside it ----
     torch.cuda.synchronize()
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    nk = max(args.steps, 20)
-    k0.record()
-    for i in range(nk):
-        plans[i % N_INPUT_SETS].launch()
-    k1.record()
+    stage = np.zeros(3)
+    n_stage = 5
+    plans[0].stage_ms()
+    for i in range(n_stage):
+        stage += np.array(plans[i % nplans].stage_ms())
+    stage /= n_stage
+    kernel_ms = _ev_ms(lambda i: plans[i % nplans].launch(), max(args.steps, 20))
+    fused_solver = pose_solver.PoseSolver(inlier_thr=INLIER_THR, weighted=True, pipeline="fused")
+    fused_plan = _plan(fused_solver, sets[0], roi_base=begin)
+    fused_ms = _ev_ms(lambda i: fused_plan.launch(), 20)
+    same_as_fused = bool(torch.equal(fused_plan.result.best_h, plans[0].launch().best_h)
+                         and torch.equal(fused_plan.result.n_inliers, plans[0].result.n_inliers))
     torch.cuda.synchronize()
-    kernel_ms = k0.elapsed_time(k1) / nk
+    del fused_plan
 
-    # ---- stage S1 alone (rdpn_correspond, the materialising HBM-bound kernel): its own roofline line ----
+    # ---- parity of the timed workload against the CPU oracle: every unique ROI (rank 0's first ROIs are the base) ----
+    if rank == 0:
+        res0 = plans[0].launch()
+        torch.cuda.synchronize()
+        parity.update(parity_vs_oracle(base, res0))
+
+    # ---- stage S1 alone (rdpn_correspond, the materialising HBM-bound kernel): its own roofline line.  One launch
+    # reads 711 MB and writes 570 MB, so neither side can live in the 126 MB L2 ----
     s1_ms = None
+    s1_B = min(B, 8192)
     try:
-        s1_in = [pose_solver._Inputs(s["depth"], s["Kp"], s["coor"][:, 0].contiguous(), s["coor"][:, 1].contiguous(),
-                                     s["coor"][:, 2].contiguous(), s["mask"], s["extent"], s["region_idx"], s["anchors"]) for s in sets]
-        s1_cam = torch.empty(ROIS_PER_GPU, 3, 4096, device=dev)
-        s1_w = torch.empty(ROIS_PER_GPU, 4096, device=dev)
-        s1_sel = torch.empty(ROIS_PER_GPU, 4096, dtype=torch.uint8, device=dev)
-        s1_n = torch.empty(ROIS_PER_GPU, dtype=torch.int32, device=dev)
+        s0 = sets[0]
+        s1_in = pose_solver._Inputs(s0["depth"][:s1_B], s0["Kp"][:s1_B], s0["coor"][:s1_B, 0].contiguous(), s0["coor"][:s1_B, 1].contiguous(),
+                                    s0["coor"][:s1_B, 2].contiguous(), s0["mask"][:s1_B], s0["extent"][:s1_B], s0["region_idx"][:s1_B],
+                                    s0["anchors"][:s1_B])
+        s1_cam = torch.empty(s1_B, 3, 4096, device=dev)
+        s1_w = torch.empty(s1_B, 4096, device=dev)
+        s1_sel = torch.empty(s1_B, 4096, dtype=torch.uint8, device=dev)
+        s1_n = torch.empty(s1_B, dtype=torch.int32, device=dev)
         cs = torch.cuda.current_stream(dev).cuda_stream
 
         def s1_launch(i):
-            _lib.check(L.rdpn_correspond(ctypes.byref(s1_in[i % N_INPUT_SETS].struct), s1_cam.data_ptr(), None, s1_w.data_ptr(),
+            _lib.check(L.rdpn_correspond(ctypes.byref(s1_in.struct), s1_cam.data_ptr(), None, s1_w.data_ptr(),
                                          s1_sel.data_ptr(), s1_n.data_ptr(), cs), "correspond")
 
-        for i in range(5):
-            s1_launch(i)
-        torch.cuda.synchronize()
-        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        q0.record()
-        for i in range(50):
-            s1_launch(i)
-        q1.record()
-        torch.cuda.synchronize()
-        s1_ms = q0.elapsed_time(q1) / 50
+        s1_ms = _ev_ms(s1_launch, 20)
+        del s1_cam, s1_w, s1_sel
     except Exception as e:  # the headline does not depend on this leg
         s1_ms = None
         print("s1 leg failed: %r" % (e,), file=sys.stderr)
 
     # ---- end to end through the host-buffer C-ABI call (pinned host buffers) ----
-    pin = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in batch.items()
+    EB = min(B, 8192)  # ROIs per end-to-end step and rank
+    eb = {k: (None if v is None else v[:EB]) for k, v in host_batch.items()}
+    pin = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in eb.items()
            if v is not None and k in ("depth", "Kp", "mask", "extent", "region_idx", "anchors", "hyp_idx")}
     for c, name in enumerate(("coor_x", "coor_y", "coor_z")):
-        pin[name] = torch.from_numpy(np.ascontiguousarray(batch["coor"][:, c])).pin_memory()
-    h_pose = torch.empty(B, 12, dtype=torch.float32).pin_memory()
-    h_ninl = torch.empty(B, dtype=torch.int32).pin_memory()
-    h_stat = torch.empty(B, dtype=torch.int32).pin_memory()
+        pin[name] = torch.from_numpy(np.ascontiguousarray(eb["coor"][:, c])).pin_memory()
+    h_pose = torch.empty(EB, 12, dtype=torch.float32).pin_memory()
+    h_ninl = torch.empty(EB, dtype=torch.int32).pin_memory()
+    h_stat = torch.empty(EB, dtype=torch.int32).pin_memory()
     inp = _lib.RoiInputs(depth=pin["depth"].data_ptr(), Kp=pin["Kp"].data_ptr(), depth_div=None,
                          coor_x=pin["coor_x"].data_ptr(), coor_y=pin["coor_y"].data_ptr(), coor_z=pin["coor_z"].data_ptr(),
                          mask=pin["mask"].data_ptr(), extent=pin["extent"].data_ptr(),
                          region_idx=pin["region_idx"].data_ptr(), anchors=pin["anchors"].data_ptr(), num_regions=R,
-                         mask_mode=1, mask_thr=0.5, B=B)
-    prm = _lib.SolveParams(inlier_thr=INLIER_THR, num_hyp=H, min_pts=4, min_inliers=4, weighted=0, refit_iters=1,
-                           with_scale=0, adaptive=0, confidence=0.995, min_iter=10)
+                         mask_mode=1, mask_thr=0.5, B=EB)
+    prm = _lib.SolveParams(inlier_thr=INLIER_THR, num_hyp=H, min_pts=4, min_inliers=4, weighted=1, refit_iters=1,
+                           with_scale=0, adaptive=0, confidence=0.995, min_iter=10, roi_base=begin)
     outs = _lib.SolveOutputs(pose=h_pose.data_ptr(), n_inliers=h_ninl.data_ptr(), status=h_stat.data_ptr())
     ctx = ctypes.c_void_p()
     _lib.check(L.rdpn_ctx_create(local_rank, ctypes.byref(ctx)), "ctx_create")
-    e2e_steps = max(3, min(args.steps, 30))
-
+    e2e_steps = max(3, min(args.steps, 20))
     hyp_arg = [pin["hyp_idx"].data_ptr()]  # [None]: the kernel draws the triplets itself
 
     def host_call():
         _lib.check(L.rdpn_pose_solve_host(ctx, ctypes.byref(inp), hyp_arg[0], None, ctypes.byref(prm),
                                           ctypes.byref(outs)), "pose_solve_host")
+
+    def reduce_max(dt):
+        if world > 1:
+            t_ = torch.tensor([dt], device=dev)
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            return float(t_)
+        return dt
 
     def time_host_calls(transfer):
         """(seconds for e2e_steps calls, bytes that crossed the bus per call, strategy used)"""
@@ -530,19 +648,14 @@ def gpu_arm(args):
         nbytes = int(L.rdpn_ctx_last_h2d_bytes(ctx))
         used = int(L.rdpn_ctx_last_transfer(ctx))
         _lib.check(L.rdpn_ctx_set_option(ctx, _lib.OPT_COUNT_BYTES, 0), "set_option")
-        for _ in range(3):
+        for _ in range(2):
             host_call()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             host_call()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t)
-        return dt, nbytes, used
+        return reduce_max(time.perf_counter() - t0), nbytes, used
 
     def time_pipelined_calls(depth=2):
         """Same plugin entry, asynchronous form (rdpn_pose_solve_host_submit / rdpn_ctx_wait): step i + 1 is submitted
@@ -551,8 +664,8 @@ def gpu_arm(args):
         _lib.check(L.rdpn_ctx_set_option(ctx, _lib.OPT_TRANSFER, _lib.TRANSFER_AUTO), "set_option")
         bufs = []
         for _ in range(depth):
-            hp, hn, hs_ = (torch.empty(B, 12).pin_memory(), torch.empty(B, dtype=torch.int32).pin_memory(),
-                           torch.empty(B, dtype=torch.int32).pin_memory())
+            hp, hn, hs_ = (torch.empty(EB, 12).pin_memory(), torch.empty(EB, dtype=torch.int32).pin_memory(),
+                           torch.empty(EB, dtype=torch.int32).pin_memory())
             bufs.append((hp, hn, hs_, _lib.SolveOutputs(pose=hp.data_ptr(), n_inliers=hn.data_ptr(), status=hs_.data_ptr())))
         tk = ctypes.c_int(-1)
 
@@ -568,16 +681,12 @@ def gpu_arm(args):
             for t_ in pending:
                 _lib.check(L.rdpn_ctx_wait(ctx, t_), "ctx_wait")
 
-        loop(4)
+        loop(3)
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         loop(e2e_steps)
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t)
+        dt = reduce_max(time.perf_counter() - t0)
         return dt, bool(torch.equal(bufs[(e2e_steps - 1) % depth][0], h_pose))
 
     copy_s, copy_bytes, _ = time_host_calls(_lib.TRANSFER_COPY)
@@ -592,42 +701,27 @@ def gpu_arm(args):
     hyp_arg[0] = pin["hyp_idx"].data_ptr()
     h_pose.copy_(e2e_pose)
     L.rdpn_ctx_destroy(ctx)
-    host_input_bytes = B * (BYTES_MAPS + H * 12 + R * 12 + 16 + 12)
-    d2h = B * (48 + 4 + 4)
-    # sanity: the host path produced the same poses as the device path
-    dev_pose = plans[0].launch().pose.reshape(B, 12)
+    host_input_bytes = EB * (BYTES_MAPS + H * 12 + R * 12 + 16 + 12)
+    d2h = EB * (48 + 4 + 4)
+    # sanity: the host path produced the same poses as the device path (the refit sums run in a different order in the
+    # pipeline and in the fused kernel the host path's 256-ROI chunks use: equal to FP32 rounding)
+    dev_pose = plans[0].launch().pose.reshape(B, 12)[:EB]
     torch.cuda.synchronize()
     ok_frac = float((plans[0].result.status == 0).float().mean())
-    host_matches_device = bool(torch.equal(dev_pose.cpu(), h_pose))
+    host_matches_device = bool(torch.allclose(dev_pose.cpu(), h_pose, rtol=0, atol=2e-6))
 
     # ---- supplementary: the deployment split of the reference -- the CNN head's outputs (coor, mask, region)
     # are already on the GPU (models/GDRN.py:291-297); only the loader's depth maps, per-ROI scalars, anchors and
     # the hypothesis triplets sit in (pinned) host memory, and the results go back to pinned host tensors.  Same
     # plugin call: it takes device pointers in place, buffer by buffer (rdpn6d_b200.pose_solver.HostPoseSolver).
     s0 = sets[0]
-    d_cx, d_cy, d_cz = [s0["coor"][:, c].contiguous() for c in range(3)]
-    mixed = pose_solver.HostPoseSolver(device=local_rank, inlier_thr=INLIER_THR, count_bytes=True)
-    mixed_args = (pin["depth"], pin["Kp"], d_cx, d_cy, d_cz, s0["mask"], pin["extent"], pin["hyp_idx"], s0["region_idx"],
-                  pin["anchors"])
-    # pin[] holds the unrolled workload, set 0 on the device is the same data rolled by 0 ROIs
-    mixed_call = mixed.plan(*mixed_args)  # C structs built once, like the e2e leg above
-    mixed_res = mixed_call()
-    mixed_bytes = mixed.last_h2d_bytes
-    mixed.set_option(_lib.OPT_COUNT_BYTES, 0)
-    mixed_ok = bool(torch.equal(mixed_res.pose.reshape(B, 12), h_pose))
-    mixed_steps = max(3, min(args.steps, 30))
-    for _ in range(3):
-        mixed_call()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(mixed_steps):
-        mixed_call()
-    mixed_s = time.perf_counter() - t0
+    d_cx, d_cy, d_cz = [s0["coor"][:EB, c].contiguous() for c in range(3)]
+    d_mask, d_rid = s0["mask"][:EB].contiguous(), s0["region_idx"][:EB].contiguous()
+    mixed_steps = e2e_steps
 
-    def pipelined_plans(solver, plan_args, n, depth=2):
+    def pipelined_plans(solver_, plan_args, n, depth=2):
         """seconds for n steps of the submit / wait loop over `depth` plans with their own result buffers"""
-        ps = [solver.plan(*plan_args, private_outputs=True) for _ in range(depth)]
+        ps = [solver_.plan(*plan_args, roi_base=begin, private_outputs=True) for _ in range(depth)]
 
         def loop(k):
             pending = []
@@ -639,49 +733,93 @@ def gpu_arm(args):
             for p_, tk_ in pending:
                 p_.wait(tk_)
 
-        loop(4)
+        loop(3)
         if world > 1:
             dist.barrier()
         t0_ = time.perf_counter()
         loop(n)
         dt_ = time.perf_counter() - t0_
-        return dt_, bool(torch.equal(ps[(n - 1) % depth]().pose.reshape(B, 12), h_pose))
+        return dt_, bool(torch.equal(ps[(n - 1) % depth]().pose.reshape(EB, 12), h_pose))
 
-    mixed_pipe_s, mixed_pipe_ok = pipelined_plans(mixed, mixed_args, mixed_steps)
-    mixed.close()
-    # ... and with the triplets drawn by the kernel (what the evaluator hook rdpn6d_b200.evaluator does)
-    mixed2 = pose_solver.HostPoseSolver(device=local_rank, inlier_thr=INLIER_THR, num_hyp=H, seed=0, count_bytes=True)
-    mixed2_call = mixed2.plan(pin["depth"], pin["Kp"], d_cx, d_cy, d_cz, s0["mask"], pin["extent"], None, s0["region_idx"],
-                              pin["anchors"])
-    mixed2_call()
-    mixed2_bytes = mixed2.last_h2d_bytes
-    mixed2.set_option(_lib.OPT_COUNT_BYTES, 0)
-    for _ in range(3):
-        mixed2_call()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(mixed_steps):
-        mixed2_call()
-    mixed2_s = time.perf_counter() - t0
-    mixed2_pipe_s, _ = pipelined_plans(mixed2, (pin["depth"], pin["Kp"], d_cx, d_cy, d_cz, s0["mask"], pin["extent"], None,
-                                                s0["region_idx"], pin["anchors"]), mixed_steps)
-    mixed2.close()
-    if world > 1:
-        t = torch.tensor([mixed_s, mixed2_s, mixed_pipe_s, mixed2_pipe_s], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        mixed_s, mixed2_s, mixed_pipe_s, mixed2_pipe_s = [float(x) for x in t]
+    def head_on_device(hyp):
+        m = pose_solver.HostPoseSolver(device=local_rank, inlier_thr=INLIER_THR, weighted=True, num_hyp=H, seed=0, count_bytes=True)
+        margs = (pin["depth"], pin["Kp"], d_cx, d_cy, d_cz, d_mask, pin["extent"], hyp, d_rid, pin["anchors"])
+        call = m.plan(*margs, roi_base=begin)
+        r = call()
+        nbytes = m.last_h2d_bytes
+        m.set_option(_lib.OPT_COUNT_BYTES, 0)
+        ok = bool(torch.equal(r.pose.reshape(EB, 12), h_pose)) if hyp is not None else None
+        for _ in range(2):
+            call()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(mixed_steps):
+            call()
+        sync_s = time.perf_counter() - t0
+        pipe_s_, pipe_ok_ = pipelined_plans(m, margs, mixed_steps)
+        m.close()
+        return reduce_max(sync_s), reduce_max(pipe_s_), nbytes, ok, pipe_ok_
+
+    mixed_s, mixed_pipe_s, mixed_bytes, mixed_ok, mixed_pipe_ok = head_on_device(pin["hyp_idx"])
+    mixed2_s, mixed2_pipe_s, mixed2_bytes, _, _ = head_on_device(None)
 
     # ---- FP32 work actually issued by the scoring stage (valid hypotheses x gated points) ----
-    diag = pose_solver.PoseSolver(inlier_thr=INLIER_THR, want_hyp=True)
-    s0 = sets[0]
-    dres = diag(s0["depth"], s0["Kp"], s0["coor"][:, 0].contiguous(), s0["coor"][:, 1].contiguous(),
-                s0["coor"][:, 2].contiguous(), s0["mask"], s0["extent"], s0["hyp_idx"], s0["region_idx"], s0["anchors"])
-    valid = (dres.hyp_poses.reshape(B, H, 12).abs().sum(-1) > 0).sum(1).double()
-    pairs = float((valid * dres.n_sel.double()).sum())
+    diag = pose_solver.PoseSolver(inlier_thr=INLIER_THR, weighted=True, want_hyp=True)
+    DB = min(B, 8192)
+    dres = diag(s0["depth"][:DB], s0["Kp"][:DB], s0["coor"][:DB, 0].contiguous(), s0["coor"][:DB, 1].contiguous(),
+                s0["coor"][:DB, 2].contiguous(), s0["mask"][:DB], s0["extent"][:DB], s0["hyp_idx"][:DB], s0["region_idx"][:DB],
+                s0["anchors"][:DB])
+    valid = (dres.hyp_poses.reshape(DB, H, 12).abs().sum(-1) > 0).sum(1).double()
+    pairs = float((valid * dres.n_sel.double()).sum()) * (B / DB)
     mean_nsel = float(dres.n_sel.double().mean())
+    mean_valid = float(valid.mean())
+    del dres, diag
     fp32_peak = ctypes.c_double(0.0)
     L.rdpn_fp32_peak_probe(20000, ctypes.byref(fp32_peak))
+
+    # ---- configs[1] (LM-O, 1024 ROIs, 64 anchors) and configs[3] (FPS) ride along on one GPU ----
+    lmo = fps = None
+    if world == 1:
+        wl = WORKLOADS["lmo"]
+        lsets = [_to_dev(tile(base_lmo, wl["rois"]), dev, 37 * i) for i in range(4)]  # 4 x 88 MB > L2
+        lsolver = pose_solver.PoseSolver(inlier_thr=INLIER_THR, weighted=True)
+        lplans = [_plan(lsolver, s) for s in lsets]
+        l_ms = _ev_ms(lambda i: lplans[i % 4].launch(), 100)
+        two = [torch.cuda.Stream(dev) for _ in range(2)]
+
+        def two_stream(i):
+            lplans[i % 4].launch(two[i % 2])
+
+        for st in two:
+            st.wait_stream(torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for st in two:
+            st.wait_stream(torch.cuda.current_stream())
+        for i in range(100):
+            two_stream(i)
+        for st in two:
+            torch.cuda.current_stream().wait_stream(st)
+        q1.record()
+        torch.cuda.synchronize()
+        l2_ms = q0.elapsed_time(q1) / 100
+        lres = lplans[0].launch()
+        torch.cuda.synchronize()
+        lmo = {"workload": wl["title"] + ", 64 anchors/object, weighted refit", "rois_per_step": wl["rois"],
+               "value": wl["rois"] / (l_ms * 1e-3), "ms_per_step": l_ms,
+               "value_two_calls_in_flight": wl["rois"] / (l2_ms * 1e-3),
+               "note": "one stream, back-to-back calls over 4 rotating input sets (352 MB > L2); two_calls_in_flight alternates two "
+                       "streams so that the tail of one launch overlaps the head of the next.  Batches below 3072 ROIs run the fused "
+                       "kernel (RDPN_PIPELINE_AUTO)",
+               "parity": parity_vs_oracle(base_lmo, lres)}
+        del lplans, lsets
+        torch.cuda.empty_cache()
+        try:
+            fps = fps_block(dev)
+        except Exception as e:
+            fps = {"error": repr(e)}
 
     if rank != 0:
         if world > 1:
@@ -696,76 +834,124 @@ def gpu_arm(args):
     alg_bytes = B * bytes_per_roi(H, R)
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     flops = 27.0 * pairs
+    front_bytes = B * (BYTES_MAPS + H * 12 + R * 12 + 28)
+    traffic = ncu_traffic()
+    s1_bytes = s1_B * (BYTES_MAPS + R * 12 + 28 + 69636)
     line = {
         "metric": METRIC, "value": total * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": nw, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
-        "e2e": {"value": total * e2e_steps / pipe_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "host_input_bytes_per_step": host_input_bytes, "steps": e2e_steps,
+        "e2e": {"value": world * EB * e2e_steps / pipe_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "host_input_bytes_per_step": host_input_bytes, "steps": e2e_steps, "rois_per_step_and_gpu": EB,
                 "transfer": "gated pull" if e2e_used == _lib.TRANSFER_PULL else "full copy",
                 "api": "rdpn_pose_solve_host_submit / rdpn_ctx_wait (C ABI, every input and output in pinned host memory; "
                        "4-stage pipeline inside a call, step i + 1 submitted before step i is waited for, two sets of pinned "
                        "result buffers)",
                 "matches_synchronous_call": pipe_ok, "depth": 2,
                 "note": "every step's inputs cross the bus and every step's results are back in host memory inside the timed "
-                        "region.  h2d_bytes_per_step is MEASURED (by the synchronous call on the same buffers): the mask planes "
-                        "(copy engine) + the per-ROI arrays, hypothesis triplets and the 32-byte sectors of depth/coor/region-id "
-                        "planes that the pull kernel fetched over PCIe for pixel groups whose mask test passes; "
-                        "host_input_bytes_per_step is the size of all input tensors.  Results are bit-identical to the full "
-                        "copy (transfers_identical).",
-                "timer": "perf_counter around the submit/wait loop"},
-        "e2e_synchronous": {"value": total * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "region.  h2d_bytes_per_step is MEASURED per GPU (by the synchronous call on the same buffers): the mask "
+                        "planes + the per-ROI arrays, hypothesis triplets and the 32-byte sectors of depth/coor/region-id planes "
+                        "that the pull kernel fetched over PCIe for pixel groups whose mask test passes; host_input_bytes_per_step "
+                        "is the size of all input tensors.  Results are bit-identical to the full copy (transfers_identical).",
+                "timer": "perf_counter around the submit/wait loop, max over ranks"},
+        "e2e_synchronous": {"value": world * EB * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                             "api": "rdpn_pose_solve_host: the same call, synchronous (what the evaluator hook does once per step)",
                             "timer": "perf_counter around synchronous calls"},
-        "e2e_full_copy": {"value": total * e2e_steps / copy_s, "unit": UNIT, "h2d_bytes_per_step": copy_bytes,
+        "e2e_full_copy": {"value": world * EB * e2e_steps / copy_s, "unit": UNIT, "h2d_bytes_per_step": copy_bytes,
                           "d2h_bytes_per_step": d2h, "note": "same call with RDPN_TRANSFER_COPY: every input tensor copied"},
-        "e2e_internal_sampling": {"value": total * e2e_steps / auto_s, "unit": UNIT, "h2d_bytes_per_step": auto_bytes,
+        "e2e_internal_sampling": {"value": world * EB * e2e_steps / auto_s, "unit": UNIT, "h2d_bytes_per_step": auto_bytes,
                                   "d2h_bytes_per_step": d2h, "solved_fraction": auto_ok,
                                   "note": "supplementary: same call with hyp_idx = NULL -- the kernel draws the 256 triplets per ROI "
                                           "itself from a seeded counter-based stream (the reference's loop samples internally too, "
                                           "misc.py:91), so no triplets cross the bus"},
         "transfers_identical": transfers_identical,
-        "e2e_head_on_device": {"value": total * mixed_steps / mixed_pipe_s, "unit": UNIT,
-                               "synchronous_value": total * mixed_steps / mixed_s,
+        "e2e_head_on_device": {"value": world * EB * mixed_steps / mixed_pipe_s, "unit": UNIT,
+                               "synchronous_value": world * EB * mixed_steps / mixed_s,
                                "h2d_bytes_per_step": mixed_bytes, "d2h_bytes_per_step": d2h,
-                               "matches_e2e": mixed_ok and mixed_pipe_ok,
+                               "matches_e2e": bool(mixed_ok and mixed_pipe_ok),
                                "note": "supplementary, the reference's deployment split: CNN-head outputs (coor / mask / region ids) "
                                        "already device-resident and used in place; depth maps, per-ROI scalars, anchors and hypothesis "
                                        "triplets in pinned host memory (depth fetched only where the mask passes); results to pinned "
                                        "host tensors.  Same plugin entry via rdpn6d_b200.pose_solver.HostPoseSolver: value = submit / wait loop "
                                        "of depth 2 like e2e, synchronous_value = one synchronous call per step."},
-        "e2e_head_on_device_internal_sampling": {"value": total * mixed_steps / mixed2_pipe_s, "unit": UNIT,
-                                                 "synchronous_value": total * mixed_steps / mixed2_s,
+        "e2e_head_on_device_internal_sampling": {"value": world * EB * mixed_steps / mixed2_pipe_s, "unit": UNIT,
+                                                 "synchronous_value": world * EB * mixed_steps / mixed2_s,
                                                  "h2d_bytes_per_step": mixed2_bytes, "d2h_bytes_per_step": d2h},
         "host_path_matches_device_path": host_matches_device,
-        "gather_ok": gather_ok,
+        "parity": parity,
         "numa_node_rank0": numa_node,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": ncu_traffic_bytes(), "traffic_source": "profiles/r1/ncu_pose_solve_summary.csv (ncu --set full, "
-                     "dram__bytes_read.sum + dram__bytes_write.sum of one launch of this workload)",
-                     "kernel": "rdpn::pose_solve_kernel<false, false>", "kernel_ms": kernel_ms,
-                     "kernel_ms_note": "average duration of back-to-back launches on ONE stream (no overlap)",
+                     "traffic": traffic.get("total"), "traffic_source": traffic.get("source"),
+                     "kernel": "rdpn_pose_solve = rdpn::front_kernel + rdpn::score_kernel + rdpn::refit_kernel (three launches, PDL-chained)",
+                     "kernel_ms": kernel_ms,
+                     "kernel_ms_note": "average duration of back-to-back solves on ONE stream, CUDA events, this run",
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                     "note": "the fused solver is FP32-pipe bound (3x4 transforms x hypotheses x points), see fp32"},
-        "fp32": {"achieved_tflops": flops / (kernel_ms * 1e-3) / 1e12, "peak_tflops": fp32_peak.value / 1e12,
-                 "frac": (flops / (kernel_ms * 1e-3)) / max(fp32_peak.value, 1.0), "flop_per_pair": 27,
-                 "pairs_per_launch": pairs, "mean_gated_points_per_roi": mean_nsel,
-                 "peak_source": "rdpn_fp32_peak_probe (FFMA chains on all SMs, this run)"},
+                     "note": "the path as a whole against the HBM roofline; its dominant kernel (score_kernel, %.0f %% of the solve) is "
+                             "FP32-issue bound, not HBM bound: see fp32 and kernels" % (100 * stage[1] / max(stage.sum(), 1e-9))},
+        "fp32": {"achieved_tflops": flops / (stage[1] * 1e-3) / 1e12, "peak_tflops": fp32_peak.value / 1e12,
+                 "frac": (flops / (stage[1] * 1e-3)) / max(fp32_peak.value, 1.0),
+                 "frac_of_whole_solve": (flops / (kernel_ms * 1e-3)) / max(fp32_peak.value, 1.0), "flop_per_pair": 27,
+                 "kernel": "rdpn::score_kernel", "kernel_ms": float(stage[1]),
+                 "pairs_per_launch": pairs, "mean_gated_points_per_roi": mean_nsel, "mean_valid_hypotheses_per_roi": mean_valid,
+                 "peak_source": "rdpn_fp32_peak_probe (FFMA chains on all SMs, this run)",
+                 "note": "27 flop per (valid hypothesis, gated point) is SURVEY 8d's algorithmic figure (3x4 transform + residual); the "
+                         "kernel hoists the transform per region run and executes 8 instructions (9 flop) per pair"},
+        "kernels": {
+            "timer": "rdpn_pose_solve_stage_ms: CUDA events between the three kernels on the launching stream, kernels strictly "
+                     "one after the other (the timed region overlaps their tails by programmatic dependent launch), mean of %d" % n_stage,
+            "front_kernel": {"ms": float(stage[0]), "bound": "hbm / latency", "algorithmic_bytes_per_launch": front_bytes,
+                             "achieved_GBps": front_bytes / (stage[0] * 1e-3) / 1e9,
+                             "frac_of_hbm_peak": front_bytes / (stage[0] * 1e-3) / 1e9 / hbm_peak,
+                             "dram_bytes_per_launch": traffic.get("front_kernel")},
+            "score_kernel": {"ms": float(stage[1]), "bound": "fp32 issue", "dram_bytes_per_launch": traffic.get("score_kernel")},
+            "refit_kernel": {"ms": float(stage[2]), "bound": "latency", "dram_bytes_per_launch": traffic.get("refit_kernel")},
+            "sum_ms": float(stage.sum()), "solve_ms_with_pdl_overlap": kernel_ms,
+            "fused_kernel_ms": fused_ms, "fused_value": B / (fused_ms * 1e-3), "pipeline_equals_fused": same_as_fused,
+        },
         "solved_fraction": ok_frac,
         "s1_roofline": None if s1_ms is None else {
-            "kernel": "rdpn::correspond_kernel<false> (S1 materialised: cam xyz + w + sel for every pixel)", "bound": "hbm",
-            "kernel_ms": s1_ms, "algorithmic_bytes_per_launch": ROIS_PER_GPU * (BYTES_MAPS + NUM_REGIONS * 12 + 28 + 69636),
-            "achieved": ROIS_PER_GPU * (BYTES_MAPS + NUM_REGIONS * 12 + 28 + 69636) / (s1_ms * 1e-3) / 1e9, "peak": hbm_peak,
-            "unit": "GB/s", "frac": ROIS_PER_GPU * (BYTES_MAPS + NUM_REGIONS * 12 + 28 + 69636) / (s1_ms * 1e-3) / 1e9 / hbm_peak},
+            "kernel": "rdpn::correspond_kernel<false> (S1 materialised: cam xyz + w + sel for every pixel of %d ROIs)" % s1_B,
+            "bound": "hbm", "kernel_ms": s1_ms, "algorithmic_bytes_per_launch": s1_bytes,
+            "achieved": s1_bytes / (s1_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            "frac": s1_bytes / (s1_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic.get("correspond_kernel"),
+            "note": "one launch reads %.0f MB and writes %.0f MB: neither the inputs nor the outputs fit the 126 MB L2, so the "
+                    "algorithmic and the DRAM-level figures coincide (traffic = dram bytes of one such launch from the committed ncu "
+                    "capture)" % (s1_B * (BYTES_MAPS + R * 12 + 28) / 1e6, s1_B * 69636 / 1e6)},
     }
+    if lmo is not None:
+        line["lmo"] = lmo
+    if fps is not None:
+        line["fps"] = fps
     if cpu_base is not None:
         line["cpu_baseline"] = cpu_base
     emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def ncu_traffic(path=None):
+    """DRAM bytes (read + write) per launch of each kernel on the N = 1 workload, from the committed `ncu --set full`
+    captures (profiles/r2/ncu_*_summary.csv); empty when the summaries are absent."""
+    import csv
+
+    out = {}
+    d = path or os.path.join(ROOT, "profiles", "r2")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for name in ("front_kernel", "score_kernel", "refit_kernel", "correspond_kernel"):
+        try:
+            rows = list(csv.reader(open(os.path.join(d, "ncu_%s_summary.csv" % name))))
+            hdr, units, vals = rows[0], rows[1], rows[2]
+            out[name] = sum(float(vals[hdr.index(m)]) * scale[units[hdr.index(m)]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        except Exception:
+            out[name] = None
+    if all(out.get(k) is not None for k in ("front_kernel", "score_kernel", "refit_kernel")):
+        out["total"] = out["front_kernel"] + out["score_kernel"] + out["refit_kernel"]
+        out["source"] = ("profiles/r2/ncu_{front,score,refit}_kernel_summary.csv (ncu --set full, dram__bytes_read.sum + "
+                         "dram__bytes_write.sum of one launch of each kernel on this workload)")
+    return out
 
 
 _JSON_OUT = None
@@ -791,13 +977,11 @@ def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--preheat", type=float, default=0.7, help="seconds of untimed load before the timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather-every", type=int, default=0,
-                    help="N>1: all-gather the result rows after every G steps (0 = once, after the last timed step)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":

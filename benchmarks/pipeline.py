@@ -19,6 +19,8 @@ CONFIGS = {
     # name: (B, H, R, n_models, n_symmetric, K, unique, occlusion)
     "ycbv": (8192, 256, 32, 21, 5, synth.K_YCBV, 84, 0.5),
     "lmo": (1024, 256, 64, 8, 0, synth.K_LM, 128, 0.6),
+    "ycbv2k": (2048, 256, 32, 21, 5, synth.K_YCBV, 84, 0.5),
+    "ycbv4k": (4096, 256, 32, 21, 5, synth.K_YCBV, 84, 0.5),
 }
 
 

@@ -153,7 +153,7 @@ typedef struct rdpn_solve_params {
     int32_t sample_size; /* S: correspondences per hypothesis, 3 .. RDPN_MAX_SAMPLE; 0 means 3.     */
                          /* misc.py:72,91 samples random_sample_num = 10 pairs per iteration        */
     int32_t pipeline;    /* RDPN_PIPELINE_*: which implementation runs (results are the same)       */
-    int32_t chunk_rois;  /* pipeline: ROIs per pass through the three kernels (0 = default, 4096)   */
+    int32_t chunk_rois;  /* pipeline: ROIs per pass through the three kernels (0 = default, 8192)   */
     int32_t select_rule; /* RDPN_SELECT_*: which pose the RANSAC stage returns                      */
 } rdpn_solve_params;
 
@@ -167,10 +167,11 @@ typedef struct rdpn_solve_params {
 #define RDPN_SELECT_MIN_MEAN_ERR 1
 
 /* Implementations of the solve (identical counts / masks / winner; refit pose equal to FP32 rounding):
- *   AUTO   the three-kernel pipeline where it applies (anchor mode, R <= 128), else the fused kernel
- *   FUSED  one kernel, one CTA per ROI (pose_solve.cu)
- *   SPLIT  gate_pack (HBM-bound, bulk-TMA ring) -> score (FP32 cores) -> refit (warp per ROI);
- *          RDPN_E_TOOLARGE where it does not apply */
+ *   AUTO   the three-kernel pipeline for batches of >= 3072 ROIs in anchor mode, else the fused kernel
+ *   FUSED  one kernel, one CTA per ROI (csrc/pose_solve.cu): lowest latency for small batches
+ *   SPLIT  csrc/solve_pipe.cu: front (warp per ROI: gate, back-projection + residual, region sort, hypothesis
+ *          poses) -> score (CTA per ROI, bulk-TMA staged, FP32 cores) -> best + refit (warp per ROI), the three
+ *          launches chained by programmatic dependent launch; RDPN_E_TOOLARGE where it does not apply (dense mode) */
 #define RDPN_PIPELINE_AUTO 0
 #define RDPN_PIPELINE_FUSED 1
 #define RDPN_PIPELINE_SPLIT 2
@@ -209,16 +210,24 @@ typedef struct rdpn_solve_outputs {
  * and demand bit-identical results). */
 int rdpn_pose_solve(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, const float* d_t_net,
                     const rdpn_solve_params* prm, const rdpn_solve_outputs* out, void* stream);
-/* Same call with a caller-owned scratch buffer for the pipeline's per-ROI packages (sorted correspondences, region
- * runs, hypothesis poses: ~20 KB touched per ROI): allocates nothing and never synchronises, so it can be captured
- * in a CUDA graph.  d_ws must be 128-byte aligned and hold at least one package (rdpn_pose_solve_workspace_bytes(1, ..));
+/* Same call with a caller-owned scratch buffer for the pipeline's per-ROI packages (raster list and region-sorted
+ * list of correspondences, region runs, hypothesis poses and counts: ~175 KB of address space, ~32 KB touched per ROI)
+ * and hand-over flags: allocates nothing and never synchronises, so it can be captured in a CUDA graph.  d_ws must be
+ * 128-byte aligned and hold at least one package (rdpn_pose_solve_workspace_bytes(1, ..));
  * rdpn_pose_solve_workspace_bytes(B, H, R, chunk_rois) is the size at which a chunk of min(B, chunk_rois) ROIs goes
- * through each kernel in one launch (R = 0: dense mode).  rdpn_pose_solve itself keeps one such buffer per (device,
+ * through each kernel in one launch (R = 0: dense mode, fused kernel, no workspace needed).  rdpn_pose_solve itself keeps one such buffer per (device,
  * stream) and grows it on demand (growing synchronises that stream once). */
 size_t rdpn_pose_solve_workspace_bytes(int B, int num_hyp, int num_regions, int chunk_rois);
 int rdpn_pose_solve_ws(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, const float* d_t_net,
                        const rdpn_solve_params* prm, const rdpn_solve_outputs* out, void* d_ws, size_t ws_bytes,
                        void* stream);
+/* Measurement aid (bench.py's per-kernel roofline lines): the same solve through the pipeline with its three kernels
+ * run strictly one after the other and CUDA events between them on `stream`; synchronises, then returns the
+ * durations in milliseconds: ms3[0] front (gate + back-projection + residual + sort + hypotheses), ms3[1] scoring,
+ * ms3[2] best + refit.  RDPN_E_TOOLARGE where the pipeline does not apply. */
+int rdpn_pose_solve_stage_ms(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, const float* d_t_net,
+                             const rdpn_solve_params* prm, const rdpn_solve_outputs* out, void* d_ws, size_t ws_bytes,
+                             void* stream, float* ms3);
 
 /* ------------------------------------------------------------------------------------------------
  * B4  Batched weighted Kabsch / Umeyama -- lib/pysixd/transform.py:913-1029

@@ -35,6 +35,7 @@ int cached_workspace(cudaStream_t st, size_t need, void** out, size_t* out_bytes
 bool split_supported(const SolveArgs& a, bool dense);                                            // solve_split.cu
 size_t split_pkg_stride(int H, int R, bool dense);                                               // solve_pipe.cu
 size_t split_workspace_bytes(int B, int H, int R, int chunk_rois);                               // solve_pipe.cu
+void set_stage_timing(float* ms3);                                                               // solve_pipe.cu
 int launch_split(const SolveArgs& a, bool dense, void* ws, size_t ws_bytes, int chunk_rois, cudaStream_t st);
 
 // Optional per-phase cycle stamps (tuning builds only: RDPN_NVCC_EXTRA=-DRDPN_PHASE_CLOCKS, benchmarks/phase_clocks.py)
@@ -1217,8 +1218,11 @@ static int solve_prepare(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, co
     return 0;
 }
 
-// which implementation runs: the three-kernel pipeline (solve_split.cu) unless the caller or RDPN_SOLVE_PIPELINE
-// (tuning: "fused" / "split") asks for the fused kernel, or the problem is outside what the pipeline supports
+// which implementation runs.  AUTO: the three-kernel pipeline (solve_pipe.cu) for batches of at least
+// RDPN_PIPELINE_MIN_ROIS ROIs (below that the fused kernel's single launch wins: measured crossover on B200 between
+// 2048 and 4096 ROIs), the fused kernel otherwise or where the pipeline does not apply (dense mode).  The caller's
+// prm->pipeline or the environment variable RDPN_SOLVE_PIPELINE ("fused" / "split", tuning) override it.
+#define RDPN_PIPELINE_MIN_ROIS 3072
 static bool use_split(const rdpn::SolveArgs& a, bool dense, int* err) {
     int mode = a.prm.pipeline;
     if (mode == RDPN_PIPELINE_AUTO) {
@@ -1228,6 +1232,7 @@ static bool use_split(const rdpn::SolveArgs& a, bool dense, int* err) {
     }
     const bool ok = rdpn::split_supported(a, dense);
     *err = (mode == RDPN_PIPELINE_SPLIT && !ok) ? RDPN_E_TOOLARGE : 0;
+    if (mode == RDPN_PIPELINE_AUTO) return ok && a.in.B >= env_int_("RDPN_PIPELINE_MIN_ROIS", RDPN_PIPELINE_MIN_ROIS);
     return mode != RDPN_PIPELINE_FUSED && ok;
 }
 
@@ -1255,6 +1260,21 @@ int rdpn_pose_solve_ws(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, cons
     if (!use_split(a, dense, &err)) return err ? err : solve_fused(a, dense, st);
     const int chunk = a.prm.chunk_rois > 0 ? a.prm.chunk_rois : env_int_("RDPN_SOLVE_CHUNK", RDPN_DEFAULT_CHUNK_ROIS);
     return rdpn::launch_split(a, dense, d_ws, ws_bytes, chunk, st);
+}
+
+int rdpn_pose_solve_stage_ms(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, const float* d_t_net, const rdpn_solve_params* prm,
+                             const rdpn_solve_outputs* out, void* d_ws, size_t ws_bytes, void* stream, float* ms3) {
+    if (!ms3) return RDPN_E_BADARG;
+    rdpn::SolveArgs a;
+    bool dense = false;
+    int rc = solve_prepare(in, d_hyp_idx, d_t_net, prm, out, &a, &dense);
+    if (rc) return rc;
+    if (!rdpn::split_supported(a, dense)) return RDPN_E_TOOLARGE;
+    ms3[0] = ms3[1] = ms3[2] = 0.f;
+    rdpn::set_stage_timing(ms3);
+    rc = rdpn::launch_split(a, dense, d_ws, ws_bytes, a.prm.chunk_rois, (cudaStream_t)stream);
+    rdpn::set_stage_timing(nullptr);
+    return rc;
 }
 
 int rdpn_pose_solve(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, const float* d_t_net,

@@ -998,15 +998,25 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// rdpn_pose_solve_stage_ms: when set, every chunk runs its kernels one after the other (no PDL overlap) with CUDA events
+// between them on the launching stream and adds the three durations here
+thread_local float* t_stage_ms = nullptr;
+
 template <bool MULTI>
 static int launch_chunk(const SolveArgs& a, unsigned char* ws, const PkgLayout& lay, cudaStream_t st) {
     const int B = a.in.B, H = a.prm.num_hyp, R = a.in.num_regions;
-    static const bool pdl = env_int("RDPN_PIPE_PDL", 1) != 0;
+    static const bool pdl_env = env_int("RDPN_PIPE_PDL", 1) != 0;
+    const bool pdl = pdl_env && !t_stage_ms;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (t_stage_ms) {
+        for (auto& e : ev) RDPN_CUDA_TRY(cudaEventCreate(&e));
+    }
     const size_t fb = flags_bytes(B);
     int* fdone = reinterpret_cast<int*>(ws);
     int* sdone = fdone + B;
     unsigned char* pk = ws + fb;
     RDPN_CUDA_TRY(cudaMemsetAsync(ws, 0, fb, st));
+    if (t_stage_ms) RDPN_CUDA_TRY(cudaEventRecord(ev[0], st));
     {  // K1
         const FrontLayout fl = make_front_layout(R);
         const size_t smem = (size_t)FR_W * fl.per_warp;
@@ -1017,6 +1027,7 @@ static int launch_chunk(const SolveArgs& a, unsigned char* ws, const PkgLayout& 
         ++g_launch_count;
         RDPN_LAUNCH_CHECK();
     }
+    if (t_stage_ms) RDPN_CUDA_TRY(cudaEventRecord(ev[1], st));
     {  // K2
         const ScoreLayout sl = make_score_layout(H, R);
         if (sl.total > 227 * 1024) return RDPN_E_TOOLARGE;
@@ -1026,6 +1037,7 @@ static int launch_chunk(const SolveArgs& a, unsigned char* ws, const PkgLayout& 
                                  (const int*)fdone, sdone));
         ++g_launch_count;
     }
+    if (t_stage_ms) RDPN_CUDA_TRY(cudaEventRecord(ev[2], st));
     {  // K3
         const size_t smem = (size_t)RF_W * 3 * R * sizeof(float);
         const int rc = ensure_func_smem((const void*)refit_kernel, SLOT_REFIT, smem);
@@ -1034,8 +1046,20 @@ static int launch_chunk(const SolveArgs& a, unsigned char* ws, const PkgLayout& 
                                  lay, (const int*)sdone));
         ++g_launch_count;
     }
+    if (t_stage_ms) {
+        RDPN_CUDA_TRY(cudaEventRecord(ev[3], st));
+        RDPN_CUDA_TRY(cudaEventSynchronize(ev[3]));
+        for (int i = 0; i < 3; ++i) {
+            float ms = 0.f;
+            RDPN_CUDA_TRY(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+            t_stage_ms[i] += ms;
+        }
+        for (auto& e : ev) cudaEventDestroy(e);
+    }
     return 0;
 }
+
+void set_stage_timing(float* ms3) { t_stage_ms = ms3; }
 
 // K1 -> K2 -> K3 on the caller's stream, in chunks of as many ROIs as the workspace holds (chunk_rois caps it).
 int launch_split(const SolveArgs& a, bool dense, void* ws, size_t ws_bytes, int chunk_rois, cudaStream_t st) {

@@ -249,6 +249,14 @@ class SolvePlan:
             _lib.check(rc, "pose_solve")
         return self.result
 
+    def stage_ms(self, stream=None):
+        """Durations (ms) of the pipeline's three kernels on this plan's inputs, run one after the other with CUDA
+        events between them (rdpn_pose_solve_stage_ms): (front, score, refit).  Synchronises."""
+        st = (stream or torch.cuda.current_stream(self._dev)).cuda_stream
+        ms = (ctypes.c_float * 3)()
+        _lib.check(_lib.lib().rdpn_pose_solve_stage_ms(*self._args, st, ms), "pose_solve_stage_ms")
+        return float(ms[0]), float(ms[1]), float(ms[2])
+
 
 def make_plan(solver, depth, Kp, coor_x, coor_y, coor_z, mask, extent, hyp_idx=None, region_idx=None, anchors=None,
               depth_div=None, t_net=None, roi_base=0):
