@@ -689,6 +689,22 @@ def gpu_arm(args):
         dt = reduce_max(time.perf_counter() - t0)
         return dt, bool(torch.equal(bufs[(e2e_steps - 1) % depth][0], h_pose))
 
+    # the bus ceiling beside it: plain cudaMemcpyAsync of one pinned plane set, every rank at the same time
+    probe_dst = torch.empty_like(sets[0]["mask"][:EB])
+    probe_bytes = pin["mask"].numel() * 4
+    for _ in range(2):
+        probe_dst.copy_(pin["mask"], non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        probe_dst.copy_(pin["mask"], non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_probe_s = reduce_max(time.perf_counter() - t0)
+    h2d_ceiling = 10 * probe_bytes / h2d_probe_s / 1e9  # GB/s per GPU with all ranks copying
+    del probe_dst
+
     copy_s, copy_bytes, _ = time_host_calls(_lib.TRANSFER_COPY)
     copy_pose = h_pose.clone()
     e2e_s, h2d, e2e_used = time_host_calls(_lib.TRANSFER_AUTO)  # pinned buffers -> gated pull
@@ -848,6 +864,14 @@ def gpu_arm(args):
                        "4-stage pipeline inside a call, step i + 1 submitted before step i is waited for, two sets of pinned "
                        "result buffers)",
                 "matches_synchronous_call": pipe_ok, "depth": 2,
+                "bus": {"h2d_GBps_per_gpu_this_path": h2d * e2e_steps / pipe_s / 1e9,
+                        "h2d_GBps_per_gpu_plain_memcpy": h2d_ceiling, "aggregate_plain_memcpy_GBps": h2d_ceiling * world,
+                        "fraction_of_plain_memcpy": (h2d * e2e_steps / pipe_s / 1e9) / h2d_ceiling,
+                        "note": "plain_memcpy = cudaMemcpyAsync of a %.0f MB pinned buffer, 10 in a row, all ranks at the same time "
+                                "(max over ranks): the ceiling of this box's PCIe / host-memory fabric for %d GPU(s) pulling at "
+                                "once.  The mask plane (16 KB / ROI) has to cross whole -- its min / max and every pixel's test need "
+                                "it -- and the gated sectors of the other planes come on top: the bytes, not the kernels, bound "
+                                "this number" % (probe_bytes / 1e6, world)},
                 "note": "every step's inputs cross the bus and every step's results are back in host memory inside the timed "
                         "region.  h2d_bytes_per_step is MEASURED per GPU (by the synchronous call on the same buffers): the mask "
                         "planes + the per-ROI arrays, hypothesis triplets and the 32-byte sectors of depth/coor/region-id planes "

@@ -64,7 +64,12 @@ void farthest_point_sampling_init_center(float* pts, int* idxs, int pn, int sn);
 
 /* Device-pointer entries.  d_ws: scratch of at least rdpn_fps_workspace_bytes(sn) bytes.
  * Indices are bit-exact with the reference C++ (squared FP32 distances without FMA, lowest index
- * wins ties, index 0 when nothing is left: cpp:40-73). */
+ * wins ties, index 0 when nothing is left: cpp:40-73).
+ * Three implementations behind the same entry, by cloud size: <= 32 768 points one thread-block cluster (arg-max
+ * through distributed shared memory); up to 148 x 512 x 16 = 1.21 M points a persistent cooperative grid with the
+ * cloud in registers; above that the same grid streaming the cloud and the running minima from global memory, which
+ * needs pn more floats behind the workspace header (ws_bytes >= rdpn_fps_workspace_bytes(sn) + 4 pn; RDPN_E_TOOLARGE
+ * otherwise). */
 size_t rdpn_fps_workspace_bytes(int sn);
 int rdpn_fps_init_center(const float* d_pts, int32_t* d_idxs, int pn, int sn, void* d_ws, size_t ws_bytes,
                          void* stream);
@@ -74,6 +79,14 @@ int rdpn_fps_from_index(const float* d_pts, int32_t* d_idxs, int pn, int sn, int
  * get_fps_and_center (core/utils/data_utils.py:217-226) computed in FP64. out: [sn,3] (+[1,3]). */
 int rdpn_fps_gather(const float* d_pts, const int32_t* d_idxs, int pn, int sn, float* d_out, double* d_center,
                     void* stream);
+/* Many objects in ONE launch (the loop of tools/lm/1_compute_fps.py:26-35 runs get_fps_and_center object by object):
+ * d_pts holds the clouds back to back, object o = points [d_offsets[o], d_offsets[o + 1]) (nobj + 1 offsets), every
+ * object gets sn picks into d_idxs[o * sn ..] (indices relative to the object's first point).  d_starts == NULL:
+ * farthest_point_sampling_init_center for every object; else d_starts[o] is the first pick of object o
+ * (farthest_point_sampling).  One thread-block cluster per object: max_pn (the largest cloud) <= 65 536 points,
+ * RDPN_E_TOOLARGE above -- use the per-object entries there. */
+int rdpn_fps_batch(const float* d_pts, const int32_t* d_offsets, int nobj, int max_pn, int sn, const int32_t* d_starts,
+                   int32_t* d_idxs, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * a1  ROI crop intrinsics -- core/utils/data_utils.py:111-152 (rot = 0) + data_loader.py:553-568.

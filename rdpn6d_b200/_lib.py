@@ -64,6 +64,7 @@ SIGNATURES = {
     "rdpn_pose_solve_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "rdpn_pose_solve_ws": (ctypes.c_int, [ctypes.POINTER(RoiInputs), c_vp, c_vp, ctypes.POINTER(SolveParams),
                                           ctypes.POINTER(SolveOutputs), c_vp, ctypes.c_size_t, c_vp]),
+    "rdpn_fps_batch": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp]),
     "rdpn_pose_solve_stage_ms": (ctypes.c_int, [ctypes.POINTER(RoiInputs), c_vp, c_vp, ctypes.POINTER(SolveParams),
                                                 ctypes.POINTER(SolveOutputs), c_vp, ctypes.c_size_t, c_vp,
                                                 ctypes.POINTER(ctypes.c_float)]),
@@ -110,11 +111,21 @@ def lib():
 
     try:
         _build.build()
-    except Exception as e:  # the sources are newer but nvcc is unavailable: use the shipped .so if any
+    except Exception as e:
+        # No silent stale binary: when the sources are newer than the shipped .so and the rebuild fails, that is an
+        # error (a GPU box has nvcc; a box without it must receive a current .so).  RDPN_ALLOW_STALE_LIB=1 opts in to
+        # loading the stale library anyway (debugging only).
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(
                 "rdpn6d_b200: librdpn6d_b200.so is missing and could not be built (%s). "
                 "This package has no CPU fallback." % e)
+        if os.environ.get("RDPN_ALLOW_STALE_LIB") != "1":
+            raise RuntimeError(
+                "rdpn6d_b200: csrc/ or include/ is newer than librdpn6d_b200.so and the rebuild failed (%s). "
+                "Rebuild with `python -m rdpn6d_b200.build`, or set RDPN_ALLOW_STALE_LIB=1 to load the stale library." % e)
+        import warnings
+
+        warnings.warn("rdpn6d_b200: loading a STALE librdpn6d_b200.so (RDPN_ALLOW_STALE_LIB=1): %s" % e)
     L = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         try:

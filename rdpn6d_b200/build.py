@@ -75,7 +75,7 @@ def _build_locked(ptxas, verbose):
         if ptxas or verbose:
             print(out)
     tmp = LIB + ".tmp.%d" % os.getpid()
-    link = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs
+    link = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs + ["-ldl"]  # dl: NVTX 3
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)

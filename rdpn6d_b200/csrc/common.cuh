@@ -20,7 +20,17 @@
         if (_e != cudaSuccess) return (int)_e;                \
     } while (0)
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX 3: a no-op unless a profiler is attached
+
 namespace rdpn {
+
+// NVTX range around a C-ABI entry point (the tracing row of SURVEY section 5: the reference has perf_counter only,
+// gdrn_evaluator.py:613-651); shows the call, its launches and its copies as one named span in Nsight Systems.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+#define RDPN_NVTX(name) ::rdpn::NvtxRange nvtx_range_guard_(name)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);

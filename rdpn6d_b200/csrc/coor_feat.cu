@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(CF_TP)
 extern "C" int rdpn_coor_feat(const float* d_coor_x, const float* d_coor_y, const float* d_coor_z, const float* d_roi_coord_2d,
                               const float* d_region, const float* d_fps, const float* d_mask, int R, int mask_mode,
                               int region_attention, int mask_attention, float* d_out, int B, void* stream) {
+    RDPN_NVTX("rdpn_coor_feat");
     if (!d_coor_x || !d_coor_y || !d_coor_z || !d_roi_coord_2d || !d_region || !d_fps || !d_out || B <= 0) return RDPN_E_BADARG;
     if (R <= 0 || R > 64) return RDPN_E_TOOLARGE;
     if (mask_attention < 0 || mask_attention > 2 || mask_mode < 0 || mask_mode > 2) return RDPN_E_BADARG;

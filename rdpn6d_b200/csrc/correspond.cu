@@ -237,6 +237,7 @@ int check_roi_inputs(const rdpn_roi_inputs* in, bool* dense);
 
 extern "C" int rdpn_correspond(const rdpn_roi_inputs* in, float* d_cam, float* d_obj, float* d_w, uint8_t* d_sel,
                                int32_t* d_nsel, void* stream) {
+    RDPN_NVTX("rdpn_correspond");
     bool dense = false;
     int rc = rdpn::check_roi_inputs(in, &dense);
     if (rc) return rc;

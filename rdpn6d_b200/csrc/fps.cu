@@ -16,6 +16,7 @@
 // cooperative-groups grid.sync, no slot reset, ~4 L2 round trips per pick.
 #include "common.cuh"
 
+#include <cooperative_groups.h>
 #include <float.h>
 #include <stdlib.h>
 
@@ -186,28 +187,348 @@ __global__ void __launch_bounds__(FPS_THREADS, 1)
     }
 }
 
-__global__ void fps_gather_kernel(const float* __restrict__ pts, const int* __restrict__ idxs, int pn, int sn,
-                                  float* __restrict__ out, double* __restrict__ center) {
-    // block 0: out[i] = pts[idxs[i]] (fps_utils.py:21); all blocks: FP64 per-axis sums for the mean row
-    if (blockIdx.x == 0)
-        for (int i = threadIdx.x; i < sn * 3; i += blockDim.x) out[i] = pts[3 * (size_t)idxs[i / 3] + (i % 3)];
-    if (center == nullptr) return;
+// Clouds beyond the register-resident limit (148 x 512 x 16 = 1.21 M points): same grid-wide arg-max, the cloud and the
+// running minima streamed from global memory every pick (20 B per point and pick: HBM-bound, SURVEY 8d's model).
+__global__ void __launch_bounds__(FPS_THREADS, 1)
+    fps_stream_kernel(const float* __restrict__ pts, float* __restrict__ md, int* __restrict__ idxs, int pn, int sn, int start,
+                      unsigned long long* keys, unsigned* cnt, unsigned* bbox) {
+    __shared__ FpsShared sh;
+    const int G = gridDim.x, b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const long long stride = (long long)G * FPS_THREADS, first = (long long)b * FPS_THREADS + t;
+    int slot = 0, cur;
+    if (start < 0) {
+        float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        for (long long i = first; i < pn; i += stride) {
+            const float x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+            mn[0] = fminf(mn[0], x); mx[0] = fmaxf(mx[0], x);
+            mn[1] = fminf(mn[1], y); mx[1] = fmaxf(mx[1], y);
+            mn[2] = fminf(mn[2], z); mx[2] = fmaxf(mx[2], z);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            mn[c] = warp_min(mn[c]);
+            mx[c] = warp_max(mx[c]);
+            if (lane == 0) { sh.fmin[warp][c] = mn[c]; sh.fmax[warp][c] = mx[c]; }
+        }
+        __syncthreads();
+        if (t < 3) {
+            float lo = FLT_MAX, hi = -FLT_MAX;
+            for (int w = 0; w < FPS_WARPS; ++w) { lo = fminf(lo, sh.fmin[w][t]); hi = fmaxf(hi, sh.fmax[w][t]); }
+            atomicMax(bbox + t, ~f2ord(lo));
+            atomicMax(bbox + 3 + t, f2ord(hi));
+        }
+        __syncthreads();
+        if (t == 0) {
+            __threadfence();
+            red_release_add_u32(cnt + slot, 1u);
+            while (ld_acquire_u32(cnt + slot) < (unsigned)G) {
+            }
+        }
+        __syncthreads();
+        if (t < 3) sh.ctr[t] = __fmul_rn(__fadd_rn(ord2f(__ldcg(bbox + 3 + t)), ord2f(~__ldcg(bbox + t))), 0.5f);
+        ++slot;
+        __syncthreads();
+        const float cx = sh.ctr[0], cy = sh.ctr[1], cz = sh.ctr[2];
+        unsigned long long key = 0ull;
+        for (long long i = first; i < pn; i += stride) {
+            const float d = sqdist_nofma(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], cx, cy, cz);
+            const float m = d < FLT_MAX ? d : FLT_MAX;
+            md[i] = m;
+            const unsigned long long kk = m > 0.f ? (((unsigned long long)__float_as_uint(m) << 32) | (0xFFFFFFFFu - (unsigned)i)) : 0ull;
+            key = kk > key ? kk : key;
+        }
+        key = grid_max_key(key, sh, keys, cnt, slot++);
+        cur = key ? (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull)) : 0;
+    } else {
+        for (long long i = first; i < pn; i += stride) md[i] = FLT_MAX;
+        cur = start;
+    }
+    for (int it = 0; it < sn; ++it) {
+        if (b == 0 && t == 0) idxs[it] = cur;
+        if (it == sn - 1) break;
+        const float cx = __ldg(pts + 3 * (size_t)cur), cy = __ldg(pts + 3 * (size_t)cur + 1), cz = __ldg(pts + 3 * (size_t)cur + 2);
+        unsigned long long key = 0ull;
+        for (long long i = first; i < pn; i += stride) {
+            float m = md[i];
+            if (i == cur) m = -1.f;  // taken: never updated, never a candidate again (cpp:50,66,152)
+            const float d = sqdist_nofma(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], cx, cy, cz);
+            m = d < m ? d : m;
+            md[i] = m;
+            const unsigned long long kk = m > 0.f ? (((unsigned long long)__float_as_uint(m) << 32) | (0xFFFFFFFFu - (unsigned)i)) : 0ull;
+            key = kk > key ? kk : key;
+        }
+        key = grid_max_key(key, sh, keys, cnt, slot++);
+        cur = key ? (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull)) : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small clouds (the sizes the reference's tools run: tools/lm/1_compute_fps.py:26-35, 10^4-10^5 model vertices, <= 256
+// picks, one object after the other): ONE THREAD-BLOCK CLUSTER per object, many objects per launch.
+// The cloud of an object is dealt to the C <= 8 CTAs of its cluster (registers, as above); the arg-max of a pick is
+// block-reduced, parked in the CTA's shared memory, and after ONE cluster barrier every CTA reads the C candidates
+// through distributed shared memory -- no global atomics, no spinning on L2.  Same arithmetic, same keys, same
+// tie rule: bit-identical picks.
+// ---------------------------------------------------------------------------------------------
+namespace cg = cooperative_groups;
+constexpr int FPS_MAX_CLUSTER = 8;   // the portable cluster size: 8 x 512 x 16 = 65 536 points per object
+
+struct __align__(16) FpsCand {  // a candidate pick travels with its coordinates: the next round needs no global load
+    unsigned long long key;
+    float x, y, z, pad;
+    float pad2[2];
+};
+struct FpsClusterShared {
+    FpsCand wcand[FPS_WARPS];
+    FpsCand ccand[2];             // this CTA's candidate, double-buffered by pick parity
+    float fmin[FPS_WARPS][3];
+    float fmax[FPS_WARPS][3];
+    float bb[6];                  // this CTA's bounding box (min xyz, max xyz)
+};
+
+// warp-wide max of a 64-bit key by two 32-bit REDUX instead of five shuffle rounds
+__device__ __forceinline__ unsigned long long warp_max_key_redux(unsigned long long key) {
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return ((unsigned long long)mh << 32) | ml;
+}
+
+template <int PPT>
+__global__ void __launch_bounds__(FPS_THREADS, 1)
+    fps_cluster_kernel(const float* __restrict__ pts_all, const int* __restrict__ offs, int* __restrict__ idxs_all, int sn,
+                       const int* __restrict__ starts, int one_pn, int one_start) {
+    __shared__ FpsClusterShared sh;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int obj = blockIdx.x / C, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int o0 = offs ? offs[obj] : 0;
+    const int pn = offs ? offs[obj + 1] - o0 : one_pn;
+    const float* pts = pts_all + 3 * (size_t)o0;
+    int* idxs = idxs_all + (size_t)obj * sn;
+    const int start = offs ? (starts ? starts[obj] : -1) : one_start;
+    float px[PPT], py[PPT], pz[PPT], md[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+        const int i = (k * C + rank) * FPS_THREADS + t;
+        if (i < pn) {
+            px[k] = pts[3 * (size_t)i + 0];
+            py[k] = pts[3 * (size_t)i + 1];
+            pz[k] = pts[3 * (size_t)i + 2];
+            md[k] = FLT_MAX;
+        } else {
+            px[k] = py[k] = pz[k] = 0.f;
+            md[k] = -1.f;
+        }
+    }
+    // Cluster-wide max of a key whose owner thread also knows the candidate's coordinates (bx, by, bz): two REDUX in
+    // the warp, one __syncthreads, two REDUX over the warp candidates, ONE cluster barrier, C remote reads of 8 bytes and
+    // one of 12.  Returns the winning key and its coordinates (cx, cy, cz).
+    int par = 0;
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    auto cluster_max_key = [&](unsigned long long key, float bx, float by, float bz) -> unsigned long long {
+        const unsigned long long wk = warp_max_key_redux(key);
+        if (wk ? key == wk : lane == 0) {  // keys embed the point index: exactly one owner (lane 0 when nothing is left)
+            FpsCand c;
+            c.key = wk; c.x = bx; c.y = by; c.z = bz; c.pad = 0.f; c.pad2[0] = c.pad2[1] = 0.f;
+            sh.wcand[warp] = c;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned long long k = lane < FPS_WARPS ? sh.wcand[lane].key : 0ull;
+            const unsigned long long bk = warp_max_key_redux(k);
+            if (bk ? (lane < FPS_WARPS && k == bk) : lane == 0) sh.ccand[par] = sh.wcand[lane];
+        }
+        cluster.sync();
+        unsigned long long best = 0ull;
+        int br = 0;
+        for (int r = 0; r < C; ++r) {
+            const unsigned long long k = cluster.map_shared_rank(&sh.ccand[par], r)->key;
+            if (k > best) { best = k; br = r; }
+        }
+        if (best) {
+            const FpsCand* w = cluster.map_shared_rank(&sh.ccand[par], br);
+            cx = w->x; cy = w->y; cz = w->z;
+        } else {  // nothing positive left: the reference returns index 0 (cpp:60,72)
+            cx = __ldg(pts); cy = __ldg(pts + 1); cz = __ldg(pts + 2);
+        }
+        par ^= 1;  // the next pick writes the other slot: its barrier orders that write after every read of this one
+        return best;
+    };
+    int cur;
+    if (start < 0) {
+        float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+#pragma unroll
+        for (int k = 0; k < PPT; ++k)
+            if (md[k] >= 0.f) {
+                mn[0] = fminf(mn[0], px[k]); mx[0] = fmaxf(mx[0], px[k]);
+                mn[1] = fminf(mn[1], py[k]); mx[1] = fmaxf(mx[1], py[k]);
+                mn[2] = fminf(mn[2], pz[k]); mx[2] = fmaxf(mx[2], pz[k]);
+            }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            mn[c] = warp_min(mn[c]);
+            mx[c] = warp_max(mx[c]);
+            if (lane == 0) { sh.fmin[warp][c] = mn[c]; sh.fmax[warp][c] = mx[c]; }
+        }
+        __syncthreads();
+        if (t < 3) {
+            float lo = FLT_MAX, hi = -FLT_MAX;
+            for (int w = 0; w < FPS_WARPS; ++w) { lo = fminf(lo, sh.fmin[w][t]); hi = fmaxf(hi, sh.fmax[w][t]); }
+            sh.bb[t] = lo;
+            sh.bb[3 + t] = hi;
+        }
+        cluster.sync();
+        float ctr[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float lo = FLT_MAX, hi = -FLT_MAX;
+            for (int r = 0; r < C; ++r) {
+                const float* rb = cluster.map_shared_rank(sh.bb, r);
+                lo = fminf(lo, rb[c]);
+                hi = fmaxf(hi, rb[3 + c]);
+            }
+            ctr[c] = __fmul_rn(__fadd_rn(hi, lo), 0.5f);  // (max+min)*(1.f/2.f), cpp:20,138
+        }
+        // the thread's best candidate by FP32 compare (strict '>' in ascending k = ascending index: the lowest index
+        // wins ties, cpp:67-71); the 64-bit key is built once per thread, not once per point
+        float bd = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
+        int bk = 0;
+#pragma unroll
+        for (int k = 0; k < PPT; ++k)
+            if (md[k] >= 0.f) {
+                const float d = sqdist_nofma(px[k], py[k], pz[k], ctr[0], ctr[1], ctr[2]);
+                md[k] = d < FLT_MAX ? d : FLT_MAX;  // cpp:141
+                if (md[k] > bd) { bd = md[k]; bk = k; bx = px[k]; by = py[k]; bz = pz[k]; }
+            }
+        unsigned long long key =
+            bd > 0.f ? (((unsigned long long)__float_as_uint(bd) << 32) | (0xFFFFFFFFu - (((unsigned)bk * C + rank) * FPS_THREADS + t))) : 0ull;
+        key = cluster_max_key(key, bx, by, bz);  // cpp:149
+        cur = key ? (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull)) : 0;
+    } else {
+        cur = start;
+        cx = __ldg(pts + 3 * (size_t)cur); cy = __ldg(pts + 3 * (size_t)cur + 1); cz = __ldg(pts + 3 * (size_t)cur + 2);
+    }
+    for (int it = 0; it < sn; ++it) {
+        if (rank == 0 && t == 0) idxs[it] = cur;  // cpp:153
+        if (it == sn - 1) break;                  // cpp:154
+        {
+            const int q = cur / FPS_THREADS;
+            if ((cur % FPS_THREADS) == t && (q % C) == rank) {
+                const int kk = q / C;
+#pragma unroll
+                for (int k = 0; k < PPT; ++k)
+                    if (k == kk) md[k] = -1.f;  // cpp:152
+            }
+        }
+        float bd = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
+        int bk = 0;
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            const float d = sqdist_nofma(px[k], py[k], pz[k], cx, cy, cz);
+            md[k] = d < md[k] ? d : md[k];  // cpp:52 (taken / padding entries hold -1 and never change)
+            if (md[k] > bd) { bd = md[k]; bk = k; bx = px[k]; by = py[k]; bz = pz[k]; }  // cpp:67-71
+        }
+        unsigned long long key =
+            bd > 0.f ? (((unsigned long long)__float_as_uint(bd) << 32) | (0xFFFFFFFFu - (((unsigned)bk * C + rank) * FPS_THREADS + t))) : 0ull;
+        key = cluster_max_key(key, bx, by, bz);
+        cur = key ? (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull)) : 0;  // cpp:60,72
+    }
+    cluster.sync();  // no CTA leaves while a sibling may still read its shared memory
+}
+
+// nobj clusters of C CTAs; offs == nullptr: one object of one_pn points.  Picks C and the points per thread so that the
+// rate per pick is best and returns RDPN_E_TOOLARGE beyond 8 CTAs x 512 threads x 16 points.
+static int fps_cluster_launch(const float* d_pts, const int* d_offs, int32_t* d_idxs, int nobj, int max_pn, int sn, const int* d_starts,
+                              int one_start, cudaStream_t st) {
+    // measured on B200 (benchmarks/fps_ppt_probe.py): 4 to 8 CTAs with 2 to 8 points per thread give the best rate
+    // (1.2-1.6 us per pick); wider clusters pay for the barrier, narrower ones for the serial distance updates
+    int ppt = 2;
+    while (ppt < 16 && (long long)FPS_MAX_CLUSTER * FPS_THREADS * ppt < max_pn) ppt *= 2;
+    if (const char* e = getenv("RDPN_FPS_CLUSTER_PPT")) {  // tuning: more points per thread = narrower cluster
+        const int v = atoi(e);
+        ppt = 1;
+        while (ppt < 16 && (ppt < v || (long long)FPS_MAX_CLUSTER * FPS_THREADS * ppt < max_pn)) ppt *= 2;
+    }
+    if ((long long)FPS_MAX_CLUSTER * FPS_THREADS * ppt < max_pn) return RDPN_E_TOOLARGE;
+    int C = (int)(((long long)max_pn + (long long)FPS_THREADS * ppt - 1) / ((long long)FPS_THREADS * ppt));
+    if (C < 1) C = 1;
+    const void* fn = nullptr;
+    switch (ppt) {
+        case 1: fn = (const void*)fps_cluster_kernel<1>; break;
+        case 2: fn = (const void*)fps_cluster_kernel<2>; break;
+        case 4: fn = (const void*)fps_cluster_kernel<4>; break;
+        case 8: fn = (const void*)fps_cluster_kernel<8>; break;
+        default: fn = (const void*)fps_cluster_kernel<16>; break;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(nobj * C));
+    cfg.blockDim = dim3(FPS_THREADS);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    void* args[] = {(void*)&d_pts, (void*)&d_offs, (void*)&d_idxs, (void*)&sn, (void*)&d_starts, (void*)&max_pn, (void*)&one_start};
+    RDPN_CUDA_TRY(cudaLaunchKernelExC(&cfg, fn, args));
+    ++g_launch_count;
+    return 0;
+}
+
+// Per-axis mean in FP64 with a FIXED summation order (run-to-run identical): every block sums a fixed slice, block
+// partials are combined in block order by the block that finishes last.
+__global__ void fps_center_kernel(const float* __restrict__ pts, int pn, double* __restrict__ partial, unsigned* __restrict__ ticket,
+                                  double* __restrict__ center) {
+    __shared__ double red[8][3];
+    __shared__ bool last;
     double s[3] = {0, 0, 0};
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pn; i += (long long)gridDim.x * blockDim.x) {
         s[0] += pts[3 * i];
         s[1] += pts[3 * i + 1];
         s[2] += pts[3 * i + 2];
     }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int c = 0; c < 3; ++c) {
-        double v = warp_sum(s[c]);
-        if ((threadIdx.x & 31) == 0) atomicAdd(center + c, v / (double)pn);
+        const double v = warp_sum(s[c]);
+        if (lane == 0) red[warp][c] = v;
     }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double a = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += red[w][threadIdx.x];
+        partial[3 * blockIdx.x + threadIdx.x] = a;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last && threadIdx.x < 3) {
+        __threadfence();
+        double a = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) a += __ldcg(partial + 3 * b + threadIdx.x);
+        center[threadIdx.x] = a / (double)pn;
+        if (threadIdx.x == 0) *ticket = 0u;
+    }
+}
+
+__global__ void fps_gather_kernel(const float* __restrict__ pts, const int* __restrict__ idxs, int sn, float* __restrict__ out) {
+    // out[i] = pts[idxs[i]] (fps_utils.py:21)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < sn * 3; i += gridDim.x * blockDim.x)
+        out[i] = pts[3 * (size_t)idxs[i / 3] + (i % 3)];
 }
 
 static int fps_launch(const float* d_pts, int32_t* d_idxs, int pn, int sn, int start, void* d_ws, size_t ws_bytes,
                       cudaStream_t st) {
     if (!d_pts || !d_idxs || pn <= 0 || sn <= 0 || start >= pn) return RDPN_E_BADARG;
     if (!d_ws || ws_bytes < rdpn_fps_workspace_bytes(sn)) return RDPN_E_WORKSPACE;
+    if (pn <= 32768 && !getenv("RDPN_FPS_NO_CLUSTER")) {
+        // small clouds: one thread-block cluster, arg-max through distributed shared memory (above ~32 k points the
+        // cooperative grid's wider spread wins: benchmarks/fps_small.py)
+        return fps_cluster_launch(d_pts, nullptr, d_idxs, 1, pn, sn, nullptr, start, st);
+    }
     int dev = 0, sms = 0, coop = 0;
     RDPN_CUDA_TRY(cudaGetDevice(&dev));
     RDPN_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -220,13 +541,23 @@ static int fps_launch(const float* d_pts, int32_t* d_idxs, int pn, int sn, int s
     }
     int ppt = 1;
     while (ppt < 16 && (long long)gmax * FPS_THREADS * ppt < pn) ppt *= 2;
-    if ((long long)gmax * FPS_THREADS * ppt < pn) return RDPN_E_TOOLARGE;
-    int G = (int)(((long long)pn + (long long)FPS_THREADS * ppt - 1) / ((long long)FPS_THREADS * ppt));
+    const bool streaming = (long long)gmax * FPS_THREADS * ppt < pn;
+    // beyond the register-resident limit the running minima live behind the workspace header: pn more floats
+    if (streaming && ws_bytes < rdpn_fps_workspace_bytes(sn) + (size_t)pn * sizeof(float)) return RDPN_E_TOOLARGE;
+    int G = streaming ? gmax : (int)(((long long)pn + (long long)FPS_THREADS * ppt - 1) / ((long long)FPS_THREADS * ppt));
     // workspace: keys[sn+2] u64 | cnt[sn+2] u32 | bbox[6] u32   (all zero-initialised per call)
     unsigned long long* keys = (unsigned long long*)d_ws;
     unsigned* cnt = (unsigned*)(keys + sn + 2);
     unsigned* bbox = cnt + sn + 2;
     RDPN_CUDA_TRY(cudaMemsetAsync(d_ws, 0, rdpn_fps_workspace_bytes(sn), st));
+    if (streaming) {
+        float* md = reinterpret_cast<float*>((char*)d_ws + rdpn_fps_workspace_bytes(sn));
+        void* sargs[] = {(void*)&d_pts, (void*)&md, (void*)&d_idxs, (void*)&pn, (void*)&sn, (void*)&start, (void*)&keys, (void*)&cnt,
+                         (void*)&bbox};
+        RDPN_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)fps_stream_kernel, dim3(G), dim3(FPS_THREADS), sargs, 0, st));
+        ++g_launch_count;
+        return 0;
+    }
     void* args[] = {(void*)&d_pts, (void*)&d_idxs, (void*)&pn, (void*)&sn, (void*)&start, (void*)&keys, (void*)&cnt, (void*)&bbox};
     const void* fn = nullptr;
     switch (ppt) {
@@ -253,30 +584,48 @@ size_t rdpn_fps_workspace_bytes(int sn) {
 
 int rdpn_fps_init_center(const float* d_pts, int32_t* d_idxs, int pn, int sn, void* d_ws, size_t ws_bytes,
                          void* stream) {
+    RDPN_NVTX("rdpn_fps_init_center");
     return rdpn::fps_launch(d_pts, d_idxs, pn, sn, -1, d_ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int rdpn_fps_from_index(const float* d_pts, int32_t* d_idxs, int pn, int sn, int start, void* d_ws, size_t ws_bytes,
                         void* stream) {
+    RDPN_NVTX("rdpn_fps_from_index");
     if (start < 0) return RDPN_E_BADARG;
     return rdpn::fps_launch(d_pts, d_idxs, pn, sn, start, d_ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int rdpn_fps_gather(const float* d_pts, const int32_t* d_idxs, int pn, int sn, float* d_out, double* d_center,
                     void* stream) {
+    RDPN_NVTX("rdpn_fps_gather");
     if (!d_pts || !d_idxs || !d_out || pn <= 0 || sn <= 0) return RDPN_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
-    int blocks = 1;
-    if (d_center) {
-        RDPN_CUDA_TRY(cudaMemsetAsync(d_center, 0, 3 * sizeof(double), st));
-        blocks = (pn + 256 * 8 - 1) / (256 * 8);
-        if (blocks > 592) blocks = 592;
-        if (blocks < 1) blocks = 1;
-    }
-    rdpn::fps_gather_kernel<<<blocks, 256, 0, st>>>(d_pts, d_idxs, pn, sn, d_out, d_center);
+    rdpn::fps_gather_kernel<<<(sn * 3 + 255) / 256, 256, 0, st>>>(d_pts, d_idxs, sn, d_out);
     ++rdpn::g_launch_count;
     RDPN_LAUNCH_CHECK();
+    if (d_center) {
+        int blocks = (pn + 256 * 8 - 1) / (256 * 8);
+        if (blocks > 592) blocks = 592;
+        if (blocks < 1) blocks = 1;
+        void* scratch = nullptr;  // block partials + ticket, stream-ordered
+        const size_t bytes = (size_t)blocks * 3 * sizeof(double) + 16;
+        RDPN_CUDA_TRY(cudaMallocAsync(&scratch, bytes, st));
+        RDPN_CUDA_TRY(cudaMemsetAsync((char*)scratch + (size_t)blocks * 3 * sizeof(double), 0, 16, st));
+        rdpn::fps_center_kernel<<<blocks, 256, 0, st>>>(d_pts, pn, (double*)scratch,
+                                                        (unsigned*)((char*)scratch + (size_t)blocks * 3 * sizeof(double)), d_center);
+        ++rdpn::g_launch_count;
+        const cudaError_t e = cudaGetLastError();
+        cudaFreeAsync(scratch, st);
+        if (e != cudaSuccess) return (int)e;
+    }
     return 0;
+}
+
+int rdpn_fps_batch(const float* d_pts, const int32_t* d_offsets, int nobj, int max_pn, int sn, const int32_t* d_starts,
+                   int32_t* d_idxs, void* stream) {
+    RDPN_NVTX("rdpn_fps_batch");
+    if (!d_pts || !d_offsets || !d_idxs || nobj <= 0 || max_pn <= 0 || sn <= 0) return RDPN_E_BADARG;
+    return rdpn::fps_cluster_launch(d_pts, d_offsets, d_idxs, nobj, max_pn, sn, d_starts, -1, (cudaStream_t)stream);
 }
 
 }  // extern "C"

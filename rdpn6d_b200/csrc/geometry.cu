@@ -158,6 +158,7 @@ extern "C" {
 
 int rdpn_roi_intrinsics(const float* d_K, const float* d_center, const float* d_scale, int crop_res, float* d_Kp, int B,
                         void* stream) {
+    RDPN_NVTX("rdpn_roi_intrinsics");
     if (!d_K || !d_center || !d_scale || !d_Kp || B <= 0 || crop_res <= 0) return RDPN_E_BADARG;
     rdpn::roi_intrinsics_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_K, d_center, d_scale, crop_res, d_Kp, B);
     ++rdpn::g_launch_count;
@@ -167,6 +168,7 @@ int rdpn_roi_intrinsics(const float* d_K, const float* d_center, const float* d_
 
 int rdpn_backproject(const float* d_depth, const float* d_K, int k_stride, float* d_out, int B, int H, int W,
                      void* stream) {
+    RDPN_NVTX("rdpn_backproject");
     if (!d_depth || !d_K || !d_out || B <= 0 || H <= 0 || W <= 0 || (k_stride != 0 && k_stride != 9)) return RDPN_E_BADARG;
     const size_t total = (size_t)B * H * W;
     int blocks = (int)((total + 255) / 256);
@@ -180,6 +182,7 @@ int rdpn_backproject(const float* d_depth, const float* d_K, int k_stride, float
 int rdpn_centroid_z_to_pose(const float* d_rot_in, int rot_is_6d, const float* d_centroid, const float* d_z,
                             const float* d_K, const float* d_center, const float* d_resize_ratio, const float* d_wh,
                             int is_allo, int z_type_rel, float* d_rot_out, float* d_trans_out, int B, void* stream) {
+    RDPN_NVTX("rdpn_centroid_z_to_pose");
     if (!d_rot_in || !d_centroid || !d_z || !d_K || !d_center || !d_wh || !d_rot_out || !d_trans_out || B <= 0)
         return RDPN_E_BADARG;
     if (z_type_rel && !d_resize_ratio) return RDPN_E_BADARG;
@@ -192,6 +195,7 @@ int rdpn_centroid_z_to_pose(const float* d_rot_in, int rot_is_6d, const float* d
 }
 
 int rdpn_region_argmax(const float* d_region, int R, uint8_t* d_region_idx, int B, void* stream) {
+    RDPN_NVTX("rdpn_region_argmax");
     if (!d_region || !d_region_idx || B <= 0 || R <= 0 || R > 255) return RDPN_E_BADARG;
     if (((uintptr_t)d_region | (uintptr_t)d_region_idx) & 15) return RDPN_E_ALIGN;
     const size_t nq = (size_t)B * (RDPN_P / 4);
@@ -202,6 +206,7 @@ int rdpn_region_argmax(const float* d_region, int R, uint8_t* d_region_idx, int 
 }
 
 int rdpn_fp32_peak_probe(int iters, double* out_flops) {
+    RDPN_NVTX("rdpn_fp32_peak_probe");
     if (iters <= 0 || !out_flops) return RDPN_E_BADARG;
     int dev = 0, sms = 0;
     RDPN_CUDA_TRY(cudaGetDevice(&dev));
@@ -266,6 +271,7 @@ __global__ void xyz_to_region_kernel(const float* __restrict__ xyz, const float*
 
 extern "C" int rdpn_xyz_to_region(const float* d_xyz, const float* d_fps, int R, int P, uint8_t* d_region, float* d_delta, int B,
                                   void* stream) {
+    RDPN_NVTX("rdpn_xyz_to_region");
     if (!d_xyz || !d_fps || !d_region || !d_delta || B <= 0 || P <= 0 || R <= 0 || R > 254) return RDPN_E_BADARG;
     dim3 grid((P + 255) / 256, B);
     rdpn::xyz_to_region_kernel<<<grid, 256, (size_t)R * 3 * sizeof(float), (cudaStream_t)stream>>>(d_xyz, d_fps, R, P, d_region, d_delta, B);

@@ -313,7 +313,9 @@ static void fps_host(float* pts, int* idxs, int pn, int sn, int start) {
     float* d_pts = nullptr;
     int* d_idx = nullptr;
     void* d_ws = nullptr;
-    const size_t ws = rdpn_fps_workspace_bytes(sn);
+    // clouds beyond the register-resident limit (1.21 M points) stream their running minima from the workspace: pn
+    // more floats behind the header (rdpn_fps_init_center's contract)
+    const size_t ws = rdpn_fps_workspace_bytes(sn) + (pn > 1000000 ? (size_t)pn * sizeof(float) : 0);
     cudaError_t e = cudaMalloc(&d_pts, (size_t)pn * 3 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&d_idx, (size_t)sn * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&d_ws, ws);
@@ -336,6 +338,7 @@ static void fps_host(float* pts, int* idxs, int pn, int sn, int start) {
 void farthest_point_sampling_init_center(float* pts, int* idxs, int pn, int sn) { fps_host(pts, idxs, pn, sn, -1); }
 
 void farthest_point_sampling(float* pts, int* idxs, int pn, int sn) {
+    RDPN_NVTX("farthest_point_sampling");
     if (pn <= 0) return;
     srand((unsigned)time(0));  // farthest_point_sampling.cpp:93-94
     fps_host(pts, idxs, pn, sn, rand() % pn);
@@ -371,9 +374,26 @@ static int env_int(const char* name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
+// The context's entry points run on the context's device and leave the CALLER's current device as they found it
+// (PyTorch and other users of the runtime API keep a per-thread current device).
+struct DeviceGuard {
+    int prev;
+    cudaError_t err;
+    explicit DeviceGuard(int device) : prev(-1), err(cudaSuccess) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) err = cudaSetDevice(device);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
 int rdpn_ctx_create(int device, rdpn_ctx** out_ctx) {
+    RDPN_NVTX("rdpn_ctx_create");
     if (!out_ctx) return RDPN_E_BADARG;
-    RDPN_CUDA_TRY(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    RDPN_CUDA_TRY(guard.err);
     rdpn_ctx* c = (rdpn_ctx*)calloc(1, sizeof(rdpn_ctx));
     c->device = device;
     for (int i = 0; i < RDPN_STAGES; ++i) RDPN_CUDA_TRY(cudaStreamCreateWithFlags(&c->st[i], cudaStreamNonBlocking));
@@ -388,7 +408,7 @@ int rdpn_ctx_create(int device, rdpn_ctx** out_ctx) {
 
 void rdpn_ctx_destroy(rdpn_ctx* c) {
     if (!c) return;
-    cudaSetDevice(c->device);
+    DeviceGuard guard(c->device);
     for (int i = 0; i < RDPN_STAGES; ++i) {
         if (c->buf[i]) cudaFree(c->buf[i]);
         if (c->st[i]) cudaStreamDestroy(c->st[i]);
@@ -442,7 +462,8 @@ static int host_queue(rdpn_ctx* c, const rdpn_roi_inputs* h, const int32_t* h_hy
     if (!ho->pose || !ho->n_inliers || !ho->status) return RDPN_E_BADARG;
     if (!h->depth || !h->coor_x || !h->coor_y || !h->coor_z || !h->mask || !h->Kp || !h->extent) return RDPN_E_BADARG;
     if ((h->region_idx == nullptr) != (h->anchors == nullptr)) return RDPN_E_BADARG;
-    RDPN_CUDA_TRY(cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
+    RDPN_CUDA_TRY(guard.err);
     const bool dense = h->region_idx == nullptr;
     const int H = prm->num_hyp, R = dense ? 0 : h->num_regions;
     if (prm->sample_size != 0 && (prm->sample_size < 3 || prm->sample_size > RDPN_MAX_SAMPLE)) return RDPN_E_BADARG;
@@ -639,6 +660,7 @@ static int host_drain(rdpn_ctx* c) {
 
 int rdpn_pose_solve_host(rdpn_ctx* c, const rdpn_roi_inputs* h, const int32_t* h_hyp, const float* h_tnet,
                          const rdpn_solve_params* prm, const rdpn_solve_outputs* ho) {
+    RDPN_NVTX("rdpn_pose_solve_host");
     HostCallInfo info;
     memset(&info, 0, sizeof(info));
     if (c && c->count && c->counted_ticket != c->next_ticket) {  // submitted calls moved the counter: step over them
@@ -666,9 +688,11 @@ int rdpn_pose_solve_host(rdpn_ctx* c, const rdpn_roi_inputs* h, const int32_t* h
 
 int rdpn_pose_solve_host_submit(rdpn_ctx* c, const rdpn_roi_inputs* h, const int32_t* h_hyp, const float* h_tnet,
                                 const rdpn_solve_params* prm, const rdpn_solve_outputs* ho, int* out_ticket) {
+    RDPN_NVTX("rdpn_pose_solve_host_submit");
     if (!c || !out_ticket) return RDPN_E_BADARG;
     const int t = (int)(c->next_ticket % RDPN_MAX_INFLIGHT);
-    RDPN_CUDA_TRY(cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
+    RDPN_CUDA_TRY(guard.err);
     for (int i = 0; i < RDPN_STAGES; ++i) {
         if (!c->ev[t][i]) RDPN_CUDA_TRY(cudaEventCreateWithFlags(&c->ev[t][i], cudaEventDisableTiming));
         else RDPN_CUDA_TRY(cudaEventSynchronize(c->ev[t][i]));  // the ring is full: wait for its oldest call
@@ -688,6 +712,7 @@ int rdpn_pose_solve_host_submit(rdpn_ctx* c, const rdpn_roi_inputs* h, const int
 }
 
 int rdpn_ctx_wait(rdpn_ctx* c, int ticket) {
+    RDPN_NVTX("rdpn_ctx_wait");
     if (!c || ticket < 0 || ticket >= RDPN_MAX_INFLIGHT || !c->ev[ticket][0]) return RDPN_E_BADARG;
     for (int i = 0; i < RDPN_STAGES; ++i) RDPN_CUDA_TRY(cudaEventSynchronize(c->ev[ticket][i]));
     return 0;

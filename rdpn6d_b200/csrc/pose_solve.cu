@@ -1251,6 +1251,7 @@ size_t rdpn_pose_solve_workspace_bytes(int B, int num_hyp, int num_regions, int 
 
 int rdpn_pose_solve_ws(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, const float* d_t_net, const rdpn_solve_params* prm,
                        const rdpn_solve_outputs* out, void* d_ws, size_t ws_bytes, void* stream) {
+    RDPN_NVTX("rdpn_pose_solve_ws");
     rdpn::SolveArgs a;
     bool dense = false;
     int rc = solve_prepare(in, d_hyp_idx, d_t_net, prm, out, &a, &dense);
@@ -1264,6 +1265,7 @@ int rdpn_pose_solve_ws(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, cons
 
 int rdpn_pose_solve_stage_ms(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, const float* d_t_net, const rdpn_solve_params* prm,
                              const rdpn_solve_outputs* out, void* d_ws, size_t ws_bytes, void* stream, float* ms3) {
+    RDPN_NVTX("rdpn_pose_solve_stage_ms");
     if (!ms3) return RDPN_E_BADARG;
     rdpn::SolveArgs a;
     bool dense = false;
@@ -1279,6 +1281,7 @@ int rdpn_pose_solve_stage_ms(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx
 
 int rdpn_pose_solve(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, const float* d_t_net,
                     const rdpn_solve_params* prm, const rdpn_solve_outputs* out, void* stream) {
+    RDPN_NVTX("rdpn_pose_solve");
     rdpn::SolveArgs a;
     bool dense = false;
     int rc = solve_prepare(in, d_hyp_idx, d_t_net, prm, out, &a, &dense);
@@ -1297,6 +1300,7 @@ int rdpn_pose_solve(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, const f
 
 int rdpn_kabsch(const float* d_src, const float* d_dst, const float* d_w, int N, int with_scale, float* d_out_M,
                 float* d_out_scale, int B, void* stream) {
+    RDPN_NVTX("rdpn_kabsch");
     if (!d_src || !d_dst || !d_out_M || B <= 0) return RDPN_E_BADARG;
     if (N < 3) return RDPN_E_BADARG;  // transform.py:917-918 raises ValueError
     rdpn::kabsch_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(d_src, d_dst, d_w, N, with_scale, d_out_M, d_out_scale);

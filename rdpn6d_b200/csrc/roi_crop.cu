@@ -79,6 +79,7 @@ __global__ void roi_crop_depth_kernel(const float* __restrict__ imgs, int H, int
 
 extern "C" int rdpn_roi_crop_depth(const float* d_depth_imgs, int H, int W, const int32_t* d_img_idx, const float* d_center,
                                    const float* d_scale, int crop_res, int out_res, float* d_out, int B, void* stream) {
+    RDPN_NVTX("rdpn_roi_crop_depth");
     if (!d_depth_imgs || !d_center || !d_scale || !d_out || B <= 0 || H <= 0 || W <= 0) return RDPN_E_BADARG;
     if (crop_res <= 0 || out_res <= 0 || crop_res % out_res != 0) return RDPN_E_BADARG;
     rdpn::roi_crop_depth_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(d_depth_imgs, H, W, d_img_idx, d_center, d_scale, crop_res,

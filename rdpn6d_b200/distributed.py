@@ -52,22 +52,28 @@ def gather_rows(rows_local, total, group=None):
     return out[:total]
 
 
-def solve_sharded(solver, batch_local, total, group=None):
-    """Run the fused solver on this rank's shard and gather [total,16] rows on every rank.
+def solve_sharded(solver, batch_local, total, group=None, roi_base=None):
+    """Run the solver on this rank's shard and gather [total,16] rows on every rank.
 
-    batch_local: dict of CUDA tensors with keys depth, Kp, coor (or coor_x/y/z), mask, extent, hyp_idx,
-    and optionally region_idx, anchors, depth_div, t_net.
+    batch_local: dict of CUDA tensors with keys depth, Kp, coor (or coor_x/y/z), mask, extent, and optionally hyp_idx
+    (absent / None: the kernel draws the samples itself), region_idx, anchors, depth_div, t_net.
+    roi_base: global index of this shard's first ROI, default = the InferenceSampler rule's `begin` for this rank
+    (my_distributed_sampler.py:189-192) -- it keys the kernel-drawn sampling stream, so results do not depend on the
+    world size.
     """
     n = batch_local["depth"].shape[0]
+    if roi_base is None:
+        W, r = (dist.get_world_size(group), dist.get_rank(group)) if dist.is_available() and dist.is_initialized() else (1, 0)
+        roi_base = shard_range(total, r, W)[0]
     if n > 0:
         if "coor" in batch_local:
             cx, cy, cz = batch_local["coor"][:, 0], batch_local["coor"][:, 1], batch_local["coor"][:, 2]
         else:
             cx, cy, cz = batch_local["coor_x"], batch_local["coor_y"], batch_local["coor_z"]
         res = solver(batch_local["depth"], batch_local["Kp"], cx, cy, cz, batch_local["mask"], batch_local["extent"],
-                     batch_local["hyp_idx"], region_idx=batch_local.get("region_idx"),
+                     batch_local.get("hyp_idx"), region_idx=batch_local.get("region_idx"),
                      anchors=batch_local.get("anchors"), depth_div=batch_local.get("depth_div"),
-                     t_net=batch_local.get("t_net"))
+                     t_net=batch_local.get("t_net"), roi_base=roi_base)
         rows = res.rows16()
     else:
         rows = torch.zeros(0, 16, dtype=torch.float32, device=batch_local["depth"].device)

@@ -37,11 +37,14 @@ class GpuRansacKabsch:
     """Stateful processor holding the solver configuration and the accumulated predictions."""
 
     def __init__(self, num_hyp=256, inlier_thr=0.005, mask_thr=0.5, mask_mode=MASK_L1, weighted=False, refit_iters=1,
-                 label_to_obj_id=None, depth_is_scale_normalised=True, seed=0, sample_size=3, adaptive=False):
+                 label_to_obj_id=None, depth_is_scale_normalised=True, seed=0, sample_size=3, adaptive=False, roi_offset=0):
         """depth_is_scale_normalised: roi_coord_2d[:, 2] holds depth / resize_ratio (data_loader.py:563); the
         solver multiplies it back (depth_div = 1 / resize_ratio) so that the 3D-3D solve is metric.
         sample_size: pairs per RANSAC sample (3 = minimal; misc.py:72 uses random_sample_num = 10); adaptive: the
-        reference loop's early stop (misc.py:134-138)."""
+        reference loop's early stop (misc.py:134-138).  roi_offset: global index of the first ROI this evaluator will
+        see -- in a multi-rank evaluation the `begin` of this rank's InferenceSampler shard
+        (my_distributed_sampler.py:189-192, e.g. distributed.shard_range(total, rank, world)[0]) -- so that every rank
+        draws from its own part of the counter-based sampling stream and results do not depend on the world size."""
         self.num_hyp = num_hyp
         # the kernel draws the RANSAC triplets itself (seeded counter-based stream): no separate S1 pass, no
         # multinomial -- the step is one launch
@@ -51,12 +54,13 @@ class GpuRansacKabsch:
         self.mask_thr, self.mask_mode = mask_thr, mask_mode
         self.label_to_obj_id = label_to_obj_id or (lambda label: int(label) + 1)
         self.depth_is_scale_normalised = depth_is_scale_normalised
-        self._roi_base = 0  # ROIs seen so far: keeps the sampling stream independent of how the job is batched
+        self.roi_offset = int(roi_offset)
+        self._roi_base = self.roi_offset  # global index of the next ROI: the sampling stream does not depend on batching
         self._predictions = []
 
     def reset(self):
         self._predictions = []
-        self._roi_base = 0
+        self._roi_base = self.roi_offset
 
     def process(self, inputs, outputs, out_dict):
         """Fills self._predictions like process_pnp_ransac; returns the rows appended by this call."""

@@ -33,6 +33,8 @@ def fps_indices(pts, sn, init_center=True, start=None, stream=None):
     if pn == 0 or sn == 0:
         return idx
     ws_bytes = int(L.rdpn_fps_workspace_bytes(sn))
+    if pn > 1_000_000:  # beyond the register-resident limit the running minima stream from the workspace (include/rdpn6d_b200.h)
+        ws_bytes += 4 * pn
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pts.device)
     st = (stream or torch.cuda.current_stream(pts.device)).cuda_stream
     with torch.cuda.device(pts.device):
@@ -81,19 +83,46 @@ def get_fps_and_center(pts, num_fps=8, init_center=True):
     return torch.cat([out.to(torch.float64), center[None]], dim=0)
 
 
+def fps_indices_batch(clouds, sn, starts=None, stream=None):
+    """FPS of many clouds in ONE launch (rdpn_fps_batch: one thread-block cluster per object).  clouds: list of [N_i,3]
+    CUDA float32 tensors (N_i <= 65 536); starts: None = init_center for every object, else one first index per
+    object.  Returns [len(clouds), sn] int32 CUDA tensor, indices relative to each cloud."""
+    _require_cuda()
+    L = _lib.lib()
+    dev = clouds[0].device
+    sizes = [int(c.shape[0]) for c in clouds]
+    assert all(c.dim() == 2 and c.shape[1] == 3 for c in clouds) and min(sizes) > 0
+    pts = torch.cat([c.contiguous().to(torch.float32) for c in clouds], dim=0)
+    offs = torch.tensor(np.concatenate([[0], np.cumsum(sizes)]), dtype=torch.int32, device=dev)
+    idx = torch.zeros(len(clouds), sn, dtype=torch.int32, device=dev)
+    st_t = None if starts is None else torch.as_tensor(starts, dtype=torch.int32, device=dev).contiguous()
+    st = (stream or torch.cuda.current_stream(dev)).cuda_stream
+    with torch.cuda.device(dev):
+        rc = L.rdpn_fps_batch(pts.data_ptr(), offs.data_ptr(), len(clouds), max(sizes), sn,
+                              st_t.data_ptr() if st_t is not None else None, idx.data_ptr(), st)
+    _lib.check(rc, "fps_batch")
+    return idx
+
+
 def fps_and_center_for_models(clouds, nums_fps=(2, 4, 8, 12, 16, 20, 32, 64, 128, 256)):
     """The loop of tools/*/..._compute_fps.py (e.g. tools/lm/1_compute_fps.py:26-35): for every object cloud and
     every sample count, `get_fps_and_center(pts, n, init_center=True)`.  clouds: dict obj_id -> [N,3] numpy array.
-    Returns {str(obj_id): {"fps{n}_and_center": [n+1,3] array}} ready for mmcv.dump(fps_points.pkl).  Each cloud
-    is uploaded once; the K-step kernel runs per sample count (FPS prefixes differ per count only in length,
-    so the largest count is computed and shorter ones are prefixes of it)."""
+    Returns {str(obj_id): {"fps{n}_and_center": [n+1,3] array}} ready for mmcv.dump(fps_points.pkl).  Every cloud is
+    uploaded once and ALL objects run in one launch (one thread-block cluster per object) when the largest cloud has at
+    most 65 536 points, object by object otherwise; FPS prefixes differ per count only in length, so the largest
+    count is computed and shorter ones are prefixes of it."""
     _require_cuda()
     out = {}
     kmax = max(nums_fps)
-    for obj_id, pts in clouds.items():
-        pts = np.asarray(pts)
-        p32 = np.ascontiguousarray(pts, np.float32)
-        idx = fps_indices(torch.from_numpy(p32).cuda(), kmax, init_center=True).cpu().numpy()
+    ids = list(clouds.keys())
+    p32 = [np.ascontiguousarray(np.asarray(clouds[i]), np.float32) for i in ids]
+    dev_clouds = [torch.from_numpy(p).cuda() for p in p32]
+    if max(p.shape[0] for p in p32) <= 65536:
+        idx_all = fps_indices_batch(dev_clouds, kmax).cpu().numpy()
+    else:
+        idx_all = np.stack([fps_indices(c, kmax, init_center=True).cpu().numpy() for c in dev_clouds])
+    for j, obj_id in enumerate(ids):
+        pts = np.asarray(clouds[obj_id])
         avg = np.array([[np.average(pts[:, 0]), np.average(pts[:, 1]), np.average(pts[:, 2])]])
-        out[str(obj_id)] = {f"fps{n}_and_center": np.concatenate([p32[idx[:n]], avg], axis=0) for n in nums_fps}
+        out[str(obj_id)] = {f"fps{n}_and_center": np.concatenate([p32[j][idx_all[j][:n]], avg], axis=0) for n in nums_fps}
     return out

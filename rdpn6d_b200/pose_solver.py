@@ -19,6 +19,7 @@ PoseSolver / correspond take CUDA tensors; HostPoseSolver takes CPU tensors and 
 plugin call).  Either way the arithmetic runs in the CUDA kernels: there is no CPU compute path.
 """
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -89,6 +90,15 @@ class _Inputs:
                 raise ValueError("num_regions must be <= 255")
             rid = region_idx.detach()
             assert rid.shape == (B, 64, 64), tuple(rid.shape)
+            # Region ids are 0-based anchor indices (argmax over the R foreground channels, GDRN.py:206-218); the
+            # loader's roi_region uses 1..R with 0 = background (data_utils.py:229-244) and must be shifted by the
+            # caller.  The kernels drop pixels whose id is outside [0, R) from the gate; a wider integer dtype is
+            # checked here before the cast to uint8 would wrap it (RDPN_CHECK_INPUTS=1 also checks uint8 inputs: it
+            # costs a device synchronisation).
+            if rid.dtype != torch.uint8 or os.environ.get("RDPN_CHECK_INPUTS") == "1":
+                lo, hi = int(rid.min()), int(rid.max())
+                if lo < 0 or hi >= max(R, 1):
+                    raise ValueError("region_idx must hold anchor indices in [0, %d): found [%d, %d]" % (R, lo, hi))
             self.t["region_idx"] = rid.to(torch.uint8).contiguous()
             self.t["anchors"] = _vec(anchors, (B, R, 3), "anchors")
         s = _lib.RoiInputs()

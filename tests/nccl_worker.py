@@ -25,6 +25,15 @@ def main():
     r = pose_solver.PoseSolver(inlier_thr=0.005)(full["depth"], full["Kp"], full["coor"][:, 0], full["coor"][:, 1], full["coor"][:, 2],
                                                   full["mask"], full["extent"], full["hyp_idx"], full["region_idx"], full["anchors"])
     ok = torch.equal(rows, r.rows16())
+    # kernel-drawn samples: every rank draws from its own part of the counter-based stream (roi_base = shard begin), so the
+    # gathered rows equal the single-GPU solve whatever the world size
+    samp = pose_solver.PoseSolver(inlier_thr=0.005, num_hyp=64, seed=3)
+    local2 = {k: v for k, v in local.items() if k != "hyp_idx"}
+    rows2 = D.solve_sharded(samp, local2, total)
+    r2 = pose_solver.PoseSolver(inlier_thr=0.005, num_hyp=64, seed=3)(
+        full["depth"], full["Kp"], full["coor"][:, 0], full["coor"][:, 1], full["coor"][:, 2], full["mask"], full["extent"], None,
+        full["region_idx"], full["anchors"])
+    ok = ok and torch.equal(rows2, r2.rows16())
     flag = torch.tensor([int(ok)], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0 and int(flag) == 1:

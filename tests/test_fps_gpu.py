@@ -108,3 +108,50 @@ def test_get_fps_and_center_matches_reference_python_surface(cuda, golden_dir):
             got = fps_utils.get_fps_and_center(g[name + "_pts"], n)
             assert got.dtype == want.dtype and got.shape == want.shape
             assert np.array_equal(got, want)
+
+
+def test_cluster_path_sizes_and_cooperative_path_agree(cuda, monkeypatch):
+    """<= 32 768 points run in one thread-block cluster (DSMEM arg-max); the same clouds through the cooperative grid
+    (RDPN_FPS_NO_CLUSTER) and the C restatement give the same indices, bit for bit."""
+    for n, k in ((100, 10), (5_000, 32), (8_192, 64), (8_193, 64), (50_000, 64), (32_768, 40), (32_769, 40)):
+        p = np.random.default_rng(n + k).standard_normal((n, 3)).astype(np.float32)
+        a = _gpu_idx(p, k)
+        assert np.array_equal(a, fps_indices_port(p, k)), (n, k)
+        monkeypatch.setenv("RDPN_FPS_NO_CLUSTER", "1")
+        assert np.array_equal(_gpu_idx(p, k), a), (n, k)
+        monkeypatch.delenv("RDPN_FPS_NO_CLUSTER")
+
+
+def test_batched_objects_one_launch(cuda):
+    """rdpn_fps_batch: every object of a model set in one launch (tools/lm/1_compute_fps.py:26-35 loops object by
+    object) equals the per-object runs -- init_center and explicit starts, ragged sizes incl. tiny clouds."""
+    rng = np.random.default_rng(11)
+    sizes = [37, 5_000, 12_345, 1, 64_000, 9_000, 513, 65_536]
+    clouds = [rng.standard_normal((n, 3)).astype(np.float32) * rng.uniform(0.05, 0.2, 3).astype(np.float32) for n in sizes]
+    dev = [torch.from_numpy(c).cuda() for c in clouds]
+    before = _lib.launch_count()
+    idx = fps_utils.fps_indices_batch(dev, 48).cpu().numpy()
+    assert _lib.launch_count() - before == 1
+    for c, row in zip(clouds, idx):
+        assert np.array_equal(row, fps_indices_port(c, 48))
+    starts = [0, 17, 12_344, 0, 63_999, 5, 512, 65_535]
+    idx = fps_utils.fps_indices_batch(dev, 20, starts=starts).cpu().numpy()
+    for c, row, s0 in zip(clouds, idx, starts):
+        assert np.array_equal(row, fps_indices_port(c, 20, start=s0))
+
+
+def test_streaming_path_beyond_register_limit(cuda):
+    """More than 148 x 512 x 16 points: cloud and running minima streamed from global memory, same indices."""
+    p = fps_cloud(1_300_000, seed=4)
+    assert np.array_equal(_gpu_idx(p, 12), fps_indices_port(p, 12))
+    assert np.array_equal(_gpu_idx(p, 5, init_center=False, start=1_299_999), fps_indices_port(p, 5, start=1_299_999))
+
+
+def test_center_row_is_deterministic(cuda):
+    """get_fps_and_center's mean row: fixed-order FP64 reduction -- identical bits run after run, equal to numpy."""
+    t = torch.from_numpy(fps_cloud(300_000, seed=2)).cuda()
+    a = fps_utils.get_fps_and_center(t, 8)
+    for _ in range(5):
+        assert torch.equal(fps_utils.get_fps_and_center(t, 8), a)
+    ref = t.double().mean(0).cpu().numpy()
+    np.testing.assert_allclose(a[-1].cpu().numpy(), ref, rtol=0, atol=1e-12)

@@ -194,8 +194,8 @@ def test_translation_sanity_fallback(cuda):
 def test_full_size_lmo_1024_properties(cuda):
     """BASELINE configs[1] at full size: size-independent properties instead of a full oracle run
     (determinism, ROI-order equivariance, ground-truth recovery) + an oracle spot check."""
-    models = synth.make_models(8, 32, seed=1)
-    base = synth.make_batch(128, models=models, H=256, seed=4242, occlusion_max=0.6)
+    models = synth.make_models(8, 64, seed=1)  # the bench's LM-O workload: 64 anchors per object (bench.py WORKLOADS["lmo"])
+    base = synth.make_batch(128, models=models, H=256, seed=20260101, occlusion_max=0.6)
     b = synth.tile_batch(base, 1024)
     g = _to_cuda(b)
     r1 = _solve(g)
@@ -214,18 +214,20 @@ def test_full_size_lmo_1024_properties(cuda):
     pose = p1.cpu().numpy()
     errs = [po.re_rad_small(pose[i][:, :3], b["gt_pose"][i][:, :3]) for i in range(128) if ok[i]]
     assert np.median(errs) < 0.01
-    sub = {k: (None if v is None else v[:8]) for k, v in base.items()}
-    ores = po.pose_solve_batch(sub, sub["hyp_idx"], THR)
-    for i in range(8):
-        assert int(n1[i]) == ores[i]["n_inl"] and int(r1.best_h[i]) == ores[i]["best_h"]
+    ores = po.pose_solve_batch(base, base["hyp_idx"], THR)  # EVERY unique ROI of the config against the oracle
+    for i in range(128):
+        assert int(r1.status[i]) == ores[i]["status"], i
+        assert int(n1[i]) == ores[i]["n_inl"] and int(r1.best_h[i]) == ores[i]["best_h"], i
+        assert np.array_equal(m1[i].reshape(-1).cpu().numpy(), ores[i]["inlier_mask"]), i
         if ores[i]["status"] == 0:
             assert po.re_rad_small(pose[i][:, :3], ores[i]["pose"][:, :3]) <= ROT_TOL_RAD
             assert po.te(pose[i][:, 3], ores[i]["pose"][:, 3]) <= TRANS_TOL_M
 
 
 def test_full_size_ycbv_8192_incl_symmetric(cuda):
-    """BASELINE configs[2]: 21 objects (5 with symmetric geometry), 8192 ROIs, YCB-V intrinsics.  Properties at
-    full size + oracle parity on a slice that covers every object."""
+    """BASELINE configs[2]: 21 objects (5 with symmetric geometry), 8192 ROIs, YCB-V intrinsics (the bench's headline
+    workload).  Properties at full size + oracle parity on EVERY unique ROI, unweighted and with the weighted refit the
+    bench runs."""
     models = synth.make_models(21, 32, seed=7, n_symmetric=5)
     base = synth.make_batch(84, models=models, H=256, seed=777, K=synth.K_YCBV, occlusion_max=0.5)
     b = synth.tile_batch(base, 8192)
@@ -233,14 +235,18 @@ def test_full_size_ycbv_8192_incl_symmetric(cuda):
     r = _solve(g)
     assert torch.equal(r.pose[:84], r.pose[84 * 96:84 * 97])  # any slot, same bits
     assert float((r.status == 0).float().mean()) > 0.95
-    ores = po.pose_solve_batch({k: (None if v is None else v[:42]) for k, v in base.items()}, base["hyp_idx"][:42], THR)
-    pose = r.pose.cpu().numpy()
-    for i in range(42):
-        assert int(r.n_inliers[i]) == ores[i]["n_inl"] and int(r.best_h[i]) == ores[i]["best_h"], i
-        assert np.array_equal(r.inlier_mask[i].reshape(-1).cpu().numpy(), ores[i]["inlier_mask"]), i
-        if ores[i]["status"] == 0:
-            assert po.re_rad_small(pose[i][:, :3], ores[i]["pose"][:, :3]) <= ROT_TOL_RAD, i
-            assert po.te(pose[i][:, 3], ores[i]["pose"][:, 3]) <= TRANS_TOL_M, i
+    for weighted in (False, True):
+        if weighted:
+            r = _solve(g, weighted=True)
+        ores = po.pose_solve_batch(base, base["hyp_idx"], THR, weighted=weighted)
+        pose = r.pose.cpu().numpy()
+        for i in range(84):
+            assert int(r.status[i]) == ores[i]["status"], i
+            assert int(r.n_inliers[i]) == ores[i]["n_inl"] and int(r.best_h[i]) == ores[i]["best_h"], i
+            assert np.array_equal(r.inlier_mask[i].reshape(-1).cpu().numpy(), ores[i]["inlier_mask"]), i
+            if ores[i]["status"] == 0:
+                assert po.re_rad_small(pose[i][:, :3], ores[i]["pose"][:, :3]) <= ROT_TOL_RAD, i
+                assert po.te(pose[i][:, 3], ores[i]["pose"][:, 3]) <= TRANS_TOL_M, i
 
 
 def test_mp6d_scale_65536_rois_shard_invariance(cuda):
