@@ -387,7 +387,7 @@ def gen_ransac_roi(tf):
     executed from source behind the 3D-3D cv2 shim on the gated (object, camera) pairs of each ROI -- 10 pairs per
     sample (misc.py:72,91), the reference's Kabsch on every solve, every point scored in float64, adaptive stop.
     Stored: the ROI planes, the sampled pixel sets of every iteration as hyp_idx [B,H,10] (-1 beyond the iteration at
-    which the loop stopped) and the loop's inlier count per iteration.  The solver is run on the same planes with the
+    which the loop stopped), the loop's inlier count per iteration and the pose the function returns (ret_pose).  The solver is run on the same planes with the
     same index sets (sample_size = 10) and must reproduce those counts (tests/test_oracle_pose.py,
     tests/test_pose_solve_gpu.py)."""
     from oracle import pose_oracle as po
@@ -404,6 +404,7 @@ def gen_ransac_roi(tf):
     hyp = np.full((B, HMAX, S), -1, np.int32)
     counts = np.full((B, HMAX), -1, np.int32)
     iters = np.zeros(B, np.int32)
+    ret_pose = np.zeros((B, 3, 4), np.float64)  # what the function RETURNS: the lowest-mean-error pose (misc.py:113-132, 139-142)
     for r in range(B):
         c = po.correspondences(b["depth"][r], b["Kp"][r], b["coor"][r], b["mask"][r], b["extent"][r], b["region_idx"][r],
                                b["anchors"][r])
@@ -413,7 +414,7 @@ def gen_ransac_roi(tf):
         shim = _Cv2Shim(tf)
         ransac = ref_functions("lib/pysixd/misc.py", ["pnp_ransac_custom"], env={"cv2": shim})["pnp_ransac_custom"]
         np.random.seed(2000 + r)
-        ransac(cpts, mpts, None, ransac_iter=100, ransac_min_iter=10, ransac_reprojErr=thr)
+        ret_pose[r] = ransac(cpts, mpts, None, ransac_iter=100, ransac_min_iter=10, ransac_reprojErr=thr)
         cr, seen = [], 0
         for _, ns, pts_ in shim.proj:  # inlier count of iteration i = first projection after the i-th sample solve
             if ns > seen:
@@ -432,7 +433,7 @@ def gen_ransac_roi(tf):
         counts[r, :n_it] = cr
         iters[r] = n_it
     out = {k: b[k] for k in ("depth", "Kp", "coor", "mask", "extent", "region_idx", "anchors")}
-    out.update(hyp_idx=hyp, counts=counts, iters=iters, thr=np.float32(thr))
+    out.update(hyp_idx=hyp, counts=counts, iters=iters, thr=np.float32(thr), ret_pose=ret_pose)
     np.savez_compressed(os.path.join(GOLD, "ransac_roi_golden.npz"), **out)
     print("ransac_roi_golden.npz iters", iters, "max counts", counts.max(axis=1))
 

@@ -406,9 +406,52 @@ def select_best(counts, valid, n_sel, min_inliers=4, adaptive=False, confidence=
     return best, H
 
 
+def reference_loop_select(obj_n3, cam_n3, ww, Rt, valid, counts, n, thr, min_inliers=4, weighted=False, adaptive=False,
+                          confidence=0.995, min_iter=10, scale=False):
+    """Selection rule of the reference loop, lib/pysixd/misc.py:108-138, on precomputed hypothesis poses and counts:
+    walk the valid hypotheses in order; (:113-116) a sample fit whose mean residual over ALL points is below the best
+    so far becomes the returned pose; (:118-132) a sample fit that raises the best inlier count (>= min_inliers) is refit
+    on its inliers and the refit is kept if its mean residual is below the best so far; (:134-138) adaptive stop.
+    Mean residuals in float64 (errs.mean(), :113), inlier sets by the FP32 contract the counts come from.
+    Returns (pose32[12] or None, source hypothesis or -1, best inlier count, inlier mask of the returned pose)."""
+    a64, c64 = obj_n3.astype(F64), cam_n3.astype(F64)
+
+    def mean_err(p12):
+        P = np.asarray(p12, F64).reshape(3, 4)
+        return float(np.linalg.norm(a64 @ P[:, :3].T + P[:, 3] - c64, axis=1).mean())
+
+    best_err, best_pose, src, best_inl, i_ransac = float("inf"), None, -1, 0, 0
+    for h in range(len(counts)):
+        if not valid[h]:
+            continue
+        i_ransac += 1
+        e = mean_err(Rt[h])
+        if e < best_err:
+            best_err, best_pose, src = e, Rt[h].copy(), h
+        c = int(counts[h])
+        if c > best_inl and c >= min_inliers:
+            best_inl = c
+            m = inlier_mask(obj_n3, cam_n3, Rt[h], thr).astype(bool)
+            if int(m.sum()) >= 3:
+                M = kabsch(obj_n3[m].T, cam_n3[m].T, w=(ww[m].astype(F64) if weighted else None), scale=scale)
+                pr = M[:3, :4].astype(F32).reshape(12)
+                er = mean_err(pr)
+                if er < best_err:
+                    best_err, best_pose, src = er, pr, h
+        if adaptive:
+            wr = c / float(n)
+            with np.errstate(divide="ignore"):
+                k = np.log10(1 - confidence) / np.log10(1 - pow(wr, 10))
+            if i_ransac > max(k, min_iter):
+                break
+    if best_pose is None:
+        return None, -1, 0, None
+    return best_pose, src, best_inl, inlier_mask(obj_n3, cam_n3, best_pose, thr)
+
+
 def solve_roi(cam, obj, w, sel, hyp_idx, thr, min_pts=4, min_inliers=4, weighted=False,
               refit_iters=1, adaptive=False, confidence=0.995, min_iter=10, scale=False,
-              t_net=None):
+              t_net=None, select_rule="most_inliers"):
     """Stages S3-S5 for one ROI on the S1 output.  cam, obj: [3,P] float32; w: [P]; sel: [P] bool.
 
     Returns dict(pose[3,4] f32, n_inl, status, best_h, n_sel, counts[H], valid[H], Rt_hyp[H,12],
@@ -429,6 +472,19 @@ def solve_roi(cam, obj, w, sel, hyp_idx, thr, min_pts=4, min_inliers=4, weighted
     Rt, valid = hypothesis_poses(obj, cam, sel, hyp_idx)
     counts = score_hypotheses(obj_n3, cam_n3, Rt, valid, thr)
     out.update(counts=counts, valid=valid, Rt_hyp=Rt)
+    if select_rule == "min_mean_err":  # the reference loop's return value (misc.py:113-132)
+        pose32, src, best_inl, m = reference_loop_select(obj_n3, cam_n3, w[pix], Rt, valid, counts, n, thr, min_inliers, weighted,
+                                                         adaptive, confidence, min_iter, scale)
+        if pose32 is None:
+            out["status"] = STATUS_NO_CONSENSUS
+            return out
+        full = np.zeros(P, np.uint8)
+        full[pix] = m
+        out.update(best_h=src, n_inl=best_inl, inlier_mask=full, pose=np.asarray(pose32, F32).reshape(3, 4).copy())
+        if t_net is not None and te(out["pose"][:, 3], np.asarray(t_net)) > 1.0:
+            out["status"] = STATUS_T_SANITY
+            out["pose"][:, 3] = np.asarray(t_net, F32)
+        return out
     best, _ = select_best(counts, valid, n, min_inliers, adaptive, confidence, min_iter)
     if best < 0:
         out["status"] = STATUS_NO_CONSENSUS

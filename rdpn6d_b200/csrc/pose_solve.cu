@@ -1204,7 +1204,7 @@ static int solve_prepare(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, co
     if (prm->num_hyp <= 0 || !(prm->inlier_thr > 0.f)) return RDPN_E_BADARG;
     if (prm->sample_size != 0 && (prm->sample_size < 3 || prm->sample_size > RDPN_MAX_SAMPLE)) return RDPN_E_BADARG;
     if (prm->pipeline < RDPN_PIPELINE_AUTO || prm->pipeline > RDPN_PIPELINE_SPLIT || prm->chunk_rois < 0) return RDPN_E_BADARG;
-    if (prm->select_rule != RDPN_SELECT_MOST_INLIERS) return RDPN_E_BADARG;  // MIN_MEAN_ERR: not yet
+    if (prm->select_rule != RDPN_SELECT_MOST_INLIERS && prm->select_rule != RDPN_SELECT_MIN_MEAN_ERR) return RDPN_E_BADARG;
     if (out->inlier_mask && ((uintptr_t)out->inlier_mask & 15)) return RDPN_E_ALIGN;
     if (out->hyp_poses && ((uintptr_t)out->hyp_poses & 15)) return RDPN_E_ALIGN;
     a->in = *in;
@@ -1231,6 +1231,10 @@ static bool use_split(const rdpn::SolveArgs& a, bool dense, int* err) {
         if (e && !strcmp(e, "split")) mode = RDPN_PIPELINE_SPLIT;
     }
     const bool ok = rdpn::split_supported(a, dense);
+    if (a.prm.select_rule == RDPN_SELECT_MIN_MEAN_ERR) {  // the reference loop's return value: pipeline only
+        *err = (!ok || mode == RDPN_PIPELINE_FUSED) ? RDPN_E_TOOLARGE : 0;
+        return *err == 0;
+    }
     *err = (mode == RDPN_PIPELINE_SPLIT && !ok) ? RDPN_E_TOOLARGE : 0;
     if (mode == RDPN_PIPELINE_AUTO) return ok && a.in.B >= env_int_("RDPN_PIPELINE_MIN_ROIS", RDPN_PIPELINE_MIN_ROIS);
     return mode != RDPN_PIPELINE_FUSED && ok;

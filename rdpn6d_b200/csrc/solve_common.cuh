@@ -131,16 +131,21 @@ struct PoseListed {
 // hypotheses: 4 LDS + 32 K arithmetic instructions per four points, so the more hypotheses a lane carries the fewer
 // instructions a pair costs.  Per run the transformed anchor R a + t once per hypothesis (misc.py:108-111 semantics,
 // FP32 contract of oracle/pose_oracle.c).
-template <int K, class POSE>
+// MEAN (select rule MIN_MEAN_ERR, misc.py:109,113): the sum of the residual norms over ALL points rides along in FP32
+// (one MUFU.SQRT + FADD per pair); it only pre-selects the candidates whose mean error the refit kernel recomputes in FP64.
+template <int K, class POSE, bool MEAN = false>
 __device__ __forceinline__ void score_pass(const float4* __restrict__ pts, const float4* __restrict__ runtab, int nruns,
-                                           const POSE pose, int j0, int nvalid, int i0, int i1, int c0, float cut, int* hcnt) {
+                                           const POSE pose, int j0, int nvalid, int i0, int i1, int c0, float cut, int* hcnt,
+                                           float* herr = nullptr) {
     const int lane = threadIdx.x & 31;
     int sl[K], cnt[K];
+    float es[K];
 #pragma unroll
     for (int u = 0; u < K; ++u) {
         const int j = j0 + 32 * u + lane;
         sl[u] = pose.slot(j < nvalid ? j : nvalid - 1);  // idle lanes recompute a valid hypothesis
         cnt[u] = 0;
+        es[u] = 0.f;
     }
 #pragma unroll 1
     for (int k = 0; k < nruns; ++k) {
@@ -157,28 +162,35 @@ __device__ __forceinline__ void score_pass(const float4* __restrict__ pts, const
             const float P[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
             xform(P, rh.x, rh.y, rh.z, tx[u], ty[u], tz[u]);
         }
+        if (!MEAN) {
 #pragma unroll 1
-        for (; p + 4 <= e; p += 4) {
-            const float4 q0 = pts[p], q1 = pts[p + 1], q2 = pts[p + 2], q3 = pts[p + 3];
+            for (; p + 4 <= e; p += 4) {
+                const float4 q0 = pts[p], q1 = pts[p + 1], q2 = pts[p + 2], q3 = pts[p + 3];
 #pragma unroll
-            for (int u = 0; u < K; ++u) {
-                count_if_lt(cnt[u], resid2_pt(tx[u], ty[u], tz[u], q0.x, q0.y, q0.z), cut);
-                count_if_lt(cnt[u], resid2_pt(tx[u], ty[u], tz[u], q1.x, q1.y, q1.z), cut);
-                count_if_lt(cnt[u], resid2_pt(tx[u], ty[u], tz[u], q2.x, q2.y, q2.z), cut);
-                count_if_lt(cnt[u], resid2_pt(tx[u], ty[u], tz[u], q3.x, q3.y, q3.z), cut);
+                for (int u = 0; u < K; ++u) {
+                    count_if_lt(cnt[u], resid2_pt(tx[u], ty[u], tz[u], q0.x, q0.y, q0.z), cut);
+                    count_if_lt(cnt[u], resid2_pt(tx[u], ty[u], tz[u], q1.x, q1.y, q1.z), cut);
+                    count_if_lt(cnt[u], resid2_pt(tx[u], ty[u], tz[u], q2.x, q2.y, q2.z), cut);
+                    count_if_lt(cnt[u], resid2_pt(tx[u], ty[u], tz[u], q3.x, q3.y, q3.z), cut);
+                }
             }
         }
 #pragma unroll 1
         for (; p < e; ++p) {
             const float4 q0 = pts[p];
 #pragma unroll
-            for (int u = 0; u < K; ++u) count_if_lt(cnt[u], resid2_pt(tx[u], ty[u], tz[u], q0.x, q0.y, q0.z), cut);
+            for (int u = 0; u < K; ++u) {
+                const float d2 = resid2_pt(tx[u], ty[u], tz[u], q0.x, q0.y, q0.z);
+                count_if_lt(cnt[u], d2, cut);
+                if (MEAN) es[u] += sqrtf(d2);
+            }
         }
     }
 #pragma unroll
     for (int u = 0; u < K; ++u) {
         const int j = j0 + 32 * u + lane;
         if (j < nvalid && cnt[u]) atomicAdd(&hcnt[sl[u]], cnt[u]);
+        if (MEAN && j < nvalid) atomicAdd(&herr[sl[u]], es[u]);
     }
 }
 
@@ -189,9 +201,10 @@ __device__ __forceinline__ int pass_cost(int k) { return 9 + 32 * k; }
 // lane (128 per pass) plus one last pass of 1..4 per lane, the (pass, point) plane is cut into nw slices of equal
 // cost, one per warp, whatever the number of valid hypotheses (the cut points are rounded to whole points the same way
 // on both sides: nothing is lost or counted twice).  Counts are ADDED to hcnt (shared-memory atomics).
-template <class POSE>
+template <class POSE, bool MEAN = false>
 __device__ __forceinline__ void score_slices(const float4* __restrict__ pts, const float4* __restrict__ runtab, int nruns,
-                                             const POSE pose, int nvalid, int c0, int c1, float cut, int* hcnt, int wi, int nw) {
+                                             const POSE pose, int nvalid, int c0, int c1, float cut, int* hcnt, int wi, int nw,
+                                             float* herr = nullptr) {
     const int nfull = nvalid >> 7;               // passes with 4 hypotheses per lane
     const int rem = nvalid - (nfull << 7);
     const int klast = (rem + 31) >> 5;           // 0 .. 4 hypotheses per lane in the last pass
@@ -209,10 +222,10 @@ __device__ __forceinline__ void score_slices(const float4* __restrict__ pts, con
             const int i1 = c0 + (a1 - off + pass_cost(k) - 1) / pass_cost(k);
             const int j0 = ps << 7;
             if (i0 < i1) {
-                if (k == 4) score_pass<4, POSE>(pts, runtab, nruns, pose, j0, nvalid, i0, i1, c0, cut, hcnt);
-                else if (k == 3) score_pass<3, POSE>(pts, runtab, nruns, pose, j0, nvalid, i0, i1, c0, cut, hcnt);
-                else if (k == 2) score_pass<2, POSE>(pts, runtab, nruns, pose, j0, nvalid, i0, i1, c0, cut, hcnt);
-                else score_pass<1, POSE>(pts, runtab, nruns, pose, j0, nvalid, i0, i1, c0, cut, hcnt);
+                if (k == 4) score_pass<4, POSE, MEAN>(pts, runtab, nruns, pose, j0, nvalid, i0, i1, c0, cut, hcnt, herr);
+                else if (k == 3) score_pass<3, POSE, MEAN>(pts, runtab, nruns, pose, j0, nvalid, i0, i1, c0, cut, hcnt, herr);
+                else if (k == 2) score_pass<2, POSE, MEAN>(pts, runtab, nruns, pose, j0, nvalid, i0, i1, c0, cut, hcnt, herr);
+                else score_pass<1, POSE, MEAN>(pts, runtab, nruns, pose, j0, nvalid, i0, i1, c0, cut, hcnt, herr);
             }
         }
         off += len;

@@ -37,6 +37,7 @@ struct PkgLayout {
     unsigned runtab;  // float4[R]      (anchor xyz, start | end << 16) per non-empty region bucket
     unsigned vh;      // uint16[H]      compacted index -> hypothesis index
     unsigned hcnt;    // int32[H]       K2: inlier count per compacted hypothesis
+    unsigned herr;    // float[H]       K2, select rule MIN_MEAN_ERR: FP32 sum of the residual norms over all points
     unsigned hyp;     // float4[3][H]   compacted FP32 hypothesis poses, row-planar (row r of pose j at [r * H + j])
     unsigned key;     // uint32[P]      raster list: pixel | region id << 16
     unsigned rast;    // float4[P]      raster list: (cam xyz, w)
@@ -53,6 +54,7 @@ static PkgLayout make_layout(int H, int R) {
     l.runtab = (unsigned)off; off = al(off + (size_t)R * 16);
     l.vh = (unsigned)off;     off = al(off + (size_t)H * 2);
     l.hcnt = (unsigned)off;   off = al(off + (size_t)H * 4);
+    l.herr = (unsigned)off;   off = al(off + (size_t)H * 4);
     l.hyp = (unsigned)off;    off = al(off + (size_t)H * 48);
     l.key = (unsigned)off;    off = al(off + (size_t)RDPN_P * 4);
     l.rast = (unsigned)off;   off = al(off + (size_t)RDPN_P * 16);
@@ -627,6 +629,7 @@ struct ScoreLayout {  // dynamic shared memory (byte offsets)
     unsigned hyp;     // float4[3][H]
     unsigned runtab;  // float4[R]
     unsigned hcnt;    // int[H]
+    unsigned herr;    // float[H] (select rule MIN_MEAN_ERR)
     unsigned bar;     // mbarrier
     unsigned total;
 };
@@ -638,6 +641,7 @@ static ScoreLayout make_score_layout(int H, int R) {
     l.hyp = (unsigned)off;    off = al(off + (size_t)H * 48);
     l.runtab = (unsigned)off; off = al(off + (size_t)R * 16);
     l.hcnt = (unsigned)off;   off = al(off + (size_t)H * 4);
+    l.herr = (unsigned)off;   off = al(off + (size_t)H * 4);
     l.bar = (unsigned)off;    off = al(off + 8);
     l.total = (unsigned)off;
     return l;
@@ -647,6 +651,7 @@ static ScoreLayout make_score_layout(int H, int R) {
 // hypothesis poses into shared memory) and one barrier before the counts are written back; the SM's other resident
 // CTAs cover both.  The (pass, point) plane is cut into SC_W slices of equal cost, one per warp, whatever the number
 // of valid hypotheses.
+template <bool MEAN>
 __global__ void __launch_bounds__(SC_T, RDPN_SCORE_REGS_CTAS) score_kernel(int H, int min_pts, float cut, unsigned char* __restrict__ ws,
                                                                             PkgLayout lay, ScoreLayout sl, const int* __restrict__ fdone,
                                                                             int* __restrict__ sdone) {
@@ -655,6 +660,7 @@ __global__ void __launch_bounds__(SC_T, RDPN_SCORE_REGS_CTAS) score_kernel(int H
     const float4* hyp = reinterpret_cast<const float4*>(sc_raw + sl.hyp);
     const float4* runtab = reinterpret_cast<const float4*>(sc_raw + sl.runtab);
     int* hcnt_s = reinterpret_cast<int*>(sc_raw + sl.hcnt);
+    float* herr_s = reinterpret_cast<float*>(sc_raw + sl.herr);
     uint64_t* bar = reinterpret_cast<uint64_t*>(sc_raw + sl.bar);
     const int warp = threadIdx.x >> 5;
     const int b = blockIdx.x;
@@ -673,7 +679,10 @@ __global__ void __launch_bounds__(SC_T, RDPN_SCORE_REGS_CTAS) score_kernel(int H
         if (threadIdx.x == 0) st_release_i32(sdone + b, 1);
         return;
     }
-    for (int j = threadIdx.x; j < nvalid; j += SC_T) hcnt_s[j] = 0;
+    for (int j = threadIdx.x; j < nvalid; j += SC_T) {
+        hcnt_s[j] = 0;
+        if (MEAN) herr_s[j] = 0.f;
+    }
     __syncthreads();  // counts zeroed
     unsigned phase = 0;
     for (int c0 = 0; c0 < n; c0 += SC_CHUNK) {
@@ -693,12 +702,16 @@ __global__ void __launch_bounds__(SC_T, RDPN_SCORE_REGS_CTAS) score_kernel(int H
             }
         }
         mbar_wait_backoff(bar, phase & 1);
-        score_slices(pts, runtab, nruns, PosePlanar{hyp, H}, nvalid, c0, c1, cut, hcnt_s, warp, SC_W);
+        score_slices<PosePlanar, MEAN>(pts, runtab, nruns, PosePlanar{hyp, H}, nvalid, c0, c1, cut, hcnt_s, warp, SC_W, herr_s);
         ++phase;
     }
     __syncthreads();  // every warp's partial counts are in
     int* hcnt = reinterpret_cast<int*>(pkg + lay.hcnt);
-    for (int j = threadIdx.x; j < nvalid; j += SC_T) hcnt[j] = hcnt_s[j];
+    float* herr = reinterpret_cast<float*>(pkg + lay.herr);
+    for (int j = threadIdx.x; j < nvalid; j += SC_T) {
+        hcnt[j] = hcnt_s[j];
+        if (MEAN) herr[j] = herr_s[j];
+    }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) st_release_i32(sdone + b, 1);
@@ -923,6 +936,226 @@ __global__ void __launch_bounds__(RF_W * 32, RDPN_REFIT_CTAS) refit_kernel(Solve
     }
 }
 
+// =============================================================================================
+// K3, select rule MIN_MEAN_ERR: the reference loop's return value (lib/pysixd/misc.py:108-142), one warp per ROI
+// =============================================================================================
+struct WarpRoi {  // what a warp needs to walk its ROI's region-sorted correspondences
+    const float4* slots;
+    const uint8_t* srid;
+    const float* anc;   // shared memory: the ROI's anchors
+    int n;
+    float4 cp0, ap0;    // pivot of the raw moments (slot 0)
+};
+// Kabsch / Umeyama refit on the inliers of Pin (misc.py:123-126 -> transform.py:913-980): FP64 raw moments about the pivot by
+// warp shuffle, closed-form rotation.  Returns the number of inliers (uniform); Pout is written when there are >= 3.
+static __device__ __noinline__ int warp_refit(const WarpRoi& w, const float* Pin, float cut, int weighted, int with_scale, float* Pout) {
+    const int lane = threadIdx.x & 31;
+    double m[18];
+#pragma unroll
+    for (int i = 0; i < 18; ++i) m[i] = 0.0;
+    int ninl = 0;
+    for (int i = lane; i < w.n; i += 32) {
+        const float4 cp = __ldcg(w.slots + i);
+        const int r3 = 3 * (int)__ldcg(w.srid + i);
+        const float ax = w.anc[r3], ay = w.anc[r3 + 1], az = w.anc[r3 + 2];
+        if (resid2(Pin, ax, ay, az, cp.x, cp.y, cp.z) < cut) {
+            ++ninl;
+            const double wt = weighted ? (double)cp.w : 1.0;
+            const double c0 = (double)cp.x - (double)w.cp0.x, c1 = (double)cp.y - (double)w.cp0.y, c2 = (double)cp.z - (double)w.cp0.z;
+            const double a0 = (double)ax - (double)w.ap0.x, a1 = (double)ay - (double)w.ap0.y, a2 = (double)az - (double)w.ap0.z;
+            const double wc0 = wt * c0, wc1 = wt * c1, wc2 = wt * c2;
+            m[0] += wt;
+            m[1] += wc0; m[2] += wc1; m[3] += wc2;
+            m[4] += wt * a0; m[5] += wt * a1; m[6] += wt * a2;
+            m[7] += wc0 * a0; m[8] += wc0 * a1; m[9] += wc0 * a2;
+            m[10] += wc1 * a0; m[11] += wc1 * a1; m[12] += wc1 * a2;
+            m[13] += wc2 * a0; m[14] += wc2 * a1; m[15] += wc2 * a2;
+            m[16] += wt * (c0 * c0 + c1 * c1 + c2 * c2);
+            m[17] += wt * (a0 * a0 + a1 * a1 + a2 * a2);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 18; ++i) m[i] = warp_sum(m[i]);
+    ninl = warp_sum(ninl);
+    if (ninl < 3) return ninl;
+    const double isw = 1.0 / m[0];
+    double S[9], Rm[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) S[3 * r + c] = m[7 + 3 * r + c] - m[1 + r] * (m[4 + c] * isw);
+    const double ga = m[17] - (m[4] * (m[4] * isw) + m[5] * (m[5] * isw) + m[6] * (m[6] * isw));
+    const double gb = m[16] - (m[1] * (m[1] * isw) + m[2] * (m[2] * isw) + m[3] * (m[3] * isw));
+    rotation_from_cov(S, ga, gb, Rm);
+    const double sc = with_scale ? sqrt(gb / ga) : 1.0;
+    const double ma0 = m[4] * isw + (double)w.ap0.x, ma1 = m[5] * isw + (double)w.ap0.y, ma2 = m[6] * isw + (double)w.ap0.z;
+    const double c0v[3] = {(double)w.cp0.x, (double)w.cp0.y, (double)w.cp0.z};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const double mcr = m[1 + r] * isw + c0v[r];
+        const double r0 = Rm[3 * r], r1 = Rm[3 * r + 1], r2 = Rm[3 * r + 2];
+        Pout[4 * r + 0] = (float)(sc * r0);
+        Pout[4 * r + 1] = (float)(sc * r1);
+        Pout[4 * r + 2] = (float)(sc * r2);
+        Pout[4 * r + 3] = (float)(mcr - sc * (r0 * ma0 + r1 * ma1 + r2 * ma2));
+    }
+    return ninl;
+}
+// mean residual norm of a pose over ALL gated points in FP64 (misc.py:109,113: errs.mean()), lane-strided sums combined
+// in a fixed order
+static __device__ __noinline__ double warp_mean_err(const WarpRoi& w, const float* P) {
+    const int lane = threadIdx.x & 31;
+    double s = 0.0;
+    for (int i = lane; i < w.n; i += 32) {
+        const float4 cp = __ldcg(w.slots + i);
+        const int r3 = 3 * (int)__ldcg(w.srid + i);
+        const double ax = w.anc[r3], ay = w.anc[r3 + 1], az = w.anc[r3 + 2];
+        const double dx = ((double)P[0] * ax + (double)P[1] * ay + (double)P[2] * az + (double)P[3]) - (double)cp.x;
+        const double dy = ((double)P[4] * ax + (double)P[5] * ay + (double)P[6] * az + (double)P[7]) - (double)cp.y;
+        const double dz = ((double)P[8] * ax + (double)P[9] * ay + (double)P[10] * az + (double)P[11]) - (double)cp.z;
+        s += sqrt(dx * dx + dy * dy + dz * dz);
+    }
+    return warp_sum(s) / (double)w.n;
+}
+
+// The loop of misc.py:89-138 on the precomputed counts: hypotheses in order (i_ransac = compacted index + 1),
+//   (:113-116) a sample fit whose mean error over all points beats the best so far becomes the best pose;
+//   (:118-132) a sample fit that raises the best inlier count (and has >= min_inliers) is refit on its inliers, and the
+//              refit becomes the best pose if ITS mean error beats the best so far;
+//   (:134-138) the adaptive stop, when enabled, ends the loop.
+// K2's FP32 sums pre-select: a sample fit is a candidate for (:113) only if its FP32 mean is within 1e-4 of the best
+// FP64 mean so far (the FP32 sum of a few hundred norms is good to ~1e-6), and only candidates are re-evaluated in FP64.
+__global__ void __launch_bounds__(RF_W * 32, RDPN_REFIT_CTAS) refit_minerr_kernel(SolveArgs a, const unsigned char* __restrict__ ws,
+                                                                                  PkgLayout lay, const int* __restrict__ sdone) {
+    extern __shared__ __align__(16) unsigned char rf_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * RF_W + warp;
+    if (b >= a.in.B) return;
+    const int H = a.prm.num_hyp;
+    const unsigned char* pkg = ws + (size_t)b * lay.stride;
+    if (lane == 0) wait_flag(sdone + b);
+    __syncwarp();
+    const int4 h0 = __ldcg(reinterpret_cast<const int4*>(pkg));
+    const int n = h0.x, nvalid = h0.z;
+    const bool enough = n >= a.prm.min_pts;
+    if (a.out.inlier_mask) {
+        uint4* im = reinterpret_cast<uint4*>(a.out.inlier_mask + (size_t)b * RDPN_P);
+        for (int i = lane; i < RDPN_P / 16; i += 32) im[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    const int* hcnt = reinterpret_cast<const int*>(pkg + lay.hcnt);
+    const float* herr = reinterpret_cast<const float*>(pkg + lay.herr);
+    const uint16_t* vh = reinterpret_cast<const uint16_t*>(pkg + lay.vh);
+    const float4* hp = reinterpret_cast<const float4*>(pkg + lay.hyp);
+    float Pbest[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) Pbest[i] = -100.f;
+    int src = -1, best_inl = 0;
+    bool have = false;
+    if (enough && nvalid > 0) {
+        const int R3 = 3 * a.in.num_regions;
+        float* anc = reinterpret_cast<float*>(rf_smem) + (size_t)warp * R3;
+        const float* ag = a.in.anchors + (size_t)b * R3;
+        for (int i = lane; i < R3; i += 32) anc[i] = __ldg(ag + i);
+        __syncwarp();
+        WarpRoi w;
+        w.slots = reinterpret_cast<const float4*>(pkg + lay.slots);
+        w.srid = pkg + lay.srid;
+        w.anc = anc;
+        w.n = n;
+        w.cp0 = __ldcg(w.slots);
+        {
+            const int r0 = 3 * (int)__ldcg(w.srid);
+            w.ap0 = make_float4(anc[r0], anc[r0 + 1], anc[r0 + 2], 0.f);
+        }
+        int jlim = nvalid;
+        if (a.prm.adaptive) {
+            const double lc = log10(1.0 - (double)a.prm.confidence);
+            int js = 0x7FFFFFFF;
+            for (int j = lane; j < nvalid; j += 32)
+                if (adaptive_stop(__ldcg(hcnt + j), n, j + 1, lc, a.prm.min_iter)) js = min(js, j);
+            js = warp_min_i(js);
+            if (js != 0x7FFFFFFF) jlim = js + 1;
+        }
+        if (a.out.hyp_counts)
+            for (int j = lane; j < nvalid; j += 32) a.out.hyp_counts[(size_t)b * H + __ldcg(vh + j)] = __ldcg(hcnt + j);
+        double best_err = 1e300;
+        const float cut = a.sq_cut;
+        for (int j = 0; j < jlim; ++j) {  // warp-uniform walk in hypothesis order
+            const int c = __ldcg(hcnt + j);
+            const double e32 = (double)__ldcg(herr + j) / (double)n;
+            const bool cand = !have || e32 < best_err * 1.0001;
+            const bool improves = c > best_inl && c >= a.prm.min_inliers;
+            if (!cand && !improves) continue;
+            float P[12];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const float4 v = __ldcg(hp + (size_t)r * H + j);
+                P[4 * r] = v.x; P[4 * r + 1] = v.y; P[4 * r + 2] = v.z; P[4 * r + 3] = v.w;
+            }
+            if (cand) {  // misc.py:113-116
+                const double e = warp_mean_err(w, P);
+                if (e < best_err) {
+                    best_err = e;
+                    have = true;
+                    src = (int)__ldcg(vh + j);
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) Pbest[i] = P[i];
+                }
+            }
+            if (improves) {  // misc.py:118-132
+                best_inl = c;
+                float Pr[12];
+                if (warp_refit(w, P, cut, a.prm.weighted, a.prm.with_scale, Pr) >= 3) {
+                    const double e = warp_mean_err(w, Pr);
+                    if (e < best_err) {
+                        best_err = e;
+                        have = true;
+                        src = (int)__ldcg(vh + j);
+#pragma unroll
+                        for (int i = 0; i < 12; ++i) Pbest[i] = Pr[i];
+                    }
+                }
+            }
+        }
+        if (have && a.out.inlier_mask) {  // the inliers of the RETURNED pose
+            const uint16_t* pixs = reinterpret_cast<const uint16_t*>(pkg + lay.pix);
+            for (int i = lane; i < n; i += 32) {
+                const float4 cp = __ldcg(w.slots + i);
+                const int r3 = 3 * (int)__ldcg(w.srid + i);
+                if (resid2(Pbest, anc[r3], anc[r3 + 1], anc[r3 + 2], cp.x, cp.y, cp.z) < cut)
+                    a.out.inlier_mask[(size_t)b * RDPN_P + __ldcg(pixs + i)] = 1;
+            }
+        }
+    }
+    int status = have ? RDPN_STATUS_OK : (enough ? RDPN_STATUS_NO_CONSENSUS : RDPN_STATUS_FEW_POINTS);
+    if (have && a.t_net) {
+        const float t0 = a.t_net[3 * b], t1 = a.t_net[3 * b + 1], t2 = a.t_net[3 * b + 2];
+        const double d0 = (double)t0 - Pbest[3], d1 = (double)t1 - Pbest[7], d2 = (double)t2 - Pbest[11];
+        if (sqrt(d0 * d0 + d1 * d1 + d2 * d2) > 1.0) {
+            status = RDPN_STATUS_T_SANITY;
+            Pbest[3] = t0;
+            Pbest[7] = t1;
+            Pbest[11] = t2;
+        }
+    }
+    float mine = 0.f;
+#pragma unroll
+    for (int i = 0; i < 12; ++i)
+        if (lane == i) mine = Pbest[i];
+    if (lane == 12) mine = (float)best_inl;
+    if (lane == 13) mine = (float)status;
+    if (lane == 14) mine = (float)n;
+    if (lane == 15) mine = (float)src;
+    if (lane < 12) a.out.pose[(size_t)b * 12 + lane] = mine;
+    if (a.out.rows16 && lane < 16) a.out.rows16[(size_t)b * 16 + lane] = mine;
+    if (lane == 0) {
+        a.out.n_inliers[b] = best_inl;
+        a.out.status[b] = status;
+        if (a.out.best_h) a.out.best_h[b] = src;
+        if (a.out.scale) a.out.scale[b] = 1.f;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -1031,18 +1264,22 @@ static int launch_chunk(const SolveArgs& a, unsigned char* ws, const PkgLayout& 
     {  // K2
         const ScoreLayout sl = make_score_layout(H, R);
         if (sl.total > 227 * 1024) return RDPN_E_TOOLARGE;
-        const int rc = ensure_func_smem((const void*)score_kernel, SLOT_SCORE, sl.total);
+        const bool mean = a.prm.select_rule == RDPN_SELECT_MIN_MEAN_ERR;
+        void (*kern)(int, int, float, unsigned char*, PkgLayout, ScoreLayout, const int*, int*) = mean ? score_kernel<true> : score_kernel<false>;
+        const int rc = ensure_func_smem((const void*)kern, SLOT_SCORE + (mean ? 1 : 0), sl.total);
         if (rc) return rc;
-        RDPN_CUDA_TRY(launch_pdl(score_kernel, dim3(B), dim3(SC_T), sl.total, st, pdl, H, a.prm.min_pts, a.sq_cut, pk, lay, sl,
+        RDPN_CUDA_TRY(launch_pdl(kern, dim3(B), dim3(SC_T), sl.total, st, pdl, H, a.prm.min_pts, a.sq_cut, pk, lay, sl,
                                  (const int*)fdone, sdone));
         ++g_launch_count;
     }
     if (t_stage_ms) RDPN_CUDA_TRY(cudaEventRecord(ev[2], st));
     {  // K3
         const size_t smem = (size_t)RF_W * 3 * R * sizeof(float);
-        const int rc = ensure_func_smem((const void*)refit_kernel, SLOT_REFIT, smem);
+        const bool mean = a.prm.select_rule == RDPN_SELECT_MIN_MEAN_ERR;
+        void (*kern)(SolveArgs, const unsigned char*, PkgLayout, const int*) = mean ? refit_minerr_kernel : refit_kernel;
+        const int rc = ensure_func_smem((const void*)kern, SLOT_REFIT + (mean ? 1 : 0), smem);
         if (rc) return rc;
-        RDPN_CUDA_TRY(launch_pdl(refit_kernel, dim3((B + RF_W - 1) / RF_W), dim3(RF_W * 32), smem, st, pdl, a, (const unsigned char*)pk,
+        RDPN_CUDA_TRY(launch_pdl(kern, dim3((B + RF_W - 1) / RF_W), dim3(RF_W * 32), smem, st, pdl, a, (const unsigned char*)pk,
                                  lay, (const int*)sdone));
         ++g_launch_count;
     }

@@ -167,9 +167,14 @@ class PoseSolver:
 
     def __init__(self, inlier_thr=0.005, min_pts=4, min_inliers=4, weighted=False, refit_iters=1, with_scale=False,
                  adaptive=False, confidence=0.995, min_iter=10, mask_mode=MASK_L1, mask_thr=0.5,
-                 want_inlier_mask=False, want_hyp=False, num_hyp=256, seed=0, sample_size=3, pipeline="auto", chunk_rois=0):
+                 want_inlier_mask=False, want_hyp=False, num_hyp=256, seed=0, sample_size=3, pipeline="auto", chunk_rois=0,
+                 select_rule="most_inliers"):
         """pipeline: "auto" (three-kernel pipeline gate_pack -> score -> refit where it applies, else the fused kernel),
         "fused", "split"; chunk_rois: ROIs per pass through the three kernels (0 = library default).
+        select_rule: "most_inliers" (misc.py:121-126: earliest hypothesis with the largest count, refit on its inliers) or
+        "min_mean_err" (the reference loop's return value, misc.py:113-132: of all sample fits and of the refits of the
+        hypotheses that raised the best count, the pose with the lowest mean residual over ALL gated points; anchor mode,
+        runs the three-kernel pipeline whatever the batch size).
         num_hyp / seed / sample_size: used when a call passes hyp_idx=None -- the kernel then draws num_hyp samples of
         sample_size pixels itself from a counter-based stream (include/rdpn6d_b200.h), the stand-in for np.random.choice
         at misc.py:91.  With explicit hyp_idx [B,H,S] both H and S come from the tensor."""
@@ -180,7 +185,8 @@ class PoseSolver:
                         weighted=int(bool(weighted)), refit_iters=int(refit_iters), with_scale=int(bool(with_scale)),
                         adaptive=int(bool(adaptive)), confidence=float(confidence), min_iter=int(min_iter),
                         seed=int(seed) & 0xFFFFFFFF, pipeline=_PIPELINES[pipeline] if isinstance(pipeline, str) else int(pipeline),
-                        chunk_rois=int(chunk_rois))
+                        chunk_rois=int(chunk_rois),
+                        select_rule={"most_inliers": _lib.SELECT_MOST_INLIERS, "min_mean_err": _lib.SELECT_MIN_MEAN_ERR}[select_rule])
         self.num_hyp = int(num_hyp)
         self._ws = {}
         self.mask_mode = mask_mode

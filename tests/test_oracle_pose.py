@@ -225,6 +225,24 @@ def test_s10_hypotheses_reproduce_reference_ransac_loop(gold):
     assert exact >= 0.97 * total
 
 
+def test_min_mean_err_rule_reproduces_the_reference_loops_return_value():
+    """What misc.pnp_ransac_custom RETURNS (misc.py:113-132, 139-142: the pose with the lowest mean error over all points
+    among the sample fits and the refits of the hypotheses that raised the inlier count) is stored in the golden as
+    ret_pose.  The oracle's select_rule="min_mean_err" on the same planes and pixel sets (10 pairs per sample, adaptive
+    stop) returns that pose: <= 1e-6 rad / 1e-6 m (float32 hypothesis poses and scoring against the float64 loop)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ransac_roi_golden.npz"))
+    b = {k: g[k] for k in ("depth", "Kp", "coor", "mask", "extent", "region_idx", "anchors")}
+    res = po.pose_solve_batch(b, g["hyp_idx"], float(g["thr"]), select_rule="min_mean_err", adaptive=True, confidence=0.995,
+                              min_iter=10)
+    for r, o in enumerate(res):
+        assert o["status"] == 0 and o["best_h"] < int(g["iters"][r])
+        assert po.re_rad_small(o["pose"][:, :3], g["ret_pose"][r][:, :3]) <= 1e-6, r
+        assert po.te(o["pose"][:, 3], g["ret_pose"][r][:, 3]) <= 1e-6, r
+    # the rule is not the most-inliers rule: on these ROIs they pick different hypotheses at least once
+    res_mi = po.pose_solve_batch(b, g["hyp_idx"], float(g["thr"]), adaptive=True, confidence=0.995, min_iter=10)
+    assert any(o["best_h"] != m["best_h"] or not np.array_equal(o["pose"], m["pose"]) for o, m in zip(res, res_mi))
+
+
 def test_s_pair_validity_rules():
     b = synth.make_batch(1, H=8, seed=5)
     c = po.correspondences(b["depth"][0], b["Kp"][0], b["coor"][0], b["mask"][0], b["extent"][0], b["region_idx"][0],

@@ -591,6 +591,42 @@ def test_s10_adaptive_stop_matches_the_reference_loop(cuda, golden_dir):
         assert int(res.n_inliers[r]) == ores[r]["n_inl"]
 
 
+def test_min_mean_err_rule_returns_the_reference_loops_pose(cuda, golden_dir):
+    """select_rule="min_mean_err": the pose misc.pnp_ransac_custom RETURNS (misc.py:113-132, 139-142), run from source on
+    four whole ROIs and stored in the golden (ret_pose).  Same planes, same pixel sets (sample_size = 10), adaptive stop:
+    the kernels return that pose within the north_star tolerance, and agree with the oracle's restatement of the rule
+    on the source hypothesis and the best count."""
+    g, b = _ransac_roi_golden(golden_dir)
+    thr = float(g["thr"])
+    kw = dict(select_rule="min_mean_err", adaptive=True, confidence=0.995, min_iter=10)
+    ores = po.pose_solve_batch(b, g["hyp_idx"], thr, **kw)
+    gd = _to_cuda({**b, "hyp_idx": g["hyp_idx"]})
+    solver = pose_solver.PoseSolver(inlier_thr=thr, want_inlier_mask=True, **kw)
+    res = solver(gd["depth"], gd["Kp"], gd["coor"][:, 0], gd["coor"][:, 1], gd["coor"][:, 2], gd["mask"], gd["extent"], gd["hyp_idx"],
+                 region_idx=gd["region_idx"], anchors=gd["anchors"])
+    pose = res.pose.cpu().numpy().astype(np.float64)
+    for r, o in enumerate(ores):
+        assert int(res.status[r]) == o["status"] == 0
+        assert int(res.best_h[r]) == o["best_h"] and int(res.n_inliers[r]) == o["n_inl"], r
+        assert np.array_equal(res.inlier_mask[r].reshape(-1).cpu().numpy(), o["inlier_mask"]), r
+        assert po.re_rad_small(pose[r][:, :3], o["pose"][:, :3]) <= ROT_TOL_RAD and po.te(pose[r][:, 3], o["pose"][:, 3]) <= TRANS_TOL_M
+        assert po.re_rad_small(pose[r][:, :3], g["ret_pose"][r][:, :3]) <= ROT_TOL_RAD, r   # the reference function's return value
+        assert po.te(pose[r][:, 3], g["ret_pose"][r][:, 3]) <= TRANS_TOL_M, r
+    # ... and on an ordinary batch (3-pair samples, no adaptive stop, weighted refit) against the oracle
+    bb = synth.make_batch(24, H=128, seed=99, occlusion_max=0.5)
+    o2 = po.pose_solve_batch(bb, bb["hyp_idx"], THR, select_rule="min_mean_err", weighted=True)
+    g2 = _to_cuda(bb)
+    r2 = pose_solver.PoseSolver(inlier_thr=THR, select_rule="min_mean_err", weighted=True)(
+        g2["depth"], g2["Kp"], g2["coor"][:, 0], g2["coor"][:, 1], g2["coor"][:, 2], g2["mask"], g2["extent"], g2["hyp_idx"],
+        region_idx=g2["region_idx"], anchors=g2["anchors"])
+    p2 = r2.pose.cpu().numpy().astype(np.float64)
+    for i, o in enumerate(o2):
+        assert int(r2.status[i]) == o["status"], i
+        if o["status"] == 0:
+            assert int(r2.best_h[i]) == o["best_h"] and int(r2.n_inliers[i]) == o["n_inl"], i
+            assert po.re_rad_small(p2[i][:, :3], o["pose"][:, :3]) <= ROT_TOL_RAD and po.te(p2[i][:, 3], o["pose"][:, 3]) <= TRANS_TOL_M, i
+
+
 @pytest.mark.parametrize("S", [4, 10, 16])
 def test_internal_sampling_with_larger_samples(cuda, S):
     """hyp_idx=None with sample_size S: kernel-drawn samples == oracle.sample_triplets(sample_size=S) fed back explicitly,
