@@ -262,6 +262,23 @@ int rdpn_centroid_z_to_pose(const float* d_rot_in, int rot_is_6d, const float* d
                             const float* d_K, const float* d_center, const float* d_resize_ratio,
                             const float* d_wh, int is_allo, int z_type_rel, float* d_rot_out, float* d_trans_out,
                             int B, void* stream);
+/* The two sibling heads of the same family, test branches:
+ *   trans_mode 2  core/gdrn_modeling/models/pose_from_pred.py:21-58: translation given (d_trans_or_centroid = [B,3])
+ *   trans_mode 1  .../pose_from_pred_centroid_z_abs.py:21-92: absolute 2-D centre [B,2] + absolute z [B], K [B,9]
+ * rot_kind: 0 = [B,9] matrices, 1 = [B,6] rot6d, 2 = [B,4] quaternions (w,x,y,z; normalised internally as
+ * RT_transform.quat_trans_to_pose_m does, lib/pysixd/RT_transform.py:177-183).  is_allo: allocentric -> egocentric. */
+int rdpn_assemble_pose(const float* d_rot_in, int rot_kind, const float* d_trans_or_centroid, const float* d_z, const float* d_K,
+                       int trans_mode, int is_allo, float* d_rot_out, float* d_trans_out, int B, void* stream);
+
+/* lib/pysixd/misc.py:288-316 (calc_emb_bp_fast / calc_xyz_bp_fast) and :352-371 (backproject_v2): the organised cloud of a
+ * depth map through the INVERSE intrinsics, float64 like the reference's numpy einsum:
+ *   out[v,u,:] = (d != 0) * R^T (d * Kinv (u,v,1)^T - T).   d_mats: Kinv (9) | R (9) | T (3) doubles (R = I, T = 0 gives
+ * backproject_v2).  depth [H,W] FP32 -> out [H,W,3] FP64. */
+int rdpn_backproject_kinv(const float* d_depth, const double* d_mats, int H, int W, double* d_out, void* stream);
+/* lib/pysixd/pose_error.py:315-337 (adi): mean nearest-neighbour distance between the model points under the
+ * ground-truth and under the estimated pose (brute force on the GPU, FP64).  d_pts [n,3] FP32; d_poses: R_est (9) t_est
+ * (3) R_gt (9) t_gt (3) doubles; d_scratch: 1 + ceil(n / 256) doubles, zeroed before the first use; d_out: one double. */
+int rdpn_adi(const float* d_pts, int n, const double* d_poses, double* d_scratch, double* d_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * f2  Region arg-max -- GDRN.py:206-209: argmax over channels 1..R of region [B,R+1,P] -> uint8.

@@ -180,6 +180,25 @@ def gen_path():
                                                    torch.from_numpy(whs), is_allo=True, z_type=zt)
         out["assm_rot_" + zt], out["assm_trans_" + zt] = ego.numpy(), tr.numpy()
     out.update(assm_rots=rots, assm_cent=cent, assm_z=zv, assm_cams=cams, assm_ctr=ctr, assm_rr=rr, assm_whs=whs)
+    # --- the two sibling heads: pose_from_pred.py:21-58 (rotation + translation given) and
+    # pose_from_pred_centroid_z_abs.py:21-92 (absolute 2-D centre + absolute z), test branches, rotation matrices and
+    # (unnormalised) quaternions.  RT_transform.quat_trans_to_pose_m (RT_transform.py:177-183) needs transforms3d's quat2mat
+    # (absent): the oracle supplies it.
+    rt = types.SimpleNamespace(quat_trans_to_pose_m=lambda q, t: np.hstack([po.quat2mat(q), np.asarray(t, np.float64).reshape(3, 1)]))
+    env = {"allocentric_to_egocentric": uf["allocentric_to_egocentric"], "RT_transform": rt}
+    p1 = ref_functions("core/gdrn_modeling/models/pose_from_pred.py", ["pose_from_predictions_test"], env=env)["pose_from_predictions_test"]
+    p2 = ref_functions("core/gdrn_modeling/models/pose_from_pred_centroid_z_abs.py", ["pose_from_predictions_test"],
+                       env=env)["pose_from_predictions_test"]
+    rng2 = np.random.default_rng(231)  # own stream: the vectors generated further down keep their values
+    quats = rng2.normal(0, 1, (n, 4)).astype(np.float32)  # unnormalised on purpose ("this allows unnormalized quat", :37)
+    trans = np.stack([rng2.uniform(-0.3, 0.3, n), rng2.uniform(-0.2, 0.2, n), rng2.uniform(0.5, 1.5, n)], 1).astype(np.float32)
+    cabs = rng2.uniform(100, 500, (n, 2)).astype(np.float32)
+    for tag, rin in (("mat", rots), ("quat", quats)):
+        ego, tr = p1(torch.from_numpy(rin), torch.from_numpy(trans), is_allo=True)
+        out["pfp_rot_" + tag], out["pfp_trans_" + tag] = ego.numpy(), tr.numpy()
+        ego, tr = p2(torch.from_numpy(rin), torch.from_numpy(cabs), torch.from_numpy(zv), torch.from_numpy(cams.copy()), is_allo=True)
+        out["pfpabs_rot_" + tag], out["pfpabs_trans_" + tag] = ego.numpy(), tr.numpy()
+    out.update(pfp_quats=quats, pfp_trans=trans, pfpabs_cent=cabs)
     # --- the loader's depth back-projection, data_loader.py:530-576 + the [:, ::4, ::4] of :625: the statements are
     # inline code of a detectron2-dependent method, so the source LINES are cut out and executed as they stand with
     # the local variables they expect.  NOTE numpy here (2.x, NEP 50) evaluates float32-array (op) np.float64-scalar
@@ -438,6 +457,44 @@ def gen_ransac_roi(tf):
     print("ransac_roi_golden.npz iters", iters, "max counts", counts.max(axis=1))
 
 
+def gen_metrics():
+    """Small helpers on the edges of the path, executed from the reference source: misc.backproject_v2 (misc.py:352-371),
+    misc.calc_emb_bp_fast (:288-316), pose_error.adi (pose_error.py:315-337, scipy cKDTree), pose_utils.get_closest_rot
+    (pose_utils.py:430-454)."""
+    from scipy import spatial
+
+    tf = _load("ref_transform", "lib/pysixd/transform.py")
+    rng = np.random.default_rng(77)
+    mf = ref_functions("lib/pysixd/misc.py", ["backproject_v2", "calc_emb_bp_fast", "transform_pts_Rt"])
+    K = np.array([[1066.778, 0, 312.9869], [0, 1067.487, 241.3109], [0, 0, 1]])
+    depth = rng.uniform(0.4, 1.6, (48, 64)).astype(np.float32)
+    depth[rng.random((48, 64)) < 0.2] = 0
+    R = tf.random_rotation_matrix(rng.random(3))[:3, :3]
+    T = rng.uniform(-0.2, 0.8, 3)
+    out = dict(bp_depth=depth, bp_K=K, bp_v2=mf["backproject_v2"](depth, K), bp_R=R, bp_T=T, bp_emb=mf["calc_emb_bp_fast"](depth, R, T, K))
+    pf = ref_functions("lib/pysixd/pose_error.py", ["adi", "re"], env={"spatial": spatial, "transform_pts_Rt": mf["transform_pts_Rt"],
+                                                                      "misc": types_ns(transform_pts_Rt=mf["transform_pts_Rt"])})
+    pts = (rng.standard_normal((700, 3)) * np.array([0.05, 0.04, 0.08])).astype(np.float32)
+    Re, Rg = tf.random_rotation_matrix(rng.random(3))[:3, :3], tf.random_rotation_matrix(rng.random(3))[:3, :3]
+    te_, tg = rng.uniform(-0.1, 0.1, (3, 1)) + np.array([[0], [0], [0.9]]), rng.uniform(-0.1, 0.1, (3, 1)) + np.array([[0], [0], [0.9]])
+    out.update(adi_pts=pts, adi_Re=Re, adi_te=te_, adi_Rg=Rg, adi_tg=tg, adi_val=np.float64(pf["adi"](Re, te_, Rg, tg, pts.astype(np.float64))))
+    import torch
+
+    gf = ref_functions("core/utils/pose_utils.py", ["get_closest_rot"], env={"re": pf["re"], "torch": torch})
+    sym = np.stack([tf.rotation_matrix(a, [0, 0, 1])[:3, :3] for a in (np.pi / 2, np.pi, 3 * np.pi / 2)])
+    est = Rg.dot(sym[1]).dot(tf.rotation_matrix(0.05, [1, 0, 0])[:3, :3])  # closest to the 180-degree copy
+    out.update(gcr_est=est, gcr_gt=Rg, gcr_sym=sym, gcr_out=gf["get_closest_rot"](est, Rg, sym), gcr_out_none=gf["get_closest_rot"](est, Rg, None),
+               gcr_out_single=gf["get_closest_rot"](est, Rg, sym[0]))
+    np.savez_compressed(os.path.join(GOLD, "metrics_golden.npz"), **out)
+    print("metrics_golden.npz adi", out["adi_val"])
+
+
+def types_ns(**kw):
+    import types
+
+    return types.SimpleNamespace(**kw)
+
+
 def gen_rows():
     """BOP result rows: GDRN_Evaluator.pose_prediction_to_json (gdrn_evaluator.py:483-513) executed from source with its
     helper to_list (test_utils.py:29-30); the evaluator hook must emit the same dicts."""
@@ -569,7 +626,7 @@ def main():
     tf = _load("ref_transform", "lib/pysixd/transform.py")
     du = _load("ref_data_utils", "core/utils/data_utils.py")
     gens = dict(fps=gen_fps, kabsch=lambda: gen_kabsch(tf), affine=lambda: gen_affine(du), region=lambda: gen_region(du),
-                pose=lambda: gen_pose(tf), path=gen_path, ransac_roi=lambda: gen_ransac_roi(tf), rows=gen_rows, fps_center=gen_fps_center, sampler=gen_sampler, roi_scalars=gen_roi_scalars)
+                pose=lambda: gen_pose(tf), path=gen_path, ransac_roi=lambda: gen_ransac_roi(tf), rows=gen_rows, metrics=gen_metrics, fps_center=gen_fps_center, sampler=gen_sampler, roi_scalars=gen_roi_scalars)
     for name in (sys.argv[1:] or list(gens)):  # python -m oracle.gen_golden [name ...]
         gens[name]()
 

@@ -577,6 +577,46 @@ def add(R_est, t_est, R_gt, t_gt, pts):
 # --------------------------------------------------------------------------------------------
 # a9: pose assembly from (rot6d | R_allo, centroid, z)
 # --------------------------------------------------------------------------------------------
+def adi(R_est, t_est, R_gt, t_gt, pts):
+    """pose_error.py:315-337: mean nearest-neighbour distance (brute force in float64; the reference uses a cKDTree,
+    which returns the same nearest distances)."""
+    pe = transform_pts_Rt(np.asarray(pts, F64), np.asarray(R_est, F64), np.asarray(t_est, F64))
+    pg = transform_pts_Rt(np.asarray(pts, F64), np.asarray(R_gt, F64), np.asarray(t_gt, F64))
+    d = np.sqrt(((pg[:, None, :] - pe[None, :, :]) ** 2).sum(-1))
+    return float(d.min(axis=1).mean())
+
+
+def get_closest_rot(rot_est, rot_gt, sym_info):
+    """core/utils/pose_utils.py:430-454."""
+    if sym_info is None:
+        return rot_gt
+    sym_info = np.asarray(sym_info)
+    if sym_info.ndim == 2:
+        sym_info = sym_info.reshape((1, 3, 3))
+    r_err, closest = re(rot_est, rot_gt), rot_gt
+    for i in range(sym_info.shape[0]):
+        cand = rot_gt.dot(sym_info[i])
+        cur = re(rot_est, cand)
+        if cur < r_err:
+            r_err, closest = cur, cand
+    return closest
+
+
+def backproject_v2(depth, K):
+    """misc.py:352-371."""
+    Kinv = np.linalg.inv(K)
+    h, w = depth.shape
+    gx, gy = np.meshgrid(np.arange(w), np.arange(h))
+    g2 = np.stack([gx, gy, np.ones((h, w))], axis=2)
+    return depth.reshape(h, w, 1) * (g2 @ Kinv.T)
+
+
+def calc_emb_bp_fast(depth, R, T, K):
+    """misc.py:288-316."""
+    pc = backproject_v2(depth, K) - np.asarray(T, F64).reshape(1, 1, 3)
+    return (pc @ np.asarray(R, F64)) * (depth != 0).astype(depth.dtype).reshape(*depth.shape, 1)
+
+
 def ortho6d_to_mat(p6):
     """rot_reps.py:34-49 (float32, batch [B,6] -> [B,3,3], columns x,y,z)."""
     p6 = np.asarray(p6, F32)
@@ -589,6 +629,21 @@ def ortho6d_to_mat(p6):
     z = _norm(np.cross(x, p6[:, 3:6]).astype(F32))
     y = np.cross(z, x).astype(F32)
     return np.stack([x, y, z], axis=2)
+
+
+def quat2mat(q):
+    """transforms3d.quaternions.quat2mat (w, x, y, z; normalises internally; identity below float eps) -- the third-party
+    call behind RT_transform.quat_trans_to_pose_m (lib/pysixd/RT_transform.py:177-183)."""
+    w, x, y, z = [float(v) for v in q]
+    Nq = w * w + x * x + y * y + z * z
+    if Nq < np.finfo(np.float64).eps:
+        return np.eye(3)
+    s = 2.0 / Nq
+    X, Y, Z = x * s, y * s, z * s
+    wX, wY, wZ = w * X, w * Y, w * Z
+    xX, xY, xZ = x * X, x * Y, x * Z
+    yY, yZ, zZ = y * Y, y * Z, z * Z
+    return np.array([[1.0 - (yY + zZ), xY - wZ, xZ + wY], [xY + wZ, 1.0 - (xX + zZ), yZ - wX], [xZ - wY, yZ + wX, 1.0 - (xX + yY)]])
 
 
 def axangle2mat(axis, angle):
@@ -604,18 +659,21 @@ def axangle2mat(axis, angle):
                      [zxC - ys, yzC + xs, z * zC + c]])
 
 
-def allocentric_to_egocentric_mat(R_allo, trans):
+def allocentric_to_egocentric_mat(R_allo, trans, pose_dtype=F32):
     """utils.py:39-94 for src_type=dst_type='mat', cam_ray=(0,0,1): R_ego = Rodrigues(cam x obj, acos(obj_z)) R_allo.
+    pose_dtype: dtype of the [R|t] array the caller hands to the reference function -- float32 from the matrix heads
+    (np.hstack of float32 tensors), float64 from the quaternion heads (RT_transform.quat_trans_to_pose_m fills a float64
+    array, RT_transform.py:177-183).
 
     dtype flow of the reference as called from pose_from_pred_centroid_z.py:127-136 (pinned by
     tests/golden/path_golden.npz): the pose is float32, so the object ray is normalised in float32; angle, axis and the
     Rodrigues matrix are float64; the product is rounded to float32 when stored into the float32 ego pose."""
     cam_ray = np.array([0, 0, 1.0])
-    trans = np.asarray(trans, F32)
-    obj_ray = trans.copy() / np.linalg.norm(trans)  # float32
+    trans = np.asarray(trans, pose_dtype)
+    obj_ray = trans.copy() / np.linalg.norm(trans)  # in the pose's dtype
     angle = math.acos(cam_ray.dot(obj_ray))
     if angle > 0:
-        return np.dot(axangle2mat(np.cross(cam_ray, obj_ray), angle), np.asarray(R_allo, F32))
+        return np.dot(axangle2mat(np.cross(cam_ray, obj_ray), angle), np.asarray(R_allo, pose_dtype))
     return np.asarray(R_allo, F64).copy()
 
 

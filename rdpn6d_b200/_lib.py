@@ -64,6 +64,9 @@ SIGNATURES = {
     "rdpn_pose_solve_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "rdpn_pose_solve_ws": (ctypes.c_int, [ctypes.POINTER(RoiInputs), c_vp, c_vp, ctypes.POINTER(SolveParams),
                                           ctypes.POINTER(SolveOutputs), c_vp, ctypes.c_size_t, c_vp]),
+    "rdpn_backproject_kinv": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
+    "rdpn_adi": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp]),
+    "rdpn_assemble_pose": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_vp, ctypes.c_int, c_vp]),
     "rdpn_fps_batch": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp]),
     "rdpn_pose_solve_stage_ms": (ctypes.c_int, [ctypes.POINTER(RoiInputs), c_vp, c_vp, ctypes.POINTER(SolveParams),
                                                 ctypes.POINTER(SolveOutputs), c_vp, ctypes.c_size_t, c_vp,

@@ -56,26 +56,58 @@ __global__ void backproject_kernel(const float* __restrict__ depth, const float*
 }
 
 // pose_from_pred_centroid_z.py:52-141 (test branch) + utils.py:39-94 + rot_reps.py:34-49
+// trans_mode: 0 = centroid relative to the box + z (pose_from_pred_centroid_z.py), 1 = absolute 2-D centre + absolute z
+// (pose_from_pred_centroid_z_abs.py:27-49), 2 = translation given in `centroid` [B,3] (pose_from_pred.py:21-23).
+// rot_is_6d: 0 = 3x3 matrix, 1 = rot6d, 2 = quaternion (w, x, y, z), normalised internally (RT_transform.py:177-183).
 __global__ void centroid_z_kernel(const float* __restrict__ rot_in, int rot_is_6d, const float* __restrict__ centroid,
                                   const float* __restrict__ zval, const float* __restrict__ K,
                                   const float* __restrict__ center, const float* __restrict__ rr,
                                   const float* __restrict__ wh, int is_allo, int z_rel, float* __restrict__ rot_out,
-                                  float* __restrict__ trans_out, int B) {
+                                  float* __restrict__ trans_out, int B, int trans_mode) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
-    const float* k = K + 9 * (size_t)b;
-    // :68-74  c = centroid * wh + center
-    const float cx = __fadd_rn(__fmul_rn(centroid[2 * b], wh[2 * b]), center[2 * b]);
-    const float cy = __fadd_rn(__fmul_rn(centroid[2 * b + 1], wh[2 * b + 1]), center[2 * b + 1]);
-    float z = zval[b];
-    if (z_rel) z = __fmul_rn(z, rr[b]);  // :84
-    const float tx = __fdiv_rn(__fmul_rn(z, __fsub_rn(cx, k[2])), k[0]);  // :102
-    const float ty = __fdiv_rn(__fmul_rn(z, __fsub_rn(cy, k[5])), k[4]);
+    float tx, ty, z;
+    if (trans_mode == 2) {
+        tx = centroid[3 * b];
+        ty = centroid[3 * b + 1];
+        z = centroid[3 * b + 2];
+    } else {
+        const float* k = K + 9 * (size_t)b;
+        float cx, cy;
+        if (trans_mode == 0) {  // :68-74  c = centroid * wh + center
+            cx = __fadd_rn(__fmul_rn(centroid[2 * b], wh[2 * b]), center[2 * b]);
+            cy = __fadd_rn(__fmul_rn(centroid[2 * b + 1], wh[2 * b + 1]), center[2 * b + 1]);
+        } else {
+            cx = centroid[2 * b];
+            cy = centroid[2 * b + 1];
+        }
+        z = zval[b];
+        if (z_rel && trans_mode == 0) z = __fmul_rn(z, rr[b]);  // :84
+        tx = __fdiv_rn(__fmul_rn(z, __fsub_rn(cx, k[2])), k[0]);  // :102
+        ty = __fdiv_rn(__fmul_rn(z, __fsub_rn(cy, k[5])), k[4]);
+    }
     trans_out[3 * b + 0] = tx;
     trans_out[3 * b + 1] = ty;
     trans_out[3 * b + 2] = z;
     float Rm[9];
-    if (rot_is_6d) {  // rot_reps.py:34-49: columns x, y, z
+    double Rq[9];
+    bool from_quat = false;
+    if (rot_is_6d == 2) {  // transforms3d quat2mat in float64, as the reference's numpy path (pose_from_pred.py:29-43)
+        const float* q = rot_in + 4 * (size_t)b;
+        const double w = q[0], x = q[1], y = q[2], zq = q[3];
+        const double Nq = w * w + x * x + y * y + zq * zq;
+        from_quat = true;
+        if (Nq < 2.220446049250313e-16) {
+            for (int i = 0; i < 9; ++i) Rq[i] = (i % 4 == 0) ? 1.0 : 0.0;
+        } else {
+            const double s2 = 2.0 / Nq, X = x * s2, Y = y * s2, Z = zq * s2;
+            const double wX = w * X, wY = w * Y, wZ = w * Z, xX = x * X, xY = x * Y, xZ = x * Z, yY = y * Y, yZ = y * Z, zZ = zq * Z;
+            Rq[0] = 1.0 - (yY + zZ); Rq[1] = xY - wZ;         Rq[2] = xZ + wY;
+            Rq[3] = xY + wZ;         Rq[4] = 1.0 - (xX + zZ); Rq[5] = yZ - wX;
+            Rq[6] = xZ - wY;         Rq[7] = yZ + wX;         Rq[8] = 1.0 - (xX + yY);
+        }
+        for (int i = 0; i < 9; ++i) Rm[i] = (float)Rq[i];
+    } else if (rot_is_6d) {  // rot_reps.py:34-49: columns x, y, z
         const float* p = rot_in + 6 * (size_t)b;
         float x0 = p[0], x1 = p[1], x2 = p[2];
         float n = fmaxf(sqrtf(x0 * x0 + x1 * x1 + x2 * x2), 1e-8f);
@@ -108,9 +140,11 @@ __global__ void centroid_z_kernel(const float* __restrict__ rot_in, int rot_is_6
                                  -ay * s, ax * s, c};
             float out[9];
             for (int r = 0; r < 3; ++r)
-                for (int cc = 0; cc < 3; ++cc)
-                    out[3 * r + cc] = (float)(M[3 * r] * (double)Rm[cc] + M[3 * r + 1] * (double)Rm[3 + cc] +
-                                              M[3 * r + 2] * (double)Rm[6 + cc]);
+                for (int cc = 0; cc < 3; ++cc) {
+                    const double r0 = from_quat ? Rq[cc] : (double)Rm[cc], r1 = from_quat ? Rq[3 + cc] : (double)Rm[3 + cc],
+                                 r2 = from_quat ? Rq[6 + cc] : (double)Rm[6 + cc];
+                    out[3 * r + cc] = (float)(M[3 * r] * r0 + M[3 * r + 1] * r1 + M[3 * r + 2] * r2);
+                }
             for (int i = 0; i < 9; ++i) Rm[i] = out[i];
         }
     }
@@ -136,6 +170,78 @@ __global__ void region_argmax_kernel(const float* __restrict__ region, int R, ui
         if (v.w > best.w) { best.w = v.w; bi.w = (uint8_t)r; }
     }
     reinterpret_cast<uchar4*>(out)[q] = bi;
+}
+
+// lib/pysixd/misc.py:288-316 (calc_emb_bp_fast) and :352-371 (backproject_v2): out[v,u,:] = m * R^T (d * Kinv (u,v,1)^T - T) in
+// float64 (the reference's numpy einsum promotes to float64), m = (d != 0) for calc_emb_bp_fast, R = I, T = 0 for
+// backproject_v2.  mats: Kinv (9) | R (9) | T (3), doubles.
+__global__ void backproject_kinv_kernel(const float* __restrict__ depth, const double* __restrict__ mats, int H, int W,
+                                        double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= H * W) return;
+    const double u = (double)(i % W), v = (double)(i / W), d = (double)depth[i];
+    const double* Ki = mats;
+    const double* R = mats + 9;
+    const double* T = mats + 18;
+    double p[3], q[3];
+    for (int r = 0; r < 3; ++r) p[r] = d * ((Ki[3 * r] * u + Ki[3 * r + 1] * v) + Ki[3 * r + 2]) - T[r];
+    for (int c = 0; c < 3; ++c) q[c] = (R[c] * p[0] + R[3 + c] * p[1]) + R[6 + c] * p[2];  // R^T p
+    const double m = depth[i] != 0.f ? 1.0 : 0.0;
+    for (int c = 0; c < 3; ++c) out[3 * (size_t)i + c] = q[c] * m;
+}
+
+// lib/pysixd/pose_error.py:315-337 (adi): mean over the ground-truth-posed model points of the distance to the nearest
+// estimate-posed model point.  Brute force: one thread per ground-truth point, the estimate-posed cloud staged through
+// shared memory in tiles; FP64 distances, block partial sums combined in block order by the last block.
+__global__ void adi_kernel(const float* __restrict__ pts, int n, const double* __restrict__ poses /* R_est t_est R_gt t_gt: 24 */,
+                           double* __restrict__ partial, unsigned* __restrict__ ticket, double* __restrict__ out) {
+    __shared__ double tile[256][3];
+    __shared__ double red[8];
+    __shared__ bool last;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const double* Re = poses;
+    const double* te = poses + 9;
+    const double* Rg = poses + 12;
+    const double* tg = poses + 21;
+    double g[3] = {0, 0, 0};
+    if (i < n) {
+        const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+        for (int r = 0; r < 3; ++r) g[r] = Rg[3 * r] * x + Rg[3 * r + 1] * y + Rg[3 * r + 2] * z + tg[r];
+    }
+    double best = 1e300;
+    for (int j0 = 0; j0 < n; j0 += 256) {
+        const int j = j0 + threadIdx.x;
+        if (j < n) {
+            const double x = pts[3 * j], y = pts[3 * j + 1], z = pts[3 * j + 2];
+            for (int r = 0; r < 3; ++r) tile[threadIdx.x][r] = Re[3 * r] * x + Re[3 * r + 1] * y + Re[3 * r + 2] * z + te[r];
+        }
+        __syncthreads();
+        const int m = min(256, n - j0);
+        for (int k = 0; k < m; ++k) {
+            const double dx = g[0] - tile[k][0], dy = g[1] - tile[k][1], dz = g[2] - tile[k][2];
+            const double d2 = dx * dx + dy * dy + dz * dz;
+            best = d2 < best ? d2 : best;
+        }
+        __syncthreads();
+    }
+    double v = i < n ? sqrt(best) : 0.0;
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0;
+        for (int w = 0; w < 8; ++w) a += red[w];
+        partial[blockIdx.x] = a;
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        if (last) {
+            __threadfence();
+            double tot = 0.0;
+            for (unsigned b = 0; b < gridDim.x; ++b) tot += __ldcg(partial + b);
+            *out = tot / (double)n;
+            *ticket = 0u;
+        }
+    }
 }
 
 __global__ void fp32_probe_kernel(float* out, int iters, float seed) {
@@ -188,7 +294,40 @@ int rdpn_centroid_z_to_pose(const float* d_rot_in, int rot_is_6d, const float* d
     if (z_type_rel && !d_resize_ratio) return RDPN_E_BADARG;
     rdpn::centroid_z_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
         d_rot_in, rot_is_6d, d_centroid, d_z, d_K, d_center, d_resize_ratio, d_wh, is_allo, z_type_rel, d_rot_out,
-        d_trans_out, B);
+        d_trans_out, B, 0);
+    ++rdpn::g_launch_count;
+    RDPN_LAUNCH_CHECK();
+    return 0;
+}
+
+int rdpn_backproject_kinv(const float* d_depth, const double* d_mats, int H, int W, double* d_out, void* stream) {
+    RDPN_NVTX("rdpn_backproject_kinv");
+    if (!d_depth || !d_mats || !d_out || H <= 0 || W <= 0) return RDPN_E_BADARG;
+    rdpn::backproject_kinv_kernel<<<(H * W + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_depth, d_mats, H, W, d_out);
+    ++rdpn::g_launch_count;
+    RDPN_LAUNCH_CHECK();
+    return 0;
+}
+
+int rdpn_adi(const float* d_pts, int n, const double* d_poses, double* d_scratch, double* d_out, void* stream) {
+    RDPN_NVTX("rdpn_adi");
+    if (!d_pts || !d_poses || !d_scratch || !d_out || n <= 0) return RDPN_E_BADARG;
+    const int blocks = (n + 255) / 256;
+    // scratch: blocks partial sums + one ticket word (zero before the first use; the kernel leaves it zero)
+    rdpn::adi_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_pts, n, d_poses, d_scratch + 1, (unsigned*)d_scratch, d_out);
+    ++rdpn::g_launch_count;
+    RDPN_LAUNCH_CHECK();
+    return 0;
+}
+
+int rdpn_assemble_pose(const float* d_rot_in, int rot_kind, const float* d_trans_or_centroid, const float* d_z, const float* d_K,
+                       int trans_mode, int is_allo, float* d_rot_out, float* d_trans_out, int B, void* stream) {
+    RDPN_NVTX("rdpn_assemble_pose");
+    if (!d_rot_in || !d_trans_or_centroid || !d_rot_out || !d_trans_out || B <= 0) return RDPN_E_BADARG;
+    if (rot_kind < 0 || rot_kind > 2 || (trans_mode != 1 && trans_mode != 2)) return RDPN_E_BADARG;
+    if (trans_mode == 1 && (!d_z || !d_K)) return RDPN_E_BADARG;
+    rdpn::centroid_z_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        d_rot_in, rot_kind, d_trans_or_centroid, d_z, d_K, nullptr, nullptr, nullptr, is_allo, 0, d_rot_out, d_trans_out, B, trans_mode);
     ++rdpn::g_launch_count;
     RDPN_LAUNCH_CHECK();
     return 0;

@@ -170,3 +170,85 @@ def region_argmax(region):
         rc = _lib.lib().rdpn_region_argmax(r.data_ptr(), R1 - 1, out.data_ptr(), B, _stream(r.device))
     _lib.check(rc, "region_argmax")
     return out
+
+
+def _kinv_mats(K, R=None, T=None, dev=None):
+    import numpy as np
+
+    Kn = K.detach().cpu().numpy() if torch.is_tensor(K) else np.asarray(K)
+    m = np.concatenate([np.linalg.inv(Kn.astype(np.float64)).reshape(9),  # misc.py:294 / :360 (a 3 x 3 host inverse)
+                        (np.eye(3) if R is None else np.asarray(R.detach().cpu() if torch.is_tensor(R) else R, np.float64)).reshape(9),
+                        (np.zeros(3) if T is None else np.asarray(T.detach().cpu() if torch.is_tensor(T) else T, np.float64)).reshape(3)])
+    return torch.from_numpy(m).to(dev)
+
+
+def backproject_v2(depth, K):
+    """lib/pysixd/misc.py:352-371: organised cloud d * Kinv (u, v, 1)^T, [H,W,3] float64 (CUDA in -> CUDA out)."""
+    d = _cuda_f32(depth, "depth")
+    H, W = d.shape
+    out = torch.empty(H, W, 3, dtype=torch.float64, device=d.device)
+    mats = _kinv_mats(K, dev=d.device)
+    with torch.cuda.device(d.device):
+        _lib.check(_lib.lib().rdpn_backproject_kinv(d.data_ptr(), mats.data_ptr(), H, W, out.data_ptr(), _stream(d.device)), "backproject_kinv")
+    return out
+
+
+def calc_emb_bp_fast(depth, R, T, K):
+    """lib/pysixd/misc.py:288-316 (= calc_xyz_bp_fast): object coordinates of a rendered depth map,
+    (depth != 0) * R^T (d * Kinv (u, v, 1)^T - T), [H,W,3] float64."""
+    d = _cuda_f32(depth, "depth")
+    H, W = d.shape
+    out = torch.empty(H, W, 3, dtype=torch.float64, device=d.device)
+    mats = _kinv_mats(K, R, T, dev=d.device)
+    with torch.cuda.device(d.device):
+        _lib.check(_lib.lib().rdpn_backproject_kinv(d.data_ptr(), mats.data_ptr(), H, W, out.data_ptr(), _stream(d.device)), "backproject_kinv")
+    return out
+
+
+calc_xyz_bp_fast = calc_emb_bp_fast  # misc.py:319
+
+
+def adi(R_est, t_est, R_gt, t_gt, pts):
+    """lib/pysixd/pose_error.py:315-337: Average Distance of model points for objects with Indistinguishable views (the
+    symmetric objects of the YCB-V config): mean distance from every ground-truth-posed model point to the nearest
+    estimate-posed one.  pts: [n,3] CUDA tensor; poses: anything array-like.  Returns a Python float (as the reference)."""
+    import numpy as np
+
+    p = _cuda_f32(pts, "pts")
+    n = p.shape[0]
+    as_np = lambda x: (x.detach().cpu().numpy() if torch.is_tensor(x) else np.asarray(x)).astype(np.float64)
+    poses = torch.from_numpy(np.concatenate([as_np(R_est).reshape(9), as_np(t_est).reshape(3), as_np(R_gt).reshape(9),
+                                             as_np(t_gt).reshape(3)])).to(p.device)
+    scratch = torch.zeros(1 + (n + 255) // 256, dtype=torch.float64, device=p.device)
+    out = torch.empty(1, dtype=torch.float64, device=p.device)
+    with torch.cuda.device(p.device):
+        _lib.check(_lib.lib().rdpn_adi(p.data_ptr(), n, poses.data_ptr(), scratch.data_ptr(), out.data_ptr(), _stream(p.device)), "adi")
+    return float(out.item())
+
+
+def get_closest_rot(rot_est, rot_gt, sym_info):
+    """core/utils/pose_utils.py:430-454: among rot_gt and rot_gt @ S for the object's symmetry transforms S ([K,3,3] or
+    [3,3] or None), the one with the smallest rotation error to rot_est (strictly smaller replaces: the plain rot_gt wins
+    ties).  A 3 x 3 host-side helper of the evaluation, numpy in -> numpy out, as the reference."""
+    import numpy as np
+
+    if sym_info is None:
+        return rot_gt
+    if torch.is_tensor(sym_info):
+        sym_info = sym_info.cpu().numpy()
+    sym_info = np.asarray(sym_info)
+    if sym_info.ndim == 2:
+        sym_info = sym_info.reshape((1, 3, 3))
+
+    def re(a, b):  # pose_error.py:400-415
+        tr = np.trace(np.asarray(a, np.float64).dot(np.asarray(b, np.float64).T))
+        tr = tr if tr <= 3 else 3
+        return np.rad2deg(np.arccos(0.5 * (tr - 1.0)))
+
+    r_err, closest = re(rot_est, rot_gt), rot_gt
+    for i in range(sym_info.shape[0]):
+        cand = rot_gt.dot(sym_info[i])
+        cur = re(rot_est, cand)
+        if cur < r_err:
+            r_err, closest = cur, cand
+    return closest

@@ -126,3 +126,33 @@ def test_bop_rows_match_reference_pose_prediction_to_json(golden_dir):
     for c in cases:
         pose = np.array(c["pose"], np.float64).astype(c["pose_dtype"])
         assert evaluator.pose_prediction_to_json(pose, **c["kwargs"]) == c["rows"]
+
+
+def test_metric_helpers_match_reference(golden_dir):
+    """misc.backproject_v2 / calc_emb_bp_fast (misc.py:288-371), pose_error.adi (pose_error.py:315-337, cKDTree) and
+    pose_utils.get_closest_rot (pose_utils.py:430-454) executed from source (oracle/gen_golden.py:gen_metrics)."""
+    m = np.load(os.path.join(golden_dir, "metrics_golden.npz"))
+    np.testing.assert_allclose(po.backproject_v2(m["bp_depth"], m["bp_K"]), m["bp_v2"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(po.calc_emb_bp_fast(m["bp_depth"], m["bp_R"], m["bp_T"], m["bp_K"]), m["bp_emb"], rtol=0, atol=1e-12)
+    assert abs(po.adi(m["adi_Re"], m["adi_te"], m["adi_Rg"], m["adi_tg"], m["adi_pts"]) - float(m["adi_val"])) <= 1e-12
+    assert np.array_equal(po.get_closest_rot(m["gcr_est"], m["gcr_gt"], m["gcr_sym"]), m["gcr_out"])
+    assert np.array_equal(po.get_closest_rot(m["gcr_est"], m["gcr_gt"], None), m["gcr_out_none"])
+    assert np.array_equal(po.get_closest_rot(m["gcr_est"], m["gcr_gt"], m["gcr_sym"][0]), m["gcr_out_single"])
+    assert not np.array_equal(m["gcr_out"], m["gcr_gt"])  # a symmetric copy really was closer
+
+
+def test_quat2mat_and_sibling_heads_match_reference(g):
+    """pose_from_pred.py:21-58 and pose_from_pred_centroid_z_abs.py:21-92 (test branches) executed from source on rotation
+    matrices and on unnormalised quaternions: the oracle's allo -> ego + quat2mat composition gives the same rotations."""
+    n = g["pfp_trans"].shape[0]
+    for tag, rin in (("mat", g["assm_rots"]), ("quat", g["pfp_quats"])):
+        for key, trans in (("pfp", g["pfp_trans"]), ("pfpabs", g["pfpabs_trans_" + tag])):
+            for i in range(n):
+                R = rin[i].astype(np.float64) if tag == "mat" else po.quat2mat(rin[i])
+                ego = po.allocentric_to_egocentric_mat(R, trans[i], np.float32 if tag == "mat" else np.float64)
+                np.testing.assert_allclose(ego, g[key + "_rot_" + tag][i], rtol=0, atol=1e-7)  # float32 outputs; the ray is normalised in the dtype of the pose the reference function receives
+    cams = g["assm_cams"]
+    z = g["assm_z"].reshape(-1)
+    c = g["pfpabs_cent"]
+    t = np.stack([z * (c[:, 0] - cams[:, 0, 2]) / cams[:, 0, 0], z * (c[:, 1] - cams[:, 1, 2]) / cams[:, 1, 1], z], 1)
+    np.testing.assert_allclose(t, g["pfpabs_trans_mat"], rtol=0, atol=1e-7)

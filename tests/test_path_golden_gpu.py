@@ -99,3 +99,33 @@ def test_loader_backprojection_matches_reference_lines(cuda, g):
     ref = g["loader_depth_xyz"]
     assert np.array_equal(cam[:, 2].view(np.uint32), ref[:, 2].view(np.uint32))
     assert (np.abs(cam[:, :2] - ref[:, :2]) <= 1.2e-7 * ref[:, 2][:, None]).all()
+
+
+def test_sibling_heads_match_reference(cuda, g):
+    """pose_from_pred (pose_from_pred.py:21-58) and pose_from_pred_centroid_z_abs (:21-92), test branches executed from
+    source: rotation matrices and unnormalised quaternions, the whole batch in one kernel."""
+    for tag, rin in (("mat", g["assm_rots"]), ("quat", g["pfp_quats"])):
+        rot, tr = pose_from_pred.pose_from_pred(_cu(rin), _cu(g["pfp_trans"]), is_allo=True, is_train=False)
+        np.testing.assert_allclose(rot.cpu().numpy(), g["pfp_rot_" + tag], rtol=0, atol=2e-6)
+        assert np.array_equal(tr.cpu().numpy(), g["pfp_trans_" + tag])
+        rot, tr = pose_from_pred.pose_from_pred_centroid_z_abs(_cu(rin), _cu(g["pfpabs_cent"]), _cu(g["assm_z"]), _cu(g["assm_cams"]),
+                                                               is_allo=True, is_train=False)
+        np.testing.assert_allclose(rot.cpu().numpy(), g["pfpabs_rot_" + tag], rtol=0, atol=2e-6)
+        np.testing.assert_allclose(tr.cpu().numpy(), g["pfpabs_trans_" + tag], rtol=0, atol=1e-7)
+
+
+def test_metric_helpers_match_reference_gpu(cuda, golden_dir):
+    """geometry.backproject_v2 / calc_emb_bp_fast / adi / get_closest_rot against the reference functions run from source."""
+    import os
+
+    from rdpn6d_b200 import geometry
+
+    m = np.load(os.path.join(golden_dir, "metrics_golden.npz"))
+    d = _cu(m["bp_depth"])
+    np.testing.assert_allclose(geometry.backproject_v2(d, m["bp_K"]).cpu().numpy(), m["bp_v2"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(geometry.calc_emb_bp_fast(d, m["bp_R"], m["bp_T"], m["bp_K"]).cpu().numpy(), m["bp_emb"], rtol=0, atol=1e-12)
+    for _ in range(2):  # the scratch ticket is left at zero: a second call gives the same bits
+        v = geometry.adi(m["adi_Re"], m["adi_te"], m["adi_Rg"], m["adi_tg"], _cu(m["adi_pts"]))
+        assert abs(v - float(m["adi_val"])) <= 1e-12
+    assert np.array_equal(geometry.get_closest_rot(m["gcr_est"], m["gcr_gt"], m["gcr_sym"]), m["gcr_out"])
+    assert np.array_equal(geometry.get_closest_rot(m["gcr_est"], m["gcr_gt"], None), m["gcr_out_none"])
