@@ -827,7 +827,7 @@ def gpu_arm(args):
                "value": wl["rois"] / (l_ms * 1e-3), "ms_per_step": l_ms,
                "value_two_calls_in_flight": wl["rois"] / (l2_ms * 1e-3),
                "note": "one stream, back-to-back calls over 4 rotating input sets (352 MB > L2); two_calls_in_flight alternates two "
-                       "streams so that the tail of one launch overlaps the head of the next.  Batches below 3072 ROIs run the fused "
+                       "streams so that the tail of one launch overlaps the head of the next.  Batches below 2048 ROIs run the fused "
                        "kernel (RDPN_PIPELINE_AUTO)",
                "parity": parity_vs_oracle(base_lmo, lres)}
         del lplans, lsets

@@ -1,4 +1,5 @@
-"""Launch the solve a few times on a BASELINE workload (for `ncu -k regex:... -s N -c 1` captures).
+"""Launch the solve a few times on a BASELINE workload (for `ncu -k regex:... -s N -c 1` captures), then S1
+(rdpn_correspond) on the same maps.
 usage: prof_pipeline.py [config=ycbv] [pipeline=split] [chunk=0] [weighted=1]"""
 import os
 import sys
@@ -20,4 +21,9 @@ plan = pose_solver.make_plan(solver, s["depth"], s["Kp"], s["coor"][:, 0].contig
                              s["coor"][:, 2].contiguous(), s["mask"], s["extent"], s["hyp_idx"], s["region_idx"], s["anchors"])
 for i in range(3):
     plan.launch()
+torch.cuda.synchronize()
+pose_solver.correspond(s["depth"], s["Kp"], s["coor"][:, 0].contiguous(), s["coor"][:, 1].contiguous(), s["coor"][:, 2].contiguous(),
+                       s["mask"], s["extent"], s["region_idx"], s["anchors"])
+pose_solver.correspond(s["depth"], s["Kp"], s["coor"][:, 0].contiguous(), s["coor"][:, 1].contiguous(), s["coor"][:, 2].contiguous(),
+                       s["mask"], s["extent"], s["region_idx"], s["anchors"])
 torch.cuda.synchronize()

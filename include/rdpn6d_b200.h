@@ -180,7 +180,7 @@ typedef struct rdpn_solve_params {
 #define RDPN_SELECT_MIN_MEAN_ERR 1
 
 /* Implementations of the solve (identical counts / masks / winner; refit pose equal to FP32 rounding):
- *   AUTO   the three-kernel pipeline for batches of >= 3072 ROIs in anchor mode, else the fused kernel
+ *   AUTO   the three-kernel pipeline for batches of >= 2048 ROIs in anchor mode, else the fused kernel
  *   FUSED  one kernel, one CTA per ROI (csrc/pose_solve.cu): lowest latency for small batches
  *   SPLIT  csrc/solve_pipe.cu: front (warp per ROI: gate, back-projection + residual, region sort, hypothesis
  *          poses) -> score (CTA per ROI, bulk-TMA staged, FP32 cores) -> best + refit (warp per ROI), the three

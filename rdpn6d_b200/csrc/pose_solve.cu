@@ -1219,10 +1219,10 @@ static int solve_prepare(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, co
 }
 
 // which implementation runs.  AUTO: the three-kernel pipeline (solve_pipe.cu) for batches of at least
-// RDPN_PIPELINE_MIN_ROIS ROIs (below that the fused kernel's single launch wins: measured crossover on B200 between
-// 2048 and 4096 ROIs), the fused kernel otherwise or where the pipeline does not apply (dense mode).  The caller's
+// RDPN_PIPELINE_MIN_ROIS ROIs (below that the fused kernel's single launch wins: measured on B200, the pipeline is ahead
+// from 2048 ROIs on -- 9.9 vs 9.5 M ROI/s there, 13.4 vs 11.5 M at 8192 -- and behind at 1024: profiles/r2/pipeline.jsonl), the fused kernel otherwise or where the pipeline does not apply (dense mode).  The caller's
 // prm->pipeline or the environment variable RDPN_SOLVE_PIPELINE ("fused" / "split", tuning) override it.
-#define RDPN_PIPELINE_MIN_ROIS 3072
+#define RDPN_PIPELINE_MIN_ROIS 2048
 static bool use_split(const rdpn::SolveArgs& a, bool dense, int* err) {
     int mode = a.prm.pipeline;
     if (mode == RDPN_PIPELINE_AUTO) {
