@@ -450,7 +450,10 @@ def gpu_arm(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+
+        # a collective that cannot complete is a bug, not a slow link: fail in two minutes, not in ten
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     L = _lib.lib()
 
     total = W["rois"] if world == 1 else JOB_ROIS
@@ -517,10 +520,12 @@ def gpu_arm(args):
     sampler = ClockSampler(local_rank if os.environ.get("CUDA_VISIBLE_DEVICES") is None else
                            int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
     sampler.start()
-    # pre-heat under the same load so that the sampled clocks are the steady-state ones
+    # pre-heat under the same load so that the sampled clocks are the steady-state ones.  Solves only: the loop is
+    # time-based, so ranks run different numbers of rounds -- it must not contain a collective
     t_heat = time.perf_counter()
     while time.perf_counter() - t_heat < args.preheat:
-        run(8)
+        for i in range(8):
+            plans[i % nplans].launch(comp)
         torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

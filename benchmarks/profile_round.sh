@@ -18,7 +18,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --steps 20 --warmup 3 --preheat 0 --no-cpu-baseline > $O/ncu_bench.log 2>&1
 # full captures of the kernels of the headline workload (YCB-V 8192) and of S1 on the same maps
 for k in front_kernel score_kernel refit_kernel correspond_kernel; do
-    ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -f -o $O/prof_$k \
+    ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -f -o $O/prof_$k \
         python benchmarks/prof_pipeline.py ycbv split 0 > $O/ncu_$k.log 2>&1
 done
 ncu --set full --clock-control none --import-source on -k regex:pose_solve_kernel -s 2 -c 1 -f -o $O/prof_pose_solve_kernel \
