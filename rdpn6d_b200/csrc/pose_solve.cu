@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(ST, MULTI ? RDPN_MULTI_CTAS : RDPN_SOLVE_CTAS)
 
     // ---- 5 + 6: per chunk of gated slots: staging, then inlier scoring ----
     if (enough) {
-        const float cut = a.sq_cut;
+        const float ncut = -a.sq_cut;  // the contract's inlier test: margin_pt(..., ncut) < 0 (solve_common.cuh)
         const int S = (nvalid >= ST || nvalid == 0) ? 1 : (ST / nvalid);
         for (int c0 = 0; c0 < n; c0 += CH) {
             const int c1 = min(n, c0 + CH);
@@ -740,20 +740,20 @@ __global__ void __launch_bounds__(ST, MULTI ? RDPN_MULTI_CTAS : RDPN_SOLVE_CTAS)
 #pragma unroll 1
                         for (; i + 4 <= e; i += 4) {
                             const float4 q0 = camw_s[i], q1 = camw_s[i + 1], q2 = camw_s[i + 2], q3 = camw_s[i + 3];
-                            count_if_lt(cA, resid2_pt(ax, ay, az, q0.x, q0.y, q0.z), cut);
-                            count_if_lt(cB, resid2_pt(bx, by, bz, q0.x, q0.y, q0.z), cut);
-                            count_if_lt(cA, resid2_pt(ax, ay, az, q1.x, q1.y, q1.z), cut);
-                            count_if_lt(cB, resid2_pt(bx, by, bz, q1.x, q1.y, q1.z), cut);
-                            count_if_lt(cA, resid2_pt(ax, ay, az, q2.x, q2.y, q2.z), cut);
-                            count_if_lt(cB, resid2_pt(bx, by, bz, q2.x, q2.y, q2.z), cut);
-                            count_if_lt(cA, resid2_pt(ax, ay, az, q3.x, q3.y, q3.z), cut);
-                            count_if_lt(cB, resid2_pt(bx, by, bz, q3.x, q3.y, q3.z), cut);
+                            count_in(cA, margin_pt(ax, ay, az, q0.x, q0.y, q0.z, ncut));
+                            count_in(cB, margin_pt(bx, by, bz, q0.x, q0.y, q0.z, ncut));
+                            count_in(cA, margin_pt(ax, ay, az, q1.x, q1.y, q1.z, ncut));
+                            count_in(cB, margin_pt(bx, by, bz, q1.x, q1.y, q1.z, ncut));
+                            count_in(cA, margin_pt(ax, ay, az, q2.x, q2.y, q2.z, ncut));
+                            count_in(cB, margin_pt(bx, by, bz, q2.x, q2.y, q2.z, ncut));
+                            count_in(cA, margin_pt(ax, ay, az, q3.x, q3.y, q3.z, ncut));
+                            count_in(cB, margin_pt(bx, by, bz, q3.x, q3.y, q3.z, ncut));
                         }
 #pragma unroll 1
                         for (; i < e; ++i) {
                             const float4 q0 = camw_s[i];
-                            count_if_lt(cA, resid2_pt(ax, ay, az, q0.x, q0.y, q0.z), cut);
-                            count_if_lt(cB, resid2_pt(bx, by, bz, q0.x, q0.y, q0.z), cut);
+                            count_in(cA, margin_pt(ax, ay, az, q0.x, q0.y, q0.z, ncut));
+                            count_in(cB, margin_pt(bx, by, bz, q0.x, q0.y, q0.z, ncut));
                         }
                     }
                     if (S2 == 1) {
@@ -779,7 +779,7 @@ __global__ void __launch_bounds__(ST, MULTI ? RDPN_MULTI_CTAS : RDPN_SOLVE_CTAS)
                     for (int i = i0; i < i1; ++i) {
                         const float4 cp = camw_s[i];
                         const float4 ap = obj_s[i];
-                        count_if_lt(c, resid2(P, ap.x, ap.y, ap.z, cp.x, cp.y, cp.z), cut);
+                        count_in(c, margin(P, ap.x, ap.y, ap.z, cp.x, cp.y, cp.z, ncut));
                     }
                 } else {
                     // slots are sorted by region: per run (non-empty bucket) the transformed anchor R a + t is
@@ -800,16 +800,16 @@ __global__ void __launch_bounds__(ST, MULTI ? RDPN_MULTI_CTAS : RDPN_SOLVE_CTAS)
 #pragma unroll 1
                         for (; i + 4 <= e; i += 4) {
                             const float4 q0 = camw_s[i], q1 = camw_s[i + 1], q2 = camw_s[i + 2], q3 = camw_s[i + 3];
-                            count_if_lt(c, resid2_pt(tx, ty, tz, q0.x, q0.y, q0.z), cut);
-                            count_if_lt(c, resid2_pt(tx, ty, tz, q1.x, q1.y, q1.z), cut);
-                            count_if_lt(c, resid2_pt(tx, ty, tz, q2.x, q2.y, q2.z), cut);
-                            count_if_lt(c, resid2_pt(tx, ty, tz, q3.x, q3.y, q3.z), cut);
+                            count_in(c, margin_pt(tx, ty, tz, q0.x, q0.y, q0.z, ncut));
+                            count_in(c, margin_pt(tx, ty, tz, q1.x, q1.y, q1.z, ncut));
+                            count_in(c, margin_pt(tx, ty, tz, q2.x, q2.y, q2.z, ncut));
+                            count_in(c, margin_pt(tx, ty, tz, q3.x, q3.y, q3.z, ncut));
                         }
                         if (i < e) {  // 1..3 left: one masked batch (warp-uniform predicates), indices clamped into the run
                             const float4 q0 = camw_s[i], q1 = camw_s[min(i + 1, e - 1)], q2 = camw_s[min(i + 2, e - 1)];
-                            count_if_lt(c, resid2_pt(tx, ty, tz, q0.x, q0.y, q0.z), cut);
-                            if (i + 1 < e) count_if_lt(c, resid2_pt(tx, ty, tz, q1.x, q1.y, q1.z), cut);
-                            if (i + 2 < e) count_if_lt(c, resid2_pt(tx, ty, tz, q2.x, q2.y, q2.z), cut);
+                            count_in(c, margin_pt(tx, ty, tz, q0.x, q0.y, q0.z, ncut));
+                            if (i + 1 < e) count_in(c, margin_pt(tx, ty, tz, q1.x, q1.y, q1.z, ncut));
+                            if (i + 2 < e) count_in(c, margin_pt(tx, ty, tz, q2.x, q2.y, q2.z, ncut));
                         }
                     }
                 }
@@ -907,7 +907,7 @@ __global__ void __launch_bounds__(ST, MULTI ? RDPN_MULTI_CTAS : RDPN_SOLVE_CTAS)
 
     // ---- 7b: refit on the inliers (misc.py:123-126 -> transform.py:913-980), FP64 accumulation ----
     if (t < 12) f.pose[t] = hyp[(size_t)best * 12 + t];  // stays if the refit bails out (< 3 inliers)
-    const float cut = a.sq_cut;
+    const float ncut = -a.sq_cut;
     float out_scale = 1.f;
     const int iters = a.prm.refit_iters < 1 ? 1 : a.prm.refit_iters;
     for (int it = 0; it < iters; ++it) {
@@ -930,7 +930,7 @@ __global__ void __launch_bounds__(ST, MULTI ? RDPN_MULTI_CTAS : RDPN_SOLVE_CTAS)
             for (int i = t; i < n; i += ST, ++slot) {
                 float4 cp, ap;
                 get_slot(i, cp, ap);
-                if (resid2(P, ap.x, ap.y, ap.z, cp.x, cp.y, cp.z) < cut) {
+                if (is_inlier(P, ap.x, ap.y, ap.z, cp.x, cp.y, cp.z, ncut)) {
                     inl_bits |= 1u << slot;
                     const double w = a.prm.weighted ? (double)cp.w : 1.0;
                     const double c0 = (double)cp.x - (double)cp0.x, c1 = (double)cp.y - (double)cp0.y, c2 = (double)cp.z - (double)cp0.z;

@@ -72,10 +72,20 @@ __device__ __forceinline__ float resid2_pt(float tx, float ty, float tz, float c
     d2 = __fmaf_rn(dz, dz, d2);
     return d2;
 }
-// c += (d2 < cut): one FSETP + one predicated IADD (the C++ form compiles to three instructions)
-__device__ __forceinline__ void count_if_lt(int& c, float d2, float cut) {
-    asm("{\n.reg .pred p;\nsetp.lt.f32 p, %1, %2;\n@p add.s32 %0, %0, 1;\n}" : "+r"(c) : "f"(d2), "f"(cut));
+// The inlier test of the FP32 contract (oracle/pose_oracle.c:inlier_margin): with ncut = -sq_cut(thr),
+//   margin = fma(dz, dz, fma(dy, dy, fma(dx, dx, ncut)))      inlier  <=>  margin < 0
+// i.e. ||R a + t - c||^2 < cut with the threshold folded into the accumulation: the three squares cost three FFMA and
+// the count one LEA.HI on the sign bit -- 7 instructions per (hypothesis, point) instead of 8 with FMUL + FSETP + IADD.
+// (The arithmetic never yields -0 or a negative NaN here: x + (-x) is +0 in round-to-nearest and the GPU's NaN is
+// 0x7fffffff, so "sign bit set" is exactly "margin < 0".)
+__device__ __forceinline__ float margin_pt(float tx, float ty, float tz, float cx, float cy, float cz, float ncut) {
+    const float dx = __fsub_rn(tx, cx), dy = __fsub_rn(ty, cy), dz = __fsub_rn(tz, cz);
+    float m = __fmaf_rn(dx, dx, ncut);
+    m = __fmaf_rn(dy, dy, m);
+    m = __fmaf_rn(dz, dz, m);
+    return m;
 }
+__device__ __forceinline__ void count_in(int& c, float margin) { c += (int)(__float_as_uint(margin) >> 31); }
 // counter-based stream of the internal hypothesis sampling (include/rdpn6d_b200.h, oracle sample_triplets)
 __device__ __forceinline__ uint32_t fmix32(uint32_t x) {
     x ^= x >> 16;
@@ -101,6 +111,14 @@ __device__ __forceinline__ float resid2(const float* P, float ax, float ay, floa
     float x, y, z;
     xform(P, ax, ay, az, x, y, z);
     return resid2_pt(x, y, z, cx, cy, cz);
+}
+__device__ __forceinline__ float margin(const float* P, float ax, float ay, float az, float cx, float cy, float cz, float ncut) {
+    float x, y, z;
+    xform(P, ax, ay, az, x, y, z);
+    return margin_pt(x, y, z, cx, cy, cz, ncut);
+}
+__device__ __forceinline__ bool is_inlier(const float* P, float ax, float ay, float az, float cx, float cy, float cz, float ncut) {
+    return margin(P, ax, ay, az, cx, cy, cz, ncut) < 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -138,6 +156,7 @@ __device__ __forceinline__ void score_pass(const float4* __restrict__ pts, const
                                            const POSE pose, int j0, int nvalid, int i0, int i1, int c0, float cut, int* hcnt,
                                            float* herr = nullptr) {
     const int lane = threadIdx.x & 31;
+    const float ncut = -cut;
     int sl[K], cnt[K];
     float es[K];
 #pragma unroll
@@ -168,10 +187,10 @@ __device__ __forceinline__ void score_pass(const float4* __restrict__ pts, const
                 const float4 q0 = pts[p], q1 = pts[p + 1], q2 = pts[p + 2], q3 = pts[p + 3];
 #pragma unroll
                 for (int u = 0; u < K; ++u) {
-                    count_if_lt(cnt[u], resid2_pt(tx[u], ty[u], tz[u], q0.x, q0.y, q0.z), cut);
-                    count_if_lt(cnt[u], resid2_pt(tx[u], ty[u], tz[u], q1.x, q1.y, q1.z), cut);
-                    count_if_lt(cnt[u], resid2_pt(tx[u], ty[u], tz[u], q2.x, q2.y, q2.z), cut);
-                    count_if_lt(cnt[u], resid2_pt(tx[u], ty[u], tz[u], q3.x, q3.y, q3.z), cut);
+                    count_in(cnt[u], margin_pt(tx[u], ty[u], tz[u], q0.x, q0.y, q0.z, ncut));
+                    count_in(cnt[u], margin_pt(tx[u], ty[u], tz[u], q1.x, q1.y, q1.z, ncut));
+                    count_in(cnt[u], margin_pt(tx[u], ty[u], tz[u], q2.x, q2.y, q2.z, ncut));
+                    count_in(cnt[u], margin_pt(tx[u], ty[u], tz[u], q3.x, q3.y, q3.z, ncut));
                 }
             }
         }
@@ -180,9 +199,8 @@ __device__ __forceinline__ void score_pass(const float4* __restrict__ pts, const
             const float4 q0 = pts[p];
 #pragma unroll
             for (int u = 0; u < K; ++u) {
-                const float d2 = resid2_pt(tx[u], ty[u], tz[u], q0.x, q0.y, q0.z);
-                count_if_lt(cnt[u], d2, cut);
-                if (MEAN) es[u] += sqrtf(d2);
+                count_in(cnt[u], margin_pt(tx[u], ty[u], tz[u], q0.x, q0.y, q0.z, ncut));
+                if (MEAN) es[u] += sqrtf(resid2_pt(tx[u], ty[u], tz[u], q0.x, q0.y, q0.z));
             }
         }
     }

@@ -811,7 +811,7 @@ __global__ void __launch_bounds__(RF_W * 32, RDPN_REFIT_CTAS) refit_kernel(Solve
     const float4* slots = reinterpret_cast<const float4*>(pkg + lay.slots);
     const uint8_t* srid = pkg + lay.srid;
     const uint16_t* pixs = reinterpret_cast<const uint16_t*>(pkg + lay.pix);
-    const float cut = a.sq_cut;
+    const float ncut = -a.sq_cut;  // the contract's inlier test: margin(..., ncut) < 0 (solve_common.cuh)
     float out_scale = 1.f;
     const int iters = a.prm.refit_iters < 1 ? 1 : a.prm.refit_iters;
     // pivot of the raw moments (exact FP32 differences): slot 0
@@ -846,7 +846,7 @@ __global__ void __launch_bounds__(RF_W * 32, RDPN_REFIT_CTAS) refit_kernel(Solve
                 if (i >= n) break;
                 const float4 cp = cpv[u];
                 const float4 ap = make_float4(anc[3 * ridv[u]], anc[3 * ridv[u] + 1], anc[3 * ridv[u] + 2], 0.f);
-                if (resid2(P, ap.x, ap.y, ap.z, cp.x, cp.y, cp.z) < cut) {
+                if (is_inlier(P, ap.x, ap.y, ap.z, cp.x, cp.y, cp.z, ncut)) {
                     ++ninl;
                     const int k = (i - lane) >> 5;
                     if (k < 32) marks |= 1u << k;
@@ -877,7 +877,7 @@ __global__ void __launch_bounds__(RF_W * 32, RDPN_REFIT_CTAS) refit_kernel(Solve
                 } else {
                     const float4 cp = __ldcg(slots + i);
                     const int r3 = 3 * (int)__ldcg(srid + i);
-                    inl = resid2(P, anc[r3], anc[r3 + 1], anc[r3 + 2], cp.x, cp.y, cp.z) < cut;
+                    inl = is_inlier(P, anc[r3], anc[r3 + 1], anc[r3 + 2], cp.x, cp.y, cp.z, ncut);
                 }
                 if (inl) a.out.inlier_mask[(size_t)b * RDPN_P + __ldcg(pixs + i)] = 1;
             }
@@ -948,7 +948,7 @@ struct WarpRoi {  // what a warp needs to walk its ROI's region-sorted correspon
 };
 // Kabsch / Umeyama refit on the inliers of Pin (misc.py:123-126 -> transform.py:913-980): FP64 raw moments about the pivot by
 // warp shuffle, closed-form rotation.  Returns the number of inliers (uniform); Pout is written when there are >= 3.
-static __device__ __noinline__ int warp_refit(const WarpRoi& w, const float* Pin, float cut, int weighted, int with_scale, float* Pout) {
+static __device__ __noinline__ int warp_refit(const WarpRoi& w, const float* Pin, float ncut, int weighted, int with_scale, float* Pout) {
     const int lane = threadIdx.x & 31;
     double m[18];
 #pragma unroll
@@ -958,7 +958,7 @@ static __device__ __noinline__ int warp_refit(const WarpRoi& w, const float* Pin
         const float4 cp = __ldcg(w.slots + i);
         const int r3 = 3 * (int)__ldcg(w.srid + i);
         const float ax = w.anc[r3], ay = w.anc[r3 + 1], az = w.anc[r3 + 2];
-        if (resid2(Pin, ax, ay, az, cp.x, cp.y, cp.z) < cut) {
+        if (is_inlier(Pin, ax, ay, az, cp.x, cp.y, cp.z, ncut)) {
             ++ninl;
             const double wt = weighted ? (double)cp.w : 1.0;
             const double c0 = (double)cp.x - (double)w.cp0.x, c1 = (double)cp.y - (double)w.cp0.y, c2 = (double)cp.z - (double)w.cp0.z;
@@ -1079,7 +1079,7 @@ __global__ void __launch_bounds__(RF_W * 32, RDPN_REFIT_CTAS) refit_minerr_kerne
         if (a.out.hyp_counts)
             for (int j = lane; j < nvalid; j += 32) a.out.hyp_counts[(size_t)b * H + __ldcg(vh + j)] = __ldcg(hcnt + j);
         double best_err = 1e300;
-        const float cut = a.sq_cut;
+        const float ncut = -a.sq_cut;
         for (int j = 0; j < jlim; ++j) {  // warp-uniform walk in hypothesis order
             const int c = __ldcg(hcnt + j);
             const double e32 = (double)__ldcg(herr + j) / (double)n;
@@ -1105,7 +1105,7 @@ __global__ void __launch_bounds__(RF_W * 32, RDPN_REFIT_CTAS) refit_minerr_kerne
             if (improves) {  // misc.py:118-132
                 best_inl = c;
                 float Pr[12];
-                if (warp_refit(w, P, cut, a.prm.weighted, a.prm.with_scale, Pr) >= 3) {
+                if (warp_refit(w, P, ncut, a.prm.weighted, a.prm.with_scale, Pr) >= 3) {
                     const double e = warp_mean_err(w, Pr);
                     if (e < best_err) {
                         best_err = e;
@@ -1122,7 +1122,7 @@ __global__ void __launch_bounds__(RF_W * 32, RDPN_REFIT_CTAS) refit_minerr_kerne
             for (int i = lane; i < n; i += 32) {
                 const float4 cp = __ldcg(w.slots + i);
                 const int r3 = 3 * (int)__ldcg(w.srid + i);
-                if (resid2(Pbest, anc[r3], anc[r3 + 1], anc[r3 + 2], cp.x, cp.y, cp.z) < cut)
+                if (is_inlier(Pbest, anc[r3], anc[r3 + 1], anc[r3 + 2], cp.x, cp.y, cp.z, ncut))
                     a.out.inlier_mask[(size_t)b * RDPN_P + __ldcg(pixs + i)] = 1;
             }
         }
