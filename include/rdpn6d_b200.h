@@ -42,6 +42,7 @@ extern "C" {
 
 /* mask post-processing modes (engine_utils.py:118-136 get_out_mask) */
 #define RDPN_MAX_SAMPLE 16 /* largest sample_size (pairs per hypothesis) */
+#define RDPN_SAMPLE_REDRAWS 7 /* kernel-drawn samples of S > 3 pairs: re-draws of a vertex that repeats an earlier pixel */
 
 #define RDPN_MASK_RAW 0 /* mask already is a probability                     */
 #define RDPN_MASK_L1 1  /* per-ROI (m - min) / (max - min), no epsilon       */
@@ -218,9 +219,13 @@ typedef struct rdpn_solve_outputs {
  *     fmix32(x): x ^= x >> 16; x *= 0x85ebca6b; x ^= x >> 13; x *= 0xc2b2ae35; x ^= x >> 16      (uint32)
  *     key      = fmix32(fmix32(fmix32(seed ^ 0x9e3779b9) ^ (roi_base + b)) ^ (S * h + v))
  *     pixel of vertex v of hypothesis h = g[(uint64(key) * n) >> 32]
- * (draws are independent, so a sample may repeat a pixel: such a hypothesis is invalid like any other and does not
- * consume an iteration.  oracle/pose_oracle.py:sample_triplets is the same arithmetic; tests feed its output back as explicit hyp_idx
- * and demand bit-identical results). */
+ * S = 3: the three draws are independent, so a sample may repeat a pixel: such a hypothesis is invalid like any other
+ * and does not consume an iteration.  S > 3: WITHOUT replacement, as misc.py:91 samples -- a vertex that repeats an earlier
+ * pixel of its sample is re-drawn with key' = fmix32(kroi ^ (S * h + v) ^ (attempt << 20)), attempt = 1 .. RDPN_SAMPLE_REDRAWS
+ * (attempt 0 is the key above), so small ROIs keep their hypotheses (with independent draws ~45 / n of the 10-pair samples
+ * would be lost); a sample still repeating a pixel after the last attempt is invalid.
+ * oracle/pose_oracle.py:sample_triplets is the same arithmetic; tests feed its output back as explicit hyp_idx and demand
+ * bit-identical results). */
 int rdpn_pose_solve(const rdpn_roi_inputs* in, const int32_t* d_hyp_idx, const float* d_t_net,
                     const rdpn_solve_params* prm, const rdpn_solve_outputs* out, void* stream);
 /* Same call with a caller-owned scratch buffer for the pipeline's per-ROI packages (raster list and region-sorted

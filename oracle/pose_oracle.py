@@ -330,11 +330,16 @@ def _fmix32(x):
     return x ^ (x >> np.uint32(16))
 
 
+SAMPLE_REDRAWS = 7  # RDPN_SAMPLE_REDRAWS
+
+
 def sample_triplets(sel, H, seed, roi_index, sample_size=3):
     """The solver's internal hypothesis sampling (include/rdpn6d_b200.h, rdpn_pose_solve with hyp_idx == NULL):
     the stand-in for np.random.choice at misc.py:91, counter-based so that it is reproducible.  sel: [P] bool gate of
-    one ROI; returns [H,S] int32 absolute pixel indices (all -1 when nothing is gated).  Draws are independent: a
-    sample that repeats a pixel is an invalid hypothesis (hypothesis_poses)."""
+    one ROI; returns [H,S] int32 absolute pixel indices (all -1 when nothing is gated).  S = 3: draws are independent, a
+    sample that repeats a pixel is an invalid hypothesis (hypothesis_poses).  S > 3: without replacement as misc.py:91
+    samples -- a vertex that repeats an earlier pixel of its sample is re-drawn with the attempt number in bits 20..23 of
+    the counter, up to SAMPLE_REDRAWS times (include/rdpn6d_b200.h)."""
     S = int(sample_size)
     g = np.nonzero(np.asarray(sel).reshape(-1))[0]
     n = len(g)
@@ -345,7 +350,17 @@ def sample_triplets(sel, H, seed, roi_index, sample_size=3):
         hv = np.arange(S * H, dtype=np.uint32)
         key = _fmix32(kroi ^ hv)
     k = (key.astype(np.uint64) * np.uint64(n)) >> np.uint64(32)
-    return g[k.astype(np.int64)].astype(np.int32).reshape(H, S)
+    out = g[k.astype(np.int64)].astype(np.int32).reshape(H, S)
+    if S > 3:
+        for h in range(H):
+            for v in range(1, S):
+                att = 0
+                while out[h, v] in out[h, :v] and att < SAMPLE_REDRAWS:
+                    att += 1
+                    with np.errstate(over="ignore"):
+                        kk = _fmix32(kroi ^ np.uint32(S * h + v) ^ np.uint32(att << 20))
+                    out[h, v] = g[int((np.uint64(kk) * np.uint64(n)) >> np.uint64(32))]
+    return out
 
 
 def sq_cut(thr):

@@ -145,8 +145,17 @@ static __device__ __noinline__ bool hyp_from_sample_list(const uint32_t* selmap,
         if (idx_in) {
             px = idx_in[v];
         } else {
-            const uint32_t kk = fmix32(kroi ^ (uint32_t)(S * h + v));
-            px = nsel ? kth_gated_pixel(selmap, selpfx, (uint32_t)(((unsigned long long)kk * nsel) >> 32)) : -1;
+            // without replacement, as np.random.choice(..., replace=False) at misc.py:91: a draw that repeats an earlier
+            // pixel of the sample is re-drawn from the same counter stream (attempt a in bits 20..23 of the counter), up to
+            // RDPN_SAMPLE_REDRAWS times; attempt 0 is the plain stream
+            px = -1;
+            for (int att = 0; att <= RDPN_SAMPLE_REDRAWS && nsel; ++att) {
+                const uint32_t kk = fmix32(kroi ^ (uint32_t)(S * h + v) ^ ((uint32_t)att << 20));
+                px = kth_gated_pixel(selmap, selpfx, (uint32_t)(((unsigned long long)kk * nsel) >> 32));
+                bool dup = false;
+                for (int u = 0; u < v; ++u) dup = dup || ii[u * 32] == px;
+                if (!dup) break;
+            }
         }
         if ((unsigned)px >= RDPN_P) return false;
         if (!((selmap[px >> 5] >> (px & 31)) & 1u)) return false;

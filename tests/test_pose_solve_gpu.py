@@ -630,7 +630,9 @@ def test_min_mean_err_rule_returns_the_reference_loops_pose(cuda, golden_dir):
 @pytest.mark.parametrize("S", [4, 10, 16])
 def test_internal_sampling_with_larger_samples(cuda, S):
     """hyp_idx=None with sample_size S: kernel-drawn samples == oracle.sample_triplets(sample_size=S) fed back explicitly,
-    on the device call and on the chunked host call; samples that repeat a pixel are invalid hypotheses."""
+    on the device call and on the chunked host call.  Samples are drawn WITHOUT replacement (a repeated pixel is
+    re-drawn from the same counter stream, as np.random.choice(replace=False) at misc.py:91), so repeats are rare; a
+    sample that still repeats a pixel is an invalid hypothesis."""
     B, H, seed = 64, 64, 77
     b = synth.tile_batch(synth.make_batch(16, H=8, seed=41, occlusion_max=0.4), B)
     g = _to_cuda(b)
@@ -649,7 +651,7 @@ def test_internal_sampling_with_larger_samples(cuda, S):
         dup = (srt[:, 1:] == srt[:, :-1]).any(axis=1)
         ndup += int(dup.sum())
         assert (auto["hyp_counts"][i].cpu().numpy()[dup] == 0).all()  # repeated pixel: invalid, scores nothing
-    assert S == 4 or ndup > 0
+    assert ndup <= 2  # re-draws: practically every sample is usable (independent draws lost ~45 / n of the 10-pair samples)
     expl = solver(*args, torch.from_numpy(hyp).cuda(), **kw)
     for k, v in auto.items():
         assert torch.equal(v, getattr(expl, k)), k
