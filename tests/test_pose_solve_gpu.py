@@ -191,6 +191,18 @@ def test_translation_sanity_fallback(cuda):
     np.testing.assert_array_equal(res.pose[1, :, 3].cpu().numpy(), t_net[1])
 
 
+@pytest.mark.parametrize("H,R", [(600, 130), (1, 3), (129, 255), (2048, 32)])
+def test_pipeline_odd_sizes_match_oracle(cuda, H, R):
+    """The three-kernel pipeline at sizes off its fast path: hypothesis counts that are not a multiple of 128 (last
+    scoring pass of 1-4 per lane, more than one full pass), one hypothesis, region counts up to the 255 the format
+    allows (8 buckets per lane in the bucket scan), B not a multiple of the warps per CTA -- against the oracle and the
+    fused kernel (_solve runs both)."""
+    models = synth.make_models(3, R, seed=11)
+    b = synth.make_batch(7, models=models, H=H, seed=1000 + H, occlusion_max=0.3)
+    res = _solve(_to_cuda(b))
+    _compare(res, po.pose_solve_batch(b, b["hyp_idx"], THR), b)
+
+
 def test_full_size_lmo_1024_properties(cuda):
     """BASELINE configs[1] at full size: size-independent properties instead of a full oracle run
     (determinism, ROI-order equivariance, ground-truth recovery) + an oracle spot check."""
