@@ -922,11 +922,15 @@ def gpu_arm(args):
         "fp32": {"achieved_tflops": flops / (stage[1] * 1e-3) / 1e12, "peak_tflops": fp32_peak.value / 1e12,
                  "frac": (flops / (stage[1] * 1e-3)) / max(fp32_peak.value, 1.0),
                  "frac_of_whole_solve": (flops / (kernel_ms * 1e-3)) / max(fp32_peak.value, 1.0), "flop_per_pair": 27,
+                 "executed_flop_per_pair": 9,
+                 "executed_frac": (9.0 * pairs / (stage[1] * 1e-3)) / max(fp32_peak.value, 1.0),
                  "kernel": "rdpn::score_kernel", "kernel_ms": float(stage[1]),
                  "pairs_per_launch": pairs, "mean_gated_points_per_roi": mean_nsel, "mean_valid_hypotheses_per_roi": mean_valid,
                  "peak_source": "rdpn_fp32_peak_probe (FFMA chains on all SMs, this run)",
                  "note": "27 flop per (valid hypothesis, gated point) is SURVEY 8d's algorithmic figure (3x4 transform + residual); the "
-                         "kernel hoists the transform per region run and executes 8 instructions (9 flop) per pair"},
+                         "kernel hoists the transform per region run and executes 7 instructions (3 FADD + 3 FFMA + LEA.HI = 9 flop) per pair, so "
+                         "`frac` can exceed 1: `executed_frac` counts the 9 flop actually issued.  The kernel is bound by instruction "
+                         "ISSUE (ncu: 84.5 % issue-active, profiles/r2/ncu_score_kernel_summary.csv), of which 6 of every 7.3 slots are FP32"},
         "kernels": {
             "timer": "rdpn_pose_solve_stage_ms: CUDA events between the three kernels on the launching stream, kernels strictly "
                      "one after the other (the timed region overlaps their tails by programmatic dependent launch), mean of %d" % n_stage,

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Host-buffer plugin call (rdpn_pose_solve_host) on the bench workload: full copy vs gated pull, swept over
-the pull granularity and the pipeline chunk size.  One JSON object per line."""
+"""Host-buffer plugin call (rdpn_pose_solve_host) on the bench workload (YCB-V maps, 4096 ROIs per call): full copy vs
+gated pull, swept over the pull granularity and the pipeline chunk size.  One JSON object per line."""
 import ctypes
 import json
 import os
@@ -17,8 +17,9 @@ from rdpn6d_b200 import _lib  # noqa: E402
 
 
 def main():
-    B, H, R = bench.ROIS_PER_GPU, bench.NUM_HYP, bench.NUM_REGIONS
-    batch = bench.make_workload()
+    W = bench.WORKLOADS["ycbv"]
+    B, H, R = 4096, W["H"], W["R"]
+    batch = bench.tile(bench.make_base("ycbv"), B)
     L = _lib.lib()
     pin = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in batch.items()
            if v is not None and k in ("depth", "Kp", "mask", "extent", "region_idx", "anchors", "hyp_idx")}
@@ -31,7 +32,7 @@ def main():
                          coor_x=pin["coor_x"].data_ptr(), coor_y=pin["coor_y"].data_ptr(), coor_z=pin["coor_z"].data_ptr(),
                          mask=pin["mask"].data_ptr(), extent=pin["extent"].data_ptr(), region_idx=pin["region_idx"].data_ptr(),
                          anchors=pin["anchors"].data_ptr(), num_regions=R, mask_mode=1, mask_thr=0.5, B=B)
-    prm = _lib.SolveParams(inlier_thr=bench.INLIER_THR, num_hyp=H, min_pts=4, min_inliers=4, weighted=0, refit_iters=1,
+    prm = _lib.SolveParams(inlier_thr=bench.INLIER_THR, num_hyp=H, min_pts=4, min_inliers=4, weighted=1, refit_iters=1,
                            with_scale=0, adaptive=0, confidence=0.995, min_iter=10)
     outs = _lib.SolveOutputs(pose=h_pose.data_ptr(), n_inliers=h_ninl.data_ptr(), status=h_stat.data_ptr())
     ctx = ctypes.c_void_p()
@@ -42,7 +43,7 @@ def main():
                                           ctypes.byref(outs)), "pose_solve_host")
 
     ref = None
-    combos = [(_lib.TRANSFER_COPY, 2, 256)] + [(_lib.TRANSFER_PULL, g, c) for c in (64, 128, 256, 512) for g in (1, 2, 4, 8, 16)]
+    combos = [(_lib.TRANSFER_COPY, 2, 256)] + [(_lib.TRANSFER_PULL, g, c) for c in (128, 256, 512, 1024) for g in (1, 2, 4, 8)]
     for mode, gran, chunk in combos:
         L.rdpn_ctx_set_option(ctx, _lib.OPT_TRANSFER, mode)
         L.rdpn_ctx_set_option(ctx, _lib.OPT_PULL_GRANULARITY, gran)
@@ -53,7 +54,7 @@ def main():
         L.rdpn_ctx_set_option(ctx, _lib.OPT_COUNT_BYTES, 0)
         for _ in range(3):
             call()
-        n = 30
+        n = 10
         t0 = time.perf_counter()
         for _ in range(n):
             call()

@@ -401,7 +401,7 @@ int rdpn_ctx_create(int device, rdpn_ctx** out_ctx) {
     RDPN_CUDA_TRY(cudaMemset(c->d_pulled, 0, sizeof(unsigned long long)));
     c->transfer = RDPN_TRANSFER_AUTO;
     c->gran = env_int("RDPN_PULL_GRAN", 2);
-    c->chunk = env_int("RDPN_HOST_CHUNK", 256);
+    c->chunk = env_int("RDPN_HOST_CHUNK", 0);  // 0 = by call size (host_queue)
     *out_ctx = c;
     return 0;
 }
@@ -468,7 +468,10 @@ static int host_queue(rdpn_ctx* c, const rdpn_roi_inputs* h, const int32_t* h_hy
     const int H = prm->num_hyp, R = dense ? 0 : h->num_regions;
     if (prm->sample_size != 0 && (prm->sample_size < 3 || prm->sample_size > RDPN_MAX_SAMPLE)) return RDPN_E_BADARG;
     const int SS = prm->sample_size ? prm->sample_size : 3;  // pairs per hypothesis
-    const size_t P = RDPN_P, CH = (size_t)c->chunk;
+    // ROIs per pipeline chunk: measured on B200 (benchmarks/host_path.py) 256 is best for calls of ~1024 ROIs (four chunks
+    // keep the four stages busy), 512 for calls of 4096 and more (+2 %)
+    const int chunk = c->chunk > 0 ? c->chunk : (h->B >= 4096 ? 512 : 256);
+    const size_t P = RDPN_P, CH = (size_t)chunk;
     const bool may_pull = c->transfer != RDPN_TRANSFER_COPY;
 
     // every buffer is classified on its own: device memory is used in place, pinned memory is pulled (planes: only
@@ -539,8 +542,8 @@ static int host_queue(rdpn_ctx* c, const rdpn_roi_inputs* h, const int32_t* h_hy
     // bulk copies of many tensors queue best over two streams (more only interleaves them on the copy engines); the
     // pull pipeline (one bulk copy + two kernels per chunk) wants all four stages
     const int nstages = any_pull ? RDPN_STAGES : 2;
-    for (int b0 = 0, stage = 0; b0 < B && rc == 0; b0 += c->chunk, stage = (stage + 1) % nstages) {
-        const size_t nb = (size_t)((B - b0) < c->chunk ? (B - b0) : c->chunk);
+    for (int b0 = 0, stage = 0; b0 < B && rc == 0; b0 += chunk, stage = (stage + 1) % nstages) {
+        const size_t nb = (size_t)((B - b0) < chunk ? (B - b0) : chunk);
         cudaStream_t st = c->st[stage];
         unsigned char* d = c->buf[stage];
         // where the solver finds input i of this chunk, and the copies
