@@ -110,3 +110,26 @@ def test_struct_field_offsets_match_the_header(tmp_path):
         assert int(got[cname]) == ctypes.sizeof(cls), cname
         for fname, _ in cls._fields_:
             assert int(got["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_stale_library_is_an_error_not_a_silent_fallback(monkeypatch):
+    """when the sources are newer than the shipped .so and the rebuild fails, loading must raise
+    (a stale binary would silently run old kernels); RDPN_ALLOW_STALE_LIB=1 is the explicit opt-in."""
+    import warnings
+
+    from rdpn6d_b200 import build as _build
+
+    def boom(*a, **k):
+        raise RuntimeError("nvcc not found")
+
+    monkeypatch.setattr(_build, "build", boom)
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.delenv("RDPN_ALLOW_STALE_LIB", raising=False)
+    with pytest.raises(RuntimeError, match="rebuild failed"):
+        _lib.lib()
+    monkeypatch.setenv("RDPN_ALLOW_STALE_LIB", "1")
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        L = _lib.lib()
+    assert L.rdpn_version() >= 200 and any("STALE" in str(x.message) for x in w)
+    monkeypatch.setattr(_lib, "_lib", None)  # the next test loads normally again
