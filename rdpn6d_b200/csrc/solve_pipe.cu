@@ -1,7 +1,7 @@
-// Dense-correspondence -> pose as a pipeline of three barrier-free kernels (BASELINE.json north_star: one kernel per
-// roofline).  Every kernel is a grid of INDEPENDENT WARPS -- no __syncthreads, no mbarrier, no cooperative launch -- so
-// the latency of one ROI's dependent steps is hidden by the 32 other warps of the SM that are at a different step of
-// a different ROI, and the scoring kernel runs with every resident warp inside the FP32 loop.
+// Dense-correspondence -> pose as a pipeline of three kernels (BASELINE.json north_star: one kernel per roofline), chained
+// by programmatic dependent launch.  No cooperative launch, no grid barrier, no block-wide barrier on the common path:
+// K1 and K3 are grids of INDEPENDENT WARPS (the latency of one ROI's dependent steps is hidden by the SM's other warps,
+// each at a different step of a different ROI), K2 is one small CTA per ROI whose warps only meet at one mbarrier wait.
 //
 //   K1  front_kernel   one WARP per ROI.  HBM / latency bound.  Mask min/max (engine_utils.py:123-124), the gate
 //                      (gdrn_evaluator.py:110-117) mask first -- only quads with a passing pixel load depth / coor /
@@ -10,17 +10,22 @@
 //                      counting sort of that list by region id (dense match_any rounds), the hypothesis poses (FP64
 //                      closed form from the list, rounded once to FP32; misc.py:91-106) compacted by validity.
 //                      Output: one "package" per ROI in the workspace.
-//   K2  score_kernel   one WARP per 64 hypotheses of one ROI.  FP32-issue bound.  Two hypotheses per lane, the region
-//                      runs streamed through L1 with warp-uniform 16-byte loads; per run the transformed anchor R a + t
-//                      once, per point 3 FADD + FMUL + 2 FFMA + FSETP + predicated IADD per hypothesis
-//                      (misc.py:108-111).  Output: inlier counts per hypothesis.
+//   K2  score_kernel   one 128-thread CTA per ROI.  FP32-issue bound.  Points, run table and hypothesis poses staged in
+//                      shared memory by bulk TMA (one mbarrier); up to FOUR hypotheses per lane, the (pass, point) plane
+//                      cut into four slices of equal cost, one per warp; per run the transformed anchor R a + t once,
+//                      per point 3 FADD + 3 FFMA + LEA.HI per hypothesis (misc.py:108-111; solve_common.cuh).
+//                      Output: inlier counts per hypothesis (and FP32 residual sums for select rule MIN_MEAN_ERR).
 //   K3  refit_kernel   one WARP per ROI: best hypothesis (misc.py:121, adaptive stop :134-138), inliers of the winner,
 //                      18 FP64 moments by warp shuffle, closed-form rotation (transform.py:913-980), every output.
+//       refit_minerr_kernel: the same warp walks the hypotheses as the reference loop does and returns the
+//                      lowest-mean-error pose (misc.py:113-132).
 //
+// Hand-over: one flag per ROI and stage (st.release / ld.acquire); K2 / K3 CTAs are scheduled as soon as every CTA of
+// the kernel before has started (griddepcontrol.launch_dependents) and wait for exactly the ROI they work on.
 // The arithmetic contracts are those of pose_solve.cu (solve_common.cuh): gate, counts, winner and inlier masks are
 // bit-identical to the fused kernel, the refit pose equal to FP32 rounding (FP64 sums in a different order).
-// Packages live in a caller-provided (or per-stream cached) workspace; large batches run in chunks of ROIs so that a
-// chunk's packages stay in the 126 MB L2 between the kernels.
+// Packages live in a caller-provided (or per-stream cached) workspace; batches larger than the workspace holds run
+// chunk after chunk.
 #include "solve_common.cuh"
 
 #include <stdlib.h>
