@@ -485,8 +485,25 @@ def gen_metrics():
     est = Rg.dot(sym[1]).dot(tf.rotation_matrix(0.05, [1, 0, 0])[:3, :3])  # closest to the 180-degree copy
     out.update(gcr_est=est, gcr_gt=Rg, gcr_sym=sym, gcr_out=gf["get_closest_rot"](est, Rg, sym), gcr_out_none=gf["get_closest_rot"](est, Rg, None),
                gcr_out_single=gf["get_closest_rot"](est, Rg, sym[0]))
+    # symmetry sets (misc.py:206-254) of a YCB-V-like model_info: two discrete symmetries and one continuous axis
+    sf = ref_functions("lib/pysixd/misc.py", ["get_symmetry_transformations"], env={"transform": tf})["get_symmetry_transformations"]
+    d1 = np.eye(4)
+    d1[:3, :3] = tf.rotation_matrix(np.pi, [0, 1, 0])[:3, :3]
+    d1[:3, 3] = [1.0, -2.0, 0.5]
+    infos = [{"symmetries_discrete": [d1.reshape(-1).tolist()]},
+             {"symmetries_continuous": [{"axis": [0, 0, 1], "offset": [0.5, -1.0, 2.0]}]},
+             {"symmetries_discrete": [d1.reshape(-1).tolist()], "symmetries_continuous": [{"axis": [0, 1, 0], "offset": [0, 0, 0]}]},
+             {}]
+    import json
+
+    out["sym_infos"] = np.array(json.dumps(infos))
+    out["sym_step"] = np.float64(0.2)
+    for i, info in enumerate(infos):
+        tr = sf(info, 0.2)
+        out["sym%d_R" % i] = np.stack([t["R"] for t in tr])
+        out["sym%d_t" % i] = np.stack([t["t"] for t in tr])
     np.savez_compressed(os.path.join(GOLD, "metrics_golden.npz"), **out)
-    print("metrics_golden.npz adi", out["adi_val"])
+    print("metrics_golden.npz adi", out["adi_val"], "symmetry sets", [out["sym%d_R" % i].shape[0] for i in range(len(infos))])
 
 
 def types_ns(**kw):

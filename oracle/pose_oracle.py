@@ -617,6 +617,44 @@ def get_closest_rot(rot_est, rot_gt, sym_info):
     return closest
 
 
+def rotation_matrix(angle, axis):
+    """lib/pysixd/transform.py:296-336 (rotation about an axis through the origin), 3x3 part."""
+    d = np.asarray(axis, F64)[:3]
+    d = d / math.sqrt(float(np.dot(d, d)))
+    sina, cosa = math.sin(angle), math.cos(angle)
+    R = np.diag([cosa, cosa, cosa])
+    R += np.outer(d, d) * (1.0 - cosa)
+    d = d * sina
+    R += np.array([[0.0, -d[2], d[1]], [d[2], 0.0, -d[0]], [-d[1], d[0], 0.0]])
+    return R
+
+
+def get_symmetry_transformations(model_info, max_sym_disc_step):
+    """lib/pysixd/misc.py:206-254: the discrete symmetries of models_info.json (identity first) combined with the
+    discretised continuous ones (ceil(pi / max_sym_disc_step) steps about each axis); list of {"R": [3,3], "t": [3,1]}."""
+    trans_disc = [{"R": np.eye(3), "t": np.array([[0, 0, 0]]).T}]
+    for sym in model_info.get("symmetries_discrete", []):
+        s44 = np.reshape(sym, (4, 4))
+        trans_disc.append({"R": s44[:3, :3], "t": s44[:3, 3].reshape((3, 1))})
+    trans_cont = []
+    for sym in model_info.get("symmetries_continuous", []):
+        axis = np.array(sym["axis"])
+        offset = np.array(sym["offset"]).reshape((3, 1))
+        steps = int(np.ceil(np.pi / max_sym_disc_step))
+        step = 2.0 * np.pi / steps
+        for i in range(1, steps):
+            R = rotation_matrix(i * step, axis)
+            trans_cont.append({"R": R, "t": -R.dot(offset) + offset})
+    trans = []
+    for td in trans_disc:
+        if len(trans_cont):
+            for tc in trans_cont:
+                trans.append({"R": tc["R"].dot(td["R"]), "t": tc["R"].dot(td["t"]) + tc["t"]})
+        else:
+            trans.append(td)
+    return trans
+
+
 def backproject_v2(depth, K):
     """misc.py:352-371."""
     Kinv = np.linalg.inv(K)

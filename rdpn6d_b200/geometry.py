@@ -252,3 +252,39 @@ def get_closest_rot(rot_est, rot_gt, sym_info):
         if cur < r_err:
             r_err, closest = cur, cand
     return closest
+
+
+def get_symmetry_transformations(model_info, max_sym_disc_step):
+    """lib/pysixd/misc.py:206-254: the symmetry set of an object model (models_info.json): discrete symmetries (identity
+    first) combined with the continuous ones discretised into ceil(pi / max_sym_disc_step) steps.  Dataset-metadata host
+    logic feeding get_closest_rot's `sym_info` (np.stack of the "R" entries); same list of {"R", "t"} dicts as the reference."""
+    import math
+
+    import numpy as np
+
+    def rot(angle, axis):  # lib/pysixd/transform.py:296-336, 3 x 3 part
+        d = np.asarray(axis, np.float64)[:3]
+        d = d / math.sqrt(float(np.dot(d, d)))
+        sina, cosa = math.sin(angle), math.cos(angle)
+        R = np.diag([cosa, cosa, cosa]) + np.outer(d, d) * (1.0 - cosa)
+        d = d * sina
+        return R + np.array([[0.0, -d[2], d[1]], [d[2], 0.0, -d[0]], [-d[1], d[0], 0.0]])
+
+    trans_disc = [{"R": np.eye(3), "t": np.array([[0, 0, 0]]).T}]
+    for sym in model_info.get("symmetries_discrete", []):
+        s44 = np.reshape(sym, (4, 4))
+        trans_disc.append({"R": s44[:3, :3], "t": s44[:3, 3].reshape((3, 1))})
+    trans_cont = []
+    for sym in model_info.get("symmetries_continuous", []):
+        axis, offset = np.array(sym["axis"]), np.array(sym["offset"]).reshape((3, 1))
+        steps = int(np.ceil(np.pi / max_sym_disc_step))
+        for i in range(1, steps):
+            R = rot(i * 2.0 * np.pi / steps, axis)
+            trans_cont.append({"R": R, "t": -R.dot(offset) + offset})
+    trans = []
+    for td in trans_disc:
+        if len(trans_cont):
+            trans.extend({"R": tc["R"].dot(td["R"]), "t": tc["R"].dot(td["t"]) + tc["t"]} for tc in trans_cont)
+        else:
+            trans.append(td)
+    return trans

@@ -156,3 +156,20 @@ def test_quat2mat_and_sibling_heads_match_reference(g):
     c = g["pfpabs_cent"]
     t = np.stack([z * (c[:, 0] - cams[:, 0, 2]) / cams[:, 0, 0], z * (c[:, 1] - cams[:, 1, 2]) / cams[:, 1, 1], z], 1)
     np.testing.assert_allclose(t, g["pfpabs_trans_mat"], rtol=0, atol=1e-7)
+
+
+def test_symmetry_sets_match_reference(golden_dir):
+    """misc.get_symmetry_transformations (misc.py:206-254) executed from source on model_info records with discrete,
+    continuous, both and no symmetries: the oracle's restatement and the package's host helper return the same sets."""
+    import json
+
+    from rdpn6d_b200 import geometry
+
+    m = np.load(os.path.join(golden_dir, "metrics_golden.npz"))
+    infos = json.loads(str(m["sym_infos"]))
+    for i, info in enumerate(infos):
+        for fn in (po.get_symmetry_transformations, geometry.get_symmetry_transformations):
+            tr = fn(info, float(m["sym_step"]))
+            assert len(tr) == m["sym%d_R" % i].shape[0]
+            np.testing.assert_allclose(np.stack([t["R"] for t in tr]), m["sym%d_R" % i], rtol=0, atol=1e-15)
+            np.testing.assert_allclose(np.stack([t["t"] for t in tr]), m["sym%d_t" % i], rtol=0, atol=1e-15)
