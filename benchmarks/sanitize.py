@@ -82,6 +82,7 @@ def main():
                                                  torch.eye(3, device="cuda")[None].repeat(4, 1, 1) * 500)
     geometry.backproject_v2(torch.rand(30, 40, device="cuda"), np.array([[500.0, 0, 20], [0, 500, 15], [0, 0, 1]]))
     geometry.adi(np.eye(3), np.zeros(3), np.eye(3), np.ones(3) * 0.01, torch.randn(600, 3, device="cuda"))
+    geometry.add(np.eye(3), np.zeros(3), np.eye(3), np.ones(3) * 0.01, torch.randn(600, 3, device="cuda"))
     torch.cuda.synchronize()
     print("sanitize driver done")
 

@@ -284,6 +284,9 @@ int rdpn_backproject_kinv(const float* d_depth, const double* d_mats, int H, int
  * ground-truth and under the estimated pose (brute force on the GPU, FP64).  d_pts [n,3] FP32; d_poses: R_est (9) t_est
  * (3) R_gt (9) t_gt (3) doubles; d_scratch: 1 + ceil(n / 256) doubles, zeroed before the first use; d_out: one double. */
 int rdpn_adi(const float* d_pts, int n, const double* d_poses, double* d_scratch, double* d_out, void* stream);
+/* lib/pysixd/pose_error.py:297-312 (add): mean distance between the SAME model point under the two poses (objects
+ * without indistinguishable views).  Arguments as rdpn_adi. */
+int rdpn_add(const float* d_pts, int n, const double* d_poses, double* d_scratch, double* d_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * f2  Region arg-max -- GDRN.py:206-209: argmax over channels 1..R of region [B,R+1,P] -> uint8.

@@ -472,12 +472,15 @@ def gen_metrics():
     R = tf.random_rotation_matrix(rng.random(3))[:3, :3]
     T = rng.uniform(-0.2, 0.8, 3)
     out = dict(bp_depth=depth, bp_K=K, bp_v2=mf["backproject_v2"](depth, K), bp_R=R, bp_T=T, bp_emb=mf["calc_emb_bp_fast"](depth, R, T, K))
-    pf = ref_functions("lib/pysixd/pose_error.py", ["adi", "re"], env={"spatial": spatial, "transform_pts_Rt": mf["transform_pts_Rt"],
+    pf = ref_functions("lib/pysixd/pose_error.py", ["adi", "add", "re", "te"], env={"spatial": spatial, "transform_pts_Rt": mf["transform_pts_Rt"],
                                                                       "misc": types_ns(transform_pts_Rt=mf["transform_pts_Rt"])})
     pts = (rng.standard_normal((700, 3)) * np.array([0.05, 0.04, 0.08])).astype(np.float32)
     Re, Rg = tf.random_rotation_matrix(rng.random(3))[:3, :3], tf.random_rotation_matrix(rng.random(3))[:3, :3]
     te_, tg = rng.uniform(-0.1, 0.1, (3, 1)) + np.array([[0], [0], [0.9]]), rng.uniform(-0.1, 0.1, (3, 1)) + np.array([[0], [0], [0.9]])
     out.update(adi_pts=pts, adi_Re=Re, adi_te=te_, adi_Rg=Rg, adi_tg=tg, adi_val=np.float64(pf["adi"](Re, te_, Rg, tg, pts.astype(np.float64))))
+    out["add_val"] = np.float64(pf["add"](Re, te_, Rg, tg, pts.astype(np.float64)))
+    out["re_val"] = np.float64(pf["re"](Re, Rg))
+    out["te_val"] = np.float64(pf["te"](te_, tg))
     import torch
 
     gf = ref_functions("core/utils/pose_utils.py", ["get_closest_rot"], env={"re": pf["re"], "torch": torch})

@@ -66,6 +66,7 @@ SIGNATURES = {
                                           ctypes.POINTER(SolveOutputs), c_vp, ctypes.c_size_t, c_vp]),
     "rdpn_backproject_kinv": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
     "rdpn_adi": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp]),
+    "rdpn_add": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp]),
     "rdpn_assemble_pose": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_vp, ctypes.c_int, c_vp]),
     "rdpn_fps_batch": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp]),
     "rdpn_pose_solve_stage_ms": (ctypes.c_int, [ctypes.POINTER(RoiInputs), c_vp, c_vp, ctypes.POINTER(SolveParams),

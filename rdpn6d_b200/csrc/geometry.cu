@@ -193,6 +193,8 @@ __global__ void backproject_kinv_kernel(const float* __restrict__ depth, const d
 // lib/pysixd/pose_error.py:315-337 (adi): mean over the ground-truth-posed model points of the distance to the nearest
 // estimate-posed model point.  Brute force: one thread per ground-truth point, the estimate-posed cloud staged through
 // shared memory in tiles; FP64 distances, block partial sums combined in block order by the last block.
+// NN = false is pose_error.py:297-312 (add): the distance to the SAME point under the estimated pose.
+template <bool NN>
 __global__ void adi_kernel(const float* __restrict__ pts, int n, const double* __restrict__ poses /* R_est t_est R_gt t_gt: 24 */,
                            double* __restrict__ partial, unsigned* __restrict__ ticket, double* __restrict__ out) {
     __shared__ double tile[256][3];
@@ -209,7 +211,15 @@ __global__ void adi_kernel(const float* __restrict__ pts, int n, const double* _
         for (int r = 0; r < 3; ++r) g[r] = Rg[3 * r] * x + Rg[3 * r + 1] * y + Rg[3 * r + 2] * z + tg[r];
     }
     double best = 1e300;
-    for (int j0 = 0; j0 < n; j0 += 256) {
+    if (!NN && i < n) {
+        const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+        best = 0.0;
+        for (int r = 0; r < 3; ++r) {
+            const double d = g[r] - (Re[3 * r] * x + Re[3 * r + 1] * y + Re[3 * r + 2] * z + te[r]);
+            best += d * d;
+        }
+    }
+    for (int j0 = 0; NN && j0 < n; j0 += 256) {
         const int j = j0 + threadIdx.x;
         if (j < n) {
             const double x = pts[3 * j], y = pts[3 * j + 1], z = pts[3 * j + 2];
@@ -314,7 +324,17 @@ int rdpn_adi(const float* d_pts, int n, const double* d_poses, double* d_scratch
     if (!d_pts || !d_poses || !d_scratch || !d_out || n <= 0) return RDPN_E_BADARG;
     const int blocks = (n + 255) / 256;
     // scratch: blocks partial sums + one ticket word (zero before the first use; the kernel leaves it zero)
-    rdpn::adi_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_pts, n, d_poses, d_scratch + 1, (unsigned*)d_scratch, d_out);
+    rdpn::adi_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(d_pts, n, d_poses, d_scratch + 1, (unsigned*)d_scratch, d_out);
+    ++rdpn::g_launch_count;
+    RDPN_LAUNCH_CHECK();
+    return 0;
+}
+
+int rdpn_add(const float* d_pts, int n, const double* d_poses, double* d_scratch, double* d_out, void* stream) {
+    RDPN_NVTX("rdpn_add");
+    if (!d_pts || !d_poses || !d_scratch || !d_out || n <= 0) return RDPN_E_BADARG;
+    const int blocks = (n + 255) / 256;
+    rdpn::adi_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(d_pts, n, d_poses, d_scratch + 1, (unsigned*)d_scratch, d_out);
     ++rdpn::g_launch_count;
     RDPN_LAUNCH_CHECK();
     return 0;

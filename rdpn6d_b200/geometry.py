@@ -208,10 +208,7 @@ def calc_emb_bp_fast(depth, R, T, K):
 calc_xyz_bp_fast = calc_emb_bp_fast  # misc.py:319
 
 
-def adi(R_est, t_est, R_gt, t_gt, pts):
-    """lib/pysixd/pose_error.py:315-337: Average Distance of model points for objects with Indistinguishable views (the
-    symmetric objects of the YCB-V config): mean distance from every ground-truth-posed model point to the nearest
-    estimate-posed one.  pts: [n,3] CUDA tensor; poses: anything array-like.  Returns a Python float (as the reference)."""
+def _model_distance(entry, what, R_est, t_est, R_gt, t_gt, pts):
     import numpy as np
 
     p = _cuda_f32(pts, "pts")
@@ -222,8 +219,41 @@ def adi(R_est, t_est, R_gt, t_gt, pts):
     scratch = torch.zeros(1 + (n + 255) // 256, dtype=torch.float64, device=p.device)
     out = torch.empty(1, dtype=torch.float64, device=p.device)
     with torch.cuda.device(p.device):
-        _lib.check(_lib.lib().rdpn_adi(p.data_ptr(), n, poses.data_ptr(), scratch.data_ptr(), out.data_ptr(), _stream(p.device)), "adi")
+        _lib.check(getattr(_lib.lib(), entry)(p.data_ptr(), n, poses.data_ptr(), scratch.data_ptr(), out.data_ptr(), _stream(p.device)), what)
     return float(out.item())
+
+
+def adi(R_est, t_est, R_gt, t_gt, pts):
+    """lib/pysixd/pose_error.py:315-337: Average Distance of model points for objects with Indistinguishable views (the
+    symmetric objects of the YCB-V config): mean distance from every ground-truth-posed model point to the nearest
+    estimate-posed one.  pts: [n,3] CUDA tensor; poses: anything array-like.  Returns a Python float (as the reference)."""
+    return _model_distance("rdpn_adi", "adi", R_est, t_est, R_gt, t_gt, pts)
+
+
+def add(R_est, t_est, R_gt, t_gt, pts):
+    """lib/pysixd/pose_error.py:297-312: Average Distance of model points (objects without indistinguishable views): mean
+    distance between the same model point under the estimated and the ground-truth pose.  Arguments as adi."""
+    return _model_distance("rdpn_add", "add", R_est, t_est, R_gt, t_gt, pts)
+
+
+def re(R_est, R_gt):
+    """lib/pysixd/pose_error.py:400-415: rotational error in degrees, acos of the clipped (trace - 1) / 2.  3 x 3 host-side
+    helper of the evaluation (numpy in -> float out, as the reference)."""
+    import numpy as np
+
+    R_est, R_gt = np.asarray(R_est), np.asarray(R_gt)
+    assert R_est.shape == R_gt.shape == (3, 3)
+    tr = min(float(np.einsum("ij,ij->", R_est, R_gt)), 3.0)  # trace(R_est R_gt^T), capped like the reference
+    return float(np.rad2deg(np.arccos(min(1.0, max(-1.0, 0.5 * (tr - 1.0))))))
+
+
+def te(t_est, t_gt):
+    """lib/pysixd/pose_error.py:425-436: translational error, the L2 norm of t_gt - t_est."""
+    import numpy as np
+
+    t_est, t_gt = np.asarray(t_est).flatten(), np.asarray(t_gt).flatten()
+    assert t_est.size == t_gt.size == 3
+    return np.linalg.norm(t_gt - t_est)
 
 
 def get_closest_rot(rot_est, rot_gt, sym_info):

@@ -135,6 +135,13 @@ def test_metric_helpers_match_reference(golden_dir):
     np.testing.assert_allclose(po.backproject_v2(m["bp_depth"], m["bp_K"]), m["bp_v2"], rtol=0, atol=1e-12)
     np.testing.assert_allclose(po.calc_emb_bp_fast(m["bp_depth"], m["bp_R"], m["bp_T"], m["bp_K"]), m["bp_emb"], rtol=0, atol=1e-12)
     assert abs(po.adi(m["adi_Re"], m["adi_te"], m["adi_Rg"], m["adi_tg"], m["adi_pts"]) - float(m["adi_val"])) <= 1e-12
+    assert abs(po.add(m["adi_Re"], m["adi_te"], m["adi_Rg"], m["adi_tg"], m["adi_pts"].astype(np.float64)) - float(m["add_val"])) <= 1e-12
+    from rdpn6d_b200 import geometry
+
+    for mod in (po, geometry):  # re / te: 3 x 3 host arithmetic in both
+        assert abs(mod.re(m["adi_Re"], m["adi_Rg"]) - float(m["re_val"])) <= 1e-12
+        assert abs(mod.te(m["adi_te"], m["adi_tg"]) - float(m["te_val"])) <= 1e-15
+    assert geometry.re(m["adi_Rg"], m["adi_Rg"]) == 0.0
     assert np.array_equal(po.get_closest_rot(m["gcr_est"], m["gcr_gt"], m["gcr_sym"]), m["gcr_out"])
     assert np.array_equal(po.get_closest_rot(m["gcr_est"], m["gcr_gt"], None), m["gcr_out_none"])
     assert np.array_equal(po.get_closest_rot(m["gcr_est"], m["gcr_gt"], m["gcr_sym"][0]), m["gcr_out_single"])

@@ -127,5 +127,7 @@ def test_metric_helpers_match_reference_gpu(cuda, golden_dir):
     for _ in range(2):  # the scratch ticket is left at zero: a second call gives the same bits
         v = geometry.adi(m["adi_Re"], m["adi_te"], m["adi_Rg"], m["adi_tg"], _cu(m["adi_pts"]))
         assert abs(v - float(m["adi_val"])) <= 1e-12
+        v = geometry.add(m["adi_Re"], m["adi_te"], m["adi_Rg"], m["adi_tg"], _cu(m["adi_pts"]))
+        assert abs(v - float(m["add_val"])) <= 1e-12
     assert np.array_equal(geometry.get_closest_rot(m["gcr_est"], m["gcr_gt"], m["gcr_sym"]), m["gcr_out"])
     assert np.array_equal(geometry.get_closest_rot(m["gcr_est"], m["gcr_gt"], None), m["gcr_out_none"])
