@@ -30,15 +30,19 @@ def ev(fn, iters=10):
 for n in (5_000, 8_192, 20_000, 32_768, 50_000):
     t = torch.from_numpy(synth.fps_cloud(n, seed=1)).cuda()
     rec = {"bench": "fps_small", "n": n}
-    for name, env in (("cluster", None), ("cooperative", "1")):
+    for name, env, xchg in (("cluster", None, None), ("cluster_flat_push", None, "flat"), ("cluster_barrier", None, "barrier"),
+                            ("cooperative", "1", None)):
+        os.environ.pop("RDPN_FPS_NO_CLUSTER", None)
+        os.environ.pop("RDPN_FPS_EXCHANGE", None)
         if env:
             os.environ["RDPN_FPS_NO_CLUSTER"] = env
-        else:
-            os.environ.pop("RDPN_FPS_NO_CLUSTER", None)
+        if xchg:
+            os.environ["RDPN_FPS_EXCHANGE"] = xchg  # the cluster-barrier exchange the push exchange replaced
         a, b = ev(lambda: fps_utils.fps_indices(t, 64)), ev(lambda: fps_utils.fps_indices(t, 256))
         rec[name + "_us_per_pick"] = 1e3 * (b - a) / 192  # marginal: launch and allocation cancel
         rec[name + "_ms_256"] = b
     os.environ.pop("RDPN_FPS_NO_CLUSTER", None)
+    os.environ.pop("RDPN_FPS_EXCHANGE", None)
     print(json.dumps(rec), flush=True)
 # 30 objects of 30 000 points, 256 picks: one launch vs object by object
 clouds = [torch.from_numpy(synth.fps_cloud(30_000, seed=s)).cuda() for s in range(30)]

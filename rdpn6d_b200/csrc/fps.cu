@@ -278,13 +278,51 @@ struct __align__(16) FpsCand {  // a candidate pick travels with its coordinates
     float x, y, z, pad;
     float pad2[2];
 };
+constexpr int FPS_SLOTS = FPS_MAX_CLUSTER * FPS_WARPS;  // one candidate per warp of the cluster
 struct FpsClusterShared {
     FpsCand wcand[FPS_WARPS];
     FpsCand ccand[2];             // this CTA's candidate, double-buffered by pick parity
     float fmin[FPS_WARPS][3];
     float fmax[FPS_WARPS][3];
     float bb[6];                  // this CTA's bounding box (min xyz, max xyz)
+    // push exchange: every warp of the cluster stores its candidate into EVERY CTA (st.async, 16 + 4 bytes) and the
+    // stores complete the destination's mbarrier; double-buffered by pick parity
+    uint4 pk[2][FPS_SLOTS];       // {distance bits, ~index, x, y}
+    float pz[2][FPS_SLOTS];
+    uint64_t bar[2];
+    uint4 wk4[FPS_WARPS];         // PUSH == 2: the warps' candidates, reduced by the warp that arrives last
+    float wz[FPS_WARPS];
+    unsigned arrived;             // running count of warp arrivals (16 per exchange)
 };
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+// remote (or own) shared-memory store that completes `bytes` on the destination CTA's mbarrier when it lands
+__device__ __forceinline__ void st_async_v4(uint32_t raddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
+                 "r"(a), "r"(b), "r"(c), "r"(d), "r"(rbar)
+                 : "memory");
+}
+__device__ __forceinline__ void st_async_b32(uint32_t raddr, uint32_t a, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr), "r"(a), "r"(rbar)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 
 // warp-wide max of a 64-bit key by two 32-bit REDUX instead of five shuffle rounds
 __device__ __forceinline__ unsigned long long warp_max_key_redux(unsigned long long key) {
@@ -294,7 +332,7 @@ __device__ __forceinline__ unsigned long long warp_max_key_redux(unsigned long l
     return ((unsigned long long)mh << 32) | ml;
 }
 
-template <int PPT>
+template <int PPT, int PUSH /* 0 cluster barrier | 1 every warp pushes | 2 one push per CTA */>
 __global__ void __launch_bounds__(FPS_THREADS, 1)
     fps_cluster_kernel(const float* __restrict__ pts_all, const int* __restrict__ offs, int* __restrict__ idxs_all, int sn,
                        const int* __restrict__ starts, int one_pn, int one_start) {
@@ -321,13 +359,139 @@ __global__ void __launch_bounds__(FPS_THREADS, 1)
             md[k] = -1.f;
         }
     }
-    // Cluster-wide max of a key whose owner thread also knows the candidate's coordinates (bx, by, bz): two REDUX in
-    // the warp, one __syncthreads, two REDUX over the warp candidates, ONE cluster barrier, C remote reads of 8 bytes and
-    // one of 12.  Returns the winning key and its coordinates (cx, cy, cz).
+    // Cluster-wide max of a key whose owner thread also knows the candidate's coordinates (bx, by, bz).  Returns the
+    // winning key and leaves its coordinates in (cx, cy, cz).
+    // PUSH (default): two REDUX in the warp, then the owner lane stores the warp's candidate into the slot
+    // [rank * 16 + warp] of EVERY CTA of the cluster (st.async: 20 bytes that complete the destination's mbarrier); a
+    // CTA waits on its OWN mbarrier for the C * 16 candidates and every warp reduces them from local shared memory.
+    // No block barrier, no cluster barrier, no remote load on the path of a pick.  Slots and barriers are double-
+    // buffered by pick parity: a CTA can receive pick i + 1 while it still reads pick i, and nobody can send pick
+    // i + 2 before every warp of the cluster has sent pick i + 1, i.e. has finished reading pick i.
+    // !PUSH (RDPN_FPS_EXCHANGE=barrier): block reduce, ONE cluster barrier, C remote reads of 8 bytes and one of 12.
     int par = 0;
+    unsigned xchg = 0;  // exchanges done (PUSH): barrier xchg & 1, phase parity (xchg >> 1) & 1
     float cx = 0.f, cy = 0.f, cz = 0.f;
+    if (PUSH) {
+        if (t == 0) {
+            mbar_init(&sh.bar[0], 1);
+            mbar_init(&sh.bar[1], 1);
+            mbar_fence_init();
+            mbar_expect_tx(&sh.bar[0], (uint32_t)(C * (PUSH == 2 ? 1 : FPS_WARPS) * 20));
+            mbar_expect_tx(&sh.bar[1], (uint32_t)(C * (PUSH == 2 ? 1 : FPS_WARPS) * 20));
+            sh.arrived = 0u;
+        }
+        cluster.sync();  // every barrier of the cluster is armed before the first store can arrive
+    }
+#ifdef RDPN_FPS_TIMING  // cycles of thread 0 between the marks of the exchange, summed over the picks, printed at the end
+    long long tk_last = clock64(), tk_sum[5] = {0, 0, 0, 0, 0};
+#define RDPN_FPS_TICK(i) { const long long now_ = clock64(); tk_sum[i] += now_ - tk_last; tk_last = now_; }
+#else
+#define RDPN_FPS_TICK(i)
+#endif
     auto cluster_max_key = [&](unsigned long long key, float bx, float by, float bz) -> unsigned long long {
+        RDPN_FPS_TICK(0);
         const unsigned long long wk = warp_max_key_redux(key);
+        if (PUSH == 2) {
+            // stage 1 inside the CTA: the warp's candidate goes to local shared memory and the warp counts itself in;
+            // the warp that arrives LAST reduces the sixteen and pushes the CTA's candidate to every CTA of the cluster
+            // (2 C mbarrier transactions per CTA and pick instead of 32 C: the transactions of one barrier serialise)
+            const int b = (int)(xchg & 1u);
+            const bool owner = wk ? key == wk : lane == 0;
+            unsigned old = 0u;
+            RDPN_FPS_TICK(1);
+            if (owner) {
+                sh.wk4[warp] = make_uint4((unsigned)(wk >> 32), (unsigned)wk, __float_as_uint(bx), __float_as_uint(by));
+                sh.wz[warp] = bz;
+                __threadfence_block();
+                old = atomicAdd(&sh.arrived, 1u);
+            }
+            old = __shfl_sync(0xffffffffu, old, __ffs(__ballot_sync(0xffffffffu, owner)) - 1);
+            RDPN_FPS_TICK(2);
+            if ((old & (FPS_WARPS - 1)) == FPS_WARPS - 1) {  // warp-uniform
+                __threadfence_block();
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                float z = 0.f;
+                if (lane < FPS_WARPS) { v = sh.wk4[lane]; z = sh.wz[lane]; }
+                const unsigned mh = __reduce_max_sync(0xffffffffu, v.x);
+                const unsigned ml = __reduce_max_sync(0xffffffffu, v.x == mh ? v.y : 0u);
+                if ((mh | ml) ? (lane < FPS_WARPS && v.x == mh && v.y == ml) : lane == 0) {
+                    const uint32_t a4 = smem_u32(&sh.pk[b][rank]), az = smem_u32(&sh.pz[b][rank]), ab = smem_u32(&sh.bar[b]);
+                    for (int r = 0; r < C; ++r) {
+                        const uint32_t rb = mapa_u32(ab, (uint32_t)r);
+                        st_async_v4(mapa_u32(a4, (uint32_t)r), v.x, v.y, v.z, v.w, rb);
+                        st_async_b32(mapa_u32(az, (uint32_t)r), __float_as_uint(z), rb);
+                    }
+                }
+            }
+            const uint32_t ph = (xchg >> 1) & 1u;
+            while (!mbar_try_cluster(&sh.bar[b], ph)) {
+            }
+            RDPN_FPS_TICK(3);
+            if (t == 0) mbar_expect_tx(&sh.bar[b], (uint32_t)(C * 20));  // armed for the exchange after the next one
+            unsigned bh = 0u, bl = 0u;
+            float lx = 0.f, ly = 0.f, lz = 0.f;
+            if (lane < C) {
+                const uint4 v = sh.pk[b][lane];
+                bh = v.x; bl = v.y; lx = __uint_as_float(v.z); ly = __uint_as_float(v.w); lz = sh.pz[b][lane];
+            }
+            const unsigned mh = __reduce_max_sync(0xffffffffu, bh);
+            const unsigned ml = __reduce_max_sync(0xffffffffu, bh == mh ? bl : 0u);
+            const unsigned long long best = ((unsigned long long)mh << 32) | ml;
+            if (best) {
+                const int src = __ffs(__ballot_sync(0xffffffffu, bh == mh && bl == ml)) - 1;
+                cx = __shfl_sync(0xffffffffu, lx, src);
+                cy = __shfl_sync(0xffffffffu, ly, src);
+                cz = __shfl_sync(0xffffffffu, lz, src);
+            } else {  // nothing positive left: the reference returns index 0 (cpp:60,72)
+                cx = __ldg(pts); cy = __ldg(pts + 1); cz = __ldg(pts + 2);
+            }
+            RDPN_FPS_TICK(4);
+            ++xchg;
+            return best;
+        }
+        if (PUSH == 1) {
+            const int b = (int)(xchg & 1u);
+            if (wk ? key == wk : lane == 0) {  // keys embed the point index: exactly one owner (lane 0 when nothing is left)
+                const uint32_t a4 = smem_u32(&sh.pk[b][rank * FPS_WARPS + warp]), az = smem_u32(&sh.pz[b][rank * FPS_WARPS + warp]);
+                const uint32_t ab = smem_u32(&sh.bar[b]);
+                const uint32_t w0 = (uint32_t)(wk >> 32), w1 = (uint32_t)wk, w2 = __float_as_uint(bx), w3 = __float_as_uint(by),
+                               w4 = __float_as_uint(bz);
+                for (int r = 0; r < C; ++r) {
+                    const uint32_t rb = mapa_u32(ab, (uint32_t)r);
+                    st_async_v4(mapa_u32(a4, (uint32_t)r), w0, w1, w2, w3, rb);
+                    st_async_b32(mapa_u32(az, (uint32_t)r), w4, rb);
+                }
+            }
+            const uint32_t ph = (xchg >> 1) & 1u;
+            while (!mbar_try_cluster(&sh.bar[b], ph)) {
+            }
+            // this phase is over for the whole CTA's barrier: arm it for the exchange after the next one
+            if (t == 0) mbar_expect_tx(&sh.bar[b], (uint32_t)(C * FPS_WARPS * 20));
+            unsigned bh = 0u, bl = 0u;
+            float lx = 0.f, ly = 0.f, lz = 0.f;
+#pragma unroll
+            for (int j = 0; j < FPS_SLOTS / 32; ++j) {
+                const int sl = j * 32 + lane;
+                if (sl < C * FPS_WARPS) {
+                    const uint4 v = sh.pk[b][sl];
+                    const float z = sh.pz[b][sl];
+                    if (v.x > bh || (v.x == bh && v.y > bl)) { bh = v.x; bl = v.y; lx = __uint_as_float(v.z); ly = __uint_as_float(v.w); lz = z; }
+                }
+            }
+            const unsigned mh = __reduce_max_sync(0xffffffffu, bh);
+            const unsigned ml = __reduce_max_sync(0xffffffffu, bh == mh ? bl : 0u);
+            const unsigned long long best = ((unsigned long long)mh << 32) | ml;
+            if (best) {
+                const int src = __ffs(__ballot_sync(0xffffffffu, bh == mh && bl == ml)) - 1;
+                cx = __shfl_sync(0xffffffffu, lx, src);
+                cy = __shfl_sync(0xffffffffu, ly, src);
+                cz = __shfl_sync(0xffffffffu, lz, src);
+            } else {  // nothing positive left: the reference returns index 0 (cpp:60,72)
+                cx = __ldg(pts); cy = __ldg(pts + 1); cz = __ldg(pts + 2);
+            }
+            ++xchg;
+            return best;
+        }
         if (wk ? key == wk : lane == 0) {  // keys embed the point index: exactly one owner (lane 0 when nothing is left)
             FpsCand c;
             c.key = wk; c.x = bx; c.y = by; c.z = bz; c.pad = 0.f; c.pad2[0] = c.pad2[1] = 0.f;
@@ -434,6 +598,11 @@ __global__ void __launch_bounds__(FPS_THREADS, 1)
         key = cluster_max_key(key, bx, by, bz);
         cur = key ? (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull)) : 0;  // cpp:60,72
     }
+#ifdef RDPN_FPS_TIMING
+    if (PUSH == 2 && t == 0 && rank == 0 && obj == 0)
+        printf("fps timing C=%d PPT=%d picks=%d: dist %lld redux %lld arrive %lld wait %lld select %lld cycles/pick\n", C, PPT, sn,
+               tk_sum[0] / sn, tk_sum[1] / sn, tk_sum[2] / sn, tk_sum[3] / sn, tk_sum[4] / sn);
+#endif
     cluster.sync();  // no CTA leaves while a sibling may still read its shared memory
 }
 
@@ -453,14 +622,20 @@ static int fps_cluster_launch(const float* d_pts, const int* d_offs, int32_t* d_
     if ((long long)FPS_MAX_CLUSTER * FPS_THREADS * ppt < max_pn) return RDPN_E_TOOLARGE;
     int C = (int)(((long long)max_pn + (long long)FPS_THREADS * ppt - 1) / ((long long)FPS_THREADS * ppt));
     if (C < 1) C = 1;
+    // RDPN_FPS_EXCHANGE = barrier | flat | (default) cta: the exchanges kept for A/B timing (benchmarks/fps_small.py)
+    const char* xe = getenv("RDPN_FPS_EXCHANGE");
+    const int mode = xe && xe[0] == 'b' ? 0 : xe && xe[0] == 'f' ? 1 : 2;
+#define RDPN_FPS_PICK(P) \
+    (mode == 0 ? (const void*)fps_cluster_kernel<P, 0> : mode == 1 ? (const void*)fps_cluster_kernel<P, 1> : (const void*)fps_cluster_kernel<P, 2>)
     const void* fn = nullptr;
     switch (ppt) {
-        case 1: fn = (const void*)fps_cluster_kernel<1>; break;
-        case 2: fn = (const void*)fps_cluster_kernel<2>; break;
-        case 4: fn = (const void*)fps_cluster_kernel<4>; break;
-        case 8: fn = (const void*)fps_cluster_kernel<8>; break;
-        default: fn = (const void*)fps_cluster_kernel<16>; break;
+        case 1: fn = RDPN_FPS_PICK(1); break;
+        case 2: fn = RDPN_FPS_PICK(2); break;
+        case 4: fn = RDPN_FPS_PICK(4); break;
+        case 8: fn = RDPN_FPS_PICK(8); break;
+        default: fn = RDPN_FPS_PICK(16); break;
     }
+#undef RDPN_FPS_PICK
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(nobj * C));
     cfg.blockDim = dim3(FPS_THREADS);

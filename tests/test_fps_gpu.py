@@ -120,6 +120,10 @@ def test_cluster_path_sizes_and_cooperative_path_agree(cuda, monkeypatch):
         monkeypatch.setenv("RDPN_FPS_NO_CLUSTER", "1")
         assert np.array_equal(_gpu_idx(p, k), a), (n, k)
         monkeypatch.delenv("RDPN_FPS_NO_CLUSTER")
+        for xchg in ("barrier", "flat"):  # the exchanges the one-push-per-CTA default replaced
+            monkeypatch.setenv("RDPN_FPS_EXCHANGE", xchg)
+            assert np.array_equal(_gpu_idx(p, k), a), (n, k, xchg)
+            monkeypatch.delenv("RDPN_FPS_EXCHANGE")
 
 
 def test_batched_objects_one_launch(cuda):
