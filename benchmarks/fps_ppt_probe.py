@@ -9,9 +9,13 @@ def ev(fn, iters=10):
     for _ in range(iters): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters
-for n in (5000, 8192, 20000, 50000):
+for n in (5000, 8192, 20000, 32768):
     t = torch.from_numpy(synth.fps_cloud(n, seed=1)).cuda()
-    for ppt in (1, 2, 4, 8, 16):
-        os.environ["RDPN_FPS_CLUSTER_PPT"] = str(ppt)
-        a, b = ev(lambda: fps_utils.fps_indices(t, 64)), ev(lambda: fps_utils.fps_indices(t, 256))
-        print(n, ppt, "C=%d" % -(-n // (512 * max(ppt, 1))), "us/pick %.3f" % (1e3 * (b - a) / 192), flush=True)
+    for ct in (128, 256, 512):
+        os.environ["RDPN_FPS_CLUSTER_THREADS"] = str(ct)
+        for ppt in (1, 2, 4, 8, 16):
+            if 8 * ct * ppt < n:
+                continue
+            os.environ["RDPN_FPS_CLUSTER_PPT"] = str(ppt)
+            a, b = ev(lambda: fps_utils.fps_indices(t, 64)), ev(lambda: fps_utils.fps_indices(t, 256))
+            print(n, "threads", ct, "ppt", ppt, "C=%d" % -(-n // (ct * ppt)), "us/pick %.3f" % (1e3 * (b - a) / 192), flush=True)

@@ -27,11 +27,10 @@ def ev(fn, iters=10):
     return e0.elapsed_time(e1) / iters
 
 
-for n in (5_000, 8_192, 20_000, 32_768, 50_000):
+for n in (5_000, 8_192, 20_000, 32_768, 50_000, 65_536):
     t = torch.from_numpy(synth.fps_cloud(n, seed=1)).cuda()
     rec = {"bench": "fps_small", "n": n}
-    for name, env, xchg in (("cluster", None, None), ("cluster_flat_push", None, "flat"), ("cluster_barrier", None, "barrier"),
-                            ("cooperative", "1", None)):
+    for name, env, xchg in (("cluster", None, None), ("cluster_barrier", None, "barrier"), ("cooperative", "1", None)):
         os.environ.pop("RDPN_FPS_NO_CLUSTER", None)
         os.environ.pop("RDPN_FPS_EXCHANGE", None)
         if env:

@@ -271,6 +271,7 @@ __global__ void __launch_bounds__(FPS_THREADS, 1)
 // tie rule: bit-identical picks.
 // ---------------------------------------------------------------------------------------------
 namespace cg = cooperative_groups;
+constexpr int FPS_CLUSTER_THREADS_DEFAULT = 128;  // narrowest CTA that holds the cloud at <= 16 points per thread
 constexpr int FPS_MAX_CLUSTER = 8;   // the portable cluster size: 8 x 512 x 16 = 65 536 points per object
 
 struct __align__(16) FpsCand {  // a candidate pick travels with its coordinates: the next round needs no global load
@@ -278,21 +279,19 @@ struct __align__(16) FpsCand {  // a candidate pick travels with its coordinates
     float x, y, z, pad;
     float pad2[2];
 };
-constexpr int FPS_SLOTS = FPS_MAX_CLUSTER * FPS_WARPS;  // one candidate per warp of the cluster
 struct FpsClusterShared {
     FpsCand wcand[FPS_WARPS];
     FpsCand ccand[2];             // this CTA's candidate, double-buffered by pick parity
     float fmin[FPS_WARPS][3];
     float fmax[FPS_WARPS][3];
     float bb[6];                  // this CTA's bounding box (min xyz, max xyz)
-    // push exchange: every warp of the cluster stores its candidate into EVERY CTA (st.async, 16 + 4 bytes) and the
+    // push exchange: every CTA of the cluster stores its candidate into EVERY CTA (st.async, 16 + 4 bytes) and the
     // stores complete the destination's mbarrier; double-buffered by pick parity
-    uint4 pk[2][FPS_SLOTS];       // {distance bits, ~index, x, y}
-    float pz[2][FPS_SLOTS];
+    uint4 pk[2][FPS_MAX_CLUSTER];  // {distance bits, ~index, x, y}, slot = sending rank
+    float pz[2][FPS_MAX_CLUSTER];
     uint64_t bar[2];
-    uint4 wk4[FPS_WARPS];         // PUSH == 2: the warps' candidates, reduced by the warp that arrives last
+    uint4 wk4[FPS_WARPS];          // the warps' candidates, reduced by warp 0 after the block barrier
     float wz[FPS_WARPS];
-    unsigned arrived;             // running count of warp arrivals (16 per exchange)
 };
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
@@ -332,11 +331,12 @@ __device__ __forceinline__ unsigned long long warp_max_key_redux(unsigned long l
     return ((unsigned long long)mh << 32) | ml;
 }
 
-template <int PPT, int PUSH /* 0 cluster barrier | 1 every warp pushes | 2 one push per CTA */>
-__global__ void __launch_bounds__(FPS_THREADS, 1)
+template <int PPT, bool PUSH, int CT /* threads per CTA */>
+__global__ void __launch_bounds__(CT, 1)
     fps_cluster_kernel(const float* __restrict__ pts_all, const int* __restrict__ offs, int* __restrict__ idxs_all, int sn,
                        const int* __restrict__ starts, int one_pn, int one_start) {
     __shared__ FpsClusterShared sh;
+    constexpr int CW = CT / 32;
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
     const int obj = blockIdx.x / C, t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(FPS_THREADS, 1)
     float px[PPT], py[PPT], pz[PPT], md[PPT];
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
-        const int i = (k * C + rank) * FPS_THREADS + t;
+        const int i = (k * C + rank) * CT + t;
         if (i < pn) {
             px[k] = pts[3 * (size_t)i + 0];
             py[k] = pts[3 * (size_t)i + 1];
@@ -376,11 +376,11 @@ __global__ void __launch_bounds__(FPS_THREADS, 1)
             mbar_init(&sh.bar[0], 1);
             mbar_init(&sh.bar[1], 1);
             mbar_fence_init();
-            mbar_expect_tx(&sh.bar[0], (uint32_t)(C * (PUSH == 2 ? 1 : FPS_WARPS) * 20));
-            mbar_expect_tx(&sh.bar[1], (uint32_t)(C * (PUSH == 2 ? 1 : FPS_WARPS) * 20));
-            sh.arrived = 0u;
+            mbar_expect_tx(&sh.bar[0], (uint32_t)(C * (1) * 20));
+            mbar_expect_tx(&sh.bar[1], (uint32_t)(C * (1) * 20));
         }
-        cluster.sync();  // every barrier of the cluster is armed before the first store can arrive
+        if (t < 2 * FPS_MAX_CLUSTER) (&sh.pk[0][0])[t] = make_uint4(0u, 0u, 0u, 0u);  // slots of absent ranks: key 0
+        cluster.sync();  // every barrier of the cluster is armed (and every slot zeroed) before the first store can arrive
     }
 #ifdef RDPN_FPS_TIMING  // cycles of thread 0 between the marks of the exchange, summed over the picks, printed at the end
     long long tk_last = clock64(), tk_sum[5] = {0, 0, 0, 0, 0};
@@ -391,30 +391,25 @@ __global__ void __launch_bounds__(FPS_THREADS, 1)
     auto cluster_max_key = [&](unsigned long long key, float bx, float by, float bz) -> unsigned long long {
         RDPN_FPS_TICK(0);
         const unsigned long long wk = warp_max_key_redux(key);
-        if (PUSH == 2) {
-            // stage 1 inside the CTA: the warp's candidate goes to local shared memory and the warp counts itself in;
-            // the warp that arrives LAST reduces the sixteen and pushes the CTA's candidate to every CTA of the cluster
-            // (2 C mbarrier transactions per CTA and pick instead of 32 C: the transactions of one barrier serialise)
+        if (PUSH) {
+            // stage 1 inside the CTA: the warps' candidates meet in local shared memory at ONE block barrier; warp 0
+            // reduces the sixteen and pushes the CTA's candidate to every CTA of the cluster (2 C mbarrier transactions
+            // per CTA and pick instead of 32 C: the transactions of one barrier serialise, ~4 cycles each)
             const int b = (int)(xchg & 1u);
-            const bool owner = wk ? key == wk : lane == 0;
-            unsigned old = 0u;
-            RDPN_FPS_TICK(1);
-            if (owner) {
+            if (wk ? key == wk : lane == 0) {
                 sh.wk4[warp] = make_uint4((unsigned)(wk >> 32), (unsigned)wk, __float_as_uint(bx), __float_as_uint(by));
                 sh.wz[warp] = bz;
-                __threadfence_block();
-                old = atomicAdd(&sh.arrived, 1u);
             }
-            old = __shfl_sync(0xffffffffu, old, __ffs(__ballot_sync(0xffffffffu, owner)) - 1);
+            RDPN_FPS_TICK(1);
+            __syncthreads();
             RDPN_FPS_TICK(2);
-            if ((old & (FPS_WARPS - 1)) == FPS_WARPS - 1) {  // warp-uniform
-                __threadfence_block();
+            if (warp == 0) {
                 uint4 v = make_uint4(0u, 0u, 0u, 0u);
                 float z = 0.f;
-                if (lane < FPS_WARPS) { v = sh.wk4[lane]; z = sh.wz[lane]; }
+                if (lane < CW) { v = sh.wk4[lane]; z = sh.wz[lane]; }
                 const unsigned mh = __reduce_max_sync(0xffffffffu, v.x);
                 const unsigned ml = __reduce_max_sync(0xffffffffu, v.x == mh ? v.y : 0u);
-                if ((mh | ml) ? (lane < FPS_WARPS && v.x == mh && v.y == ml) : lane == 0) {
+                if ((mh | ml) ? (lane < CW && v.x == mh && v.y == ml) : lane == 0) {
                     const uint32_t a4 = smem_u32(&sh.pk[b][rank]), az = smem_u32(&sh.pz[b][rank]), ab = smem_u32(&sh.bar[b]);
                     for (int r = 0; r < C; ++r) {
                         const uint32_t rb = mapa_u32(ab, (uint32_t)r);
@@ -428,67 +423,29 @@ __global__ void __launch_bounds__(FPS_THREADS, 1)
             }
             RDPN_FPS_TICK(3);
             if (t == 0) mbar_expect_tx(&sh.bar[b], (uint32_t)(C * 20));  // armed for the exchange after the next one
-            unsigned bh = 0u, bl = 0u;
-            float lx = 0.f, ly = 0.f, lz = 0.f;
-            if (lane < C) {
-                const uint4 v = sh.pk[b][lane];
-                bh = v.x; bl = v.y; lx = __uint_as_float(v.z); ly = __uint_as_float(v.w); lz = sh.pz[b][lane];
+            // every thread reads the (at most eight) CTA candidates by broadcast loads and picks the best in a tree;
+            // the slots of ranks >= C stay zero (key 0 never wins)
+            unsigned long long kk[FPS_MAX_CLUSTER];
+            int wi[FPS_MAX_CLUSTER];
+#pragma unroll
+            for (int r = 0; r < FPS_MAX_CLUSTER; ++r) {
+                const uint2 v = *reinterpret_cast<const uint2*>(&sh.pk[b][r]);
+                kk[r] = ((unsigned long long)v.x << 32) | v.y;
+                wi[r] = r;
             }
-            const unsigned mh = __reduce_max_sync(0xffffffffu, bh);
-            const unsigned ml = __reduce_max_sync(0xffffffffu, bh == mh ? bl : 0u);
-            const unsigned long long best = ((unsigned long long)mh << 32) | ml;
+#pragma unroll
+            for (int w = 1; w < FPS_MAX_CLUSTER; w *= 2)
+#pragma unroll
+                for (int r = 0; r < FPS_MAX_CLUSTER; r += 2 * w)
+                    if (kk[r + w] > kk[r]) { kk[r] = kk[r + w]; wi[r] = wi[r + w]; }
+            const unsigned long long best = kk[0];
             if (best) {
-                const int src = __ffs(__ballot_sync(0xffffffffu, bh == mh && bl == ml)) - 1;
-                cx = __shfl_sync(0xffffffffu, lx, src);
-                cy = __shfl_sync(0xffffffffu, ly, src);
-                cz = __shfl_sync(0xffffffffu, lz, src);
+                const uint4 v = sh.pk[b][wi[0]];
+                cx = __uint_as_float(v.z); cy = __uint_as_float(v.w); cz = sh.pz[b][wi[0]];
             } else {  // nothing positive left: the reference returns index 0 (cpp:60,72)
                 cx = __ldg(pts); cy = __ldg(pts + 1); cz = __ldg(pts + 2);
             }
             RDPN_FPS_TICK(4);
-            ++xchg;
-            return best;
-        }
-        if (PUSH == 1) {
-            const int b = (int)(xchg & 1u);
-            if (wk ? key == wk : lane == 0) {  // keys embed the point index: exactly one owner (lane 0 when nothing is left)
-                const uint32_t a4 = smem_u32(&sh.pk[b][rank * FPS_WARPS + warp]), az = smem_u32(&sh.pz[b][rank * FPS_WARPS + warp]);
-                const uint32_t ab = smem_u32(&sh.bar[b]);
-                const uint32_t w0 = (uint32_t)(wk >> 32), w1 = (uint32_t)wk, w2 = __float_as_uint(bx), w3 = __float_as_uint(by),
-                               w4 = __float_as_uint(bz);
-                for (int r = 0; r < C; ++r) {
-                    const uint32_t rb = mapa_u32(ab, (uint32_t)r);
-                    st_async_v4(mapa_u32(a4, (uint32_t)r), w0, w1, w2, w3, rb);
-                    st_async_b32(mapa_u32(az, (uint32_t)r), w4, rb);
-                }
-            }
-            const uint32_t ph = (xchg >> 1) & 1u;
-            while (!mbar_try_cluster(&sh.bar[b], ph)) {
-            }
-            // this phase is over for the whole CTA's barrier: arm it for the exchange after the next one
-            if (t == 0) mbar_expect_tx(&sh.bar[b], (uint32_t)(C * FPS_WARPS * 20));
-            unsigned bh = 0u, bl = 0u;
-            float lx = 0.f, ly = 0.f, lz = 0.f;
-#pragma unroll
-            for (int j = 0; j < FPS_SLOTS / 32; ++j) {
-                const int sl = j * 32 + lane;
-                if (sl < C * FPS_WARPS) {
-                    const uint4 v = sh.pk[b][sl];
-                    const float z = sh.pz[b][sl];
-                    if (v.x > bh || (v.x == bh && v.y > bl)) { bh = v.x; bl = v.y; lx = __uint_as_float(v.z); ly = __uint_as_float(v.w); lz = z; }
-                }
-            }
-            const unsigned mh = __reduce_max_sync(0xffffffffu, bh);
-            const unsigned ml = __reduce_max_sync(0xffffffffu, bh == mh ? bl : 0u);
-            const unsigned long long best = ((unsigned long long)mh << 32) | ml;
-            if (best) {
-                const int src = __ffs(__ballot_sync(0xffffffffu, bh == mh && bl == ml)) - 1;
-                cx = __shfl_sync(0xffffffffu, lx, src);
-                cy = __shfl_sync(0xffffffffu, ly, src);
-                cz = __shfl_sync(0xffffffffu, lz, src);
-            } else {  // nothing positive left: the reference returns index 0 (cpp:60,72)
-                cx = __ldg(pts); cy = __ldg(pts + 1); cz = __ldg(pts + 2);
-            }
             ++xchg;
             return best;
         }
@@ -499,9 +456,9 @@ __global__ void __launch_bounds__(FPS_THREADS, 1)
         }
         __syncthreads();
         if (warp == 0) {
-            const unsigned long long k = lane < FPS_WARPS ? sh.wcand[lane].key : 0ull;
+            const unsigned long long k = lane < CW ? sh.wcand[lane].key : 0ull;
             const unsigned long long bk = warp_max_key_redux(k);
-            if (bk ? (lane < FPS_WARPS && k == bk) : lane == 0) sh.ccand[par] = sh.wcand[lane];
+            if (bk ? (lane < CW && k == bk) : lane == 0) sh.ccand[par] = sh.wcand[lane];
         }
         cluster.sync();
         unsigned long long best = 0ull;
@@ -538,7 +495,7 @@ __global__ void __launch_bounds__(FPS_THREADS, 1)
         __syncthreads();
         if (t < 3) {
             float lo = FLT_MAX, hi = -FLT_MAX;
-            for (int w = 0; w < FPS_WARPS; ++w) { lo = fminf(lo, sh.fmin[w][t]); hi = fmaxf(hi, sh.fmax[w][t]); }
+            for (int w = 0; w < CW; ++w) { lo = fminf(lo, sh.fmin[w][t]); hi = fmaxf(hi, sh.fmax[w][t]); }
             sh.bb[t] = lo;
             sh.bb[3 + t] = hi;
         }
@@ -566,7 +523,7 @@ __global__ void __launch_bounds__(FPS_THREADS, 1)
                 if (md[k] > bd) { bd = md[k]; bk = k; bx = px[k]; by = py[k]; bz = pz[k]; }
             }
         unsigned long long key =
-            bd > 0.f ? (((unsigned long long)__float_as_uint(bd) << 32) | (0xFFFFFFFFu - (((unsigned)bk * C + rank) * FPS_THREADS + t))) : 0ull;
+            bd > 0.f ? (((unsigned long long)__float_as_uint(bd) << 32) | (0xFFFFFFFFu - (((unsigned)bk * C + rank) * CT + t))) : 0ull;
         key = cluster_max_key(key, bx, by, bz);  // cpp:149
         cur = key ? (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull)) : 0;
     } else {
@@ -576,9 +533,9 @@ __global__ void __launch_bounds__(FPS_THREADS, 1)
     for (int it = 0; it < sn; ++it) {
         if (rank == 0 && t == 0) idxs[it] = cur;  // cpp:153
         if (it == sn - 1) break;                  // cpp:154
-        {
-            const int q = cur / FPS_THREADS;
-            if ((cur % FPS_THREADS) == t && (q % C) == rank) {
+        if (it == 0 || !PUSH) {  // with the push exchange the owner recognises its own key below (no divisions per pick)
+            const int q = cur / CT;
+            if ((cur % CT) == t && (q % C) == rank) {
                 const int kk = q / C;
 #pragma unroll
                 for (int k = 0; k < PPT; ++k)
@@ -594,13 +551,19 @@ __global__ void __launch_bounds__(FPS_THREADS, 1)
             if (md[k] > bd) { bd = md[k]; bk = k; bx = px[k]; by = py[k]; bz = pz[k]; }  // cpp:67-71
         }
         unsigned long long key =
-            bd > 0.f ? (((unsigned long long)__float_as_uint(bd) << 32) | (0xFFFFFFFFu - (((unsigned)bk * C + rank) * FPS_THREADS + t))) : 0ull;
+            bd > 0.f ? (((unsigned long long)__float_as_uint(bd) << 32) | (0xFFFFFFFFu - (((unsigned)bk * C + rank) * CT + t))) : 0ull;
+        const unsigned long long mine = key;
         key = cluster_max_key(key, bx, by, bz);
         cur = key ? (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull)) : 0;  // cpp:60,72
+        if (PUSH && key && mine == key) {  // cpp:152: the pick is taken (keys embed the index: exactly one thread matches;
+#pragma unroll                             // when nothing is left the pick is index 0, whose distance is already <= 0)
+            for (int k = 0; k < PPT; ++k)
+                if (k == bk) md[k] = -1.f;
+        }
     }
 #ifdef RDPN_FPS_TIMING
-    if (PUSH == 2 && t == 0 && rank == 0 && obj == 0)
-        printf("fps timing C=%d PPT=%d picks=%d: dist %lld redux %lld arrive %lld wait %lld select %lld cycles/pick\n", C, PPT, sn,
+    if (PUSH && t == 0 && rank == 0 && obj == 0)
+        printf("fps timing C=%d PPT=%d picks=%d: dist %lld redux %lld block-barrier %lld wait %lld select %lld cycles/pick\n", C, PPT, sn,
                tk_sum[0] / sn, tk_sum[1] / sn, tk_sum[2] / sn, tk_sum[3] / sn, tk_sum[4] / sn);
 #endif
     cluster.sync();  // no CTA leaves while a sibling may still read its shared memory
@@ -610,23 +573,29 @@ __global__ void __launch_bounds__(FPS_THREADS, 1)
 // rate per pick is best and returns RDPN_E_TOOLARGE beyond 8 CTAs x 512 threads x 16 points.
 static int fps_cluster_launch(const float* d_pts, const int* d_offs, int32_t* d_idxs, int nobj, int max_pn, int sn, const int* d_starts,
                               int one_start, cudaStream_t st) {
-    // measured on B200 (benchmarks/fps_ppt_probe.py): 4 to 8 CTAs with 2 to 8 points per thread give the best rate
-    // (1.2-1.6 us per pick); wider clusters pay for the barrier, narrower ones for the serial distance updates
+    // threads per CTA x points per thread (benchmarks/fps_ppt_probe.py on B200): the fixed cost of a pick is paid per
+    // warp (reductions, barrier, selection), the distance updates per point and SM
+    int ct = FPS_CLUSTER_THREADS_DEFAULT;
+    if (const char* e = getenv("RDPN_FPS_CLUSTER_THREADS")) {
+        const int v = atoi(e);
+        ct = v <= 128 ? 128 : v <= 256 ? 256 : 512;
+    }
+    while (ct < 512 && (long long)FPS_MAX_CLUSTER * ct * 16 < max_pn) ct *= 2;
     int ppt = 2;
-    while (ppt < 16 && (long long)FPS_MAX_CLUSTER * FPS_THREADS * ppt < max_pn) ppt *= 2;
+    while (ppt < 16 && (long long)FPS_MAX_CLUSTER * ct * ppt < max_pn) ppt *= 2;
     if (const char* e = getenv("RDPN_FPS_CLUSTER_PPT")) {  // tuning: more points per thread = narrower cluster
         const int v = atoi(e);
         ppt = 1;
-        while (ppt < 16 && (ppt < v || (long long)FPS_MAX_CLUSTER * FPS_THREADS * ppt < max_pn)) ppt *= 2;
+        while (ppt < 16 && (ppt < v || (long long)FPS_MAX_CLUSTER * ct * ppt < max_pn)) ppt *= 2;
     }
-    if ((long long)FPS_MAX_CLUSTER * FPS_THREADS * ppt < max_pn) return RDPN_E_TOOLARGE;
-    int C = (int)(((long long)max_pn + (long long)FPS_THREADS * ppt - 1) / ((long long)FPS_THREADS * ppt));
+    if ((long long)FPS_MAX_CLUSTER * ct * ppt < max_pn) return RDPN_E_TOOLARGE;
+    int C = (int)(((long long)max_pn + (long long)ct * ppt - 1) / ((long long)ct * ppt));
     if (C < 1) C = 1;
-    // RDPN_FPS_EXCHANGE = barrier | flat | (default) cta: the exchanges kept for A/B timing (benchmarks/fps_small.py)
+    // RDPN_FPS_EXCHANGE = barrier: the cluster-barrier exchange, kept for A/B timing (benchmarks/fps_small.py)
     const char* xe = getenv("RDPN_FPS_EXCHANGE");
-    const int mode = xe && xe[0] == 'b' ? 0 : xe && xe[0] == 'f' ? 1 : 2;
-#define RDPN_FPS_PICK(P) \
-    (mode == 0 ? (const void*)fps_cluster_kernel<P, 0> : mode == 1 ? (const void*)fps_cluster_kernel<P, 1> : (const void*)fps_cluster_kernel<P, 2>)
+    const bool push = !(xe && xe[0] == 'b');
+#define RDPN_FPS_PICK2(P, T) (push ? (const void*)fps_cluster_kernel<P, true, T> : (const void*)fps_cluster_kernel<P, false, T>)
+#define RDPN_FPS_PICK(P) (ct == 128 ? RDPN_FPS_PICK2(P, 128) : ct == 256 ? RDPN_FPS_PICK2(P, 256) : RDPN_FPS_PICK2(P, 512))
     const void* fn = nullptr;
     switch (ppt) {
         case 1: fn = RDPN_FPS_PICK(1); break;
@@ -636,9 +605,10 @@ static int fps_cluster_launch(const float* d_pts, const int* d_offs, int32_t* d_
         default: fn = RDPN_FPS_PICK(16); break;
     }
 #undef RDPN_FPS_PICK
+#undef RDPN_FPS_PICK2
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(nobj * C));
-    cfg.blockDim = dim3(FPS_THREADS);
+    cfg.blockDim = dim3((unsigned)ct);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -699,7 +669,7 @@ static int fps_launch(const float* d_pts, int32_t* d_idxs, int pn, int sn, int s
                       cudaStream_t st) {
     if (!d_pts || !d_idxs || pn <= 0 || sn <= 0 || start >= pn) return RDPN_E_BADARG;
     if (!d_ws || ws_bytes < rdpn_fps_workspace_bytes(sn)) return RDPN_E_WORKSPACE;
-    if (pn <= 32768 && !getenv("RDPN_FPS_NO_CLUSTER")) {
+    if (pn <= FPS_MAX_CLUSTER * FPS_THREADS * 16 && !getenv("RDPN_FPS_NO_CLUSTER")) {
         // small clouds: one thread-block cluster, arg-max through distributed shared memory (above ~32 k points the
         // cooperative grid's wider spread wins: benchmarks/fps_small.py)
         return fps_cluster_launch(d_pts, nullptr, d_idxs, 1, pn, sn, nullptr, start, st);

@@ -111,19 +111,22 @@ def test_get_fps_and_center_matches_reference_python_surface(cuda, golden_dir):
 
 
 def test_cluster_path_sizes_and_cooperative_path_agree(cuda, monkeypatch):
-    """<= 32 768 points run in one thread-block cluster (DSMEM arg-max); the same clouds through the cooperative grid
+    """<= 65 536 points run in one thread-block cluster (candidates pushed through DSMEM); the same clouds through the cooperative grid
     (RDPN_FPS_NO_CLUSTER) and the C restatement give the same indices, bit for bit."""
-    for n, k in ((100, 10), (5_000, 32), (8_192, 64), (8_193, 64), (50_000, 64), (32_768, 40), (32_769, 40)):
+    for n, k in ((100, 10), (5_000, 32), (8_192, 64), (8_193, 64), (16_385, 24), (50_000, 64), (32_768, 40), (32_769, 40), (65_536, 16), (65_537, 16)):
         p = np.random.default_rng(n + k).standard_normal((n, 3)).astype(np.float32)
         a = _gpu_idx(p, k)
         assert np.array_equal(a, fps_indices_port(p, k)), (n, k)
         monkeypatch.setenv("RDPN_FPS_NO_CLUSTER", "1")
         assert np.array_equal(_gpu_idx(p, k), a), (n, k)
         monkeypatch.delenv("RDPN_FPS_NO_CLUSTER")
-        for xchg in ("barrier", "flat"):  # the exchanges the one-push-per-CTA default replaced
-            monkeypatch.setenv("RDPN_FPS_EXCHANGE", xchg)
-            assert np.array_equal(_gpu_idx(p, k), a), (n, k, xchg)
-            monkeypatch.delenv("RDPN_FPS_EXCHANGE")
+        monkeypatch.setenv("RDPN_FPS_EXCHANGE", "barrier")  # the cluster-barrier exchange the push exchange replaced
+        assert np.array_equal(_gpu_idx(p, k), a), (n, k)
+        monkeypatch.delenv("RDPN_FPS_EXCHANGE")
+        for ct in ("128", "256", "512"):  # every CTA width of the cluster kernel
+            monkeypatch.setenv("RDPN_FPS_CLUSTER_THREADS", ct)
+            assert np.array_equal(_gpu_idx(p, k), a), (n, k, ct)
+            monkeypatch.delenv("RDPN_FPS_CLUSTER_THREADS")
 
 
 def test_batched_objects_one_launch(cuda):
