@@ -66,8 +66,8 @@ void farthest_point_sampling_init_center(float* pts, int* idxs, int pn, int sn);
 /* Device-pointer entries.  d_ws: scratch of at least rdpn_fps_workspace_bytes(sn) bytes.
  * Indices are bit-exact with the reference C++ (squared FP32 distances without FMA, lowest index
  * wins ties, index 0 when nothing is left: cpp:40-73).
- * Three implementations behind the same entry, by cloud size: <= 32 768 points one thread-block cluster (arg-max
- * through distributed shared memory); up to 148 x 512 x 16 = 1.21 M points a persistent cooperative grid with the
+ * Three implementations behind the same entry, by cloud size: <= 65 536 points one thread-block cluster (the CTAs'
+ * candidates pushed into each other's shared memory, one mbarrier wait per pick); up to 148 x 512 x 16 = 1.21 M points a persistent cooperative grid with the
  * cloud in registers; above that the same grid streaming the cloud and the running minima from global memory, which
  * needs pn more floats behind the workspace header (ws_bytes >= rdpn_fps_workspace_bytes(sn) + 4 pn; RDPN_E_TOOLARGE
  * otherwise). */
