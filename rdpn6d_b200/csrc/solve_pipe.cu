@@ -232,6 +232,21 @@ static __device__ __noinline__ bool hyp_from_sample_list(const uint32_t* selmap,
 // Mask test of one quad -> 4 bits.  L1 mode: the two-sided FP32 filter of gate.cuh decides almost every pixel; the
 // exact FP64 comparison runs only when some lane of the warp has a pixel inside the filter's band (warp vote), so the
 // common path is 4 FADD + 8 FSETP.  Decisions are those of mask_pass(), bit for bit.
+// the exact comparison of the pixels inside the filter's band: rare, kept out of line so that the unrolled mask test
+// stays short in the instruction cache
+static __device__ __noinline__ unsigned mask_nibble_exact(float a0, float a1, float a2, float a3, unsigned amb, float gb, double cut,
+                                                          int incl) {
+    const float av[4] = {a0, a1, a2, a3};
+    const double r = __dmul_rn((double)gb, cut);
+    unsigned nib = 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if ((amb >> j) & 1u) {
+            const double l = (double)av[j];
+            if (incl ? (l >= r) : (l > r)) nib |= 1u << j;  // NaN -> false
+        }
+    return nib;
+}
 __device__ __forceinline__ unsigned mask_nibble(const float4& m, int mode, float thr, float mn, const RoiGate& g) {
     const float mm[4] = {m.x, m.y, m.z, m.w};
     unsigned nib = 0u;
@@ -246,15 +261,7 @@ __device__ __forceinline__ unsigned mask_nibble(const float4& m, int mode, float
             nib |= (in ? 1u : 0u) << j;
             amb |= ((!in && !out) ? 1u : 0u) << j;
         }
-        if (__any_sync(0xffffffffu, amb != 0u)) {
-            const double r = __dmul_rn((double)g.b, g.cut);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if ((amb >> j) & 1u) {
-                    const double l = (double)av[j];
-                    if (g.incl ? (l >= r) : (l > r)) nib |= 1u << j;  // NaN -> false
-                }
-        }
+        if (__any_sync(0xffffffffu, amb != 0u)) nib |= mask_nibble_exact(av[0], av[1], av[2], av[3], amb, g.b, g.cut, g.incl);
         return nib;
     }
 #pragma unroll
@@ -262,7 +269,9 @@ __device__ __forceinline__ unsigned mask_nibble(const float4& m, int mode, float
     return nib;
 }
 
-template <bool MULTI>
+// L1MASK: the mask mode is RDPN_MASK_L1 (the default of the reference, gdrn_base.py:46) at compile time -- the sigmoid /
+// plain-probability code of the other modes stays out of the instruction stream of the unrolled mask test
+template <bool MULTI, bool L1MASK>
 __global__ void __launch_bounds__(FR_T, RDPN_FRONT_CTAS) front_kernel(SolveArgs a, unsigned char* __restrict__ ws, PkgLayout lay,
                                                                         FrontLayout fl, int* __restrict__ fdone) {
     extern __shared__ __align__(128) unsigned char fsm[];
@@ -324,7 +333,8 @@ __global__ void __launch_bounds__(FR_T, RDPN_FRONT_CTAS) front_kernel(SolveArgs 
     gate.hi = gate.lo = gate.b = 0.f;
     gate.cut = 0.0;
     gate.incl = 0;
-    if (in.mask_mode == RDPN_MASK_L1) {
+    const int mask_mode = L1MASK ? (int)RDPN_MASK_L1 : in.mask_mode;
+    if (mask_mode == RDPN_MASK_L1) {
         float mn = FLT_MAX, mx = -FLT_MAX;
 #pragma unroll 8
         for (int k = 0; k < 32; ++k) minmax4(__ldg(mask4 + 32 * k + lane), mn, mx);
@@ -350,7 +360,7 @@ __global__ void __launch_bounds__(FR_T, RDPN_FRONT_CTAS) front_kernel(SolveArgs 
 #pragma unroll
         for (int k8 = 0; k8 < 8; ++k8) {
             const int q = 32 * (8 * kk + k8) + lane;
-            const unsigned nib = mask_nibble(mq[k8], in.mask_mode, in.mask_thr, rc.mn, gate);
+            const unsigned nib = mask_nibble(mq[k8], mask_mode, in.mask_thr, rc.mn, gate);
             const unsigned bal = __ballot_sync(0xffffffffu, nib != 0u);
             if (nib) {
                 qlist[nq + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)((unsigned)q | (nib << 10));
@@ -412,7 +422,7 @@ __global__ void __launch_bounds__(FR_T, RDPN_FRONT_CTAS) front_kernel(SolveArgs 
                 const int p = 4 * q + j;
                 float cam[3], obj[3];
                 pixel_s1<false>(rc, p, dd[j], cxn[j], cyn[j], czn[j], cam, obj);
-                const float w = a.prm.weighted ? mask_prob(__ldg(in.mask + po + p), in.mask_mode, rc.mn, rc.mx) : 1.f;
+                const float w = a.prm.weighted ? mask_prob(__ldg(in.mask + po + p), mask_mode, rc.mn, rc.mx) : 1.f;
                 rast_g[slot] = make_float4(cam[0], cam[1], cam[2], w);
                 key_g[slot] = (uint32_t)p | ((uint32_t)rr[j] << 16);
                 atomicAdd(&cur[rr[j]], 1u);
@@ -1204,7 +1214,7 @@ static SolveArgs shifted(const SolveArgs& a, int b0, int nb) {
     return c;
 }
 
-enum { SLOT_FRONT = 8, SLOT_SCORE = 10, SLOT_REFIT = 12 };  // attribute-cache slots (+ multi)
+enum { SLOT_FRONT = 8, SLOT_SCORE = 10, SLOT_REFIT = 12 };  // attribute-cache slots (+ multi; front: + 8 for the generic mask mode)
 
 bool split_supported(const SolveArgs& a, bool dense) {
     if (dense) return false;               // dense mode (no region runs to share the transformed anchor) stays fused
@@ -1268,9 +1278,11 @@ static int launch_chunk(const SolveArgs& a, unsigned char* ws, const PkgLayout& 
         const FrontLayout fl = make_front_layout(R);
         const size_t smem = (size_t)FR_W * fl.per_warp;
         if (smem > 227 * 1024) return RDPN_E_TOOLARGE;
-        const int rc = ensure_func_smem((const void*)front_kernel<MULTI>, SLOT_FRONT + (MULTI ? 1 : 0), smem);
+        const bool l1 = a.in.mask_mode == RDPN_MASK_L1;
+        void (*kern)(SolveArgs, unsigned char*, PkgLayout, FrontLayout, int*) = l1 ? front_kernel<MULTI, true> : front_kernel<MULTI, false>;
+        const int rc = ensure_func_smem((const void*)kern, SLOT_FRONT + (MULTI ? 1 : 0) + (l1 ? 0 : 8), smem);
         if (rc) return rc;
-        front_kernel<MULTI><<<(B + FR_W - 1) / FR_W, FR_T, smem, st>>>(a, pk, lay, fl, fdone);
+        kern<<<(B + FR_W - 1) / FR_W, FR_T, smem, st>>>(a, pk, lay, fl, fdone);
         ++g_launch_count;
         RDPN_LAUNCH_CHECK();
     }
