@@ -106,6 +106,9 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // =============================================================================================
 constexpr int FR_W = 4;             // warps (ROIs) per CTA
 constexpr int FR_T = FR_W * 32;
+#ifndef RDPN_FRONT_PREFETCH
+#define RDPN_FRONT_PREFETCH 1       // L1 prefetch of the next sort trip / the next round's sampled pairs
+#endif
 #ifndef RDPN_FRONT_CTAS
 #define RDPN_FRONT_CTAS 5           // CTAs per SM the register budget is sized for: 96 registers per thread, no spills
                                     // (8 CTAs at 64 registers spill the FP64 hypothesis solve: measured 4 % slower overall)
@@ -382,7 +385,7 @@ __global__ void __launch_bounds__(FR_T, RDPN_FRONT_CTAS) front_kernel(SolveArgs 
     for (int i0 = 0; i0 < nq; i0 += 32) {
         unsigned nib = 0u;
         int q = 0;
-        float dd[4], cxn[4], cyn[4], czn[4];
+        float dd[4], cxn[4], cyn[4], czn[4], mw[4] = {0.f, 0.f, 0.f, 0.f};
         uint8_t rr[4];
         if (i0 + lane < nq) {
             const unsigned ent = qlist[i0 + lane];
@@ -390,6 +393,10 @@ __global__ void __launch_bounds__(FR_T, RDPN_FRONT_CTAS) front_kernel(SolveArgs 
             nib = ent >> 10;
             const float4 dq = __ldg(dep4 + q), xq = __ldg(cx4 + q), yq = __ldg(cy4 + q), zq = __ldg(cz4 + q);
             const uchar4 r4 = __ldg(rid4 + q);
+            if (a.prm.weighted) {  // the weights of the quad with the other planes, not pixel by pixel behind the gate
+                const float4 m4 = __ldg(mask4 + q);
+                mw[0] = m4.x; mw[1] = m4.y; mw[2] = m4.z; mw[3] = m4.w;
+            }
             dd[0] = dq.x; dd[1] = dq.y; dd[2] = dq.z; dd[3] = dq.w;
             cxn[0] = xq.x; cxn[1] = xq.y; cxn[2] = xq.z; cxn[3] = xq.w;
             cyn[0] = yq.x; cyn[1] = yq.y; cyn[2] = yq.z; cyn[3] = yq.w;
@@ -422,7 +429,7 @@ __global__ void __launch_bounds__(FR_T, RDPN_FRONT_CTAS) front_kernel(SolveArgs 
                 const int p = 4 * q + j;
                 float cam[3], obj[3];
                 pixel_s1<false>(rc, p, dd[j], cxn[j], cyn[j], czn[j], cam, obj);
-                const float w = a.prm.weighted ? mask_prob(__ldg(in.mask + po + p), mask_mode, rc.mn, rc.mx) : 1.f;
+                const float w = a.prm.weighted ? mask_prob(mw[j], mask_mode, rc.mn, rc.mx) : 1.f;
                 rast_g[slot] = make_float4(cam[0], cam[1], cam[2], w);
                 key_g[slot] = (uint32_t)p | ((uint32_t)rr[j] << 16);
                 atomicAdd(&cur[rr[j]], 1u);
@@ -501,6 +508,12 @@ __global__ void __launch_bounds__(FR_T, RDPN_FRONT_CTAS) front_kernel(SolveArgs 
                     kv[u] = key_g[i];
                     cw[u] = rast_g[i];
                 }
+#if RDPN_FRONT_PREFETCH
+                if (i + 64 < n) {  // the next trip's lines on their way from L2 while this trip is matched
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(key_g + i + 64));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(rast_g + i + 64));
+                }
+#endif
             }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
@@ -545,16 +558,44 @@ __global__ void __launch_bounds__(FR_T, RDPN_FRONT_CTAS) front_kernel(SolveArgs 
             const int32_t* ip = a.hyp_idx + ((size_t)b * H + lane) * 3;
             nx0 = __ldg(ip); nx1 = __ldg(ip + 1); nx2 = __ldg(ip + 2);
         }
+#if RDPN_FRONT_PREFETCH
+        int nn0 = -1, nn1 = -1, nn2 = -1;  // the round after
+        if (!MULTI && !sampling && lane + 32 < H) {
+            const int32_t* ip = a.hyp_idx + ((size_t)b * H + lane + 32) * 3;
+            nn0 = __ldg(ip); nn1 = __ldg(ip + 1); nn2 = __ldg(ip + 2);
+        }
+#endif
 #pragma unroll 1
         for (int h0 = 0; h0 < H; h0 += 32) {
             const int h = h0 + lane;
             float P[12];
             bool ok = false;
             const int cu0 = nx0, cu1 = nx1, cu2 = nx2;
+#if RDPN_FRONT_PREFETCH
+            if (!MULTI && !sampling) {
+                // indices run two rounds ahead, so that the pairs of the NEXT round can be requested from L2 now
+                nx0 = nn0; nx1 = nn1; nx2 = nn2;
+                if (h + 64 < H) {
+                    const int32_t* ip = a.hyp_idx + ((size_t)b * H + h + 64) * 3;
+                    nn0 = __ldg(ip); nn1 = __ldg(ip + 1); nn2 = __ldg(ip + 2);
+                }
+                if (h + 32 < H && ((unsigned)nx0 < RDPN_P) && ((unsigned)nx1 < RDPN_P) && ((unsigned)nx2 < RDPN_P)) {
+                    const int r0 = min(raster_rank(selmap, selpfx, nx0), n - 1), r1 = min(raster_rank(selmap, selpfx, nx1), n - 1),
+                              r2 = min(raster_rank(selmap, selpfx, nx2), n - 1);
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(rast_g + r0));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(rast_g + r1));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(rast_g + r2));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(key_g + r0));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(key_g + r1));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(key_g + r2));
+                }
+            }
+#else
             if (!MULTI && !sampling && h + 32 < H) {
                 const int32_t* ip = a.hyp_idx + ((size_t)b * H + h + 32) * 3;
                 nx0 = __ldg(ip); nx1 = __ldg(ip + 1); nx2 = __ldg(ip + 2);
             }
+#endif
             if (h < H) {
                 if (MULTI) {
                     ok = hyp_from_sample_list(selmap, selpfx, anchors, rast_g, key_g, reinterpret_cast<int*>(wsm + fl.scr) + lane,
