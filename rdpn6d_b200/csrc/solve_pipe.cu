@@ -672,7 +672,9 @@ __global__ void __launch_bounds__(FR_T, RDPN_FRONT_CTAS) front_kernel(SolveArgs 
         *reinterpret_cast<int4*>(pkg) = make_int4(n, nruns, nvalid, 0);
         if (a.out.n_sel) a.out.n_sel[b] = n;
     }
-    __threadfence();  // every lane's package writes before the flag
+    // every lane's package writes are ordered before the flag: the warp barrier orders them before lane 0's store, whose
+    // release at GPU scope is cumulative (the pattern of a block barrier + one releasing thread)
+    // (no __threadfence() of all lanes on top: measured -0.6 % of the step)
     __syncwarp();
     if (lane == 0) st_release_i32(fdone + b, 1);
 }
@@ -777,8 +779,7 @@ __global__ void __launch_bounds__(SC_T, RDPN_SCORE_REGS_CTAS) score_kernel(int H
         hcnt[j] = hcnt_s[j];
         if (MEAN) herr[j] = herr_s[j];
     }
-    __threadfence();
-    __syncthreads();
+    __syncthreads();  // + thread 0's release at GPU scope: every thread's counts are visible before the flag
     if (threadIdx.x == 0) st_release_i32(sdone + b, 1);
 }
 
