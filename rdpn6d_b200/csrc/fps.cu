@@ -290,8 +290,8 @@ struct FpsClusterShared {
     uint4 pk[2][FPS_MAX_CLUSTER];  // {distance bits, ~index, x, y}, slot = sending rank
     float pz[2][FPS_MAX_CLUSTER];
     uint64_t bar[2];
-    uint4 wk4[FPS_WARPS];          // the warps' candidates, reduced by warp 0 after the block barrier
-    float wz[FPS_WARPS];
+    uint4 wk4[2][FPS_WARPS];       // the warps' candidates, reduced by warp 0 after the block barrier; by pick parity, so
+    float wz[2][FPS_WARPS];        // that the block barrier of pick i + 1 separates warp 0's reads of pick i from the writes of i + 2
 };
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
@@ -397,8 +397,8 @@ __global__ void __launch_bounds__(CT, 1)
             // per CTA and pick instead of 32 C: the transactions of one barrier serialise, ~4 cycles each)
             const int b = (int)(xchg & 1u);
             if (wk ? key == wk : lane == 0) {
-                sh.wk4[warp] = make_uint4((unsigned)(wk >> 32), (unsigned)wk, __float_as_uint(bx), __float_as_uint(by));
-                sh.wz[warp] = bz;
+                sh.wk4[b][warp] = make_uint4((unsigned)(wk >> 32), (unsigned)wk, __float_as_uint(bx), __float_as_uint(by));
+                sh.wz[b][warp] = bz;
             }
             RDPN_FPS_TICK(1);
             __syncthreads();
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(CT, 1)
             if (warp == 0) {
                 uint4 v = make_uint4(0u, 0u, 0u, 0u);
                 float z = 0.f;
-                if (lane < CW) { v = sh.wk4[lane]; z = sh.wz[lane]; }
+                if (lane < CW) { v = sh.wk4[b][lane]; z = sh.wz[b][lane]; }
                 const unsigned mh = __reduce_max_sync(0xffffffffu, v.x);
                 const unsigned ml = __reduce_max_sync(0xffffffffu, v.x == mh ? v.y : 0u);
                 if ((mh | ml) ? (lane < CW && v.x == mh && v.y == ml) : lane == 0) {

@@ -104,7 +104,10 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // =============================================================================================
 // K1: gate + S1 + sort + hypotheses, one warp per ROI
 // =============================================================================================
-constexpr int FR_W = 4;             // warps (ROIs) per CTA
+#ifndef RDPN_FRONT_WARPS
+#define RDPN_FRONT_WARPS 4          // warps (ROIs) per CTA
+#endif
+constexpr int FR_W = RDPN_FRONT_WARPS;
 constexpr int FR_T = FR_W * 32;
 #ifndef RDPN_FRONT_PREFETCH
 #define RDPN_FRONT_PREFETCH 1       // L1 prefetch of the next sort trip / the next round's sampled pairs
