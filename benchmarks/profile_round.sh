@@ -12,6 +12,7 @@ python benchmarks/pipeline.py --configs ycbv,ycbv4k,ycbv2k,lmo --chunks 0 > $O/p
 python benchmarks/pipeline.py --configs ycbv,lmo --chunks 0 --streams 2 >> $O/pipeline.jsonl 2>> $O/pipeline.err
 python benchmarks/kernels.py > $O/kernels.jsonl 2> $O/kernels.err
 python benchmarks/fps_small.py > $O/fps_small.jsonl 2> $O/fps_small.err
+python benchmarks/fps_ppt_probe.py > $O/fps_ppt_probe.txt 2> $O/fps_ppt_probe.err
 python benchmarks/host_path.py > $O/host_path.jsonl 2> $O/host_path.err
 # launch list of the bench command (cold-cache, serialised: shares, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_bench.csv \
@@ -25,6 +26,8 @@ ncu --set full --clock-control none --import-source on -k regex:pose_solve_kerne
     python benchmarks/prof_pipeline.py ycbv fused 0 > $O/ncu_pose_solve_kernel.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:fps_cluster -s 2 -c 1 -f -o $O/prof_fps_cluster \
     python benchmarks/fps_small.py > $O/ncu_fps_cluster.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:coor_feat -s 3 -c 1 -f -o $O/prof_coor_feat \
+    python benchmarks/kernels.py --only misc --no-cpu > $O/ncu_coor_feat.log 2>&1
 for tool in memcheck racecheck synccheck; do
     echo "== $tool" >> $O/sanitizer.txt
     compute-sanitizer --tool $tool python benchmarks/sanitize.py 2>&1 | tail -3 >> $O/sanitizer.txt
