@@ -284,37 +284,36 @@ def get_closest_rot(rot_est, rot_gt, sym_info):
     return closest
 
 
-def get_symmetry_transformations(model_info, max_sym_disc_step):
-    """lib/pysixd/misc.py:206-254: the symmetry set of an object model (models_info.json): discrete symmetries (identity
-    first) combined with the continuous ones discretised into ceil(pi / max_sym_disc_step) steps.  Dataset-metadata host
-    logic feeding get_closest_rot's `sym_info` (np.stack of the "R" entries); same list of {"R", "t"} dicts as the reference."""
-    import math
-
+def _axis_rotations(axis, angles):
+    """Rodrigues rotations about `axis` (through the origin) for a vector of angles: [n,3,3] float64."""
     import numpy as np
 
-    def rot(angle, axis):  # lib/pysixd/transform.py:296-336, 3 x 3 part
-        d = np.asarray(axis, np.float64)[:3]
-        d = d / math.sqrt(float(np.dot(d, d)))
-        sina, cosa = math.sin(angle), math.cos(angle)
-        R = np.diag([cosa, cosa, cosa]) + np.outer(d, d) * (1.0 - cosa)
-        d = d * sina
-        return R + np.array([[0.0, -d[2], d[1]], [d[2], 0.0, -d[0]], [-d[1], d[0], 0.0]])
+    u = np.asarray(axis, np.float64)[:3]
+    u = u / np.sqrt(u @ u)
+    K = np.array([[0.0, -u[2], u[1]], [u[2], 0.0, -u[0]], [-u[1], u[0], 0.0]])
+    c, s_ = np.cos(angles)[:, None, None], np.sin(angles)[:, None, None]
+    return c * np.eye(3) + (1.0 - c) * np.outer(u, u) + s_ * K
 
-    trans_disc = [{"R": np.eye(3), "t": np.array([[0, 0, 0]]).T}]
-    for sym in model_info.get("symmetries_discrete", []):
-        s44 = np.reshape(sym, (4, 4))
-        trans_disc.append({"R": s44[:3, :3], "t": s44[:3, 3].reshape((3, 1))})
-    trans_cont = []
+
+def get_symmetry_transformations(model_info, max_sym_disc_step):
+    """lib/pysixd/misc.py:206-254: the symmetry set of an object model (models_info.json) as a list of {"R": [3,3],
+    "t": [3,1]} -- every discrete symmetry (identity first) composed with every step of every continuous one, the
+    continuous ones discretised into ceil(pi / max_sym_disc_step) steps of a full turn about (axis, offset).  Dataset-
+    metadata host logic; np.stack of the "R" entries is the `sym_info` get_closest_rot takes."""
+    import numpy as np
+
+    discrete = [np.eye(4)] + [np.reshape(m, (4, 4)).astype(np.float64) for m in model_info.get("symmetries_discrete", [])]
+    steps = int(np.ceil(np.pi / max_sym_disc_step))
+    continuous = []  # (R, t) of the rotation about the offset point: x -> R (x - o) + o
     for sym in model_info.get("symmetries_continuous", []):
-        axis, offset = np.array(sym["axis"]), np.array(sym["offset"]).reshape((3, 1))
-        steps = int(np.ceil(np.pi / max_sym_disc_step))
-        for i in range(1, steps):
-            R = rot(i * 2.0 * np.pi / steps, axis)
-            trans_cont.append({"R": R, "t": -R.dot(offset) + offset})
-    trans = []
-    for td in trans_disc:
-        if len(trans_cont):
-            trans.extend({"R": tc["R"].dot(td["R"]), "t": tc["R"].dot(td["t"]) + tc["t"]} for tc in trans_cont)
+        o = np.asarray(sym["offset"], np.float64).reshape(3, 1)
+        for R in _axis_rotations(sym["axis"], 2.0 * np.pi / steps * np.arange(1, steps)):
+            continuous.append((R, o - R @ o))
+    out = []
+    for D in discrete:
+        Rd, td = D[:3, :3], D[:3, 3:4]
+        if continuous:
+            out.extend({"R": Rc @ Rd, "t": Rc @ td + tc} for Rc, tc in continuous)
         else:
-            trans.append(td)
-    return trans
+            out.append({"R": Rd, "t": td})
+    return out

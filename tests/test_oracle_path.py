@@ -175,8 +175,9 @@ def test_symmetry_sets_match_reference(golden_dir):
     m = np.load(os.path.join(golden_dir, "metrics_golden.npz"))
     infos = json.loads(str(m["sym_infos"]))
     for i, info in enumerate(infos):
-        for fn in (po.get_symmetry_transformations, geometry.get_symmetry_transformations):
+        # the oracle follows the reference's operation order (1e-15); the package builds the rotations in one batch (1e-12)
+        for fn, tol in ((po.get_symmetry_transformations, 1e-15), (geometry.get_symmetry_transformations, 1e-12)):
             tr = fn(info, float(m["sym_step"]))
             assert len(tr) == m["sym%d_R" % i].shape[0]
-            np.testing.assert_allclose(np.stack([t["R"] for t in tr]), m["sym%d_R" % i], rtol=0, atol=1e-15)
-            np.testing.assert_allclose(np.stack([t["t"] for t in tr]), m["sym%d_t" % i], rtol=0, atol=1e-15)
+            np.testing.assert_allclose(np.stack([t["R"] for t in tr]), m["sym%d_R" % i], rtol=0, atol=tol)
+            np.testing.assert_allclose(np.stack([t["t"] for t in tr]), m["sym%d_t" % i], rtol=0, atol=tol)
