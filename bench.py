@@ -415,6 +415,22 @@ def fps_block(dev):
         cpu_ms = 1e3 * (time.perf_counter() - t0)
         out["runs"].append({"k": k, "ms": ms, "us_per_pick": 1e3 * ms / k, "cpu_ms": cpu_ms, "speedup": cpu_ms / ms,
                             "bit_exact": bool(np.array_equal(idx, ref))})
+    # the sizes the reference's tools run (tools/lm/1_compute_fps.py:26-35: model meshes, <= 256 picks): the cluster path.
+    # Marginal time per pick = (256 picks - 64 picks) / 192, so that launch and allocation cancel (benchmarks/fps_small.py)
+    try:
+        small = []
+        for n in (8_192, 32_768):
+            c = synth.fps_cloud(n, seed=1)
+            tc = torch.from_numpy(c).to(dev)
+            a = _ev_ms(lambda i: fps_utils.fps_indices(tc, 64), 10)
+            b = _ev_ms(lambda i: fps_utils.fps_indices(tc, 256), 10)
+            idx = fps_utils.fps_indices(tc, 256).cpu().numpy()
+            ref = (fps_indices_reference if have_ref else fps_indices_port)(c, 256)
+            small.append({"n_points": n, "k": 256, "ms": b, "us_per_pick_marginal": 1e3 * (b - a) / 192,
+                          "bit_exact": bool(np.array_equal(idx, ref))})
+        out["model_sized"] = small
+    except Exception as e:  # never lose the 1 M-point runs above
+        out["model_sized"] = {"error": repr(e)}
     return out
 
 
