@@ -266,9 +266,9 @@ __global__ void __launch_bounds__(FPS_THREADS, 1)
 // Small clouds (the sizes the reference's tools run: tools/lm/1_compute_fps.py:26-35, 10^4-10^5 model vertices, <= 256
 // picks, one object after the other): ONE THREAD-BLOCK CLUSTER per object, many objects per launch.
 // The cloud of an object is dealt to the C <= 8 CTAs of its cluster (registers, as above); the arg-max of a pick is
-// block-reduced, parked in the CTA's shared memory, and after ONE cluster barrier every CTA reads the C candidates
-// through distributed shared memory -- no global atomics, no spinning on L2.  Same arithmetic, same keys, same
-// tie rule: bit-identical picks.
+// block-reduced and every CTA PUSHES its candidate (key + coordinates) into the shared memory of every CTA of the
+// cluster, where it is counted by the receiver's own mbarrier -- no cluster barrier, no global atomics, no spinning on
+// L2, no remote load.  Same arithmetic, same keys, same tie rule: bit-identical picks.
 // ---------------------------------------------------------------------------------------------
 namespace cg = cooperative_groups;
 constexpr int FPS_CLUSTER_THREADS_DEFAULT = 128;  // narrowest CTA that holds the cloud at <= 16 points per thread
@@ -361,12 +361,13 @@ __global__ void __launch_bounds__(CT, 1)
     }
     // Cluster-wide max of a key whose owner thread also knows the candidate's coordinates (bx, by, bz).  Returns the
     // winning key and leaves its coordinates in (cx, cy, cz).
-    // PUSH (default): two REDUX in the warp, then the owner lane stores the warp's candidate into the slot
-    // [rank * 16 + warp] of EVERY CTA of the cluster (st.async: 20 bytes that complete the destination's mbarrier); a
-    // CTA waits on its OWN mbarrier for the C * 16 candidates and every warp reduces them from local shared memory.
-    // No block barrier, no cluster barrier, no remote load on the path of a pick.  Slots and barriers are double-
-    // buffered by pick parity: a CTA can receive pick i + 1 while it still reads pick i, and nobody can send pick
-    // i + 2 before every warp of the cluster has sent pick i + 1, i.e. has finished reading pick i.
+    // PUSH (default): two REDUX in the warp, the warps' candidates meet in local shared memory at one block barrier,
+    // warp 0 reduces them and stores the CTA's candidate into slot [rank] of EVERY CTA of the cluster (st.async: 16 + 4
+    // bytes, each store completing the DESTINATION's mbarrier); a CTA waits on its OWN mbarrier for the 20 C bytes and
+    // every thread picks the best of the <= 8 candidates from local shared memory.  No cluster barrier, no remote load
+    // on the path of a pick.  Slots and barriers are double-buffered by pick parity: a CTA can receive pick i + 1 while
+    // it still reads pick i, and nobody can send pick i + 2 before every CTA of the cluster has sent pick i + 1, i.e.
+    // has finished reading pick i.
     // !PUSH (RDPN_FPS_EXCHANGE=barrier): block reduce, ONE cluster barrier, C remote reads of 8 bytes and one of 12.
     int par = 0;
     unsigned xchg = 0;  // exchanges done (PUSH): barrier xchg & 1, phase parity (xchg >> 1) & 1
