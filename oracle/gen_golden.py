@@ -505,6 +505,13 @@ def gen_metrics():
         tr = sf(info, 0.2)
         out["sym%d_R" % i] = np.stack([t["R"] for t in tr])
         out["sym%d_t" % i] = np.stack([t["t"] for t in tr])
+    # batched rigid apply (misc.py:930-949, torch) on float64 inputs; drawn last so that the vectors above keep their values
+    bf = ref_functions("lib/pysixd/misc.py", ["transform_pts_batch"])["transform_pts_batch"]
+    bp = rng.standard_normal((3, 17, 3))
+    bR = np.stack([tf.random_rotation_matrix(rng.random(3))[:3, :3] for _ in range(3)])
+    bt = rng.standard_normal((3, 3, 1))
+    out.update(tpb_pts=bp, tpb_R=bR, tpb_t=bt, tpb_out=bf(torch.from_numpy(bp), torch.from_numpy(bR), torch.from_numpy(bt)).numpy(),
+               tpb_out_not=bf(torch.from_numpy(bp), torch.from_numpy(bR)).numpy())
     np.savez_compressed(os.path.join(GOLD, "metrics_golden.npz"), **out)
     print("metrics_golden.npz adi", out["adi_val"], "symmetry sets", [out["sym%d_R" % i].shape[0] for i in range(len(infos))])
 

@@ -584,6 +584,18 @@ def transform_pts_Rt(pts, R, t):
     return (R.dot(pts.T) + np.asarray(t).reshape((3, 1))).T
 
 
+def transform_pts_batch(pts, R, t=None):
+    """misc.py:930-949 (torch, batched): pts [B,P,3], R [B,3,3], t [B,3,1] or None -> [B,P,3] in the dtype of the inputs."""
+    pts, R = np.asarray(pts), np.asarray(R)
+    bs, n_pts = R.shape[0], pts.shape[1]
+    assert pts.shape == (bs, n_pts, 3)
+    out = np.matmul(R.reshape(bs, 1, 3, 3), pts.reshape(bs, n_pts, 3, 1))
+    if t is not None:
+        assert t.shape[0] == bs
+        out = out + np.asarray(t).reshape(bs, 1, 3, 1)
+    return out[..., 0]
+
+
 def add(R_est, t_est, R_gt, t_gt, pts):
     """pose_error.py:297-312."""
     return float(np.linalg.norm(transform_pts_Rt(pts, R_est, t_est) - transform_pts_Rt(pts, R_gt, t_gt), axis=1).mean())

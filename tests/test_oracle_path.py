@@ -146,6 +146,9 @@ def test_metric_helpers_match_reference(golden_dir):
     assert np.array_equal(po.get_closest_rot(m["gcr_est"], m["gcr_gt"], None), m["gcr_out_none"])
     assert np.array_equal(po.get_closest_rot(m["gcr_est"], m["gcr_gt"], m["gcr_sym"][0]), m["gcr_out_single"])
     assert not np.array_equal(m["gcr_out"], m["gcr_gt"])  # a symmetric copy really was closer
+    # misc.transform_pts_batch (misc.py:930-949): the batched rigid apply, with and without the translation
+    np.testing.assert_allclose(po.transform_pts_batch(m["tpb_pts"], m["tpb_R"], m["tpb_t"]), m["tpb_out"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(po.transform_pts_batch(m["tpb_pts"], m["tpb_R"]), m["tpb_out_not"], rtol=0, atol=1e-15)
 
 
 def test_quat2mat_and_sibling_heads_match_reference(g):
