@@ -63,8 +63,24 @@ def _vec(x, shape, name, dtype=torch.float32):
 
 def _mask_mode(m):
     if isinstance(m, str):
+        if m.lower() == "ce":
+            raise ValueError("mask_mode 'ce' is resolved by the tensor entries (argmax over the two channels, then 'raw'); "
+                             "this entry takes the arg-maxed plane with mask_mode='raw'")
         return _MASK_MODES[m.lower()]
     return int(m)
+
+
+def out_mask_ce(pred_mask):
+    """engine_utils.py:131-132, MASK_LOSS_TYPE == "CE": the mask is the arg-max over the class channels, [B,C,64,64] ->
+    [B,64,64] float32 of 0 / 1 (the gate's `> mask_thr` then reads it as a probability, mask_mode 'raw')."""
+    return torch.argmax(pred_mask, dim=1).to(torch.float32)
+
+
+def _resolve_mask(mask, mode):
+    """(plane, integer mode) for the C struct: 'ce' becomes the arg-maxed plane in 'raw' mode."""
+    if isinstance(mode, str) and mode.lower() == "ce":
+        return out_mask_ce(mask), MASK_RAW
+    return mask, _mask_mode(mode)
 
 
 class _Inputs:
@@ -75,6 +91,7 @@ class _Inputs:
         B = depth.shape[0]
         self.B = B
         self.dev = depth.device
+        mask, mask_mode = _resolve_mask(mask, mask_mode)
         self.t = dict(
             depth=_map(depth, "depth", B), coor_x=_map(coor_x, "coor_x", B), coor_y=_map(coor_y, "coor_y", B),
             coor_z=_map(coor_z, "coor_z", B), mask=_map(mask, "mask", B),

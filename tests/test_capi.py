@@ -133,3 +133,23 @@ def test_stale_library_is_an_error_not_a_silent_fallback(monkeypatch):
         L = _lib.lib()
     assert L.rdpn_version() >= 200 and any("STALE" in str(x.message) for x in w)
     monkeypatch.setattr(_lib, "_lib", None)  # the next test loads normally again
+
+
+def test_ce_mask_mode_resolves_to_the_argmaxed_plane():
+    """engine_utils.get_out_mask, MASK_LOSS_TYPE == "CE" (engine_utils.py:131-132): torch.argmax over the class channels.
+    The tensor entries turn mask_mode="ce" into that plane in 'raw' mode (the gate's `> 0.5` then keeps class 1); the
+    host-buffer entry, which only sees planes, says what to pass instead."""
+    import pytest
+    import torch
+
+    from rdpn6d_b200 import pose_solver as ps
+
+    x = torch.randn(3, 2, 64, 64)
+    plane, mode = ps._resolve_mask(x, "ce")
+    assert mode == ps.MASK_RAW and plane.dtype == torch.float32 and plane.shape == (3, 64, 64)
+    assert torch.equal(plane, torch.argmax(x, dim=1, keepdim=True)[:, 0].float())
+    assert torch.equal(plane > 0.5, x[:, 1] > x[:, 0])
+    same, mode = ps._resolve_mask(x[:, 0], "L1")
+    assert same is not plane and mode == ps.MASK_L1
+    with pytest.raises(ValueError):
+        ps._mask_mode("ce")
