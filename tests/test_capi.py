@@ -153,3 +153,31 @@ def test_ce_mask_mode_resolves_to_the_argmaxed_plane():
     assert same is not plane and mode == ps.MASK_L1
     with pytest.raises(ValueError):
         ps._mask_mode("ce")
+
+
+def test_bench_reference_arm_contract_and_no_cpu_fallback_of_the_gpu_arm():
+    """bench.py --impl reference (the CPU implementation of the path on the host cores) prints ONE JSON line with the
+    contract's keys; the default arm refuses to run without a CUDA device instead of falling back to the CPU."""
+    import json
+    import subprocess
+    import sys
+
+    import torch
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "ROI poses/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["metric"].startswith("ROI poses/sec") and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+    if not torch.cuda.is_available():
+        r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "0", "--no-cpu-baseline"],
+                           capture_output=True, text=True, timeout=600, cwd=root)
+        assert r.returncode != 0 and "no CPU fallback" in r.stderr
